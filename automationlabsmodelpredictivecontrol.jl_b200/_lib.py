@@ -1,0 +1,105 @@
+"""ctypes binding of libmpcb200.so (include/mpcb200.h).  The product path: if the CUDA library is missing or no
+B200 is visible, calls FAIL LOUDLY -- there is no CPU fallback (the oracle under oracle/ is test infrastructure and is
+never imported from here)."""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmpcb200.so"
+
+MPCB_OK = 0
+KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED = 0, 1, 2
+TERMINAL_NONE, TERMINAL_EQUALITY = 0, 1
+STATUS_SOLVED, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE = 1, -2, -3
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class Settings(C.Structure):
+    _fields_ = [("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("rho", C.c_double),
+                ("rho_eq_scale", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("max_iter", C.c_int32),
+                ("check_every", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class LinearDesc(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("horizon", C.c_int32), ("A", _dp), ("B", _dp), ("Q", _dp), ("R", _dp),
+                ("S", _dp), ("P", _dp), ("umin", _dp), ("umax", _dp), ("xmin", _dp), ("xmax", _dp),
+                ("state_constraint", C.c_int32), ("terminal_mode", C.c_int32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("nu", C.c_int32), ("horizon", C.c_int32), ("nz", C.c_int32), ("mg", C.c_int32),
+                ("nt", C.c_int32), ("nt_pad", C.c_int32), ("kernel", C.c_int32), ("device", C.c_int32), ("sm_count", C.c_int32),
+                ("rho", C.c_double), ("lambda_min", C.c_double), ("lambda_max", C.c_double)]
+
+
+class BatchIO(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("x0", C.c_void_p), ("xref", C.c_void_p), ("uref", C.c_void_p),
+                ("xref_broadcast", C.c_int32), ("uref_broadcast", C.c_int32), ("warm_u", C.c_void_p), ("warm_y", C.c_void_p),
+                ("u", C.c_void_p), ("e_u", C.c_void_p), ("x", C.c_void_p), ("e_x", C.c_void_p), ("u0", C.c_void_p),
+                ("status", C.c_void_p), ("iters", C.c_void_p), ("prim_res", C.c_void_p), ("dual_res", C.c_void_p),
+                ("objective", C.c_void_p), ("y", C.c_void_p)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("h2d_ms", C.c_float), ("solve_ms", C.c_float), ("recover_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("total_ms", C.c_float), ("batch", C.c_int64), ("total_iterations", C.c_int64), ("kernel_launches", C.c_int32)]
+
+
+# every symbol include/mpcb200.h declares (tests assert the library exports all of them)
+EXPORTED_SYMBOLS = (
+    "mpcb_version", "mpcb_device_count", "mpcb_last_error", "mpcb_default_settings", "mpcb_dare", "mpcb_create_linear",
+    "mpcb_destroy", "mpcb_get_info", "mpcb_get_timing", "mpcb_get_design", "mpcb_solve_linear_batch",
+    "mpcb_solve_linear_batch_device", "mpcb_alloc_pinned", "mpcb_free_pinned",
+)
+
+_lib = None
+
+
+class MpcbError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libmpcb200.so from the package directory (built in-tree by csrc/build.sh / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise MpcbError(f"{LIB_PATH} is missing: build it with automationlabsmodelpredictivecontrol.jl_b200/csrc/build.sh "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        L.mpcb_last_error.restype = C.c_char_p
+        L.mpcb_create_linear.argtypes = [C.POINTER(LinearDesc), C.POINTER(Settings), C.POINTER(C.c_void_p)]
+        L.mpcb_destroy.argtypes = [C.c_void_p]
+        L.mpcb_destroy.restype = None
+        L.mpcb_get_info.argtypes = [C.c_void_p, C.POINTER(Info)]
+        L.mpcb_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+        L.mpcb_get_design.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
+        L.mpcb_solve_linear_batch.argtypes = [C.c_void_p, C.POINTER(BatchIO)]
+        L.mpcb_solve_linear_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIO), C.c_void_p]
+        L.mpcb_dare.argtypes = [C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]
+        L.mpcb_alloc_pinned.argtypes = [C.c_size_t]
+        L.mpcb_alloc_pinned.restype = C.c_void_p
+        L.mpcb_free_pinned.argtypes = [C.c_void_p]
+        L.mpcb_free_pinned.restype = None
+        _lib = L
+    return _lib
+
+
+def check(rc, what):
+    if rc != MPCB_OK:
+        msg = lib().mpcb_last_error()
+        raise MpcbError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def default_settings(**kw) -> Settings:
+    s = Settings()
+    lib().mpcb_default_settings(C.byref(s))
+    for k, v in kw.items():
+        if not hasattr(s, k):
+            raise TypeError(f"unknown solver setting {k!r}")
+        setattr(s, k, v)
+    return s

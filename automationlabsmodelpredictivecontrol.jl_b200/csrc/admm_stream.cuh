@@ -1,0 +1,50 @@
+// Streamed batched ADMM for operators that do not fit the register file (nz + mg > 64): placeholder interface,
+// filled in by admm_stream.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/mpcb200.h"
+#include "host_design.hpp"
+
+namespace mpcb {
+
+struct StreamConsts {
+  double* T = nullptr;     // [NTp][NTp] row-major (symmetric), zero padded
+  double* C = nullptr;     // [NTp][NTp]
+  double* Lt = nullptr;    // [np][NTp]
+  double* lo = nullptr;    // [NTp]
+  double* hi = nullptr;
+  double* rho = nullptr;
+  double* rinv = nullptr;
+  int NTp = 0;
+};
+
+struct StreamWork {
+  double *X = nullptr, *Q = nullptr, *Z = nullptr, *YS = nullptr, *R0 = nullptr, *R1 = nullptr, *DY = nullptr;
+  double* red = nullptr;       // [cap][8] per-problem reductions
+  int* idx = nullptr;          // [cap] compact position -> original problem
+  int* idx2 = nullptr;
+  int* count = nullptr;        // device: [0] = active count
+  int* h_count = nullptr;      // pinned mirror
+  long long cap = 0;
+};
+
+struct StreamBatch {
+  long long batch;
+  const double *x0, *xref, *uref;
+  int xref_bc, uref_bc;
+  const double *warm_v, *warm_y;
+  double *v_out, *y_out;
+  int32_t *status, *iters;
+  double *pres, *dres;
+};
+
+int stream_padded(int nt);
+cudaError_t stream_upload(const Design& D, StreamConsts& sc, std::string& err);
+cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamConsts& sc, StreamWork& sw, const StreamBatch& b,
+                         int sm_count, cudaStream_t stream, int* launches, std::string& err);
+void stream_release(StreamConsts& sc, StreamWork& sw);
+
+}  // namespace mpcb

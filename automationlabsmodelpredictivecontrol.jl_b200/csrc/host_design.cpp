@@ -1,0 +1,352 @@
+// Host-side controller design (see host_design.hpp).  Reference anchors, relative to /root/reference:
+//   weights            src/sub/design_mpc.jl:264-283
+//   terminal cost P    src/sub/design_mpc.jl:327           (ControlSystems.are -> dare_sda here)
+//   terminal equality  src/sub/design_mpc.jl:330-331
+//   cost               src/sub/design_mpc.jl:405-465       (no 1/2 factor; S-term only with R != 0 and S != 0)
+//   constraints        src/sub/model_modeler_implementation/linear/mpc_modeler_implementation_linear.jl:58-87
+#include "host_design.hpp"
+
+#include <algorithm>
+#include <cmath>
+
+namespace mpcb {
+
+Mat matmul(const Mat& A, const Mat& B) {
+  Mat C(A.r, B.c);
+  const int m = A.r, k = A.c, n = B.c;
+  for (int j = 0; j < n; j++) {
+    double* cj = &C.a[(size_t)j * m];
+    for (int l = 0; l < k; l++) {
+      const double b = B(l, j);
+      if (b == 0.0) continue;
+      const double* al = &A.a[(size_t)l * m];
+      for (int i = 0; i < m; i++) cj[i] += al[i] * b;
+    }
+  }
+  return C;
+}
+
+Mat matmul_tn(const Mat& A, const Mat& B) {  // A' * B, A is k x m, B is k x n
+  Mat C(A.c, B.c);
+  const int m = A.c, k = A.r, n = B.c;
+  for (int j = 0; j < n; j++) {
+    const double* bj = &B.a[(size_t)j * k];
+    for (int i = 0; i < m; i++) {
+      const double* ai = &A.a[(size_t)i * k];
+      double s = 0.0;
+      for (int l = 0; l < k; l++) s += ai[l] * bj[l];
+      C(i, j) = s;
+    }
+  }
+  return C;
+}
+
+Mat transpose(const Mat& A) {
+  Mat T(A.c, A.r);
+  for (int j = 0; j < A.c; j++)
+    for (int i = 0; i < A.r; i++) T(j, i) = A(i, j);
+  return T;
+}
+
+Mat add(const Mat& A, const Mat& B, double sb) {
+  Mat C = A;
+  for (size_t i = 0; i < C.a.size(); i++) C.a[i] += sb * B.a[i];
+  return C;
+}
+
+bool cholesky_lower(Mat& A) {
+  const int n = A.r;
+  for (int j = 0; j < n; j++) {
+    double d = A(j, j);
+    for (int k = 0; k < j; k++) d -= A(j, k) * A(j, k);
+    if (!(d > 0.0)) return false;
+    d = std::sqrt(d);
+    A(j, j) = d;
+    // column j below the diagonal: A(i,j) = (A(i,j) - sum_k A(i,k) A(j,k)) / d, done as axpys over columns k
+    for (int k = 0; k < j; k++) {
+      const double ljk = A(j, k);
+      if (ljk == 0.0) continue;
+      double* cj = &A.a[(size_t)j * n];
+      const double* ck = &A.a[(size_t)k * n];
+      for (int i = j + 1; i < n; i++) cj[i] -= ck[i] * ljk;
+    }
+    const double inv = 1.0 / d;
+    for (int i = j + 1; i < n; i++) A(i, j) *= inv;
+    for (int i = 0; i < j; i++) A(i, j) = 0.0;
+  }
+  return true;
+}
+
+bool spd_inverse(const Mat& A, Mat& Ainv) {
+  const int n = A.r;
+  Mat L = A;
+  if (!cholesky_lower(L)) return false;
+  // Linv = L^-1 (lower), column by column
+  Mat Li(n, n);
+  for (int j = 0; j < n; j++) {
+    Li(j, j) = 1.0 / L(j, j);
+    for (int i = j + 1; i < n; i++) {
+      double s = 0.0;
+      for (int k = j; k < i; k++) s += L(i, k) * Li(k, j);
+      Li(i, j) = -s / L(i, i);
+    }
+  }
+  Ainv = matmul_tn(Li, Li);  // L^-T L^-1
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < j; i++) {
+      const double v = 0.5 * (Ainv(i, j) + Ainv(j, i));
+      Ainv(i, j) = v;
+      Ainv(j, i) = v;
+    }
+  return true;
+}
+
+bool lu_solve(Mat A, Mat& B) {
+  const int n = A.r, m = B.c;
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    double best = std::fabs(A(k, k));
+    for (int i = k + 1; i < n; i++)
+      if (std::fabs(A(i, k)) > best) { best = std::fabs(A(i, k)); piv = i; }
+    if (best == 0.0) return false;
+    if (piv != k) {
+      for (int j = 0; j < n; j++) std::swap(A(k, j), A(piv, j));
+      for (int j = 0; j < m; j++) std::swap(B(k, j), B(piv, j));
+    }
+    const double inv = 1.0 / A(k, k);
+    for (int i = k + 1; i < n; i++) {
+      const double f = A(i, k) * inv;
+      if (f == 0.0) continue;
+      for (int j = k + 1; j < n; j++) A(i, j) -= f * A(k, j);
+      for (int j = 0; j < m; j++) B(i, j) -= f * B(k, j);
+    }
+  }
+  for (int j = 0; j < m; j++)
+    for (int i = n - 1; i >= 0; i--) {
+      double s = B(i, j);
+      for (int k = i + 1; k < n; k++) s -= A(i, k) * B(k, j);
+      B(i, j) = s / A(i, i);
+    }
+  return true;
+}
+
+bool sym_extreme_eigs(const Mat& A, double& lmin, double& lmax) {
+  const int n = A.r;
+  std::vector<double> v(n), w(n);
+  auto normalize = [&](std::vector<double>& x) {
+    double s = 0;
+    for (double t : x) s += t * t;
+    s = std::sqrt(s);
+    for (double& t : x) t /= s;
+    return s;
+  };
+  // largest: power iteration from a fixed, non-degenerate start
+  for (int i = 0; i < n; i++) v[i] = 1.0 + 0.37 * std::sin(1.0 + 1.7 * i);
+  normalize(v);
+  double lam = 0;
+  for (int it = 0; it < 3000; it++) {
+    for (int i = 0; i < n; i++) w[i] = 0;
+    for (int j = 0; j < n; j++) {
+      const double vj = v[j];
+      const double* aj = &A.a[(size_t)j * n];
+      for (int i = 0; i < n; i++) w[i] += aj[i] * vj;
+    }
+    double nl = 0;
+    for (int i = 0; i < n; i++) nl += w[i] * v[i];
+    normalize(w);
+    v.swap(w);
+    if (it > 5 && std::fabs(nl - lam) <= 1e-15 * std::fabs(nl)) { lam = nl; break; }
+    lam = nl;
+  }
+  lmax = lam;
+  // smallest: inverse iteration through the Cholesky factor
+  Mat L = A;
+  if (!cholesky_lower(L)) return false;
+  for (int i = 0; i < n; i++) v[i] = 1.0 + 0.41 * std::cos(0.3 + 2.3 * i);
+  normalize(v);
+  double mu = 0;
+  for (int it = 0; it < 3000; it++) {
+    w = v;
+    for (int i = 0; i < n; i++) {  // L y = v
+      double s = w[i];
+      for (int k = 0; k < i; k++) s -= L(i, k) * w[k];
+      w[i] = s / L(i, i);
+    }
+    for (int i = n - 1; i >= 0; i--) {  // L' x = y
+      double s = w[i];
+      for (int k = i + 1; k < n; k++) s -= L(k, i) * w[k];
+      w[i] = s / L(i, i);
+    }
+    double nm = 0;
+    for (int i = 0; i < n; i++) nm += w[i] * v[i];  // Rayleigh quotient of A^-1
+    normalize(w);
+    v.swap(w);
+    if (it > 5 && std::fabs(nm - mu) <= 1e-15 * std::fabs(nm)) { mu = nm; break; }
+    mu = nm;
+  }
+  lmin = 1.0 / mu;
+  return lmin > 0 && lmax > 0;
+}
+
+// Structure-preserving doubling algorithm for X = A'X(I + G X)^-1 A + Q,  G = B R^-1 B'.
+bool dare_sda(const Mat& A, const Mat& B, const Mat& Q, const Mat& R, Mat& P, std::string& err) {
+  const int n = A.r;
+  Mat Rinv_Bt = transpose(B);
+  if (!lu_solve(R, Rinv_Bt)) { err = "dare: R is singular"; return false; }
+  Mat Gk = matmul(B, Rinv_Bt);
+  Mat Ak = A, Hk = Q;
+  for (int it = 0; it < 100; it++) {
+    Mat W = add(Mat::eye(n), matmul(Gk, Hk));
+    Mat V1 = Ak, V2 = Gk;
+    if (!lu_solve(W, V1) || !lu_solve(W, V2)) { err = "dare: singular I + G H"; return false; }
+    Mat Akt = transpose(Ak);
+    Mat An = matmul(Ak, V1);
+    Mat Gn = add(Gk, matmul(matmul(Ak, V2), Akt));
+    Mat Hn = add(Hk, matmul(matmul(Akt, Hk), V1));
+    double diff = 0, nrm = 0;
+    for (size_t i = 0; i < Hn.a.size(); i++) {
+      diff = std::max(diff, std::fabs(Hn.a[i] - Hk.a[i]));
+      nrm = std::max(nrm, std::fabs(Hn.a[i]));
+    }
+    Ak = An; Gk = Gn; Hk = Hn;
+    if (!std::isfinite(nrm)) { err = "dare: diverged"; return false; }
+    if (diff <= 1e-15 * std::max(1.0, nrm)) {
+      P = Hk;
+      for (int j = 0; j < n; j++)
+        for (int i = 0; i < j; i++) { const double v = 0.5 * (P(i, j) + P(j, i)); P(i, j) = v; P(j, i) = v; }
+      return true;
+    }
+  }
+  err = "dare: doubling did not converge (is (A,B) stabilisable?)";
+  return false;
+}
+
+int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, std::string& err) {
+  if (d.nx <= 0 || d.nu <= 0 || d.horizon <= 0) { err = "nx, nu, horizon must be positive"; return MPCB_ERR_INVALID; }
+  if (!d.A || !d.B || !d.Q || !d.R || !d.umin || !d.umax) { err = "A, B, Q, R, umin, umax are required"; return MPCB_ERR_INVALID; }
+  if (d.terminal_mode != MPCB_TERMINAL_NONE && d.terminal_mode != MPCB_TERMINAL_EQUALITY) {
+    err = "terminal_mode: only none / equality are supported (contractive is a QCQP, neighborhood is unimplemented in the reference)";
+    return MPCB_ERR_INVALID;
+  }
+  if (d.state_constraint && (!d.xmin || !d.xmax)) { err = "state_constraint needs xmin/xmax"; return MPCB_ERR_INVALID; }
+  const int nx = d.nx, nu = d.nu, H = d.horizon, nz = nu * H, np = 2 * nx + nu;
+  D.nx = nx; D.nu = nu; D.H = H; D.nz = nz; D.np = np;
+  D.A = Mat::from(d.A, nx, nx); D.B = Mat::from(d.B, nx, nu);
+  D.Q = Mat::from(d.Q, nx, nx); D.R = Mat::from(d.R, nu, nu); D.S = Mat::from(d.S, nu, nu);
+  D.use_R = D.R(0, 0) != 0.0;                       // design_mpc.jl:436,449
+  D.use_S = D.use_R && D.S(0, 0) != 0.0;            // design_mpc.jl:436 (S-term only in the R != 0 branch)
+  for (int i = 0; i < nu; i++)
+    if (!(d.umin[i] <= d.umax[i])) { err = "umin > umax"; return MPCB_ERR_INVALID; }
+  if (d.P) D.P = Mat::from(d.P, nx, nx);
+  else if (!dare_sda(D.A, D.B, D.Q, D.R, D.P, err)) return MPCB_ERR_NUMERIC;
+
+  // prediction matrices: e_k = Phi_k e0 + Gam_k eps,  Gam_{k+1} = A Gam_k + [.. B at block k ..]
+  std::vector<Mat> Phi(H + 1), Gam(H + 1);
+  Phi[0] = Mat::eye(nx); Gam[0] = Mat(nx, nz);
+  for (int k = 0; k < H; k++) {
+    Phi[k + 1] = matmul(D.A, Phi[k]);
+    Gam[k + 1] = matmul(D.A, Gam[k]);
+    for (int j = 0; j < nu; j++)
+      for (int i = 0; i < nx; i++) Gam[k + 1](i, k * nu + j) += D.B(i, j);
+  }
+  // Hessian / gradient map in deviation inputs: J = eps' M eps + 2 (Fe e0)' eps + const, Pc_dev = 2M
+  Mat M(nz, nz), Fe(nz, nx);
+  for (int k = 0; k <= H; k++) {
+    const Mat& W = (k == H) ? D.P : D.Q;
+    Mat WG = matmul(W, Gam[k]);                 // nx x nz
+    M = add(M, matmul_tn(Gam[k], WG));
+    Fe = add(Fe, matmul_tn(WG, Phi[k]));        // Gam' W Phi  (W symmetric)
+  }
+  if (D.use_R)
+    for (int k = 0; k < H; k++)
+      for (int j = 0; j < nu; j++)
+        for (int i = 0; i < nu; i++) M(k * nu + i, k * nu + j) += D.R(i, j);
+  Mat Pdev(nz, nz);
+  for (size_t i = 0; i < M.a.size(); i++) Pdev.a[i] = 2.0 * M.a[i];
+  D.Pc = Pdev;
+  if (D.use_S) {  // sum_{k<H-1} (u_k - u_{k+1})' S (u_k - u_{k+1})   (design_mpc.jl:423-446)
+    for (int k = 0; k + 1 < H; k++)
+      for (int j = 0; j < nu; j++)
+        for (int i = 0; i < nu; i++) {
+          const double v = 2.0 * D.S(i, j);
+          D.Pc(k * nu + i, k * nu + j) += v;
+          D.Pc((k + 1) * nu + i, (k + 1) * nu + j) += v;
+          D.Pc(k * nu + i, (k + 1) * nu + j) -= v;
+          D.Pc((k + 1) * nu + i, k * nu + j) -= v;
+        }
+  }
+  for (int j = 0; j < nz; j++)
+    for (int i = 0; i < j; i++) { const double v = 0.5 * (D.Pc(i, j) + D.Pc(j, i)); D.Pc(i, j) = v; D.Pc(j, i) = v; }
+  // q(p) = 2 Fe (x0 - xref) - Pdev (1 (x) uref)
+  D.Lq = Mat(nz, np);
+  for (int i = 0; i < nz; i++) {
+    for (int j = 0; j < nx; j++) { D.Lq(i, j) = 2.0 * Fe(i, j); D.Lq(i, nx + j) = -2.0 * Fe(i, j); }
+    for (int j = 0; j < nu; j++) {
+      double sacc = 0;
+      for (int k = 0; k < H; k++) sacc += Pdev(i, k * nu + j);
+      D.Lq(i, 2 * nx + j) = -sacc;
+    }
+  }
+  // general rows
+  const int mg = (d.terminal_mode == MPCB_TERMINAL_EQUALITY ? nx : 0) + (d.state_constraint ? nx * H : 0);
+  D.mg = mg; D.nt = nz + mg;
+  D.G = Mat(mg, nz); D.Lb = Mat(mg, np);
+  D.lo.assign(D.nt, 0.0); D.hi.assign(D.nt, 0.0); D.is_eq.assign(D.nt, 0);
+  for (int k = 0; k < H; k++)
+    for (int j = 0; j < nu; j++) { D.lo[k * nu + j] = d.umin[j]; D.hi[k * nu + j] = d.umax[j]; }
+  int row = 0;
+  auto add_rows = [&](int k, bool equality) {
+    // Gam_k v in [lo,hi] + b,  b = -Phi_k x0 + (Phi_k - I*[!equality]) xref + Gam_k (1 (x) uref)
+    for (int i = 0; i < nx; i++, row++) {
+      for (int j = 0; j < nz; j++) D.G(row, j) = Gam[k](i, j);
+      for (int j = 0; j < nx; j++) {
+        D.Lb(row, j) = -Phi[k](i, j);
+        D.Lb(row, nx + j) = Phi[k](i, j) - ((!equality && i == j) ? 1.0 : 0.0);
+      }
+      for (int j = 0; j < nu; j++) {
+        double sacc = 0;
+        for (int kk = 0; kk < H; kk++) sacc += Gam[k](i, kk * nu + j);
+        D.Lb(row, 2 * nx + j) = sacc;
+      }
+      D.lo[nz + row] = equality ? 0.0 : d.xmin[i];
+      D.hi[nz + row] = equality ? 0.0 : d.xmax[i];
+      D.is_eq[nz + row] = equality ? 1 : 0;
+    }
+  };
+  if (d.terminal_mode == MPCB_TERMINAL_EQUALITY) add_rows(H, true);
+  if (d.state_constraint)
+    for (int k = 1; k <= H; k++) add_rows(k, false);
+
+  // rho
+  if (!sym_extreme_eigs(D.Pc, D.lmin, D.lmax)) { err = "condensed Hessian is not positive definite (need R != 0 or full-rank Q)"; return MPCB_ERR_NUMERIC; }
+  D.rho = s.rho > 0 ? s.rho : std::sqrt(D.lmin * D.lmax);
+  D.rho_vec.assign(D.nt, D.rho);
+  for (int i = 0; i < mg; i++)
+    if (D.is_eq[nz + i]) D.rho_vec[nz + i] = s.rho_eq_scale * D.rho;
+  // K = Pc + (sigma + rho) I + G' diag(rho_g) G ;  T = [I;G] K^-1 [I,G'] ;  C = [[Pc,G'],[G,0]]
+  Mat K = D.Pc;
+  for (int i = 0; i < nz; i++) K(i, i) += s.sigma + D.rho;
+  if (mg) {
+    Mat RG = D.G;
+    for (int j = 0; j < nz; j++)
+      for (int i = 0; i < mg; i++) RG(i, j) *= D.rho_vec[nz + i];
+    K = add(K, matmul_tn(D.G, RG));
+  }
+  Mat Kinv;
+  if (!spd_inverse(K, Kinv)) { err = "K = Pc + (sigma+rho) I + G' rho G is not positive definite"; return MPCB_ERR_NUMERIC; }
+  D.Ac = Mat(D.nt, nz);
+  for (int i = 0; i < nz; i++) D.Ac(i, i) = 1.0;
+  for (int j = 0; j < nz; j++)
+    for (int i = 0; i < mg; i++) D.Ac(nz + i, j) = D.G(i, j);
+  D.T = matmul(matmul(D.Ac, Kinv), transpose(D.Ac));
+  for (int j = 0; j < D.nt; j++)
+    for (int i = 0; i < j; i++) { const double v = 0.5 * (D.T(i, j) + D.T(j, i)); D.T(i, j) = v; D.T(j, i) = v; }
+  D.C = Mat(D.nt, D.nt);
+  for (int j = 0; j < nz; j++) {
+    for (int i = 0; i < nz; i++) D.C(i, j) = D.Pc(i, j);
+    for (int i = 0; i < mg; i++) { D.C(nz + i, j) = D.G(i, j); D.C(j, nz + i) = D.G(i, j); }
+  }
+  return MPCB_OK;
+}
+
+}  // namespace mpcb

@@ -1,0 +1,469 @@
+// C ABI of libmpcb200.so (see include/mpcb200.h).  Host plumbing only: design upload, buffer management, kernel
+// dispatch, CUDA-event timing.  There is deliberately NO CPU fallback: without a usable sm_100 device every entry
+// point that computes fails with MPCB_ERR_NO_DEVICE / MPCB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpcb200.h"
+#include "admm_onchip.cuh"
+#include "admm_stream.cuh"
+#include "host_design.hpp"
+#include "recover.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(MPCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <typename T>
+struct PinBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+bool is_pinned_or_device(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+struct mpcb_handle {
+  mpcb::Design D;
+  mpcb_settings st;
+  mpcb_info info;
+  mpcb_timing timing;
+  int NT = 0;  // padded operator size of the on-chip kernel
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  // per-system constants
+  DevBuf<double> Tfrag, Cfrag, Lt, lo, hi, rho, rinv, A, B, Q, R, S, P;
+  DevBuf<unsigned long long> counter;
+  mpcb::StreamConsts sc;  // streamed-kernel constants
+  // batch workspaces (device)
+  DevBuf<double> x0, xref, uref, warm_v, warm_y, v, y, pres, dres, u, e_u, x, e_x, u0, obj;
+  DevBuf<int32_t> status, iters;
+  mpcb::StreamWork sw;
+  // pinned staging for pageable user memory
+  PinBuf<double> stage_in, stage_out;
+  PinBuf<int32_t> stage_int;
+  int onchip_blocks_per_sm = 0;
+};
+
+namespace {
+
+using mpcb::OnchipParams;
+
+template <int NT, bool HAS_G, int MINB>
+cudaError_t launch_onchip_t(const OnchipParams& P, int sm_count, int* blocks_per_sm_cache, cudaStream_t st) {
+  auto kern = mpcb::admm_onchip_kernel<NT, HAS_G, MINB>;
+  const size_t smem = mpcb::onchip_smem_bytes(NT, P.np);
+  if (*blocks_per_sm_cache == 0) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, mpcb::ONCHIP_THREADS, smem);
+    if (e != cudaSuccess) return e;
+    *blocks_per_sm_cache = std::max(occ, 1);
+  }
+  const long long warps_needed = (P.batch + 7) / 8;
+  const long long blocks_needed = (warps_needed + mpcb::ONCHIP_WARPS - 1) / mpcb::ONCHIP_WARPS;
+  const long long grid = std::min<long long>(blocks_needed, (long long)sm_count * *blocks_per_sm_cache);
+  kern<<<(unsigned)std::max<long long>(grid, 1), mpcb::ONCHIP_THREADS, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+template <bool HAS_G>
+cudaError_t launch_onchip_g(int NT, const OnchipParams& P, int sm_count, int* cache, cudaStream_t st) {
+  // MINB (CTAs of 128 threads per SM) is the register budget: box-only kernels hold 4 doubles per owned row,
+  // kernels with general rows also carry delta_y and per-row rho loads.
+  switch (NT) {
+    case 8: return launch_onchip_t<8, HAS_G, 4>(P, sm_count, cache, st);
+    case 16: return launch_onchip_t<16, HAS_G, 4>(P, sm_count, cache, st);
+    case 24: return launch_onchip_t<24, HAS_G, HAS_G ? 3 : 4>(P, sm_count, cache, st);
+    case 32: return launch_onchip_t<32, HAS_G, HAS_G ? 2 : 3>(P, sm_count, cache, st);
+    case 40: return launch_onchip_t<40, HAS_G, HAS_G ? 2 : 3>(P, sm_count, cache, st);
+    case 48: return launch_onchip_t<48, HAS_G, 2>(P, sm_count, cache, st);
+    case 56: return launch_onchip_t<56, HAS_G, 2>(P, sm_count, cache, st);
+    case 64: return launch_onchip_t<64, HAS_G, 2>(P, sm_count, cache, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t upload(DevBuf<double>& b, const double* src, size_t n) {
+  cudaError_t e = b.ensure(n);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(b.p, src, n * sizeof(double), cudaMemcpyHostToDevice);
+}
+
+// fragment order of a symmetric NT x NT operator for the on-chip kernel (see admm_onchip.cuh)
+std::vector<double> to_fragments(const mpcb::Mat& M, int nt, int NT) {
+  const int KS = NT / 4, NTL = NT / 8;
+  std::vector<double> f((size_t)NT * NT, 0.0);
+  for (int s = 0; s < KS; s++)
+    for (int tn = 0; tn < NTL; tn++)
+      for (int lane = 0; lane < 32; lane++) {
+        const int g = lane >> 2, l4 = lane & 3;
+        const int row = 8 * (s >> 1) + 2 * l4 + (s & 1), col = 8 * tn + g;
+        f[((size_t)s * NTL + tn) * 32 + lane] = (row < nt && col < nt) ? M(row, col) : 0.0;
+      }
+  return f;
+}
+
+int upload_design(mpcb_handle* h) {
+  const mpcb::Design& D = h->D;
+  CUDA_TRY(upload(h->A, D.A.a.data(), D.A.a.size()));
+  CUDA_TRY(upload(h->B, D.B.a.data(), D.B.a.size()));
+  CUDA_TRY(upload(h->Q, D.Q.a.data(), D.Q.a.size()));
+  CUDA_TRY(upload(h->R, D.R.a.data(), D.R.a.size()));
+  CUDA_TRY(upload(h->S, D.S.a.data(), D.S.a.size()));
+  CUDA_TRY(upload(h->P, D.P.a.data(), D.P.a.size()));
+  CUDA_TRY(h->counter.ensure(1));
+  if (h->info.kernel == MPCB_KERNEL_ONCHIP) {
+    const int NT = h->NT, nt = D.nt, np = D.np;
+    std::vector<double> tf = to_fragments(D.T, nt, NT), cf = to_fragments(D.C, nt, NT);
+    std::vector<double> Lt((size_t)np * NT, 0.0), lo(NT, 0.0), hi(NT, 0.0), rho(NT, 1.0), rinv(NT, 1.0);
+    for (int j = 0; j < np; j++) {
+      for (int i = 0; i < D.nz; i++) Lt[(size_t)j * NT + i] = D.Lq(i, j);
+      for (int i = 0; i < D.mg; i++) Lt[(size_t)j * NT + D.nz + i] = D.Lb(i, j);
+    }
+    for (int i = 0; i < nt; i++) { lo[i] = D.lo[i]; hi[i] = D.hi[i]; rho[i] = D.rho_vec[i]; rinv[i] = 1.0 / D.rho_vec[i]; }
+    CUDA_TRY(upload(h->Tfrag, tf.data(), tf.size()));
+    CUDA_TRY(upload(h->Cfrag, cf.data(), cf.size()));
+    CUDA_TRY(upload(h->Lt, Lt.data(), Lt.size()));
+    CUDA_TRY(upload(h->lo, lo.data(), NT));
+    CUDA_TRY(upload(h->hi, hi.data(), NT));
+    CUDA_TRY(upload(h->rho, rho.data(), NT));
+    CUDA_TRY(upload(h->rinv, rinv.data(), NT));
+  } else {
+    std::string err;
+    cudaError_t e = mpcb::stream_upload(D, h->sc, err);
+    if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, "stream_upload: " + err + cudaGetErrorString(e));
+  }
+  return MPCB_OK;
+}
+
+// Enqueue solve + recover on `st` with device-resident io.  Internal scratch is used for anything the caller skipped.
+int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cudaEvent_t ev_mid) {
+  const mpcb::Design& D = h->D;
+  const long long Bn = io.batch;
+  if (Bn <= 0) return fail(MPCB_ERR_INVALID, "batch must be positive");
+  if (!io.x0 || !io.xref || !io.uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  if ((io.warm_u == nullptr) != (io.warm_y == nullptr)) return fail(MPCB_ERR_INVALID, "warm_u and warm_y must be given together");
+  CUDA_TRY(h->v.ensure((size_t)Bn * D.nz));
+  int32_t* d_status = io.status; int32_t* d_iters = io.iters; double* d_pres = io.prim_res; double* d_dres = io.dual_res;
+  if (!d_status) { CUDA_TRY(h->status.ensure(Bn)); d_status = h->status.p; }
+  if (!d_iters) { CUDA_TRY(h->iters.ensure(Bn)); d_iters = h->iters.p; }
+  if (!d_pres) { CUDA_TRY(h->pres.ensure(Bn)); d_pres = h->pres.p; }
+  if (!d_dres) { CUDA_TRY(h->dres.ensure(Bn)); d_dres = h->dres.p; }
+  int launches = 0;
+  if (h->info.kernel == MPCB_KERNEL_ONCHIP) {
+    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), st));
+    OnchipParams P;
+    P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
+    P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu;
+    P.rho_box = D.rho; P.sigma = h->st.sigma; P.alpha = h->st.alpha; P.eps_abs = h->st.eps_abs; P.eps_rel = h->st.eps_rel;
+    P.eps_pinf = h->st.eps_prim_inf; P.max_iter = h->st.max_iter; P.check_every = h->st.check_every;
+    P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
+    P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = h->v.p; P.y_out = io.y;
+    P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres; P.counter = h->counter.p;
+    cudaError_t e = D.mg > 0 ? launch_onchip_g<true>(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st)
+                             : launch_onchip_g<false>(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+    if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
+    launches += 1;
+  } else {
+    std::string err;
+    mpcb::StreamBatch sb;
+    sb.batch = Bn; sb.x0 = io.x0; sb.xref = io.xref; sb.uref = io.uref; sb.xref_bc = io.xref_broadcast; sb.uref_bc = io.uref_broadcast;
+    sb.warm_v = io.warm_u; sb.warm_y = io.warm_y; sb.v_out = h->v.p; sb.y_out = io.y;
+    sb.status = d_status; sb.iters = d_iters; sb.pres = d_pres; sb.dres = d_dres;
+    int nl = 0;
+    cudaError_t e = mpcb::stream_solve(h->D, h->st, h->sc, h->sw, sb, h->info.sm_count, st, &nl, err);
+    if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, "admm_stream: " + err + " " + cudaGetErrorString(e));
+    launches += nl;
+  }
+  if (ev_mid) CUDA_TRY(cudaEventRecord(ev_mid, st));
+  if (io.u || io.e_u || io.x || io.e_x || io.u0 || io.objective) {
+    mpcb::RecoverParams R;
+    R.A = h->A.p; R.B = h->B.p; R.Q = h->Q.p; R.R = h->R.p; R.S = h->S.p; R.Pt = h->P.p;
+    R.nx = D.nx; R.nu = D.nu; R.H = D.H; R.use_R = D.use_R; R.use_S = D.use_S; R.batch = Bn;
+    R.x0 = io.x0; R.xref = io.xref; R.uref = io.uref; R.xref_bc = io.xref_broadcast; R.uref_bc = io.uref_broadcast;
+    R.v = h->v.p; R.u = io.u; R.e_u = io.e_u; R.x = io.x; R.e_x = io.e_x; R.u0 = io.u0; R.objective = io.objective;
+    const size_t smem = mpcb::recover_smem_bytes(D.nx, D.nu);
+    static thread_local size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+      CUDA_TRY(cudaFuncSetAttribute(mpcb::recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    const unsigned grid = (unsigned)((Bn + mpcb::RECOVER_THREADS - 1) / mpcb::RECOVER_THREADS);
+    mpcb::recover_kernel<<<grid, mpcb::RECOVER_THREADS, smem, st>>>(R);
+    CUDA_TRY(cudaGetLastError());
+    launches += 1;
+  }
+  h->timing.kernel_launches = launches;
+  h->timing.batch = Bn;
+  return MPCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpcb_version(void) { return MPCB_VERSION; }
+
+int mpcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* mpcb_last_error(void) { return g_err.c_str(); }
+
+void mpcb_default_settings(mpcb_settings* s) {
+  if (!s) return;
+  std::memset(s, 0, sizeof(*s));
+  s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->rho = 0.0; s->rho_eq_scale = 1e3;
+  s->sigma = 1e-6; s->alpha = 1.6; s->max_iter = 4000; s->check_every = 25; s->device = 0; s->kernel = MPCB_KERNEL_AUTO;
+}
+
+void* mpcb_alloc_pinned(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { g_err = "cudaMallocHost failed"; cudaGetLastError(); return nullptr; }
+  return p;
+}
+void mpcb_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+int mpcb_dare(int32_t nx, int32_t nu, const double* A, const double* B, const double* Q, const double* R, double* P_out) {
+  if (nx <= 0 || nu <= 0 || !A || !B || !Q || !R || !P_out) return fail(MPCB_ERR_INVALID, "mpcb_dare: bad arguments");
+  mpcb::Mat P;
+  std::string err;
+  if (!mpcb::dare_sda(mpcb::Mat::from(A, nx, nx), mpcb::Mat::from(B, nx, nu), mpcb::Mat::from(Q, nx, nx), mpcb::Mat::from(R, nu, nu), P, err))
+    return fail(MPCB_ERR_NUMERIC, err);
+  std::memcpy(P_out, P.a.data(), sizeof(double) * nx * nx);
+  return MPCB_OK;
+}
+
+int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settings, mpcb_handle** out) {
+  if (!desc || !out) return fail(MPCB_ERR_INVALID, "mpcb_create_linear: null argument");
+  *out = nullptr;
+  mpcb_settings st;
+  if (settings) st = *settings; else mpcb_default_settings(&st);
+  if (st.check_every <= 0 || st.max_iter <= 0 || !(st.alpha > 0 && st.alpha < 2) || !(st.sigma >= 0) || !(st.eps_abs >= 0) || !(st.eps_rel >= 0))
+    return fail(MPCB_ERR_INVALID, "mpcb_create_linear: invalid settings");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(MPCB_ERR_NO_DEVICE, "no CUDA device visible: libmpcb200 has no CPU fallback");
+  }
+  if (st.device < 0 || st.device >= ndev) return fail(MPCB_ERR_INVALID, "settings.device out of range");
+  CUDA_TRY(cudaSetDevice(st.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, st.device));
+  if (prop.major < 10) return fail(MPCB_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: this library is built for B200 only");
+
+  mpcb_handle* h = new mpcb_handle();
+  std::string err;
+  int rc = mpcb::build_design(*desc, st, h->D, err);
+  if (rc != MPCB_OK) { delete h; return fail(rc, err); }
+  h->st = st;
+  std::memset(&h->info, 0, sizeof(h->info));
+  std::memset(&h->timing, 0, sizeof(h->timing));
+  const mpcb::Design& D = h->D;
+  h->info.nx = D.nx; h->info.nu = D.nu; h->info.horizon = D.H; h->info.nz = D.nz; h->info.mg = D.mg; h->info.nt = D.nt;
+  h->info.rho = D.rho; h->info.lambda_min = D.lmin; h->info.lambda_max = D.lmax;
+  h->info.device = st.device; h->info.sm_count = prop.multiProcessorCount;
+  int kernel = st.kernel;
+  if (kernel == MPCB_KERNEL_AUTO) kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : MPCB_KERNEL_STREAMED;
+  if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
+  if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
+  h->info.kernel = kernel;
+  h->NT = (kernel == MPCB_KERNEL_ONCHIP) ? ((D.nt + 7) / 8) * 8 : mpcb::stream_padded(D.nt);
+  h->info.nt_pad = h->NT;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
+  for (auto& e : h->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
+  rc = upload_design(h);
+  if (rc != MPCB_OK) { std::string keep = g_err; mpcb_destroy(h); return fail(rc, keep); }
+  *out = h;
+  return MPCB_OK;
+}
+
+void mpcb_destroy(mpcb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->st.device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (DevBuf<double>* b : {&h->Tfrag, &h->Cfrag, &h->Lt, &h->lo, &h->hi, &h->rho, &h->rinv, &h->A, &h->B, &h->Q, &h->R, &h->S, &h->P, &h->x0,
+                            &h->xref, &h->uref, &h->warm_v, &h->warm_y, &h->v, &h->y, &h->pres, &h->dres, &h->u, &h->e_u, &h->x, &h->e_x,
+                            &h->u0, &h->obj})
+    b->release();
+  h->status.release(); h->iters.release(); h->counter.release();
+  mpcb::stream_release(h->sc, h->sw);
+  h->stage_in.release(); h->stage_out.release(); h->stage_int.release();
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mpcb_get_info(const mpcb_handle* h, mpcb_info* info) {
+  if (!h || !info) return fail(MPCB_ERR_INVALID, "null argument");
+  *info = h->info;
+  return MPCB_OK;
+}
+
+int mpcb_get_timing(const mpcb_handle* h, mpcb_timing* t) {
+  if (!h || !t) return fail(MPCB_ERR_INVALID, "null argument");
+  *t = h->timing;
+  return MPCB_OK;
+}
+
+int mpcb_get_design(const mpcb_handle* h, double* Pc, double* Lq, double* G, double* Lb, double* T) {
+  if (!h) return fail(MPCB_ERR_INVALID, "null handle");
+  const mpcb::Design& D = h->D;
+  if (Pc) std::memcpy(Pc, D.Pc.a.data(), sizeof(double) * D.Pc.a.size());
+  if (Lq) std::memcpy(Lq, D.Lq.a.data(), sizeof(double) * D.Lq.a.size());
+  if (G && D.mg) std::memcpy(G, D.G.a.data(), sizeof(double) * D.G.a.size());
+  if (Lb && D.mg) std::memcpy(Lb, D.Lb.a.data(), sizeof(double) * D.Lb.a.size());
+  if (T) std::memcpy(T, D.T.a.data(), sizeof(double) * D.T.a.size());
+  return MPCB_OK;
+}
+
+int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* io, void* cuda_stream) {
+  if (!h || !io) return fail(MPCB_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->st.device));
+  return enqueue_device(h, *io, (cudaStream_t)cuda_stream, nullptr);
+}
+
+int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
+  if (!h || !hio) return fail(MPCB_ERR_INVALID, "null argument");
+  const mpcb::Design& D = h->D;
+  const long long Bn = hio->batch;
+  if (Bn <= 0) return fail(MPCB_ERR_INVALID, "batch must be positive");
+  if (!hio->x0 || !hio->xref || !hio->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  if ((hio->warm_u == nullptr) != (hio->warm_y == nullptr)) return fail(MPCB_ERR_INVALID, "warm_u and warm_y must be given together");
+  CUDA_TRY(cudaSetDevice(h->st.device));
+  cudaStream_t st = h->stream;
+  const size_t nx = D.nx, nu = D.nu, H = D.H, nz = D.nz, nt = D.nt;
+  const size_t n_xref = hio->xref_broadcast ? nx : nx * Bn, n_uref = hio->uref_broadcast ? nu : nu * Bn;
+
+  // ---- inputs: pageable user memory goes through one pinned staging buffer, pinned memory is copied directly
+  struct In { const double* src; DevBuf<double>* dst; size_t n; };
+  In ins[5] = {{hio->x0, &h->x0, nx * Bn}, {hio->xref, &h->xref, n_xref}, {hio->uref, &h->uref, n_uref},
+               {hio->warm_u, &h->warm_v, nz * Bn}, {hio->warm_y, &h->warm_y, nt * Bn}};
+  size_t stage_need = 0;
+  for (auto& in : ins)
+    if (in.src && !is_pinned_or_device(in.src)) stage_need += in.n;
+  CUDA_TRY(h->stage_in.ensure(stage_need));
+  CUDA_TRY(cudaEventRecord(h->ev[0], st));
+  size_t off = 0;
+  for (auto& in : ins) {
+    if (!in.src) continue;
+    CUDA_TRY(in.dst->ensure(in.n));
+    const double* src = in.src;
+    if (!is_pinned_or_device(in.src)) {
+      std::memcpy(h->stage_in.p + off, in.src, in.n * sizeof(double));
+      src = h->stage_in.p + off;
+      off += in.n;
+    }
+    CUDA_TRY(cudaMemcpyAsync(in.dst->p, src, in.n * sizeof(double), cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[1], st));
+
+  // ---- device buffers for the requested outputs
+  mpcb_batch_io dio = *hio;
+  dio.x0 = h->x0.p; dio.xref = h->xref.p; dio.uref = h->uref.p;
+  dio.warm_u = hio->warm_u ? h->warm_v.p : nullptr; dio.warm_y = hio->warm_y ? h->warm_y.p : nullptr;
+  struct Out { double* host; DevBuf<double>* dev; size_t n; double** slot; };
+  Out outs[9] = {{hio->u, &h->u, nu * H * Bn, &dio.u}, {hio->e_u, &h->e_u, nu * H * Bn, &dio.e_u}, {hio->x, &h->x, nx * (H + 1) * Bn, &dio.x},
+                 {hio->e_x, &h->e_x, nx * (H + 1) * Bn, &dio.e_x}, {hio->u0, &h->u0, nu * Bn, &dio.u0}, {hio->prim_res, &h->pres, (size_t)Bn, &dio.prim_res},
+                 {hio->dual_res, &h->dres, (size_t)Bn, &dio.dual_res}, {hio->objective, &h->obj, (size_t)Bn, &dio.objective}, {hio->y, &h->y, nt * Bn, &dio.y}};
+  for (auto& o : outs) {
+    if (!o.host) { *o.slot = nullptr; continue; }
+    CUDA_TRY(o.dev->ensure(o.n));
+    *o.slot = o.dev->p;
+  }
+  CUDA_TRY(h->status.ensure(Bn)); CUDA_TRY(h->iters.ensure(Bn));
+  dio.status = h->status.p; dio.iters = h->iters.p;
+
+  int rc = enqueue_device(h, dio, st, h->ev[2]);
+  if (rc != MPCB_OK) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev[3], st));
+
+  // ---- outputs
+  size_t out_stage = 0;
+  for (auto& o : outs)
+    if (o.host && !is_pinned_or_device(o.host)) out_stage += o.n;
+  CUDA_TRY(h->stage_out.ensure(out_stage));
+  CUDA_TRY(h->stage_int.ensure(2 * (size_t)Bn));
+  off = 0;
+  std::vector<std::pair<double*, std::pair<size_t, size_t>>> post;  // host dst, (stage offset, n)
+  for (auto& o : outs) {
+    if (!o.host) continue;
+    if (is_pinned_or_device(o.host)) {
+      CUDA_TRY(cudaMemcpyAsync(o.host, o.dev->p, o.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    } else {
+      CUDA_TRY(cudaMemcpyAsync(h->stage_out.p + off, o.dev->p, o.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+      post.push_back({o.host, {off, o.n}});
+      off += o.n;
+    }
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->stage_int.p, h->status.p, Bn * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->stage_int.p + Bn, h->iters.p, Bn * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(h->ev[4], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (auto& p : post) std::memcpy(p.first, h->stage_out.p + p.second.first, p.second.second * sizeof(double));
+  if (hio->status) std::memcpy(hio->status, h->stage_int.p, Bn * sizeof(int32_t));
+  if (hio->iters) std::memcpy(hio->iters, h->stage_int.p + Bn, Bn * sizeof(int32_t));
+  long long tot = 0;
+  for (long long i = 0; i < Bn; i++) tot += h->stage_int.p[Bn + i];
+  h->timing.total_iterations = tot;
+  cudaEventElapsedTime(&h->timing.h2d_ms, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->timing.solve_ms, h->ev[1], h->ev[2]);
+  cudaEventElapsedTime(&h->timing.recover_ms, h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[3], h->ev[4]);
+  cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[4]);
+  return MPCB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,188 @@
+/*
+ * mpcb200.h -- C ABI of libmpcb200.so: the B200-native replacement for the MPC solve loop of
+ * AutomationLabsModelPredictiveControl.jl (reference paths below are relative to /root/reference).
+ *
+ * The reference has no FFI of its own: its hot path is `JuMP.optimize!(C.tuning.modeler)`
+ * (src/main/computation_mpc.jl:41) into OSQP / Ipopt.  The seam this library plugs into is the solver table
+ * `_IMPLEMENTATION_SOLVER_LIST` + `_selection_solver_JuMP_model` (src/sub/solver_selection.jl:9-14, 92-114) and the
+ * untyped `ModelPredictiveControlTuning.modeler::Any` (src/types/types.jl:115): with `mpc_solver = "b200"` the
+ * modeler holds an opaque `mpcb_handle*` instead of a JuMP model, and `update_initialization!` / `calculate!`
+ * (src/main/computation_mpc.jl:17-55) `ccall` the entry points declared here.
+ *
+ * Conventions: plain C, no C++ types, no exceptions cross the boundary.  All matrices are COLUMN-MAJOR Float64
+ * exactly as Julia stores them.  Every function returning `int` returns 0 on success and a negative code on failure;
+ * `mpcb_last_error()` then holds a thread-local message.  Per-problem solver outcomes are DATA (status[] uses OSQP's
+ * codes), not errors -- the reference itself never inspects termination_status (computation_mpc.jl:41-53).
+ * A handle is not re-entrant (one call in flight per handle, like a JuMP model); distinct handles may be used from
+ * distinct threads.  The caller owns every array it passes for the duration of the call only.
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define MPCB_OK 0
+#define MPCB_ERR_INVALID -1   /* bad argument / unsupported configuration */
+#define MPCB_ERR_CUDA -2      /* CUDA runtime failure (message has the cudaError string) */
+#define MPCB_ERR_NUMERIC -3   /* host-side design failed (DARE diverged, K not positive definite, ...) */
+#define MPCB_ERR_NO_DEVICE -4 /* no usable sm_100 device: there is NO CPU fallback */
+
+/* per-problem status, OSQP's codes (what JuMP.termination_status would be derived from) */
+#define MPCB_STATUS_SOLVED 1
+#define MPCB_STATUS_MAX_ITER -2
+#define MPCB_STATUS_PRIMAL_INFEASIBLE -3
+#define MPCB_STATUS_UNSOLVED -10
+
+/* terminal ingredient (src/sub/design_mpc.jl:298-394: "none" | "equality"; "contractive" is a QCQP and
+ * "neighborhood" is unimplemented in the reference -> rejected with MPCB_ERR_INVALID) */
+#define MPCB_TERMINAL_NONE 0
+#define MPCB_TERMINAL_EQUALITY 1
+
+/* kernel selection */
+#define MPCB_KERNEL_AUTO 0
+#define MPCB_KERNEL_ONCHIP 1   /* register/shared-memory resident DMMA ADMM (nz + m_g <= 64) */
+#define MPCB_KERNEL_STREAMED 2 /* per-iteration FP64 tensor GEMM over HBM/L2-resident state */
+
+typedef struct mpcb_handle mpcb_handle;
+
+/* Solver settings.  Defaults (mpcb_default_settings) are OSQP 0.6's -- what the reference gets because
+ * solver_selection.jl:94-95 sets no attribute -- except rho, which is chosen per system because the KKT factor is
+ * cached once for the whole batch (rho <= 0: sqrt(lambda_min * lambda_max) of the condensed Hessian). */
+typedef struct {
+  double eps_abs;       /* 1e-3 */
+  double eps_rel;       /* 1e-3 */
+  double eps_prim_inf;  /* 1e-4 */
+  double rho;           /* <= 0 : automatic */
+  double rho_eq_scale;  /* 1e3  (OSQP RHO_EQ_OVER_RHO_INEQ) */
+  double sigma;         /* 1e-6 */
+  double alpha;         /* 1.6 */
+  int32_t max_iter;     /* 4000 (rounded up to a multiple of check_every) */
+  int32_t check_every;  /* 25 */
+  int32_t device;       /* CUDA device ordinal this handle lives on */
+  int32_t kernel;       /* MPCB_KERNEL_* */
+  int32_t reserved[4];
+} mpcb_settings;
+
+/* Linear (or linearised) MPC description = the data `_model_predictive_control_design` assembles for a
+ * ConstrainedLinearControlDiscreteSystem (src/sub/design_mpc.jl:54-129):
+ *   A, B        system.A, system.B                         (linear.jl:41-42)
+ *   Q, R, S     WeightsCoefficient                          (design_mpc.jl:264-283)
+ *   P           TerminalIngredient.P = are(Discrete,A,B,Q,R)  (design_mpc.jl:327); NULL -> computed here (mpcb_dare)
+ *   umin/umax   first/last vertex of system.U               (linear.jl:35-38, 73-78)
+ *   xmin/xmax   first/last vertex of system.X, used only when state_constraint != 0 (kw `mpc_state_constraint`
+ *               present, linear.jl:62-70)
+ */
+typedef struct {
+  int32_t nx, nu, horizon;
+  const double* A; /* nx x nx */
+  const double* B; /* nx x nu */
+  const double* Q; /* nx x nx */
+  const double* R; /* nu x nu */
+  const double* S; /* nu x nu or NULL (= 0) */
+  const double* P; /* nx x nx or NULL */
+  const double* umin;
+  const double* umax; /* nu */
+  const double* xmin;
+  const double* xmax; /* nx or NULL */
+  int32_t state_constraint;
+  int32_t terminal_mode; /* MPCB_TERMINAL_* */
+} mpcb_linear_desc;
+
+/* What the design produced (for logging, tests and the roofline arithmetic). */
+typedef struct {
+  int32_t nx, nu, horizon;
+  int32_t nz;      /* nu*horizon decision variables (absolute inputs, stage-major) */
+  int32_t mg;      /* general (non-box) constraint rows */
+  int32_t nt;      /* nz + mg rows of the stacked ADMM operator */
+  int32_t nt_pad;  /* padded to the MMA tile */
+  int32_t kernel;  /* MPCB_KERNEL_* actually selected */
+  int32_t device;
+  int32_t sm_count;
+  double rho;      /* rho in use */
+  double lambda_min, lambda_max; /* of the condensed Hessian */
+} mpcb_info;
+
+/* One batch of independent problems sharing the designed controller.  Pointers are HOST pointers for
+ * mpcb_solve_linear_batch and DEVICE pointers for mpcb_solve_linear_batch_device.  Layouts (column-major):
+ *   x0    nx x batch                      the `initialization` of update_initialization! (computation_mpc.jl:17-29)
+ *   xref  nx x batch, or nx x 1 if xref_broadcast   constant-over-horizon references (main_mpc.jl:105-117)
+ *   uref  nu x batch, or nu x 1 if uref_broadcast
+ *   u,e_u nu x horizon x batch ; x,e_x  nx x (horizon+1) x batch   == computation_results of calculate!
+ *         (computation_mpc.jl:50-53), one reference-shaped matrix per problem, back to back
+ *   u0    nu x batch                      first input column (what a closed loop applies)
+ *   warm_u  nu x horizon x batch absolute inputs, warm_y  nt x batch duals (both or neither; NULL = cold start)
+ *   y     nt x batch duals of [box rows; general rows] (for warm starting the next call)
+ * Any output pointer may be NULL (skipped). */
+typedef struct {
+  int64_t batch;
+  const double* x0;
+  const double* xref;
+  const double* uref;
+  int32_t xref_broadcast;
+  int32_t uref_broadcast;
+  const double* warm_u;
+  const double* warm_y;
+  double* u;
+  double* e_u;
+  double* x;
+  double* e_x;
+  double* u0;
+  int32_t* status;
+  int32_t* iters;
+  double* prim_res;
+  double* dual_res;
+  double* objective; /* the reference's J (design_mpc.jl:449-456), constants included */
+  double* y;
+} mpcb_batch_io;
+
+/* CUDA-event timings of the last solve call on this handle, milliseconds. */
+typedef struct {
+  float h2d_ms, solve_ms, recover_ms, d2h_ms, total_ms;
+  int64_t batch;
+  int64_t total_iterations; /* sum over problems of ADMM iterations */
+  int32_t kernel_launches;  /* kernels of this library launched by the call */
+} mpcb_timing;
+
+int mpcb_version(void);
+int mpcb_device_count(void);
+const char* mpcb_last_error(void);
+void mpcb_default_settings(mpcb_settings* s);
+
+/* Discrete algebraic Riccati equation (replaces ControlSystems.are, design_mpc.jl:327), structure-preserving
+ * doubling on the host.  All matrices column-major. */
+int mpcb_dare(int32_t nx, int32_t nu, const double* A, const double* B, const double* Q, const double* R, double* P_out);
+
+/* Design: condense, choose rho, factor K, build the stacked operators, upload to `settings->device`.
+ * Replaces modeler construction + OSQP setup (linear.jl:20-103, solver_selection.jl:92-98). */
+int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settings, mpcb_handle** out);
+void mpcb_destroy(mpcb_handle* h);
+int mpcb_get_info(const mpcb_handle* h, mpcb_info* info);
+int mpcb_get_timing(const mpcb_handle* h, mpcb_timing* t);
+
+/* Host copies of the design matrices, for tests / inspection.  Any pointer may be NULL.
+ *   Pc nz x nz, Lq nz x (2nx+nu), G mg x nz, Lb mg x (2nx+nu), T nt x nt  (all column-major) */
+int mpcb_get_design(const mpcb_handle* h, double* Pc, double* Lq, double* G, double* Lb, double* T);
+
+/* The hot path: replaces update_initialization! + calculate! (computation_mpc.jl:17-55) for `batch` problems. */
+int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* host_io);
+/* Same with device-resident buffers on the handle's device; `cuda_stream` is a cudaStream_t (NULL = default
+ * stream).  Asynchronous: returns after enqueueing. */
+int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* dev_io, void* cuda_stream);
+
+/* Page-locked host memory helpers: arrays allocated here are copied to/from the device without the extra staging
+ * copy that pageable memory needs (Julia: unsafe_wrap the pointer; Python: numpy.frombuffer). */
+void* mpcb_alloc_pinned(size_t bytes);
+void mpcb_free_pinned(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H */

@@ -1,0 +1,39 @@
+import json
+import pathlib
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def qt():
+    """Quadruple-tank linear model decoded from the reference fixture + the scenario of
+    test/computation_mpc_test.jl:981-1040 (tests/golden/make_golden_qt_model.py)."""
+    g = json.loads((ROOT / "tests" / "golden" / "qt_linear_model.json").read_text())
+    sc = g["scenario"]
+    return {"A": np.array(g["A"]), "B": np.array(g["B"]), "Q": sc["Q"] * np.eye(4), "R": sc["R"] * np.eye(2), "S": np.zeros((2, 2)),
+            "xmin": np.array(sc["xmin"]), "xmax": np.array(sc["xmax"]), "umin": np.array(sc["umin"]), "umax": np.array(sc["umax"]),
+            "x_ref": np.array(sc["x_ref"]), "u_ref": np.array(sc["u_ref"]), "x0": np.array(sc["x0"])}
+
+
+def qt_batch(qt, n, seed=0):
+    """BASELINE.md section 4, config 2 inputs."""
+    rng = np.random.default_rng(seed)
+    x0 = rng.uniform(qt["xmin"], qt["xmax"], (n, 4))
+    xref = rng.uniform(0.4, 1.0, (n, 4))
+    return x0, xref, qt["u_ref"].copy()
+
+
+@pytest.fixture(scope="session")
+def mpc():
+    import almpc_b200
+    return almpc_b200

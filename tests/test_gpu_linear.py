@@ -1,0 +1,172 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+
+from conftest import qt_batch
+from oracle import mpc_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+U0_TOL = 1e-4        # north_star: optimal u0 within 1e-4 (metric of oracle.u0_metric)
+OBJ_TOL = 1e-6       # objective within 1e-6 relative
+RES_TOL = 1e-5       # primal/dual residual <= 1e-5
+
+
+def make_controller(mpc, qt, H, terminal="none", **kw):
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(qt["xmin"], qt["xmax"]),
+                                                      mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    return mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                                  mpc_terminal_ingredient=terminal, **kw)
+
+
+def oracle_condensed(qt, H, P, terminal="none", state_constraint=False, S=None):
+    return mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"] if S is None else S, P, H, qt["umin"], qt["umax"], qt["xmin"], qt["xmax"],
+                       state_constraint=state_constraint, terminal=terminal)
+
+
+def test_design_matches_oracle(mpc, qt):
+    C = make_controller(mpc, qt, 20)
+    d = C.tuning.modeler.design()
+    c = oracle_condensed(qt, 20, C.tuning.terminal_ingredient.P)
+    assert np.allclose(d["Pc"], c.Pc, rtol=1e-12, atol=1e-10)
+    assert np.allclose(d["Lq"], c.Lq, rtol=1e-12, atol=1e-10)
+    T, _, _, rho = mo.admm_matrices(c, mo.AdmmSettings(rho=C.tuning.modeler.info.rho))
+    assert np.allclose(d["T"], T, rtol=1e-10, atol=1e-12)
+    assert abs(C.tuning.modeler.info.rho - mo.auto_rho(c.Pc)) < 1e-3 * rho      # heuristic value: power / inverse iteration accuracy is enough
+
+
+def test_kat_lqr_single_problem(mpc, qt):
+    """Known answer: no bound is active from x0 = 0.6, so u0* is the LQR law for every horizon."""
+    for H in (5, 20):
+        C = make_controller(mpc, qt, H, mpc_b200_eps_abs=1e-8, mpc_b200_eps_rel=1e-8, mpc_b200_check_every=5)
+        mpc.update_initialization(C, qt["x0"])
+        res = mpc.calculate(C)
+        assert res["status"][0] == 1
+        assert np.allclose(C.computation_results.u[:, 0], [2.75594127, 2.95507466], atol=2e-6)
+        assert C.computation_results.x.shape == (4, H + 1) and C.computation_results.e_u.shape == (2, H)
+        assert np.allclose(C.computation_results.x[:, 0], qt["x0"])
+        assert np.allclose(C.computation_results.e_x, C.computation_results.x - 0.65)
+        assert np.allclose(C.computation_results.e_u, C.computation_results.u - 1.2)
+
+
+@pytest.mark.parametrize("H,eps,check", [(20, 1e-7, 5), (20, 1e-6, 5), (20, 1e-3, 25), (5, 1e-7, 5), (10, 1e-5, 4), (13, 1e-7, 5)])
+def test_batch_matches_twin_and_exact(mpc, qt, H, eps, check):
+    n = 2048
+    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check)
+    m = C.tuning.modeler
+    x0, xref, uref = qt_batch(qt, n)
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P)
+    p = mo.pack_params(x0, xref, uref)
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=check))
+    # same algorithm, same iteration counts (summation order differs -> allow a vanishing fraction of off-by-one-check)
+    same = res["iters"] == tw["iters"]
+    assert same.mean() > 0.995, same.mean()
+    assert (res["status"] == 1).all()
+    v = res["u"].reshape(n, -1)
+    assert np.abs(v[same] - tw["v"][same]).max() < 1e-9
+    assert np.abs(res["prim_res"][same] - tw["prim_res"][same]).max() < 1e-9
+    rec = mo.recover(c, v, p)
+    for k in ("x", "e_x", "u", "e_u"):
+        assert np.abs(res[k] - rec[k]).max() < 1e-11, k
+    assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-11 * np.abs(rec["objective"]).max()
+    assert np.array_equal(res["u0"], res["u"][:, 0, :])
+    if eps <= 1e-6:   # against the exact optimum
+        ne = 256
+        ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in range(ne)])
+        assert mo.u0_metric(res["u0"][:ne], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
+        if eps <= 1e-7:   # the parity settings: eps_abs = eps_rel = 1e-7
+            assert res["prim_res"].max() < RES_TOL and res["dual_res"].max() < RES_TOL
+            Jex = mo.recover(c, ex, p[:ne])["objective"]
+            assert (np.abs(res["objective"][:ne] - Jex) / np.maximum(np.abs(Jex), 1e-9)).max() < OBJ_TOL
+
+
+def test_terminal_equality_matches_twin_and_exact(mpc, qt):
+    H, n, eps = 10, 1024, 1e-7
+    C = make_controller(mpc, qt, H, terminal="equality", mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=10,
+                        mpc_b200_max_iter=20000)
+    m = C.tuning.modeler
+    assert m.info.mg == 4 and m.info.nt == 24
+    rng = np.random.default_rng(3)
+    xref = np.tile(qt["x_ref"], (n, 1))
+    x0 = xref + 0.002 * rng.standard_normal((n, 4))     # small deviations: the terminal equality is mostly feasible
+    mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
+    res = mpc.calculate(C)
+    c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P, terminal="equality")
+    p = mo.pack_params(x0, xref, qt["u_ref"])
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=10, max_iter=20000))
+    same = res["iters"] == tw["iters"]
+    assert same.mean() > 0.99
+    assert np.array_equal(res["status"][same], tw["status"][same])
+    v = res["u"].reshape(n, -1)
+    assert np.abs(v[same] - tw["v"][same]).max() < 1e-8
+    ok = res["status"] == 1
+    assert ok.mean() > 0.5
+    assert np.abs(res["e_x"][ok][:, -1, :]).max() < 1e-5       # terminal deviation driven to zero
+    idx = np.flatnonzero(ok)[:64]
+    ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in idx])
+    assert mo.u0_metric(res["u0"][idx], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
+
+
+def test_terminal_equality_infeasible_is_flagged(mpc, qt):
+    """Far-away initial states cannot reach the reference in H steps within the input box: OSQP's primal
+    infeasibility certificate must fire per problem (status -3), not crash."""
+    H, n = 5, 256
+    C = make_controller(mpc, qt, H, terminal="equality", mpc_b200_check_every=10, mpc_b200_max_iter=4000)
+    rng = np.random.default_rng(4)
+    x0 = rng.uniform(qt["xmin"], qt["xmax"], (n, 4))
+    mpc.update_initialization(C, x0)
+    res = mpc.calculate(C)
+    c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P, terminal="equality")
+    p = mo.pack_params(x0, qt["x_ref"], qt["u_ref"])
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=C.tuning.modeler.info.rho, check_every=10, max_iter=4000))
+    assert (res["status"] == tw["status"]).mean() > 0.98
+    assert (res["status"] == -3).sum() > 0
+
+
+def test_warm_start_closed_loop(mpc, qt):
+    """Config 1: closed loop from x0 = 0.6 with warm starts (OSQP's default behaviour on a persistent model)."""
+    H = 20
+    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=1e-6, mpc_b200_eps_rel=1e-6, mpc_b200_check_every=5)
+    x = qt["x0"].copy()
+    iters = []
+    for k in range(30):
+        mpc.update_initialization(C, x)
+        res = mpc.calculate(C, warm_start=True)
+        assert res["status"][0] == 1
+        iters.append(int(res["iters"][0]))
+        u0 = C.computation_results.u[:, 0]
+        assert (u0 >= qt["umin"] - 1e-6).all() and (u0 <= qt["umax"] + 1e-6).all()
+        x = qt["x_ref"] + qt["A"] @ (x - qt["x_ref"]) + qt["B"] @ (u0 - qt["u_ref"])
+    assert np.abs(x - qt["x_ref"]).max() < np.abs(qt["x0"] - qt["x_ref"]).max()
+    assert np.mean(iters[1:]) <= iters[0]       # warm starts do not cost more than the cold first solve
+
+
+def test_input_rate_weight_S(mpc, qt):
+    H, n, eps = 10, 512, 1e-6
+    C = make_controller(mpc, qt, H, mpc_S=5.0, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5)
+    x0, xref, uref = qt_batch(qt, n, seed=5)
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P, S=5.0 * np.eye(2))
+    p = mo.pack_params(x0, xref, uref)
+    ex = np.array([mo.qp_exact(c, p[i])[0] for i in range(64)])
+    assert mo.u0_metric(res["u0"][:64], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
+    rec = mo.recover(c, res["u"].reshape(n, -1), p)
+    assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
+
+
+def test_empty_and_ragged_batches(mpc, qt):
+    C = make_controller(mpc, qt, 20, mpc_b200_eps_abs=1e-6, mpc_b200_eps_rel=1e-6, mpc_b200_check_every=5)
+    m = C.tuning.modeler
+    with pytest.raises(mpc.MpcbError):
+        m.solve_batch(np.zeros((0, 4)), qt["x_ref"], qt["u_ref"])
+    ref = None
+    X0, XREF, uref = qt_batch(qt, 1000, seed=11)
+    for n in (1, 7, 8, 9, 33, 1000):      # not multiples of the 8 problem slots a warp holds
+        x0, xref = X0[:n], XREF[:n]
+        r = m.solve_batch(x0, xref, uref)
+        assert (r["status"] == 1).all() and r["u"].shape == (n, 20, 2)
+        if ref is None: ref = r["u"][0].copy()
+        assert np.abs(r["u"][0] - ref).max() < 1e-12       # a problem's answer does not depend on its batch
