@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- the driver contract for this repo.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (libmpcb200 on B200)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port of OSQP, all host threads)
+
+Workload = BASELINE.json configs[1]: quadruple-tank linear tracking MPC (nx=4, nu=2, H=20), batch of 65,536 random initial
+states / references per GPU, cold start.  One "step" = one pass of the hot path (update_initialization! + calculate! for the
+whole batch: condensed ADMM solve + result recovery).  Solver settings are the PARITY settings (eps_abs = eps_rel = 1e-7,
+check every 5 iterations), under which tests/test_gpu_linear.py proves u0 within 1e-4, objective within 1e-6 and residuals
+<= 1e-5 of the exact optimum.
+
+  value : solves/s, inputs already resident in HBM, device-pointer C-ABI entry, CUDA events on the launching stream
+  e2e   : solves/s through the host-array C-ABI entry with pinned HOST buffers (H2D + solve + recover + D2H of u, e_u, x,
+          e_x, u0, objective, status, iters, residuals -- everything calculate! hands back) inside the timed region
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+H = 20
+BATCH = 65536
+EPS = 1e-7
+CHECK = 5
+FP64_PEAK_TFLOPS = 37.1   # DMMA.8x8x4 peak measured on this pool's B200 (profiles/micro/fp64_peak_r01.jsonl);
+                          # MEASURED_PEAKS.json has no FP64 entry (cuBLAS DGEMM 8192^3 measured 35.5 in the same run)
+
+
+def qt_model():
+    g = json.loads((ROOT / "tests" / "golden" / "qt_linear_model.json").read_text())
+    sc = g["scenario"]
+    return (np.array(g["A"]), np.array(g["B"]), np.array(sc["xmin"]), np.array(sc["xmax"]), np.array(sc["umin"]), np.array(sc["umax"]),
+            np.array(sc["x_ref"]), np.array(sc["u_ref"]), np.array(sc["x0"]))
+
+
+def make_batch(n, seed):
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
+    rng = np.random.default_rng(seed)
+    return rng.uniform(xmin, xmax, (n, 4)), rng.uniform(0.4, 1.0, (n, 4)), u_ref.copy()
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 7: continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"): reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def algorithmic_flops(info, iters, check_every):
+    """per solve  it*(2 nt^2) [T r]  +  (it/check)*(2 nt^2) [termination pass]  +  2 nt np [q = Lq p]."""
+    nt, npar = info.nt, 2 * info.nx + info.nu
+    it = iters.astype(np.float64)
+    return float((it * 2 * nt * nt + (it / check_every) * 2 * nt * nt + 2 * nt * npar).sum())
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import almpc_b200 as mpc
+    from almpc_b200 import _lib
+
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
+    Cn = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200",
+                                mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_device=local)
+    m = Cn.tuning.modeler
+    info = m.info
+    n = args.batch
+    x0_h, xref_h, uref_h = make_batch(n, seed=rank)       # rng(0) on rank 0 == BASELINE.md config 2; other ranks: other shards
+
+    # ---------------- device-resident leg ----------------
+    f64 = dict(dtype=torch.float64, device=dev)
+    x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
+    u = torch.empty((n, H, 2), **f64); e_u = torch.empty_like(u); x = torch.empty((n, H + 1, 4), **f64); e_x = torch.empty_like(x)
+    u0 = torch.empty((n, 2), **f64); obj = torch.empty(n, **f64); pres = torch.empty(n, **f64); dres = torch.empty(n, **f64)
+    status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
+    io = _lib.BatchIO()
+    io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.xref_broadcast = 0; io.uref_broadcast = 1
+    io.u = u.data_ptr(); io.e_u = e_u.data_ptr(); io.x = x.data_ptr(); io.e_x = e_x.data_ptr(); io.u0 = u0.data_ptr()
+    io.objective = obj.data_ptr(); io.prim_res = pres.data_ptr(); io.dual_res = dres.data_ptr(); io.status = status.data_ptr(); io.iters = iters.data_ptr()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    gathered = None
+    if world > 1:
+        # the one collective of the path: final gather of u0 + convergence stats on rank 0 (NCCL over NVLink)
+        payload = torch.empty((n, 4), **f64)
+        gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+
+    def step():
+        stream = torch.cuda.current_stream().cuda_stream
+        m.solve_batch_device(io, stream)
+        if world > 1:
+            payload[:, :2] = u0; payload[:, 2] = iters.to(torch.float64); payload[:, 3] = status.to(torch.float64)
+            dist.gather(payload, gathered, dst=0)
+
+    def barrier():
+        if world > 1: dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        flush.zero_()                                   # L2 flush between timed iterations (outside the per-step events)
+        evs[k][0].record()
+        step()
+        evs[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    ms_steps = [a.elapsed_time(b) for a, b in evs]
+    ms_total = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    clocks = sampler.stop() if sampler else None
+
+    it_np = iters.cpu().numpy(); st_np = status.cpu().numpy()
+    # dominant kernel alone (solve kernel, no recover): time it live with events for the roofline
+    io_solve = _lib.BatchIO()
+    for f, _t in io._fields_: setattr(io_solve, f, getattr(io, f))
+    for f in ("u", "e_u", "x", "e_x", "u0", "objective"): setattr(io_solve, f, None)
+    torch.cuda.synchronize()
+    kms = []
+    for k in range(args.steps):
+        flush.zero_()
+        kev[k][0].record(); m.solve_batch_device(io_solve, torch.cuda.current_stream().cuda_stream); kev[k][1].record()
+    torch.cuda.synchronize()
+    kms = [a.elapsed_time(b) for a, b in kev]
+    k_ms = sum(kms) / len(kms)
+    flops = algorithmic_flops(info, it_np, CHECK)
+    achieved = flops / (k_ms * 1e-3) / 1e12
+
+    line = None
+    if rank == 0:
+        # ---------------- end-to-end leg: host-array C ABI with pinned host buffers ----------------
+        pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory()
+        hx0 = pin((n, 4)); hxr = pin((n, 4)); hx0.copy_(torch.from_numpy(x0_h)); hxr.copy_(torch.from_numpy(xref_h))
+        out = {"u": pin((n, H, 2)).numpy(), "e_u": pin((n, H, 2)).numpy(), "x": pin((n, H + 1, 4)).numpy(), "e_x": pin((n, H + 1, 4)).numpy(),
+               "u0": pin((n, 2)).numpy(), "objective": pin((n,)).numpy(), "prim_res": pin((n,)).numpy(), "dual_res": pin((n,)).numpy(),
+               "status": pin((n,), torch.int32).numpy(), "iters": pin((n,), torch.int32).numpy()}
+        h2d = hx0.numel() * 8 + hxr.numel() * 8 + uref_h.size * 8
+        d2h = sum(v.nbytes for v in out.values())
+        for _ in range(3):
+            m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, out=out)
+        e2e_t = []
+        for _ in range(args.steps):
+            flush.zero_(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, out=out)      # synchronous: returns with results on the host
+            e2e_t.append(time.perf_counter() - t0)
+        tim = m.timing()
+        e2e_val = n / (sum(e2e_t) / len(e2e_t))
+        assert np.array_equal(out["iters"], it_np)
+        # ---------------- config 1: closed-loop single-solve latency (B = 1, warm start), p50 ----------------
+        lat = closed_loop_latency(mpc, Cn)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            cpu = cpu_baseline(sample=args.cpu_sample)
+            lat["cpu_p50_us"] = cpu.pop("latency_p50_us")
+        line = {
+            "metric": "MPC QP solves/sec", "value": world * n * args.steps / (ms_total * 1e-3), "unit": "solves/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: quadruple-tank linear tracking MPC nx=4 nu=2 H=20, batch 65536 random x0/x_ref per GPU, cold start",
+                       "batch_per_gpu": n, "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "rho": info.rho, "kernel": "onchip-dmma",
+                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"batch-shard x{world}, NCCL gather of u0+stats" if world > 1 else "single GPU",
+                       "outputs": "u,e_u,x,e_x,u0,objective,status,iters,residuals"},
+            "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "phases_ms": {k: round(v, 4) for k, v in tim.items() if k.endswith("_ms")}},
+            "gpu_launches": int(2 * args.steps),
+            "roofline": {"bound": "tensor", "kernel": "admm_onchip_kernel<40,false,3>", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "peak_source": "FP64 DMMA peak measured by profiles/micro/fp64_peak.cu on this pool (MEASURED_PEAKS.json has no FP64 number)",
+                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops, "mean_iters": float(it_np.mean())},
+            "solver": {"mean_iters": float(it_np.mean()), "max_iters": int(it_np.max()), "solved_frac": float((st_np == 1).mean())},
+            "latency": lat, "clocks": clocks, "wall_s_timed_region": t_wall,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def closed_loop_latency(mpc, Cn, steps=200):
+    """x0 = 0.6, 200 closed-loop steps of x+ = A x + B u0 in deviation form, warm start."""
+    A, B, *_rest, x_ref, u_ref, x0 = qt_model()
+    x = x0.copy(); ts = []
+    for k in range(steps + 20):
+        t0 = time.perf_counter()
+        mpc.update_initialization(Cn, x)
+        mpc.calculate(Cn, warm_start=True, want=("u", "e_u", "x", "e_x"))
+        dt = time.perf_counter() - t0
+        if k >= 20: ts.append(dt)
+        u0 = Cn.computation_results.u[:, 0]
+        x = x_ref + A @ (x - x_ref) + B @ (u0 - u_ref)
+    return {"p50_us": statistics.median(ts) * 1e6, "p99_us": float(np.percentile(ts, 99)) * 1e6, "steps": steps,
+            "what": "update_initialization!+calculate! B=1 warm start, host wall clock incl. H2D/D2H"}
+
+
+def _reference_problem():
+    from oracle import mpc_oracle as mo, osqp_ref as orf
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, x0 = qt_model()
+    Q = 100.0 * np.eye(4); R = 0.1 * np.eye(2); S = np.zeros((2, 2)); P = mo.dare(A, B, Q, R)
+    qp = mo.build_reference_qp(A, B, Q, R, S, P, H, x_ref, u_ref, x0, umin, umax)
+    prob = orf.Problem(qp.P, qp.q, qp.A, qp.l, qp.u)
+    rows = np.concatenate([qp.x0_rows, qp.xref_rows, qp.uref_rows])
+    sel = np.concatenate([qp.idx["u"].T.ravel(), qp.idx["x"].T.ravel()])
+    return mo, orf, qp, prob, rows, sel
+
+
+def _reference_vals(x0, xref, uref):
+    n = x0.shape[0]
+    return np.hstack([x0, np.tile(xref, (1, H + 1)), np.tile(np.broadcast_to(uref, (n, 2)), (1, H))])
+
+
+def cpu_baseline(sample):
+    """The reference's CPU path restated (oracle/osqp_ref.c: OSQP 0.6 defaults on the reference's sparse formulation, one
+    persistent workspace per thread, cold start), timed on this box's host cores on a bounded sample of the same workload."""
+    mo, orf, qp, prob, rows, sel = _reference_problem()
+    x0, xref, uref = make_batch(sample, seed=0)
+    st = orf.default_settings()
+    vals = _reference_vals(x0, xref, uref)
+    orf.solve_batch(prob, st, rows, vals[:256], sel)          # warm the threads / page in
+    t0 = time.perf_counter()
+    r = orf.solve_batch(prob, st, rows, vals, sel, cold_start=True)
+    dt = time.perf_counter() - t0
+    # single-solve latency: closed loop, warm start, persistent workspace (what one JuMP model + OSQP does)
+    A, B, *_rest, x_ref, u_ref, xx0 = qt_model()
+    w = orf.Workspace(prob, st); x = xx0.copy(); ts = []
+    ucols = qp.idx["u"][:, 0]
+    for k in range(220):
+        t1 = time.perf_counter()
+        w.update_bounds(qp.x0_rows, x); s = w.solve(cold_start=False)
+        d = time.perf_counter() - t1
+        if k >= 20: ts.append(d)
+        x = x_ref + A @ (x - x_ref) + B @ (s["x"][ucols] - u_ref)
+    return {"value": sample / dt, "unit": "solves/s", "cores": orf.max_threads(), "kind": "port",
+            "sample": f"{sample} problems of configs[1] (rng(0)), OSQP 0.6 defaults eps=1e-3 (the reference sets no solver attribute), "
+                      f"cold start, OpenMP over problems; mean iters {float(r['iters'].mean()):.1f}; solved {float((r['status'] == 1).mean()):.3f}",
+            "latency_p50_us": statistics.median(ts) * 1e6}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    mo, orf, qp, prob, rows, sel = _reference_problem()
+    st = orf.default_settings()
+    n = args.ref_sample
+    x0, xref, uref = make_batch(n, seed=0)
+    vals = _reference_vals(x0, xref, uref)
+    for _ in range(max(args.warmup, 1)):
+        orf.solve_batch(prob, st, rows, vals[: max(256, n // 8)], sel)
+    t0 = time.perf_counter()
+    its = []
+    for _ in range(args.steps):
+        r = orf.solve_batch(prob, st, rows, vals, sel, cold_start=True); its.append(float(r["iters"].mean()))
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    sample = (f"{n} problems of configs[1] per step (rng(0)); oracle port of OSQP 0.6 (oracle/osqp_ref.c) on the reference's sparse "
+              f"formulation (n=372, m=412), library defaults eps=1e-3, cold start, one workspace per thread; mean iters {np.mean(its):.1f}")
+    print(json.dumps({
+        "impl": "reference", "metric": "MPC QP solves/sec", "value": val, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: quadruple-tank linear tracking MPC nx=4 nu=2 H=20, bounded sample of the 65536 batch", "batch_per_step": n},
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": orf.max_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--cpu-sample", type=int, default=32768)
+    ap.add_argument("--ref-sample", type=int, default=8192)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
