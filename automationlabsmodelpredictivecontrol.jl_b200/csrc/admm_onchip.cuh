@@ -3,13 +3,22 @@
 // Replaces the per-problem `JuMP.optimize!` -> OSQP call (/root/reference/src/main/computation_mpc.jl:41) for
 // thousands of problems that share one designed controller.  One warp owns 8 problem SLOTS (one per lane quad).
 // Per ADMM iteration the multi-RHS contraction  [x~; z~_g] = T r  (T = [I;G] K^-1 [I,G'], cached per system) runs on
-// the FP64 tensor pipe as DMMA.8x8x4 with problems along M, the fragment-ordered T streamed from shared memory as
+// the FP64 tensor path as DMMA.8x8x4 with problems along M, the fragment-ordered T streamed from shared memory as
 // the B operand and the per-problem right-hand side produced in registers as the A operand.  Because T is symmetric
 // and we control the row order of the B fragments, the C fragment of one iteration IS the A fragment layout of the
-// next: the ADMM state (x, q, z, y/rho: 4 doubles per row) never leaves the register file between iterations, and
-// projection / dual update / residual reductions are fused right behind the MMAs (quad shuffles only).
+// next: the ADMM state never leaves the register file between iterations, and projection / dual update / residual
+// reductions are fused right behind the MMAs (quad shuffles only).
 // Slots that terminate are written out and refilled from a global work counter at every check point, so iteration
-// count variance across the batch (10x on the quadruple-tank batch) does not idle the tensor pipe.
+// count variance across the batch does not idle the FP64 pipe.
+//
+// On B200 DMMA and scalar FP64 instructions share one pipe (ncu: math-pipe-throttle on DFMA while DMMA runs; see
+// profiles/), so the elementwise step is written for the fewest FP64 instructions.  Box-only problems (mg = 0) keep
+//     c = (1-alpha) z + y/rho        r = rho (z - y/rho) + sigma x - q   (the next MMA operand)
+// per row, so that one iteration is  w = alpha t + c;  z+ = clamp(w);  c+ = w - alpha z+;  r+ = rho (2 z+ - w) + ...
+// (6 FP64 instructions per row with sigma = 0, 9 with sigma > 0).  Termination is evaluated at (x~, z+, y+): the dual
+// residual of the x-subproblem minimiser is available in closed form from the cached factor,
+//     Pc x~ = r - (sigma + rho) x~     (mg = 0),
+// so box-only problems need no second operator pass; problems with general rows run one pass with C = [[Pc,G'],[G,0]].
 //
 // Row -> lane mapping: lane = 4*g + l4 (g = slot 0..7, l4 = 0..3); local row le = 2*t + j  <->  row e = 8*t + 2*l4 + j.
 #pragma once
@@ -38,7 +47,7 @@ struct OnchipParams {
   int xref_bc, uref_bc;
   const double* warm_v; // [batch][nz] or null
   const double* warm_y; // [batch][nt] or null
-  double* v_out;        // [batch][nz]  absolute inputs (OSQP's x)
+  double* v_out;        // [batch][nz]  absolute inputs
   double* y_out;        // [batch][nt] or null
   int32_t* status;
   int32_t* iters;
@@ -53,9 +62,15 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
+// max / clamp without fmax's NaN plumbing (inputs are finite): one DSETP + two FSEL each
+__device__ __forceinline__ double dmaxf(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dclamp(double w, double lo, double hi) {
+  const double t = w < lo ? lo : w;
+  return t > hi ? hi : t;
+}
 __device__ __forceinline__ double quad_max(double v) {
-  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 1));
-  v = fmax(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = dmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = dmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
   return v;
 }
 __device__ __forceinline__ double quad_sum(double v) {
@@ -64,60 +79,83 @@ __device__ __forceinline__ double quad_sum(double v) {
   return v;
 }
 
+#ifndef MPCB_R_SMEM
+#define MPCB_R_SMEM 0
+#endif
+constexpr bool R_SMEM = MPCB_R_SMEM != 0;
 constexpr int ONCHIP_THREADS = 128;
 constexpr int ONCHIP_WARPS = ONCHIP_THREADS / 32;
 
 // shared memory: T, C fragments, Lt, lo, hi, rho, rinv, then per-warp parameter staging [8][npad]
-__host__ __device__ inline size_t onchip_smem_bytes(int NT, int np) {
+__host__ __device__ inline size_t onchip_smem_bytes(int NT, int np, bool has_g) {
   int npad = (np + 1) & ~1;
-  return sizeof(double) * ((size_t)2 * NT * NT + (size_t)np * NT + 4 * NT + (size_t)ONCHIP_WARPS * 8 * npad);
+  return sizeof(double) * ((size_t)(has_g ? 2 : 1) * NT * NT + (size_t)np * NT + 4 * NT + (size_t)ONCHIP_WARPS * 8 * npad +
+                           (has_g ? 0 : (size_t)ONCHIP_WARPS * (NT / 4) * 32 * 3));
 }
 
-template <int NT, bool HAS_G, int MINB>
+// NT: padded operator size; HAS_G: general rows present; SIG: sigma != 0 (box-only kernels drop the x state otherwise)
+template <int NT, bool HAS_G, bool SIG, int MINB>
 __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const OnchipParams P) {
   constexpr int EPL = NT / 4;  // rows per lane
   constexpr int KS = NT / 4;   // k-steps
   constexpr int NTL = NT / 8;  // n-tiles
+  constexpr bool KEEP_X = HAS_G || SIG;
   extern __shared__ __align__(16) double smem[];
   double* sT = smem;
-  double* sC = sT + NT * NT;
-  double* sL = sC + NT * NT;
+  double* sC = sT + NT * NT;                       // only present (and only read) when HAS_G
+  double* sL = sT + (HAS_G ? 2 : 1) * NT * NT;
   double* sLo = sL + P.np * NT;
   double* sHi = sLo + NT;
   double* sRho = sHi + NT;
   double* sRinv = sRho + NT;
   const int npad = (P.np + 1) & ~1;
   double* sP = sRinv + NT + (threadIdx.x >> 5) * 8 * npad;
+  // Experiment knob MPCB_R_SMEM (default off): stage the MMA A operand r through shared memory ([k-step][lane], each
+  // lane reads back only what it wrote) so the k-step loop is a REAL loop and the DMMA issue order stays k-step-major
+  // (fully unrolled, ptxas chains the DMMAs of one accumulator back to back: 26-cycle dependent latency vs a 16-cycle
+  // issue interval).  Measured on B200 (QT, H=20, 65536 problems): 0.531 ms staged vs 0.493 ms with r in registers --
+  // the extra LDS/STS traffic costs more than the chaining, which three warps per scheduler already hide.
+  double* sR = sRinv + NT + ONCHIP_WARPS * 8 * npad + (threadIdx.x >> 5) * KS * 32 * 3 + (threadIdx.x & 31);
+  double* sXt = sR + KS * 32;   // candidate solution x~ / y+ of the checking iteration, same [row][lane] layout
+  double* sYo = sXt + KS * 32;
 
-  for (int i = threadIdx.x; i < NT * NT; i += ONCHIP_THREADS) { sT[i] = P.Tfrag[i]; sC[i] = P.Cfrag[i]; }
+  for (int i = threadIdx.x; i < NT * NT; i += ONCHIP_THREADS) {
+    sT[i] = P.Tfrag[i];
+    if (HAS_G) sC[i] = P.Cfrag[i];
+  }
   for (int i = threadIdx.x; i < P.np * NT; i += ONCHIP_THREADS) sL[i] = P.Lt[i];
   for (int i = threadIdx.x; i < NT; i += ONCHIP_THREADS) { sLo[i] = P.lo[i]; sHi[i] = P.hi[i]; sRho[i] = P.rho[i]; sRinv[i] = P.rinv[i]; }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
   const double sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha;
-  const double rho_s = P.rho_box, rinv_s = 1.0 / P.rho_box;
+  const double rho_s = P.rho_box, rinv_s = 1.0 / P.rho_box, sig_rho = P.sigma + P.rho_box;
   const int nz = P.nz;
 
-  // ADMM state, one entry per owned row.  Box rows: x, q, z, ys (= y/rho).  General rows (HAS_G): the x slot holds
-  // the per-problem bound offset b(p) and q is 0.
-  double x[EPL], q[EPL], z[EPL], ys[EPL];
+  // Per owned row.  Box-only: c, r, q (+ x when SIG).  With general rows: z, ys (kept in c, r), q (box rows) or the
+  // per-problem bound offset b(p) (general rows), x.
+  double c[EPL], q[EPL];
+  double r[(HAS_G || !R_SMEM) ? EPL : 1];
+  double x[KEEP_X ? EPL : 1];
   double dys[HAS_G ? EPL : 1];
   unsigned boxbits = 0;
 #pragma unroll
   for (int le = 0; le < EPL; le++) {
     const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
     if (!HAS_G || e < nz) boxbits |= 1u << le;
-    x[le] = q[le] = z[le] = ys[le] = 0.0;
+    c[le] = q[le] = 0.0;
+    if (HAS_G || !R_SMEM) r[le] = 0.0; else sR[le * 32] = 0.0;
+    if (KEEP_X) x[le] = 0.0;
+    if (HAS_G) dys[le] = 0.0;
   }
-  (void)dys;
+  (void)dys; (void)x; (void)r;
   long long pi = -1;   // problem held by this slot (quad-uniform)
   int it_s = 0;        // its iteration count
   double qn = 0.0;     // ||q||_inf
   bool exhausted = false;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
 
-  // one product  out = M in  with M in fragment order (sT or sC)
+  // one product  out = M in  with M in fragment order
   auto mma_pass = [&](const double* __restrict__ sM, const double (&in)[EPL], double (&out)[EPL]) {
 #pragma unroll
     for (int i = 0; i < EPL; i++) out[i] = 0.0;
@@ -130,7 +168,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
 
   while (true) {
     // ------------------------------------------------------------------ refill finished / empty slots
-    bool need = (pi < 0) && !exhausted;
+    const bool need = (pi < 0) && !exhausted;
     if (__any_sync(0xffffffffu, need)) {
       long long np_i = -1;
       if (need && l4 == 0) np_i = (long long)atomicAdd(P.counter, 1ULL);
@@ -149,6 +187,8 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         }
       }
       __syncwarp();
+      double zw[HAS_G ? EPL : 1];   // warm-start z of general rows needs G x0 (one C pass)
+      (void)zw;
       if (fresh) {
         double acc[EPL];
 #pragma unroll
@@ -167,129 +207,174 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         for (int le = 0; le < EPL; le++) {
           const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
           const bool box = (boxbits >> le) & 1u;
-          if (box) { q[le] = acc[le]; x[le] = 0.0; m = fmax(m, fabs(acc[le])); }
-          else { q[le] = 0.0; x[le] = acc[le]; }
-          z[le] = 0.0; ys[le] = 0.0;
+          q[le] = acc[le];               // box rows: q ; general rows: bound offset b(p)
+          if (box) m = dmaxf(m, fabs(acc[le]));
+          double v0 = 0.0, ys0 = 0.0;    // OSQP warm start: x = v0, z = A x, y = y0
           if (P.warm_v != nullptr) {
-            if (box && e < nz) { x[le] = P.warm_v[pi * nz + e]; z[le] = x[le]; }
-            if (e < P.nt) ys[le] = P.warm_y[pi * P.nt + e] * (HAS_G ? sRinv[e] : rinv_s);
+            if (box && e < nz) v0 = P.warm_v[pi * nz + e];
+            if (e < P.nt) ys0 = P.warm_y[pi * P.nt + e] * (HAS_G ? sRinv[e] : rinv_s);
+          }
+          if (KEEP_X) x[le] = box ? v0 : 0.0;
+          if (!HAS_G) {
+            c[le] = fma(oma, v0, ys0);
+            const double r0 = fma(rho_s, v0 - ys0, fma(sigma, v0, -acc[le]));
+            if (R_SMEM) sR[le * 32] = r0; else r[le] = r0;
+          } else {
+            c[le] = v0;    // z
+            r[le] = ys0;   // ys
           }
         }
         qn = m;
       }
       qn = quad_max(qn);
-      if (HAS_G && P.warm_v != nullptr) {  // OSQP warm start sets z = A x: general rows need G x
+      if (HAS_G && P.warm_v != nullptr) {
         double in[EPL], out[EPL];
 #pragma unroll
-        for (int le = 0; le < EPL; le++) in[le] = (fresh && ((boxbits >> le) & 1u)) ? x[le] : 0.0;
+        for (int le = 0; le < EPL; le++) in[le] = (fresh && ((boxbits >> le) & 1u)) ? c[le] : 0.0;
         mma_pass(sC, in, out);
 #pragma unroll
         for (int le = 0; le < EPL; le++)
-          if (fresh && !((boxbits >> le) & 1u)) z[le] = out[le];
+          if (fresh && !((boxbits >> le) & 1u)) c[le] = out[le];
       }
     }
     if (!__any_sync(0xffffffffu, pi >= 0)) break;
 
-    // ------------------------------------------------------------------ check_every ADMM iterations
+    // ------------------------------------------------------------------ check_every ADMM iterations, the last one checks
+    double rp = 0.0, rd = 0.0, nA = 0.0, nD = 0.0;
+    double xt[HAS_G ? EPL : 1], yo[HAS_G ? EPL : 1];   // x~ (general rows: z~) and y+ of the checking iteration
+    (void)xt; (void)yo;
     for (int ii = 0; ii < P.check_every; ii++) {
-      const bool last = HAS_G && (ii == P.check_every - 1);
+      const bool chk = (ii == P.check_every - 1);
       double t[EPL];
 #pragma unroll
       for (int i = 0; i < EPL; i++) t[i] = 0.0;
+      if (!HAS_G) {
+        // -------- box-only fast path: r (staged in shared memory) is the MMA operand
+        if (R_SMEM) {
+          const double* tp = sT + lane;
+#pragma unroll 1
+          for (int s = 0; s < KS; s++) {
+            const double a = sR[s * 32];
 #pragma unroll
-      for (int s = 0; s < KS; s++) {
-        double r;
-        if (!HAS_G) {
-          r = fma(rho_s, z[s] - ys[s], fma(sigma, x[s], -q[s]));
+            for (int tn = 0; tn < NTL; tn++) dmma884(t[2 * tn], t[2 * tn + 1], a, tp[(s * NTL + tn) * 32]);
+          }
         } else {
-          const int e = 8 * (s >> 1) + 2 * l4 + (s & 1);
-          r = sRho[e] * (z[s] - ys[s]);
-          if ((boxbits >> s) & 1u) r += fma(sigma, x[s], -q[s]);
+#pragma unroll
+          for (int s = 0; s < KS; s++) {
+#pragma unroll
+            for (int tn = 0; tn < NTL; tn++) dmma884(t[2 * tn], t[2 * tn + 1], r[s], sT[(s * NTL + tn) * 32 + lane]);
+          }
         }
 #pragma unroll
-        for (int tn = 0; tn < NTL; tn++) dmma884(t[2 * tn], t[2 * tn + 1], r, sT[(s * NTL + tn) * 32 + lane]);
-      }
+        for (int tn = 0; tn < NTL; tn++) {
+          const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
+          const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
 #pragma unroll
-      for (int tn = 0; tn < NTL; tn++) {
-        const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
-        const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
-#pragma unroll
-        for (int jj = 0; jj < 2; jj++) {
-          const int le = 2 * tn + jj;
-          const double at = alpha * t[le];
-          const double w = fma(oma, z[le], at) + ys[le];
-          double lo_e = jj ? lo2.y : lo2.x, hi_e = jj ? hi2.y : hi2.x;
-          if (HAS_G) {
-            const bool box = (boxbits >> le) & 1u;
-            if (box) x[le] = fma(oma, x[le], at);
-            else { lo_e += x[le]; hi_e += x[le]; }
-          } else {
-            x[le] = fma(oma, x[le], at);
+          for (int jj = 0; jj < 2; jj++) {
+            const int le = 2 * tn + jj;
+            const double w = fma(alpha, t[le], c[le]);
+            const double zn = dclamp(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x);
+            if (chk) {   // residuals of (x~, z+, y+): Pc x~ = r - (sigma + rho) x~
+              const double pc = fma(-sig_rho, t[le], R_SMEM ? sR[le * 32] : r[le]);
+              const double yb = rho_s * (w - zn);
+              rp = dmaxf(rp, fabs(t[le] - zn));
+              rd = dmaxf(rd, fabs(pc + q[le] + yb));
+              nA = dmaxf(nA, dmaxf(fabs(t[le]), fabs(zn)));
+              nD = dmaxf(nD, dmaxf(fabs(pc), fabs(yb)));
+              sXt[le * 32] = t[le];
+              if (P.y_out != nullptr) sYo[le * 32] = yb;
+            }
+            c[le] = fma(-alpha, zn, w);
+            const double d = fma(2.0, zn, -w);
+            if (SIG) {
+              x[le] = fma(alpha, t[le], oma * x[le]);
+              const double rn = fma(rho_s, d, fma(sigma, x[le], -q[le]));
+              if (R_SMEM) sR[le * 32] = rn; else r[le] = rn;
+            } else {
+              const double rn = fma(rho_s, d, -q[le]);
+              if (R_SMEM) sR[le * 32] = rn; else r[le] = rn;
+            }
           }
-          const double zn = fmin(fmax(w, lo_e), hi_e);
-          const double yn = w - zn;
-          if (HAS_G) { if (last) dys[le] = yn - ys[le]; }
-          z[le] = zn;
-          ys[le] = yn;
+        }
+      } else {
+        // -------- general rows present: c = z, r = ys, q = q (box) / b (general), per-row rho
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+          const int e = 8 * (s >> 1) + 2 * l4 + (s & 1);
+          double rr = sRho[e] * (c[s] - r[s]);
+          if ((boxbits >> s) & 1u) rr += fma(sigma, x[s], -q[s]);
+#pragma unroll
+          for (int tn = 0; tn < NTL; tn++) dmma884(t[2 * tn], t[2 * tn + 1], rr, sT[(s * NTL + tn) * 32 + lane]);
+        }
+#pragma unroll
+        for (int tn = 0; tn < NTL; tn++) {
+          const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
+          const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
+          const double2 rh2 = *reinterpret_cast<const double2*>(&sRho[8 * tn + 2 * l4]);
+#pragma unroll
+          for (int jj = 0; jj < 2; jj++) {
+            const int le = 2 * tn + jj;
+            const bool box = (boxbits >> le) & 1u;
+            const double at = alpha * t[le];
+            const double w = fma(oma, c[le], at) + r[le];
+            double lo_e = jj ? lo2.y : lo2.x, hi_e = jj ? hi2.y : hi2.x;
+            if (box) x[le] = fma(oma, x[le], at);
+            else { lo_e += q[le]; hi_e += q[le]; }
+            const double zn = dclamp(w, lo_e, hi_e);
+            const double yn = w - zn;
+            if (chk) {
+              const double rho_e = jj ? rh2.y : rh2.x;
+              dys[le] = rho_e * (yn - r[le]);
+              rp = dmaxf(rp, fabs(t[le] - zn));                    // A x~ = [x~; G x~] = t
+              nA = dmaxf(nA, dmaxf(fabs(t[le]), fabs(zn)));
+              xt[le] = t[le];
+              yo[le] = rho_e * yn;
+            }
+            c[le] = zn;
+            r[le] = yn;
+          }
         }
       }
     }
     it_s += P.check_every;
 
-    // ------------------------------------------------------------------ termination check (OSQP criteria)
-    double rp = 0.0, rd = 0.0, nA = 0.0, nD = 0.0;
-    {
-      double in[EPL], c[EPL];
+    // ------------------------------------------------------------------ termination (OSQP criteria at x~, z+, y+)
+    bool pinf = false;
+    if (HAS_G) {
+      double in[EPL], cc[EPL];
 #pragma unroll
-      for (int le = 0; le < EPL; le++) {
-        if (!HAS_G) in[le] = x[le];
-        else {
-          const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
-          in[le] = ((boxbits >> le) & 1u) ? x[le] : sRho[e] * ys[le];
-        }
-      }
-      mma_pass(sC, in, c);
+      for (int le = 0; le < EPL; le++) in[le] = ((boxbits >> le) & 1u) ? xt[le] : yo[le];   // [x~; y_g]
+      mma_pass(sC, in, cc);                                                                 // [Pc x~ + G' y_g ; G x~]
 #pragma unroll
-      for (int le = 0; le < EPL; le++) {
-        const bool box = (boxbits >> le) & 1u;
-        if (box) {
-          const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
-          const double y = (HAS_G ? sRho[e] : rho_s) * ys[le];
-          rp = fmax(rp, fabs(x[le] - z[le]));
-          rd = fmax(rd, fabs(c[le] + q[le] + y));
-          nA = fmax(nA, fmax(fabs(x[le]), fabs(z[le])));
-          nD = fmax(nD, fmax(fabs(c[le]), fabs(y)));
-        } else {
-          rp = fmax(rp, fabs(c[le] - z[le]));
-          nA = fmax(nA, fmax(fabs(c[le]), fabs(z[le])));
+      for (int le = 0; le < EPL; le++)
+        if ((boxbits >> le) & 1u) {
+          rd = dmaxf(rd, fabs(cc[le] + q[le] + yo[le]));
+          nD = dmaxf(nD, dmaxf(fabs(cc[le]), fabs(yo[le])));
         }
-      }
     }
     rp = quad_max(rp); rd = quad_max(rd); nA = quad_max(nA); nD = quad_max(nD);
-    const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * fmax(nD, qn));
-    bool pinf = false;
+    const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
     if (HAS_G) {  // OSQP primal infeasibility certificate on delta_y of the last iteration
       double ndy = 0.0, supp = 0.0;
 #pragma unroll
       for (int le = 0; le < EPL; le++) {
         const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
-        const double dy = sRho[e] * dys[le];
-        dys[le] = dy;
-        const double off = ((boxbits >> le) & 1u) ? 0.0 : x[le];
-        ndy = fmax(ndy, fabs(dy));
-        supp += (sHi[e] + off) * fmax(dy, 0.0) + (sLo[e] + off) * fmin(dy, 0.0);
+        const double dy = dys[le];
+        const double off = ((boxbits >> le) & 1u) ? 0.0 : q[le];
+        ndy = dmaxf(ndy, fabs(dy));
+        supp += (sHi[e] + off) * dmaxf(dy, 0.0) + (sLo[e] + off) * (dy < 0.0 ? dy : 0.0);
       }
       ndy = quad_max(ndy); supp = quad_sum(supp);
       const bool cand = (pi >= 0) && !conv && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);
       if (__any_sync(0xffffffffu, cand)) {
-        double in[EPL], c[EPL];
+        double in[EPL], cc[EPL];
 #pragma unroll
         for (int le = 0; le < EPL; le++) in[le] = ((boxbits >> le) & 1u) ? 0.0 : dys[le];
-        mma_pass(sC, in, c);
+        mma_pass(sC, in, cc);
         double atdy = 0.0;
 #pragma unroll
         for (int le = 0; le < EPL; le++)
-          if ((boxbits >> le) & 1u) atdy = fmax(atdy, fabs(c[le] + dys[le]));
+          if ((boxbits >> le) & 1u) atdy = dmaxf(atdy, fabs(cc[le] + dys[le]));
         atdy = quad_max(atdy);
         pinf = cand && (atdy <= P.eps_pinf * ndy);
       }
@@ -299,16 +384,17 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
 #pragma unroll
       for (int tn = 0; tn < NTL; tn++) {
         const int e = 8 * tn + 2 * l4;
+        const double x0v = HAS_G ? xt[2 * tn] : sXt[(2 * tn) * 32], x1v = HAS_G ? xt[2 * tn + 1] : sXt[(2 * tn + 1) * 32];
         if (((nz & 1) == 0) && e + 1 < nz) {
-          *reinterpret_cast<double2*>(&P.v_out[pi * nz + e]) = make_double2(x[2 * tn], x[2 * tn + 1]);
+          *reinterpret_cast<double2*>(&P.v_out[pi * nz + e]) = make_double2(x0v, x1v);
         } else {
-          if (e < nz) P.v_out[pi * nz + e] = x[2 * tn];
-          if (e + 1 < nz) P.v_out[pi * nz + e + 1] = x[2 * tn + 1];
+          if (e < nz) P.v_out[pi * nz + e] = x0v;
+          if (e + 1 < nz) P.v_out[pi * nz + e + 1] = x1v;
         }
         if (P.y_out != nullptr) {
 #pragma unroll
           for (int jj = 0; jj < 2; jj++)
-            if (e + jj < P.nt) P.y_out[pi * P.nt + e + jj] = (HAS_G ? sRho[e + jj] : rho_s) * ys[2 * tn + jj];
+            if (e + jj < P.nt) P.y_out[pi * P.nt + e + jj] = HAS_G ? yo[2 * tn + jj] : sYo[(2 * tn + jj) * 32];
         }
       }
       if (l4 == 0) {

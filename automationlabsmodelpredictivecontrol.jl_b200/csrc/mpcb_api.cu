@@ -96,10 +96,10 @@ namespace {
 
 using mpcb::OnchipParams;
 
-template <int NT, bool HAS_G, int MINB>
+template <int NT, bool HAS_G, bool SIG, int MINB>
 cudaError_t launch_onchip_t(const OnchipParams& P, int sm_count, int* blocks_per_sm_cache, cudaStream_t st) {
-  auto kern = mpcb::admm_onchip_kernel<NT, HAS_G, MINB>;
-  const size_t smem = mpcb::onchip_smem_bytes(NT, P.np);
+  auto kern = mpcb::admm_onchip_kernel<NT, HAS_G, SIG, MINB>;
+  const size_t smem = mpcb::onchip_smem_bytes(NT, P.np, HAS_G);
   if (*blocks_per_sm_cache == 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -115,21 +115,26 @@ cudaError_t launch_onchip_t(const OnchipParams& P, int sm_count, int* blocks_per
   return cudaGetLastError();
 }
 
-template <bool HAS_G>
-cudaError_t launch_onchip_g(int NT, const OnchipParams& P, int sm_count, int* cache, cudaStream_t st) {
-  // MINB (CTAs of 128 threads per SM) is the register budget: box-only kernels hold 4 doubles per owned row,
-  // kernels with general rows also carry delta_y and per-row rho loads.
+// MINB (CTAs of 128 threads per SM) is the register budget of each variant (checked with -Xptxas -v: no spills for
+// the box-only kernels; the general-row kernels above NT = 40 spill a few hundred bytes).
+template <bool HAS_G, bool SIG>
+cudaError_t launch_onchip_gs(int NT, const OnchipParams& P, int sm_count, int* cache, cudaStream_t st) {
   switch (NT) {
-    case 8: return launch_onchip_t<8, HAS_G, 4>(P, sm_count, cache, st);
-    case 16: return launch_onchip_t<16, HAS_G, 4>(P, sm_count, cache, st);
-    case 24: return launch_onchip_t<24, HAS_G, HAS_G ? 3 : 4>(P, sm_count, cache, st);
-    case 32: return launch_onchip_t<32, HAS_G, HAS_G ? 2 : 3>(P, sm_count, cache, st);
-    case 40: return launch_onchip_t<40, HAS_G, HAS_G ? 2 : 3>(P, sm_count, cache, st);
-    case 48: return launch_onchip_t<48, HAS_G, 2>(P, sm_count, cache, st);
-    case 56: return launch_onchip_t<56, HAS_G, 2>(P, sm_count, cache, st);
-    case 64: return launch_onchip_t<64, HAS_G, 2>(P, sm_count, cache, st);
+    case 8: return launch_onchip_t<8, HAS_G, SIG, 4>(P, sm_count, cache, st);
+    case 16: return launch_onchip_t<16, HAS_G, SIG, 4>(P, sm_count, cache, st);
+    case 24: return launch_onchip_t<24, HAS_G, SIG, HAS_G ? 3 : 4>(P, sm_count, cache, st);
+    case 32: return launch_onchip_t<32, HAS_G, SIG, HAS_G ? 2 : 4>(P, sm_count, cache, st);
+    case 40: return launch_onchip_t<40, HAS_G, SIG, HAS_G ? 2 : 3>(P, sm_count, cache, st);
+    case 48: return launch_onchip_t<48, HAS_G, SIG, 2>(P, sm_count, cache, st);
+    case 56: return launch_onchip_t<56, HAS_G, SIG, 2>(P, sm_count, cache, st);
+    case 64: return launch_onchip_t<64, HAS_G, SIG, 2>(P, sm_count, cache, st);
     default: return cudaErrorInvalidValue;
   }
+}
+
+cudaError_t launch_onchip(int NT, bool has_g, const OnchipParams& P, int sm_count, int* cache, cudaStream_t st) {
+  if (has_g) return launch_onchip_gs<true, true>(NT, P, sm_count, cache, st);
+  return P.sigma != 0.0 ? launch_onchip_gs<false, true>(NT, P, sm_count, cache, st) : launch_onchip_gs<false, false>(NT, P, sm_count, cache, st);
 }
 
 cudaError_t upload(DevBuf<double>& b, const double* src, size_t n) {
@@ -209,8 +214,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
     P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = h->v.p; P.y_out = io.y;
     P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres; P.counter = h->counter.p;
-    cudaError_t e = D.mg > 0 ? launch_onchip_g<true>(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st)
-                             : launch_onchip_g<false>(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+    cudaError_t e = launch_onchip(h->NT, D.mg > 0, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
     launches += 1;
   } else {
@@ -231,14 +235,16 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     R.nx = D.nx; R.nu = D.nu; R.H = D.H; R.use_R = D.use_R; R.use_S = D.use_S; R.batch = Bn;
     R.x0 = io.x0; R.xref = io.xref; R.uref = io.uref; R.xref_bc = io.xref_broadcast; R.uref_bc = io.uref_broadcast;
     R.v = h->v.p; R.u = io.u; R.e_u = io.e_u; R.x = io.x; R.e_x = io.e_x; R.u0 = io.u0; R.objective = io.objective;
-    const size_t smem = mpcb::recover_smem_bytes(D.nx, D.nu);
-    static thread_local size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
-      CUDA_TRY(cudaFuncSetAttribute(mpcb::recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
+    if (!mpcb::launch_recover_small(R, st)) {
+      const size_t smem = mpcb::recover_smem_bytes(D.nx, D.nu);
+      static thread_local size_t smem_set = 0;
+      if (smem > 48 * 1024 && smem > smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(mpcb::recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+      }
+      const unsigned grid = (unsigned)((Bn + mpcb::RECOVER_THREADS - 1) / mpcb::RECOVER_THREADS);
+      mpcb::recover_kernel<<<grid, mpcb::RECOVER_THREADS, smem, st>>>(R);
     }
-    const unsigned grid = (unsigned)((Bn + mpcb::RECOVER_THREADS - 1) / mpcb::RECOVER_THREADS);
-    mpcb::recover_kernel<<<grid, mpcb::RECOVER_THREADS, smem, st>>>(R);
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }

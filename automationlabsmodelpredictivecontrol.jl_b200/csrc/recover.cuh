@@ -119,4 +119,122 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
   if (P.objective) P.objective[p] = J;
 }
 
+// Register-resident specialisation for small systems (the quadruple tank is NX=4, NU=2): the deviation state, the
+// references and the weights' rows live in registers, every result column leaves as 16-byte stores that fill whole
+// 32-byte sectors, and the per-problem input row is fetched with 16-byte loads.
+template <int NX, int NU>
+__global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const RecoverParams P) {
+  __shared__ double sA[NX * NX], sB[NX * NU], sQ[NX * NX], sPt[NX * NX], sR[NU * NU], sS[NU * NU];
+  const int tid = threadIdx.x, H = P.H;
+  for (int i = tid; i < NX * NX; i += RECOVER_THREADS) { sA[i] = P.A[i]; sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
+  for (int i = tid; i < NX * NU; i += RECOVER_THREADS) sB[i] = P.B[i];
+  for (int i = tid; i < NU * NU; i += RECOVER_THREADS) { sR[i] = P.R[i]; sS[i] = P.S ? P.S[i] : 0.0; }
+  __syncthreads();
+  const long long p = (long long)blockIdx.x * RECOVER_THREADS + tid;
+  if (p >= P.batch) return;
+  double e[NX], xr[NX], ur[NU], eu[NU], up[NU];
+#pragma unroll
+  for (int i = 0; i < NX; i++) { xr[i] = P.xref[(P.xref_bc ? 0 : p) * NX + i]; e[i] = P.x0[p * NX + i] - xr[i]; }
+#pragma unroll
+  for (int i = 0; i < NU; i++) { ur[i] = P.uref[(P.uref_bc ? 0 : p) * NU + i]; up[i] = 0.0; }
+  const double* v = P.v + p * (long long)NU * H;
+  auto store_run = [](double* dst, const double (&val)[NX > NU ? NX : NU], int n) {
+    if ((n & 1) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+      for (int i = 0; i < (NX > NU ? NX : NU); i += 2)
+        if (i < n) *reinterpret_cast<double2*>(dst + i) = make_double2(val[i], val[i + 1]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < (NX > NU ? NX : NU); i++)
+        if (i < n) dst[i] = val[i];
+    }
+  };
+  constexpr int NM = NX > NU ? NX : NU;
+  double J = 0.0;
+  for (int k = 0; k <= H; k++) {
+    double tmp[NM];
+    if (P.e_x) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) tmp[i] = e[i];
+      store_run(P.e_x + (p * (H + 1) + k) * NX, tmp, NX);
+    }
+    if (P.x) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) tmp[i] = e[i] + xr[i];
+      store_run(P.x + (p * (H + 1) + k) * NX, tmp, NX);
+    }
+    const double* W = (k == H) ? sPt : sQ;
+    double quad = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; j++) s = fma(W[j * NX + i], e[j], s);
+      quad = fma(e[i], s, quad);
+    }
+    J += quad;
+    if (k == H) break;
+    double uk[NM];
+#pragma unroll
+    for (int i = 0; i < NU; i++) { uk[i] = v[k * NU + i]; eu[i] = uk[i] - ur[i]; }
+    if (P.u) store_run(P.u + (p * H + k) * NU, uk, NU);
+    if (P.e_u) {
+#pragma unroll
+      for (int i = 0; i < NU; i++) tmp[i] = eu[i];
+      store_run(P.e_u + (p * H + k) * NU, tmp, NU);
+    }
+    if (k == 0 && P.u0) store_run(P.u0 + p * NU, uk, NU);
+    if (P.use_R) {
+      double quadr = 0.0;
+#pragma unroll
+      for (int i = 0; i < NU; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU; j++) s = fma(sR[j * NU + i], eu[j], s);
+        quadr = fma(eu[i], s, quadr);
+      }
+      J += quadr;
+      if (P.use_S) {
+        if (k > 0) {
+          double quads = 0.0;
+#pragma unroll
+          for (int i = 0; i < NU; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NU; j++) s = fma(sS[j * NU + i], up[j] - uk[j], s);
+            quads = fma(up[i] - uk[i], s, quads);
+          }
+          J += quads;
+        }
+#pragma unroll
+        for (int i = 0; i < NU; i++) up[i] = uk[i];
+      }
+    }
+    double en[NX];
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < NX; j++) s = fma(sA[j * NX + i], e[j], s);
+#pragma unroll
+      for (int j = 0; j < NU; j++) s = fma(sB[j * NX + i], eu[j], s);
+      en[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; i++) e[i] = en[i];
+  }
+  if (P.objective) P.objective[p] = J;
+}
+
+// returns false when no specialisation exists (caller falls back to recover_kernel)
+inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
+  const unsigned grid = (unsigned)((R.batch + RECOVER_THREADS - 1) / RECOVER_THREADS);
+#define MPCB_RS(NX_, NU_) \
+  if (R.nx == NX_ && R.nu == NU_) { recover_small_kernel<NX_, NU_><<<grid, RECOVER_THREADS, 0, st>>>(R); return true; }
+  MPCB_RS(2, 1) MPCB_RS(2, 2) MPCB_RS(3, 1) MPCB_RS(3, 2) MPCB_RS(4, 1) MPCB_RS(4, 2) MPCB_RS(4, 4) MPCB_RS(6, 2) MPCB_RS(6, 3)
+  MPCB_RS(8, 2) MPCB_RS(8, 4)
+#undef MPCB_RS
+  return false;
+}
+
 }  // namespace mpcb

@@ -336,9 +336,15 @@ def admm_matrices(c: CondensedQP, s: AdmmSettings):
 
 def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
     """Batched over problems (rows of p).  Mirrors OSQP's iteration (update_xz_tilde / update_x / update_z /
-    update_y, osqp 0.6 `osqp_solve`) on the reduced KKT system; termination is OSQP's
-    (eps_abs + eps_rel * max(...)) evaluated on the condensed problem every `check_every` iterations, with
-    the normalisation  max(|Pc x + G' y_g|, |y_box|, |q|)  for the dual residual (equal to OSQP's when mg = 0).
+    update_y, osqp 0.6 `osqp_solve`) on the reduced KKT system with a cached operator.
+
+    Termination (every `check_every` iterations; max_iter is rounded up to a multiple of it) applies OSQP's
+    criteria  r <= eps_abs + eps_rel * max(...)  to the triple (x~, z+, y+) -- the exact minimiser x~ of the
+    x-subproblem instead of OSQP's relaxed x -- because its dual residual is available from the cached factor
+    without a second operator pass; x~ is also the returned solution.  Both sequences have
+    the same limit.  Residuals:
+        prim = |[x~; G x~] - z+|_inf                      norm: max(|[x~; G x~]|, |z+|)
+        dual = |Pc x~ + G' y+_g + q + y+_box|_inf         norm: max(|Pc x~ + G' y+_g|, |y+_box|, |q|)
     """
     nz, mg = c.nz, c.mg; nt = nz + mg
     T, C, rho_vec, rho = admm_matrices(c, s)
@@ -348,50 +354,49 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
     b = p @ c.Lb.T if mg else np.zeros((Bn, 0))
     lo = np.concatenate([np.broadcast_to(c.lb, (Bn, nz)), c.lg + b], axis=1)
     hi = np.concatenate([np.broadcast_to(c.ub, (Bn, nz)), c.ug + b], axis=1)
-    x = np.zeros((Bn, nz)) if v0 is None else np.array(v0, float).reshape(Bn, nz)
     Ac = np.vstack([np.eye(nz), c.G])
-    z = np.clip(x @ Ac.T, lo, hi) if v0 is not None else np.zeros((Bn, nt))
-    y = np.zeros((Bn, nt)) if y0 is None else np.array(y0, float).reshape(Bn, nt)
+    if v0 is None:
+        x = np.zeros((Bn, nz)); z = np.zeros((Bn, nt)); ys = np.zeros((Bn, nt))
+    else:                                   # OSQP warm start: x = x0, z = A x0, y = y0
+        x = np.array(v0, float).reshape(Bn, nz); z = x @ Ac.T; ys = np.array(y0, float).reshape(Bn, nt) * rinv
+    max_iter = -(-s.max_iter // s.check_every) * s.check_every
     iters = np.zeros(Bn, np.int32); status = np.full(Bn, STATUS_MAX_ITER, np.int32)
     pres = np.zeros(Bn); dres = np.zeros(Bn)
     xo = np.zeros((Bn, nz)); yo = np.zeros((Bn, nt))
     active = np.ones(Bn, bool)
     qn = np.abs(q).max(1)
-    for it in range(1, s.max_iter + 1):
-        r = s.rho * 0 + rho_vec * z - y
+    for it in range(1, max_iter + 1):
+        r = rho_vec * (z - ys)
         r[:, :nz] += s.sigma * x - q
-        t = r @ T                      # T symmetric: [x_tilde; z_tilde_g]
-        xn = s.alpha * t[:, :nz] + (1 - s.alpha) * x
-        w = s.alpha * t + (1 - s.alpha) * z + y * rinv
+        t = r @ T                      # T symmetric: [x~; z~_g] with z~_g = G x~
+        w = s.alpha * t + (1 - s.alpha) * z + ys
         zn = np.minimum(np.maximum(w, lo), hi)
-        yn = rho_vec * (w - zn)
-        dy = yn - y
-        x, z, y = xn, zn, yn
-        if it % s.check_every == 0 or it == s.max_iter:
-            xy = np.concatenate([x, y[:, nz:]], axis=1)
-            cv = xy @ C                # [Pc x + G' y_g ; G x]
-            ax = np.concatenate([x, cv[:, nz:]], axis=1)
-            rp = np.abs(ax - z).max(1)
-            rd = np.abs(cv[:, :nz] + q + y[:, :nz]).max(1)
-            ep = s.eps_abs + s.eps_rel * np.maximum(np.abs(ax).max(1), np.abs(z).max(1))
-            ed = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(cv[:, :nz]).max(1), np.abs(y[:, :nz]).max(1)), qn)
+        ysn = w - zn
+        x = s.alpha * t[:, :nz] + (1 - s.alpha) * x
+        dy = rho_vec * (ysn - ys)
+        z, ys = zn, ysn
+        if it % s.check_every == 0:
+            y = rho_vec * ys
+            g = t[:, :nz] @ c.Pc + y[:, nz:] @ c.G
+            rp = np.abs(t - z).max(1)
+            rd = np.abs(g + q + y[:, :nz]).max(1)
+            ep = s.eps_abs + s.eps_rel * np.maximum(np.abs(t).max(1), np.abs(z).max(1))
+            ed = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(g).max(1), np.abs(y[:, :nz]).max(1)), qn)
             conv = (rp <= ep) & (rd <= ed)
             # OSQP primal infeasibility certificate on delta_y (osqp 0.6 is_primal_infeasible)
             ndy = np.abs(dy).max(1)
-            supp = (np.where(np.isfinite(hi), hi, 0.0) * np.maximum(dy, 0)).sum(1) + \
-                   (np.where(np.isfinite(lo), lo, 0.0) * np.minimum(dy, 0)).sum(1)
+            supp = (hi * np.maximum(dy, 0)).sum(1) + (lo * np.minimum(dy, 0)).sum(1)
             atdy = np.abs(dy @ Ac).max(1)
             pinf = (ndy > s.eps_prim_inf) & (supp < -s.eps_prim_inf * ndy) & (atdy <= s.eps_prim_inf * ndy) & ~conv
-            fin = active & (conv | pinf)
-            upd = active
-            pres[upd] = rp[upd]; dres[upd] = rd[upd]
+            if mg == 0: pinf[:] = False     # a non-empty box is always feasible
+            fin = active & (conv | pinf | (it >= max_iter))
             status[active & conv] = STATUS_SOLVED
             status[active & pinf] = STATUS_PRIMAL_INF
-            iters[fin] = it; xo[fin] = x[fin]; yo[fin] = y[fin]
+            pres[fin] = rp[fin]; dres[fin] = rd[fin]
+            iters[fin] = it; xo[fin] = t[fin, :nz]; yo[fin] = y[fin]
             active = active & ~fin
             if not active.any():
                 break
-    iters[active] = s.max_iter; xo[active] = x[active]; yo[active] = y[active]
     return {"v": xo, "y": yo, "iters": iters, "status": status, "prim_res": pres, "dual_res": dres, "rho": rho}
 
 
