@@ -1,0 +1,155 @@
+# B200ModelPredictiveControl.jl -- the reference-side binding of libmpcb200 (include/mpcb200.h).
+#
+# UNTESTED HERE: neither the build container nor the GPU box has a Julia toolchain (probed: `julia` missing), so this
+# file has not been executed.  It is the thin `ccall` shim a maintainer of AutomationLabsModelPredictiveControl.jl
+# would add (INTEGRATION.md walks through it); the identical C ABI is exercised from Python ctypes by tests/.
+#
+# How it plugs into the reference (paths relative to the reference repo):
+#   src/types/types.jl:168-192         add    struct b200_solver_def <: AbstractSolvers end
+#   src/sub/solver_selection.jl:9-14   add    b200 = b200_solver_def()  to _IMPLEMENTATION_SOLVER_LIST
+#   src/sub/design_mpc.jl:84-104       when the solver tag is b200, build a B200Modeler instead of the JuMP model
+#   src/main/computation_mpc.jl:17,38  methods of update_initialization! / calculate! for a B200Modeler (below)
+module B200ModelPredictiveControl
+
+using LinearAlgebra
+
+const libmpcb200 = get(ENV, "MPCB200_LIB", "libmpcb200.so")
+
+# ---- C structs (field order and types exactly as in include/mpcb200.h) -------------------------------------------
+struct MpcbSettings
+    eps_abs::Cdouble; eps_rel::Cdouble; eps_prim_inf::Cdouble; rho::Cdouble; rho_eq_scale::Cdouble
+    sigma::Cdouble; alpha::Cdouble
+    max_iter::Int32; check_every::Int32; device::Int32; kernel::Int32
+    reserved::NTuple{4,Int32}
+end
+
+struct MpcbLinearDesc
+    nx::Int32; nu::Int32; horizon::Int32
+    A::Ptr{Cdouble}; B::Ptr{Cdouble}; Q::Ptr{Cdouble}; R::Ptr{Cdouble}; S::Ptr{Cdouble}; P::Ptr{Cdouble}
+    umin::Ptr{Cdouble}; umax::Ptr{Cdouble}; xmin::Ptr{Cdouble}; xmax::Ptr{Cdouble}
+    state_constraint::Int32; terminal_mode::Int32
+end
+
+struct MpcbInfo
+    nx::Int32; nu::Int32; horizon::Int32; nz::Int32; mg::Int32; nt::Int32; nt_pad::Int32; kernel::Int32
+    device::Int32; sm_count::Int32
+    rho::Cdouble; lambda_min::Cdouble; lambda_max::Cdouble
+end
+
+struct MpcbBatchIO
+    batch::Int64
+    x0::Ptr{Cdouble}; xref::Ptr{Cdouble}; uref::Ptr{Cdouble}
+    xref_broadcast::Int32; uref_broadcast::Int32
+    warm_u::Ptr{Cdouble}; warm_y::Ptr{Cdouble}
+    u::Ptr{Cdouble}; e_u::Ptr{Cdouble}; x::Ptr{Cdouble}; e_x::Ptr{Cdouble}; u0::Ptr{Cdouble}
+    status::Ptr{Int32}; iters::Ptr{Int32}
+    prim_res::Ptr{Cdouble}; dual_res::Ptr{Cdouble}; objective::Ptr{Cdouble}; y::Ptr{Cdouble}
+end
+
+last_error() = unsafe_string(ccall((:mpcb_last_error, libmpcb200), Cstring, ()))
+check(rc, what) = rc == 0 || error("$what failed (rc=$rc): $(last_error())")   # no CPU fallback: errors surface here
+
+function default_settings(; kw...)
+    s = Ref{MpcbSettings}()
+    ccall((:mpcb_default_settings, libmpcb200), Cvoid, (Ref{MpcbSettings},), s)
+    d = Dict{Symbol,Any}(n => getfield(s[], n) for n in fieldnames(MpcbSettings))
+    for (k, v) in kw
+        d[k] = v
+    end
+    return MpcbSettings((convert(fieldtype(MpcbSettings, n), d[n]) for n in fieldnames(MpcbSettings))...)
+end
+
+# ---- what `tuning.modeler` holds for mpc_solver = "b200" (types.jl:115 leaves the field untyped) ------------------
+mutable struct B200Modeler
+    handle::Ptr{Cvoid}
+    info::MpcbInfo
+    X0::Matrix{Float64}        # nx x batch, set by update_initialization!
+    xref::Matrix{Float64}      # nx x (1 | batch)
+    uref::Matrix{Float64}      # nu x (1 | batch)
+    # batched results (reference layout per problem, problems along the last dimension)
+    u::Array{Float64,3}; e_u::Array{Float64,3}; x::Array{Float64,3}; e_x::Array{Float64,3}
+    status::Vector{Int32}; iterations::Vector{Int32}
+    prim_res::Vector{Float64}; dual_res::Vector{Float64}; objective::Vector{Float64}
+end
+
+"""
+    B200Modeler(A, B, Q, R, S, P, umin, umax, xmin, xmax, horizon; state_constraint, terminal, settings)
+
+Replaces `_model_predictive_control_modeler_implementation(::LinearProgramming, system, ...)` (linear.jl:20-103) +
+`_create_terminal_ingredient` constraints (design_mpc.jl:330-331) + `_create_quadratic_cost_function`
+(design_mpc.jl:405-468): the same data, condensed and factored once, cached on the GPU.
+"""
+function B200Modeler(A, B, Q, R, S, P, umin, umax, xmin, xmax, horizon::Int;
+                     state_constraint::Bool=false, terminal::String="none", settings::MpcbSettings=default_settings())
+    terminal in ("none", "equality") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\" and \"equality\" only")
+    nx, nu = size(B)
+    mats = map(M -> Matrix{Float64}(M), (A, B, Q, R, S, P))
+    vecs = map(v -> Vector{Float64}(v), (umin, umax, xmin, xmax))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve mats vecs begin
+        d = MpcbLinearDesc(nx, nu, horizon, map(pointer, mats)..., map(pointer, vecs)..., state_constraint ? 1 : 0,
+                           terminal == "equality" ? 1 : 0)
+        check(ccall((:mpcb_create_linear, libmpcb200), Cint, (Ref{MpcbLinearDesc}, Ref{MpcbSettings}, Ref{Ptr{Cvoid}}), d, settings, h),
+              "mpcb_create_linear")
+    end
+    info = Ref{MpcbInfo}()
+    check(ccall((:mpcb_get_info, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbInfo}), h[], info), "mpcb_get_info")
+    m = B200Modeler(h[], info[], zeros(nx, 0), zeros(nx, 1), zeros(nu, 1), zeros(nu, horizon, 0), zeros(nu, horizon, 0),
+                    zeros(nx, horizon + 1, 0), zeros(nx, horizon + 1, 0), Int32[], Int32[], Float64[], Float64[], Float64[])
+    finalizer(m -> ccall((:mpcb_destroy, libmpcb200), Cvoid, (Ptr{Cvoid},), m.handle), m)
+    return m
+end
+
+# ---- the hot path: methods the reference's two compute functions gain (computation_mpc.jl:17-55) ------------------
+"update_initialization!(C, x0::Vector): single problem, reference semantics (JuMP.fix of x[:,1] becomes the x0 operand)."
+function update_initialization!(m::B200Modeler, initialization::AbstractVector, references)
+    m.X0 = reshape(Vector{Float64}(initialization), :, 1)
+    m.xref = reshape(Vector{Float64}(references.x[:, 1]), :, 1)
+    m.uref = reshape(Vector{Float64}(references.u[:, 1]), :, 1)
+end
+
+"Batched overload: X0 is nx x batch; xref / uref are nx x 1 (broadcast) or nx x batch."
+function update_initialization!(m::B200Modeler, X0::AbstractMatrix; xref::AbstractMatrix, uref::AbstractMatrix)
+    m.X0 = Matrix{Float64}(X0); m.xref = Matrix{Float64}(xref); m.uref = Matrix{Float64}(uref)
+end
+
+"calculate!(C): one batched solve; fills the batched result arrays (and, in the reference wrapper, C.computation_results)."
+function calculate!(m::B200Modeler)
+    nx, nu, H = Int(m.info.nx), Int(m.info.nu), Int(m.info.horizon)
+    batch = size(m.X0, 2)
+    batch > 0 || error("calculate!: call update_initialization! first")
+    m.u = Array{Float64}(undef, nu, H, batch); m.e_u = similar(m.u)
+    m.x = Array{Float64}(undef, nx, H + 1, batch); m.e_x = similar(m.x)
+    m.status = Vector{Int32}(undef, batch); m.iterations = Vector{Int32}(undef, batch)
+    m.prim_res = Vector{Float64}(undef, batch); m.dual_res = similar(m.prim_res); m.objective = similar(m.prim_res)
+    GC.@preserve m begin
+        io = MpcbBatchIO(batch, pointer(m.X0), pointer(m.xref), pointer(m.uref), size(m.xref, 2) == 1 ? 1 : 0,
+                         size(m.uref, 2) == 1 ? 1 : 0, C_NULL, C_NULL, pointer(m.u), pointer(m.e_u), pointer(m.x), pointer(m.e_x),
+                         C_NULL, pointer(m.status), pointer(m.iterations), pointer(m.prim_res), pointer(m.dual_res),
+                         pointer(m.objective), C_NULL)
+        check(ccall((:mpcb_solve_linear_batch, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbBatchIO}), m.handle, io), "mpcb_solve_linear_batch")
+    end
+    return m
+end
+
+# In AutomationLabsModelPredictiveControl (computation_mpc.jl) the two new methods read:
+#
+#   function update_initialization!(C::ModelPredictiveControlController, initialization::Vector)
+#       C.initialization = initialization
+#       if C.tuning.modeler isa B200Modeler
+#           return B200ModelPredictiveControl.update_initialization!(C.tuning.modeler, initialization, C.tuning.reference)
+#       end
+#       ...                                   # existing JuMP.fix loop, unchanged
+#   end
+#
+#   function calculate!(C::ModelPredictiveControlController)
+#       if C.tuning.modeler isa B200Modeler
+#           m = B200ModelPredictiveControl.calculate!(C.tuning.modeler)
+#           C.computation_results.u[:, :]   = m.u[:, :, 1];   C.computation_results.e_u[:, :] = m.e_u[:, :, 1]
+#           C.computation_results.x[:, :]   = m.x[:, :, 1];   C.computation_results.e_x[:, :] = m.e_x[:, :, 1]
+#           return
+#       end
+#       ...                                   # existing JuMP.optimize! path, unchanged
+#   end
+
+end # module
