@@ -1,5 +1,5 @@
-// Streamed batched ADMM for operators that do not fit the register file (nz + mg > 64): placeholder interface,
-// filled in by admm_stream.cu.
+// Streamed batched ADMM for operators that do not fit the register file (nz + mg > 64); implementation and design
+// notes in admm_stream.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -22,13 +22,17 @@ struct StreamConsts {
 };
 
 struct StreamWork {
+  // state (problem-major [rows][NTp]): Z holds c = (1-alpha) z + y/rho, Q holds q (box cols) / bound offset (general cols)
   double *X = nullptr, *Q = nullptr, *Z = nullptr, *YS = nullptr, *R0 = nullptr, *R1 = nullptr, *DY = nullptr;
-  double* red = nullptr;       // [cap][8] per-problem reductions
-  int* idx = nullptr;          // [cap] compact position -> original problem
-  int* idx2 = nullptr;
-  int* count = nullptr;        // device: [0] = active count
+  double *X2 = nullptr, *Q2 = nullptr, *Z2 = nullptr;             // compaction targets
+  double *XT = nullptr, *YO = nullptr, *YP = nullptr;             // candidate x~ / y+ and y of the iteration before
+  double *qn = nullptr, *qn2 = nullptr, *cert = nullptr;          // per-row |q|_inf, certificate partials [rows][3]
+  unsigned long long *red = nullptr, *red2 = nullptr;             // [rows][4] residual reductions
+  int *idx = nullptr, *idx2 = nullptr, *done = nullptr, *done2 = nullptr, *newly = nullptr;
+  int* count = nullptr;        // device: [0] active rows after a check, [1] compaction cursor
   int* h_count = nullptr;      // pinned mirror
   long long cap = 0;
+  int NTp = 0;
 };
 
 struct StreamBatch {

@@ -35,6 +35,7 @@ H = 20
 BATCH = 65536
 EPS = 1e-7
 CHECK = 5
+SIGMA = 0.0    # OSQP's sigma only regularises a semidefinite P; the condensed K = Pc + rho I is positive definite without it
 FP64_PEAK_TFLOPS = 37.1   # DMMA.8x8x4 peak measured on this pool's B200 (profiles/micro/fp64_peak_r01.jsonl);
                           # MEASURED_PEAKS.json has no FP64 entry (cuBLAS DGEMM 8192^3 measured 35.5 in the same run)
 
@@ -112,7 +113,7 @@ def run_ours(args):
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
     Cn = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200",
-                                mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_device=local)
+                                mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA, mpc_b200_device=local)
     m = Cn.tuning.modeler
     info = m.info
     n = args.batch
@@ -215,13 +216,13 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: quadruple-tank linear tracking MPC nx=4 nu=2 H=20, batch 65536 random x0/x_ref per GPU, cold start",
-                       "batch_per_gpu": n, "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "rho": info.rho, "kernel": "onchip-dmma",
+                       "batch_per_gpu": n, "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "sigma": SIGMA, "alpha": 1.6, "rho": info.rho, "kernel": "onchip-dmma",
                        "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"batch-shard x{world}, NCCL gather of u0+stats" if world > 1 else "single GPU",
                        "outputs": "u,e_u,x,e_x,u0,objective,status,iters,residuals"},
             "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "phases_ms": {k: round(v, 4) for k, v in tim.items() if k.endswith("_ms")}},
             "gpu_launches": int(2 * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "admm_onchip_kernel<40,false,3>", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+            "roofline": {"bound": "tensor", "kernel": "admm_onchip_kernel<40,false,false,3>", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
                          "peak_source": "FP64 DMMA peak measured by profiles/micro/fp64_peak.cu on this pool (MEASURED_PEAKS.json has no FP64 number)",
                          "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops, "mean_iters": float(it_np.mean())},
@@ -275,9 +276,10 @@ def cpu_baseline(sample):
     x0, xref, uref = make_batch(sample, seed=0)
     st = orf.default_settings()
     vals = _reference_vals(x0, xref, uref)
-    orf.solve_batch(prob, st, rows, vals[:256], sel)          # warm the threads / page in
+    ncores = os.cpu_count() or 1                               # torchrun exports OMP_NUM_THREADS=1: ask for every host core explicitly
+    orf.solve_batch(prob, st, rows, vals[:256], sel, nthreads=ncores)          # warm the threads / page in
     t0 = time.perf_counter()
-    r = orf.solve_batch(prob, st, rows, vals, sel, cold_start=True)
+    r = orf.solve_batch(prob, st, rows, vals, sel, cold_start=True, nthreads=ncores)
     dt = time.perf_counter() - t0
     # single-solve latency: closed loop, warm start, persistent workspace (what one JuMP model + OSQP does)
     A, B, *_rest, x_ref, u_ref, xx0 = qt_model()
@@ -289,7 +291,7 @@ def cpu_baseline(sample):
         d = time.perf_counter() - t1
         if k >= 20: ts.append(d)
         x = x_ref + A @ (x - x_ref) + B @ (s["x"][ucols] - u_ref)
-    return {"value": sample / dt, "unit": "solves/s", "cores": orf.max_threads(), "kind": "port",
+    return {"value": sample / dt, "unit": "solves/s", "cores": ncores, "kind": "port",
             "sample": f"{sample} problems of configs[1] (rng(0)), OSQP 0.6 defaults eps=1e-3 (the reference sets no solver attribute), "
                       f"cold start, OpenMP over problems; mean iters {float(r['iters'].mean()):.1f}; solved {float((r['status'] == 1).mean()):.3f}",
             "latency_p50_us": statistics.median(ts) * 1e6}
@@ -304,12 +306,13 @@ def run_reference(args):
     n = args.ref_sample
     x0, xref, uref = make_batch(n, seed=0)
     vals = _reference_vals(x0, xref, uref)
+    ncores = os.cpu_count() or 1
     for _ in range(max(args.warmup, 1)):
-        orf.solve_batch(prob, st, rows, vals[: max(256, n // 8)], sel)
+        orf.solve_batch(prob, st, rows, vals[: max(256, n // 8)], sel, nthreads=ncores)
     t0 = time.perf_counter()
     its = []
     for _ in range(args.steps):
-        r = orf.solve_batch(prob, st, rows, vals, sel, cold_start=True); its.append(float(r["iters"].mean()))
+        r = orf.solve_batch(prob, st, rows, vals, sel, cold_start=True, nthreads=ncores); its.append(float(r["iters"].mean()))
     dt = time.perf_counter() - t0
     val = n * args.steps / dt
     sample = (f"{n} problems of configs[1] per step (rng(0)); oracle port of OSQP 0.6 (oracle/osqp_ref.c) on the reference's sparse "
@@ -319,7 +322,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[1]: quadruple-tank linear tracking MPC nx=4 nu=2 H=20, bounded sample of the 65536 batch", "batch_per_step": n},
-        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": orf.max_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "solves/s", "cores": ncores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 

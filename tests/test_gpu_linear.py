@@ -49,17 +49,18 @@ def test_kat_lqr_single_problem(mpc, qt):
         assert np.allclose(C.computation_results.e_u, C.computation_results.u - 1.2)
 
 
-@pytest.mark.parametrize("H,eps,check", [(20, 1e-7, 5), (20, 1e-6, 5), (20, 1e-3, 25), (5, 1e-7, 5), (10, 1e-5, 4), (13, 1e-7, 5)])
-def test_batch_matches_twin_and_exact(mpc, qt, H, eps, check):
+@pytest.mark.parametrize("H,eps,check,sigma", [(20, 1e-7, 5, 0.0), (20, 1e-7, 5, 1e-6), (20, 1e-6, 5, 1e-6), (20, 1e-3, 25, 1e-6), (5, 1e-7, 5, 0.0),
+                                                (10, 1e-5, 4, 1e-6), (13, 1e-7, 5, 0.0), (7, 1e-7, 3, 1e-6)])
+def test_batch_matches_twin_and_exact(mpc, qt, H, eps, check, sigma):
     n = 2048
-    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check)
+    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma)
     m = C.tuning.modeler
     x0, xref, uref = qt_batch(qt, n)
     mpc.update_initialization(C, x0, references=(xref, uref))
     res = mpc.calculate(C)
     c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P)
     p = mo.pack_params(x0, xref, uref)
-    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=check))
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=check, sigma=sigma))
     # same algorithm, same iteration counts (summation order differs -> allow a vanishing fraction of off-by-one-check)
     same = res["iters"] == tw["iters"]
     assert same.mean() > 0.995, same.mean()
@@ -170,3 +171,94 @@ def test_empty_and_ragged_batches(mpc, qt):
         assert (r["status"] == 1).all() and r["u"].shape == (n, 20, 2)
         if ref is None: ref = r["u"][0].copy()
         assert np.abs(r["u"][0] - ref).max() < 1e-12       # a problem's answer does not depend on its batch
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# streamed kernel (nt > 64, or forced with mpc_b200_kernel = 2)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("H,force,sigma", [(20, 2, 0.0), (20, 2, 1e-6), (50, 0, 0.0), (35, 0, 1e-6)])
+def test_streamed_matches_twin_and_exact(mpc, qt, H, force, sigma):
+    n, eps, check = 700, 1e-7, 5          # 700: not a multiple of the 128-row GEMM tile
+    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma,
+                        mpc_b200_kernel=force)
+    m = C.tuning.modeler
+    assert m.info.kernel == 2
+    x0, xref, uref = qt_batch(qt, n, seed=21)
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P)
+    p = mo.pack_params(x0, xref, uref)
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=check, sigma=sigma))
+    same = res["iters"] == tw["iters"]
+    assert same.mean() > 0.99 and (res["status"] == 1).all()
+    v = res["u"].reshape(n, -1)
+    assert np.abs(v[same] - tw["v"][same]).max() < 1e-9
+    ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in range(64)])
+    assert mo.u0_metric(res["u0"][:64], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
+    rec = mo.recover(c, v, p)
+    assert np.abs(res["x"] - rec["x"]).max() < 1e-10 and np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
+
+
+def test_streamed_equals_onchip(mpc, qt):
+    """Two independent kernels, one algorithm: identical iteration counts and (to rounding) identical solutions."""
+    n = 1500
+    x0, xref, uref = qt_batch(qt, n, seed=22)
+    out = []
+    for kern in (1, 2):
+        C = make_controller(mpc, qt, 20, mpc_b200_eps_abs=1e-7, mpc_b200_eps_rel=1e-7, mpc_b200_check_every=5, mpc_b200_kernel=kern)
+        mpc.update_initialization(C, x0, references=(xref, uref))
+        out.append(mpc.calculate(C))
+    assert (out[0]["iters"] == out[1]["iters"]).mean() > 0.995
+    same = out[0]["iters"] == out[1]["iters"]
+    assert np.abs(out[0]["u"][same] - out[1]["u"][same]).max() < 1e-10
+
+
+def test_streamed_terminal_equality(mpc, qt):
+    H, n, eps = 40, 300, 1e-7
+    C = make_controller(mpc, qt, H, terminal="equality", mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=10, mpc_b200_max_iter=6000,
+                        mpc_b200_rho=10.0)
+    m = C.tuning.modeler
+    assert m.info.kernel == 2 and m.info.mg == 4 and m.info.nt == 84
+    rng = np.random.default_rng(5)
+    xref = np.tile(qt["x_ref"], (n, 1))
+    x0 = xref + 0.05 * rng.standard_normal((n, 4))
+    mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
+    res = mpc.calculate(C)
+    c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P, terminal="equality")
+    p = mo.pack_params(x0, xref, qt["u_ref"])
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=10, max_iter=6000))
+    assert (res["status"] == tw["status"]).mean() > 0.98
+    same = (res["iters"] == tw["iters"]) & (res["status"] == 1)
+    assert same.mean() > 0.5
+    assert np.abs(res["u"].reshape(n, -1)[same] - tw["v"][same]).max() < 1e-7
+    assert np.abs(res["e_x"][same][:, -1, :]).max() < 1e-5
+    assert set(np.unique(res["status"])) <= {1, -2, -3}
+
+
+def test_random_lti_generic_recover(mpc):
+    """nx=5, nu=3: no register-resident recover specialisation -> generic recover kernel; nz = 36 -> on-chip NT = 40 with padding rows."""
+    rng = np.random.default_rng(9)
+    nx, nu, H, n = 5, 3, 12, 400
+    G = rng.standard_normal((nx, nx)); A = 0.9 * G / np.abs(np.linalg.eigvals(G)).max(); B = rng.standard_normal((nx, nu)) / 2
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(-5 * np.ones(nx), 5 * np.ones(nx)), mpc.Hyperrectangle(-np.ones(nu), np.ones(nu)))
+    eps = 1e-7
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 1, [0.0] * nx, [0.0] * nu, mpc_solver="b200", mpc_Q=10.0, mpc_R=1.0,
+                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5)
+    m = C.tuning.modeler
+    assert m.info.nz == 36 and m.info.nt_pad == 40
+    x0 = 2.0 * rng.standard_normal((n, nx)); xref = 0.2 * rng.standard_normal((n, nx)); uref = 0.1 * rng.standard_normal((n, nu))
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    c = mo.condense(A, B, 10 * np.eye(nx), np.eye(nu), np.zeros((nu, nu)), C.tuning.terminal_ingredient.P, H, -np.ones(nu), np.ones(nu))
+    p = mo.pack_params(x0, xref, uref)
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5))
+    same = res["iters"] == tw["iters"]
+    assert same.mean() > 0.99 and (res["status"] == 1).all()
+    v = res["u"].reshape(n, -1)
+    assert np.abs(v[same] - tw["v"][same]).max() < 1e-9
+    rec = mo.recover(c, v, p)
+    for k in ("x", "e_x", "u", "e_u"):
+        assert np.abs(res[k] - rec[k]).max() < 1e-10, k
+    assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
+    ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in range(48)])
+    assert mo.u0_metric(res["u0"][:48], ex[:, :nu], -np.ones(nu), np.ones(nu)).max() < U0_TOL
