@@ -90,6 +90,7 @@ struct mpcb_handle {
   PinBuf<double> stage_in, stage_out;
   PinBuf<int32_t> stage_int;
   int onchip_blocks_per_sm = 0;
+  size_t recover_smem_set = 0;
 };
 
 namespace {
@@ -236,14 +237,15 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     R.x0 = io.x0; R.xref = io.xref; R.uref = io.uref; R.xref_bc = io.xref_broadcast; R.uref_bc = io.uref_broadcast;
     R.v = h->v.p; R.u = io.u; R.e_u = io.e_u; R.x = io.x; R.e_x = io.e_x; R.u0 = io.u0; R.objective = io.objective;
     if (!mpcb::launch_recover_small(R, st)) {
-      const size_t smem = mpcb::recover_smem_bytes(D.nx, D.nu);
-      static thread_local size_t smem_set = 0;
-      if (smem > 48 * 1024 && smem > smem_set) {
+      const int rt = mpcb::recover_threads_for(D.nx, D.nu);
+      if (rt == 0) return fail(MPCB_ERR_INVALID, "result recovery: system too wide for the generic kernel (nx, nu)");
+      const size_t smem = mpcb::recover_smem_bytes(D.nx, D.nu, rt);
+      if (smem > 48 * 1024 && smem > h->recover_smem_set) {
         CUDA_TRY(cudaFuncSetAttribute(mpcb::recover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
+        h->recover_smem_set = smem;
       }
-      const unsigned grid = (unsigned)((Bn + mpcb::RECOVER_THREADS - 1) / mpcb::RECOVER_THREADS);
-      mpcb::recover_kernel<<<grid, mpcb::RECOVER_THREADS, smem, st>>>(R);
+      const unsigned grid = (unsigned)((Bn + rt - 1) / rt);
+      mpcb::recover_kernel<<<grid, rt, smem, st>>>(R);
     }
     CUDA_TRY(cudaGetLastError());
     launches += 1;

@@ -36,45 +36,52 @@ struct RecoverParams {
 
 constexpr int RECOVER_THREADS = 128;
 
-__host__ __device__ inline size_t recover_smem_bytes(int nx, int nu) {
-  return sizeof(double) * ((size_t)(2 * nx + 2 * nu) * RECOVER_THREADS + 3 * nx * nx + nx * nu + 2 * nu * nu);
+__host__ __device__ inline size_t recover_smem_bytes(int nx, int nu, int threads = RECOVER_THREADS) {
+  return sizeof(double) * ((size_t)(2 * nx + 2 * nu) * threads + 3 * nx * nx + nx * nu + 2 * nu * nu);
+}
+// CTA width of the generic kernel: the per-thread deviation columns live in shared memory, so wide systems run
+// narrower CTAs (nx = 64, nu = 16: 64 threads, 192 KB).  Returns 0 when even one warp does not fit.
+inline int recover_threads_for(int nx, int nu) {
+  for (int t = RECOVER_THREADS; t >= 32; t >>= 1)
+    if (recover_smem_bytes(nx, nu, t) <= 200 * 1024) return t;
+  return 0;
 }
 
 __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverParams P) {
   extern __shared__ __align__(16) double sm[];
-  const int nx = P.nx, nu = P.nu, H = P.H, tid = threadIdx.x;
+  const int nx = P.nx, nu = P.nu, H = P.H, tid = threadIdx.x, TT = blockDim.x;
   double* se = sm;                                   // [nx][T] current deviation
-  double* sn = se + nx * RECOVER_THREADS;            // [nx][T] next deviation
-  double* su = sn + nx * RECOVER_THREADS;            // [nu][T] current input deviation
-  double* sp = su + nu * RECOVER_THREADS;            // [nu][T] previous absolute input (S term)
-  double* sA = sp + nu * RECOVER_THREADS;
+  double* sn = se + nx * TT;            // [nx][T] next deviation
+  double* su = sn + nx * TT;            // [nu][T] current input deviation
+  double* sp = su + nu * TT;            // [nu][T] previous absolute input (S term)
+  double* sA = sp + nu * TT;
   double* sB = sA + nx * nx;
   double* sQ = sB + nx * nu;
   double* sPt = sQ + nx * nx;
   double* sR = sPt + nx * nx;
   double* sS = sR + nu * nu;
-  for (int i = tid; i < nx * nx; i += RECOVER_THREADS) { sA[i] = P.A[i]; sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
-  for (int i = tid; i < nx * nu; i += RECOVER_THREADS) sB[i] = P.B[i];
-  for (int i = tid; i < nu * nu; i += RECOVER_THREADS) { sR[i] = P.R[i]; sS[i] = P.S ? P.S[i] : 0.0; }
+  for (int i = tid; i < nx * nx; i += TT) { sA[i] = P.A[i]; sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
+  for (int i = tid; i < nx * nu; i += TT) sB[i] = P.B[i];
+  for (int i = tid; i < nu * nu; i += TT) { sR[i] = P.R[i]; sS[i] = P.S ? P.S[i] : 0.0; }
   __syncthreads();
-  const long long p = (long long)blockIdx.x * RECOVER_THREADS + tid;
+  const long long p = (long long)blockIdx.x * TT + tid;
   if (p >= P.batch) return;
   const double* x0 = P.x0 + p * nx;
   const double* xr = P.xref + (P.xref_bc ? 0 : p) * nx;
   const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
   const double* v = P.v + p * (long long)nu * H;
-  for (int i = 0; i < nx; i++) se[i * RECOVER_THREADS + tid] = x0[i] - xr[i];
+  for (int i = 0; i < nx; i++) se[i * TT + tid] = x0[i] - xr[i];
   double J = 0.0;
   for (int k = 0; k <= H; k++) {
     // write x_k, e_x_k and accumulate e' W e
     const double* W = (k == H) ? sPt : sQ;
     double quad = 0.0;
     for (int i = 0; i < nx; i++) {
-      const double ei = se[i * RECOVER_THREADS + tid];
+      const double ei = se[i * TT + tid];
       if (P.e_x) P.e_x[(p * (H + 1) + k) * nx + i] = ei;
       if (P.x) P.x[(p * (H + 1) + k) * nx + i] = ei + xr[i];
       double s = 0.0;
-      for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], se[j * RECOVER_THREADS + tid], s);
+      for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], se[j * TT + tid], s);
       quad = fma(ei, s, quad);
     }
     J += quad;
@@ -82,7 +89,7 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
     for (int i = 0; i < nu; i++) {
       const double ui = v[k * nu + i];
       const double eu = ui - ur[i];
-      su[i * RECOVER_THREADS + tid] = eu;
+      su[i * TT + tid] = eu;
       if (P.u) P.u[(p * H + k) * nu + i] = ui;
       if (P.e_u) P.e_u[(p * H + k) * nu + i] = eu;
       if (k == 0 && P.u0) P.u0[p * nu + i] = ui;
@@ -91,8 +98,8 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
       double quadr = 0.0;
       for (int i = 0; i < nu; i++) {
         double s = 0.0;
-        for (int j = 0; j < nu; j++) s = fma(sR[j * nu + i], su[j * RECOVER_THREADS + tid], s);
-        quadr = fma(su[i * RECOVER_THREADS + tid], s, quadr);
+        for (int j = 0; j < nu; j++) s = fma(sR[j * nu + i], su[j * TT + tid], s);
+        quadr = fma(su[i * TT + tid], s, quadr);
       }
       J += quadr;
       if (P.use_S) {
@@ -100,19 +107,19 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
           double quads = 0.0;
           for (int i = 0; i < nu; i++) {
             double s = 0.0;
-            for (int j = 0; j < nu; j++) s = fma(sS[j * nu + i], sp[j * RECOVER_THREADS + tid] - v[k * nu + j], s);
-            quads = fma(sp[i * RECOVER_THREADS + tid] - v[k * nu + i], s, quads);
+            for (int j = 0; j < nu; j++) s = fma(sS[j * nu + i], sp[j * TT + tid] - v[k * nu + j], s);
+            quads = fma(sp[i * TT + tid] - v[k * nu + i], s, quads);
           }
           J += quads;
         }
-        for (int i = 0; i < nu; i++) sp[i * RECOVER_THREADS + tid] = v[k * nu + i];
+        for (int i = 0; i < nu; i++) sp[i * TT + tid] = v[k * nu + i];
       }
     }
     for (int i = 0; i < nx; i++) {
       double s = 0.0;
-      for (int j = 0; j < nx; j++) s = fma(sA[j * nx + i], se[j * RECOVER_THREADS + tid], s);
-      for (int j = 0; j < nu; j++) s = fma(sB[j * nx + i], su[j * RECOVER_THREADS + tid], s);
-      sn[i * RECOVER_THREADS + tid] = s;
+      for (int j = 0; j < nx; j++) s = fma(sA[j * nx + i], se[j * TT + tid], s);
+      for (int j = 0; j < nu; j++) s = fma(sB[j * nx + i], su[j * TT + tid], s);
+      sn[i * TT + tid] = s;
     }
     double* tmp = se; se = sn; sn = tmp;
   }

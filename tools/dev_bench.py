@@ -37,6 +37,48 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0):
                       "mean_iters": round(float(it.mean()), 2), "solves_per_s": round(n / ms * 1e3), "tflops": round(fl / ms / 1e9, 2),
                       "frac": round(fl / ms / 1e9 / bench.FP64_PEAK_TFLOPS, 3), "solved": float((status.cpu().numpy() == 1).mean()), "rho": round(m.info.rho, 4)}), flush=True)
 
+def lti64(seed=1, nx=64, nu=16):
+    """random stable LTI."""
+    rng = np.random.default_rng(seed)
+    G = rng.standard_normal((nx, nx)); A = 0.95 * G / np.abs(np.linalg.eigvals(G)).max(); B = rng.standard_normal((nx, nu)) / 8
+    return A, B
+
+
+def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="equality", reps=2, rho=0.0, max_iter=4000):
+    import time
+    A, B = lti64()
+    nx, nu = B.shape
+    big = 1e3
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(-big * np.ones(nx), big * np.ones(nx)), mpc.Hyperrectangle(-np.ones(nu), np.ones(nu)))
+    t0 = time.perf_counter()
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 1, [0.0] * nx, [0.0] * nu, mpc_solver="b200", mpc_terminal_ingredient=terminal,
+                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho, mpc_b200_max_iter=max_iter)
+    t_design = time.perf_counter() - t0
+    m = C.tuning.modeler
+    rng = np.random.default_rng(3)
+    x0_h = scale * rng.standard_normal((n, nx)); xref_h = np.zeros(nx); uref_h = np.zeros(nu)
+    dev = torch.device("cuda", 0)
+    x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
+    u0 = torch.empty((n, nu), dtype=torch.float64, device=dev)
+    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 1; io.xref_broadcast = 1
+    io.status = status.data_ptr(); io.iters = iters.data_ptr(); io.u0 = u0.data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    m.solve_batch_device(io, st); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); m.solve_batch_device(io, st); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    it = iters.cpu().numpy(); stt = status.cpu().numpy()
+    i = m.info
+    fl = float((it.astype(float) * 2 * i.nt * i.nt).sum())
+    ms = min(ts)
+    print(json.dumps({"cfg": "lti", "nx": nx, "nu": nu, "H": H, "n": n, "eps": eps, "check": check, "scale": scale, "terminal": terminal, "nt": i.nt, "nt_pad": i.nt_pad,
+                      "kernel": i.kernel, "rho": round(i.rho, 4), "design_s": round(t_design, 2), "ms": round(ms, 2), "mean_iters": round(float(it.mean()), 1),
+                      "max_iters": int(it.max()), "solved": float((stt == 1).mean()), "infeasible": float((stt == -3).mean()), "maxiter": float((stt == -2).mean()),
+                      "solves_per_s": round(n / ms * 1e3), "tflops_active_rows": round(fl / ms / 1e9, 2), "launches": m.timing()["kernel_launches"]}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--set", default="qt")
     a = ap.parse_args()
@@ -49,3 +91,12 @@ if __name__ == "__main__":
         run(20, 65536, 1e-3, 5, 0.0)
     elif a.set == "one":
         run(20, 65536, 1e-7, 5, 0.0)
+    elif a.set == "onefull":
+        run(20, 65536, 1e-7, 5, 0.0, full=True, reps=2)
+    elif a.set == "hsweep":
+        for H in (10, 20, 30, 50, 75, 100, 150, 200):
+            run(H, 16384, 1e-7, 5, 0.0, reps=2)
+    elif a.set == "lti":
+        for scale in (0.1, 0.3, 1.0):
+            run_lti(scale=scale)
+        run_lti(scale=0.3, terminal="none")
