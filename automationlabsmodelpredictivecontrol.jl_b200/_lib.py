@@ -12,7 +12,9 @@ LIB_PATH = _PKG / "libmpcb200.so"
 MPCB_OK = 0
 KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED = 0, 1, 2
 TERMINAL_NONE, TERMINAL_EQUALITY = 0, 1
-STATUS_SOLVED, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE = 1, -2, -3
+STATUS_SOLVED, STATUS_SOLVED_INACCURATE, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE = 1, 2, -2, -3
+NN_FNN, NN_RESNET = 0, 1
+ACTIVATION_IDS = {"relu": 0, "tanh": 1, "sigmoid": 2, "swish": 3, "identity": 4}
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -41,7 +43,7 @@ class BatchIO(C.Structure):
                 ("xref_broadcast", C.c_int32), ("uref_broadcast", C.c_int32), ("warm_u", C.c_void_p), ("warm_y", C.c_void_p),
                 ("u", C.c_void_p), ("e_u", C.c_void_p), ("x", C.c_void_p), ("e_x", C.c_void_p), ("u0", C.c_void_p),
                 ("status", C.c_void_p), ("iters", C.c_void_p), ("prim_res", C.c_void_p), ("dual_res", C.c_void_p),
-                ("objective", C.c_void_p), ("y", C.c_void_p)]
+                ("objective", C.c_void_p), ("y", C.c_void_p), ("inner_iters", C.c_void_p)]
 
 
 class Timing(C.Structure):
@@ -49,11 +51,29 @@ class Timing(C.Structure):
                 ("total_ms", C.c_float), ("batch", C.c_int64), ("total_iterations", C.c_int64), ("kernel_launches", C.c_int32)]
 
 
+class NnDesc(C.Structure):
+    _fields_ = [("arch", C.c_int32), ("activation", C.c_int32), ("nx", C.c_int32), ("nu", C.c_int32), ("n_neurons", C.c_int32),
+                ("n_hidden", C.c_int32), ("W_in", _dp), ("W_hidden", _dp), ("b_hidden", _dp), ("W_out", _dp)]
+
+
+class NmpcDesc(C.Structure):
+    _fields_ = [("nn", C.POINTER(NnDesc)), ("horizon", C.c_int32), ("Q", _dp), ("R", _dp), ("S", _dp), ("P", _dp), ("umin", _dp),
+                ("umax", _dp), ("xref", _dp), ("uref", _dp), ("terminal_mode", C.c_int32)]
+
+
+class NmpcSettings(C.Structure):
+    _fields_ = [("qp", Settings), ("sqp_tol", C.c_double), ("ls_armijo", C.c_double), ("ls_noise", C.c_double), ("sqp_max_iter", C.c_int32),
+                ("ls_max_halvings", C.c_int32)]
+
+
 # every symbol include/mpcb200.h declares (tests assert the library exports all of them)
 EXPORTED_SYMBOLS = (
     "mpcb_version", "mpcb_device_count", "mpcb_last_error", "mpcb_default_settings", "mpcb_dare", "mpcb_create_linear",
     "mpcb_destroy", "mpcb_get_info", "mpcb_get_timing", "mpcb_get_design", "mpcb_solve_linear_batch",
     "mpcb_solve_linear_batch_device", "mpcb_alloc_pinned", "mpcb_free_pinned",
+    "mpcb_create_nn", "mpcb_destroy_nn", "mpcb_nn_rollout_batch", "mpcb_nn_rollout_batch_device", "mpcb_nn_jacobian_batch",
+    "mpcb_nn_jacobian_batch_device", "mpcb_default_nmpc_settings", "mpcb_create_nmpc", "mpcb_destroy_nmpc", "mpcb_nmpc_get_design",
+    "mpcb_nmpc_get_timing", "mpcb_solve_nmpc_batch", "mpcb_solve_nmpc_batch_device",
 )
 
 _lib = None
@@ -85,6 +105,22 @@ def lib():
         L.mpcb_alloc_pinned.restype = C.c_void_p
         L.mpcb_free_pinned.argtypes = [C.c_void_p]
         L.mpcb_free_pinned.restype = None
+        L.mpcb_create_nn.argtypes = [C.POINTER(NnDesc), C.c_int32, C.POINTER(C.c_void_p)]
+        L.mpcb_destroy_nn.argtypes = [C.c_void_p]
+        L.mpcb_destroy_nn.restype = None
+        L.mpcb_nn_rollout_batch.argtypes = [C.c_void_p, C.c_int64, C.c_int32, _dp, _dp, _dp]
+        L.mpcb_nn_rollout_batch_device.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mpcb_nn_jacobian_batch.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _dp, _dp]
+        L.mpcb_nn_jacobian_batch_device.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 6
+        L.mpcb_default_nmpc_settings.argtypes = [C.POINTER(NmpcSettings)]
+        L.mpcb_default_nmpc_settings.restype = None
+        L.mpcb_create_nmpc.argtypes = [C.POINTER(NmpcDesc), C.POINTER(NmpcSettings), C.POINTER(C.c_void_p)]
+        L.mpcb_destroy_nmpc.argtypes = [C.c_void_p]
+        L.mpcb_destroy_nmpc.restype = None
+        L.mpcb_nmpc_get_design.argtypes = [C.c_void_p, C.POINTER(C.c_double), _dp, _dp, _dp]
+        L.mpcb_nmpc_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+        L.mpcb_solve_nmpc_batch.argtypes = [C.c_void_p, C.POINTER(BatchIO)]
+        L.mpcb_solve_nmpc_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIO), C.c_void_p]
         _lib = L
     return _lib
 
@@ -93,6 +129,17 @@ def check(rc, what):
     if rc != MPCB_OK:
         msg = lib().mpcb_last_error()
         raise MpcbError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")
+
+
+def default_nmpc_settings(**kw) -> NmpcSettings:
+    """kw: sqp_tol, ls_armijo, ls_noise, sqp_max_iter, ls_max_halvings, or any inner-QP setting of `Settings`."""
+    s = NmpcSettings()
+    lib().mpcb_default_nmpc_settings(C.byref(s))
+    for k, v in kw.items():
+        if hasattr(s, k) and k != "qp": setattr(s, k, v)
+        elif hasattr(s.qp, k): setattr(s.qp, k, v)
+        else: raise TypeError(f"unknown NMPC setting {k!r}")
+    return s
 
 
 def default_settings(**kw) -> Settings:

@@ -11,63 +11,29 @@
 #include <vector>
 
 #include "../../include/mpcb200.h"
+#include "api_common.hpp"
 #include "admm_onchip.cuh"
 #include "admm_stream.cuh"
 #include "host_design.hpp"
 #include "recover.cuh"
 
 namespace {
-
 thread_local std::string g_err;
+}  // namespace
 
-int fail(int code, const std::string& msg) {
+namespace mpcb {
+int api_fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
 }
+}  // namespace mpcb
 
-#define CUDA_TRY(expr)                                                                                   \
-  do {                                                                                                   \
-    cudaError_t _e = (expr);                                                                             \
-    if (_e != cudaSuccess)                                                                               \
-      return fail(MPCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
-  } while (0)
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-template <typename T>
-struct PinBuf {
-  T* p = nullptr;
-  size_t cap = 0;
-  cudaError_t ensure(size_t n) {
-    if (n <= cap) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMallocHost(&p, std::max<size_t>(n, 1) * sizeof(T));
-    if (e == cudaSuccess) cap = n;
-    return e;
-  }
-  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
-};
-
-bool is_pinned_or_device(const void* p) {
-  cudaPointerAttributes a;
-  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
-
+namespace {
+using mpcb::DevBuf;
+using mpcb::PinBuf;
+using mpcb::is_pinned_or_device;
+using mpcb::upload;
+int fail(int code, const std::string& msg) { return mpcb::api_fail(code, msg); }
 }  // namespace
 
 struct mpcb_handle {
@@ -136,12 +102,6 @@ cudaError_t launch_onchip_gs(int NT, const OnchipParams& P, int sm_count, int* c
 cudaError_t launch_onchip(int NT, bool has_g, const OnchipParams& P, int sm_count, int* cache, cudaStream_t st) {
   if (has_g) return launch_onchip_gs<true, true>(NT, P, sm_count, cache, st);
   return P.sigma != 0.0 ? launch_onchip_gs<false, true>(NT, P, sm_count, cache, st) : launch_onchip_gs<false, false>(NT, P, sm_count, cache, st);
-}
-
-cudaError_t upload(DevBuf<double>& b, const double* src, size_t n) {
-  cudaError_t e = b.ensure(n);
-  if (e != cudaSuccess) return e;
-  return cudaMemcpy(b.p, src, n * sizeof(double), cudaMemcpyHostToDevice);
 }
 
 // fragment order of a symmetric NT x NT operator for the on-chip kernel (see admm_onchip.cuh)

@@ -1,0 +1,557 @@
+// Nonlinear path (sm_100a): batched rollout of the Flux-style neural dynamics, their forward-mode Jacobians, and a
+// Gauss-Newton SQP loop whose QP subproblem is solved by the same OSQP-style ADMM as the linear path.
+//
+// Replaces, for thousands of problems at once, what the reference does per problem with JuMP + Ipopt on the NL modelers
+//   /root/reference/src/sub/model_modeler_implementation/fnn/mpc_modeler_implementation_fnn.jl:63-189
+//   /root/reference/src/sub/model_modeler_implementation/resnet/mpc_modeler_implementation_resnet.jl:62-188
+// (network layout: W_in without bias, n_hidden x [W_j, b_j] with activation -- resnet adds the skip --, W_out without
+// bias; dynamics in absolute coordinates x_{k+1} = f(x_k, u_k); input box; cost of src/sub/design_mpc.jl:405-465) and the
+// linearisation `proceed_system_linearization` used by the linear method on black-box models (fnn.jl:37-46).
+//
+// One WARP owns one problem.  All per-problem data (trajectory, sensitivities Gamma, the Gauss-Newton Hessian, its
+// inverse, ADMM vectors) lives in that warp's slice of shared memory; the network weights and cost matrices are staged
+// once per CTA.  Every matrix is stored so that the 32 lanes of a product read consecutive addresses (Julia's
+// column-major weights are used as they come).  Per SQP iteration:
+//   1. rollout + forward-mode Jacobians A_k, B_k;  Gamma_{k+1} = A_k Gamma_k (+ B_k in block k);
+//      K += 2 Gamma' W Gamma,  g += 2 Gamma' W e  (W = Q, last stage P)              [Gauss-Newton condensed QP]
+//   2. q = g - K u;  K += (sigma + rho) I;  K <- K^-1 in place (Gauss-Jordan, SPD, no pivoting)
+//   3. ADMM in absolute inputs v (box umin <= v <= umax), warm-started at (u, y): per iteration one K^-1 mat-vec from
+//      shared memory + the fused projection / dual update / residual reductions of admm_onchip.cuh (box-only form)
+//   4. step d = v - u; accept if ||d||_inf <= tol, else Armijo backtracking on the TRUE cost (forward rollouts only)
+// Problems are handed out through a global atomic counter (SQP iteration counts vary from 2 to the cap).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpcb {
+
+enum : int { NN_FNN = 0, NN_RESNET = 1 };
+enum : int { ACT_RELU = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_SWISH = 3, ACT_IDENTITY = 4 };
+
+struct NetDev {            // device pointers, Julia column-major
+  const double* W_in;      // nn x nin
+  const double* W_h;       // nh x (nn x nn)
+  const double* b_h;       // nh x nn
+  const double* W_out;     // nx x nn
+  int arch, act, nx, nu, nn, nh, nin;
+  __host__ __device__ size_t weight_count() const { return (size_t)nn * nin + (size_t)nh * nn * nn + (size_t)nh * nn + (size_t)nx * nn; }
+};
+
+// The weights of one network staged in shared memory.
+struct NetSm {
+  const double *W_in, *W_h, *b_h, *W_out;
+  int arch, act, nx, nu, nn, nh, nin;
+};
+
+__device__ __forceinline__ NetSm stage_network(const NetDev& N, double* dst, int tid, int nthreads) {
+  NetSm S;
+  S.arch = N.arch; S.act = N.act; S.nx = N.nx; S.nu = N.nu; S.nn = N.nn; S.nh = N.nh; S.nin = N.nin;
+  const int n1 = N.nn * N.nin, n2 = N.nh * N.nn * N.nn, n3 = N.nh * N.nn, n4 = N.nx * N.nn;
+  for (int i = tid; i < n1; i += nthreads) dst[i] = N.W_in[i];
+  for (int i = tid; i < n2; i += nthreads) dst[n1 + i] = N.W_h[i];
+  for (int i = tid; i < n3; i += nthreads) dst[n1 + n2 + i] = N.b_h[i];
+  for (int i = tid; i < n4; i += nthreads) dst[n1 + n2 + n3 + i] = N.W_out[i];
+  S.W_in = dst; S.W_h = dst + n1; S.b_h = dst + n1 + n2; S.W_out = dst + n1 + n2 + n3;
+  return S;
+}
+
+__device__ __forceinline__ void act_eval(int id, double h, double& a, double& da) {
+  switch (id) {
+    case ACT_RELU: a = h > 0.0 ? h : 0.0; da = h > 0.0 ? 1.0 : 0.0; break;     // NNlib.relu, derivative 0 at 0
+    case ACT_TANH: { const double t = tanh(h); a = t; da = 1.0 - t * t; break; }
+    case ACT_SIGMOID: { const double s = 1.0 / (1.0 + exp(-h)); a = s; da = s * (1.0 - s); break; }
+    case ACT_SWISH: { const double s = 1.0 / (1.0 + exp(-h)); a = h * s; da = s + h * s * (1.0 - s); break; }
+    default: a = h; da = 1.0; break;
+  }
+}
+
+// Warp-cooperative network evaluation.  xu[nin] (shared) -> f[nx] (shared).  Scratch: ya, yb [nn].  With JAC also
+// AB[nin][nx] (column-major nx x nin: d f / d [x;u]) using Ja, Jb [nin][nn].  Ends with a __syncwarp().
+template <bool JAC>
+__device__ __forceinline__ void nn_eval_warp(const NetSm& N, const double* xu, double* f, double* ya, double* yb, double* Ja, double* Jb,
+                                             double* AB, int lane) {
+  const int nn = N.nn, nin = N.nin, nx = N.nx;
+  for (int i = lane; i < nn; i += 32) {
+    double s = 0.0;
+    for (int j = 0; j < nin; j++) s = fma(N.W_in[j * nn + i], xu[j], s);
+    ya[i] = s;
+  }
+  if (JAC)
+    for (int i = lane; i < nn * nin; i += 32) Ja[i] = N.W_in[i];
+  __syncwarp();
+  double *yc = ya, *yn = yb, *Jc = Ja, *Jn = Jb;
+  for (int l = 0; l < N.nh; l++) {
+    const double* W = N.W_h + (size_t)l * nn * nn;
+    const double* b = N.b_h + l * nn;
+    for (int i = lane; i < nn; i += 32) {
+      double s = b[i];
+      for (int j = 0; j < nn; j++) s = fma(W[j * nn + i], yc[j], s);
+      double a, da;
+      act_eval(N.act, s, a, da);
+      yn[i] = N.arch == NN_RESNET ? a + yc[i] : a;
+      if (JAC) {                                    // d y_new[i] / d in[c] = da * (W Jc)[i][c] (+ Jc[i][c])
+        for (int c = 0; c < nin; c++) {
+          double t = 0.0;
+          for (int j = 0; j < nn; j++) t = fma(W[j * nn + i], Jc[c * nn + j], t);
+          t *= da;
+          Jn[c * nn + i] = N.arch == NN_RESNET ? t + Jc[c * nn + i] : t;
+        }
+      }
+    }
+    __syncwarp();
+    double* tp = yc; yc = yn; yn = tp;
+    if (JAC) { tp = Jc; Jc = Jn; Jn = tp; }
+  }
+  for (int i = lane; i < nx; i += 32) {
+    double s = 0.0;
+    for (int j = 0; j < nn; j++) s = fma(N.W_out[j * nx + i], yc[j], s);
+    f[i] = s;
+  }
+  if (JAC)
+    for (int o = lane; o < nx * nin; o += 32) {
+      const int i = o % nx, c = o / nx;
+      double s = 0.0;
+      for (int j = 0; j < nn; j++) s = fma(N.W_out[j * nx + i], Jc[c * nn + j], s);
+      AB[o] = s;
+    }
+  __syncwarp();
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { const double w = __shfl_xor_sync(0xffffffffu, v, o); v = v > w ? v : w; }
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int NN_WARPS = 4;
+constexpr int NN_THREADS = NN_WARPS * 32;
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mpcb_nn_rollout_batch / mpcb_nn_jacobian_batch
+// ---------------------------------------------------------------------------------------------------------------------
+struct NnBatchParams {
+  NetDev net;
+  long long batch;
+  int H;
+  const double* x0;   // [batch][nx]       (jacobian: the evaluation points x)
+  const double* u;    // [batch][H][nu]    (jacobian: [batch][nu])
+  double* x;          // [batch][H+1][nx]  (jacobian: f [batch][nx], may be null)
+  double* A;          // [batch][nx x nx column-major]
+  double* B;          // [batch][nx x nu column-major]
+};
+
+__host__ __device__ inline size_t nn_eval_scratch_doubles(const NetDev& N, bool jac) {
+  return (size_t)N.nin + N.nx + 2 * N.nn + (jac ? (size_t)2 * N.nn * N.nin + (size_t)N.nx * N.nin : 0);
+}
+__host__ __device__ inline size_t nn_batch_smem_bytes(const NetDev& N, bool jac) {
+  return sizeof(double) * (N.weight_count() + NN_WARPS * nn_eval_scratch_doubles(N, jac));
+}
+
+template <bool JAC>
+__global__ void __launch_bounds__(NN_THREADS) nn_batch_kernel(const NnBatchParams P) {
+  extern __shared__ __align__(16) double sm[];
+  const NetSm N = stage_network(P.net, sm, threadIdx.x, NN_THREADS);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nx = N.nx, nu = N.nu, nin = N.nin, nn = N.nn;
+  double* w = sm + P.net.weight_count() + warp * nn_eval_scratch_doubles(P.net, JAC);
+  double* xu = w; double* f = xu + nin; double* ya = f + nx; double* yb = ya + nn;
+  double* Ja = yb + nn; double* Jb = Ja + (JAC ? nn * nin : 0); double* AB = Jb + (JAC ? nn * nin : 0);
+  for (long long p = (long long)blockIdx.x * NN_WARPS + warp; p < P.batch; p += (long long)gridDim.x * NN_WARPS) {
+    if (JAC) {
+      for (int i = lane; i < nx; i += 32) xu[i] = P.x0[p * nx + i];
+      for (int i = lane; i < nu; i += 32) xu[nx + i] = P.u[p * nu + i];
+      __syncwarp();
+      nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, lane);
+      if (P.x) for (int i = lane; i < nx; i += 32) P.x[p * nx + i] = f[i];
+      for (int o = lane; o < nx * nx; o += 32) P.A[p * nx * nx + o] = AB[o];
+      for (int o = lane; o < nx * nu; o += 32) P.B[p * nx * nu + o] = AB[nx * nx + o];
+      __syncwarp();
+    } else {
+      for (int i = lane; i < nx; i += 32) { const double v = P.x0[p * nx + i]; xu[i] = v; P.x[p * (P.H + 1) * nx + i] = v; }
+      for (int k = 0; k < P.H; k++) {
+        for (int i = lane; i < nu; i += 32) xu[nx + i] = P.u[(p * P.H + k) * nu + i];
+        __syncwarp();
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, lane);
+        for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; P.x[(p * (P.H + 1) + k + 1) * nx + i] = v; }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mpcb_solve_nmpc_batch: the SQP kernel
+// ---------------------------------------------------------------------------------------------------------------------
+struct NmpcParams {
+  NetDev net;
+  const double* Q;    // nx x nx
+  const double* Pt;   // nx x nx terminal weight
+  const double* Hc;   // nz x nz constant Hessian part 2(I (x) R) + 2 D'(I (x) S) D   (design_mpc.jl:436-447)
+  const double* lb;   // nz
+  const double* ub;   // nz
+  int H, nz;
+  double rho, sigma, alpha, eps_abs, eps_rel;
+  int max_iter, check_every;
+  double sqp_tol, ls_c1, ls_noise;
+  int sqp_max_iter, ls_max;
+  long long batch;
+  const double* x0; const double* xref; const double* uref;
+  int xref_bc, uref_bc;
+  const double* warm_u;   // [batch][nz] initial guess (null: the reference input clipped to the box)
+  const double* warm_y;   // [batch][nz] duals of the box rows (null: 0)
+  double *u, *e_u, *x, *e_x, *u0, *objective, *y;   // outputs, any may be null
+  int32_t *status, *iters, *inner_iters;
+  double *step, *qp_dres;
+  unsigned long long* counter;
+};
+
+__host__ __device__ inline int nmpc_ldk(int nz) { return nz | 1; }
+// per-warp shared memory (doubles)
+__host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int nz) {
+  return (size_t)nz * nmpc_ldk(nz)            // K
+         + 2 * (size_t)N.nx * nz              // Gamma double buffer (the idle one holds W Gamma)
+         + 6 * (size_t)nz                     // u, v, r, g, q, col
+         + (size_t)(H + 1) * N.nx             // trajectory
+         + 2 * (size_t)N.nx                   // e, We
+         + nn_eval_scratch_doubles(N, true);
+}
+__host__ __device__ inline size_t nmpc_const_doubles(const NetDev& N, int nz) {
+  return N.weight_count() + 2 * (size_t)N.nx * N.nx + (size_t)nz * nz + 2 * (size_t)nz;
+}
+__host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz, int warps) {
+  return sizeof(double) * (nmpc_const_doubles(N, nz) + (size_t)warps * nmpc_warp_doubles(N, H, nz));
+}
+
+// ROWS = ceil(nz / 32): decision-variable rows owned by each lane (row e = lane + 32 * i)
+template <int ROWS>
+__global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P) {
+  extern __shared__ __align__(16) double sm[];
+  const int nwarps = blockDim.x >> 5;
+  const NetSm N = stage_network(P.net, sm, threadIdx.x, blockDim.x);
+  const int nx = N.nx, nu = N.nu, nin = N.nin, nn = N.nn, H = P.H, nz = P.nz, ldk = nmpc_ldk(nz);
+  double* sQ = sm + P.net.weight_count();
+  double* sPt = sQ + nx * nx;
+  double* sHc = sPt + nx * nx;
+  double* sLb = sHc + (size_t)nz * nz;
+  double* sUb = sLb + nz;
+  for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) { sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
+  for (int i = threadIdx.x; i < nz * nz; i += blockDim.x) sHc[i] = P.Hc[i];
+  for (int i = threadIdx.x; i < nz; i += blockDim.x) { sLb[i] = P.lb[i]; sUb[i] = P.ub[i]; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  (void)nwarps;
+  double* w = sUb + nz + (size_t)warp * nmpc_warp_doubles(P.net, H, nz);
+  double* K = w;                         w += (size_t)nz * ldk;
+  double* G0 = w;                        w += (size_t)nx * nz;
+  double* G1 = w;                        w += (size_t)nx * nz;
+  double* su = w;                        w += nz;     // current iterate u
+  double* sv = w;                        w += nz;     // QP solution / line-search candidate
+  double* sr = w;                        w += nz;     // ADMM right-hand side
+  double* sg = w;                        w += nz;     // gradient
+  double* sq = w;                        w += nz;     // q = g - K u
+  double* scol = w;                      w += nz;     // Gauss-Jordan pivot column
+  double* traj = w;                      w += (size_t)(H + 1) * nx;
+  double* se = w;                        w += nx;
+  double* sWe = w;                       w += nx;
+  double* xu = w; double* f = xu + nin; double* ya = f + nx; double* yb = ya + nn;
+  double* Ja = yb + nn; double* Jb = Ja + nn * nin; double* AB = Jb + nn * nin;
+
+  const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha, sig_rho = P.sigma + P.rho;
+  const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
+
+  while (true) {
+    long long p = 0;
+    if (lane == 0) p = (long long)atomicAdd(P.counter, 1ULL);
+    p = __shfl_sync(0xffffffffu, p, 0);
+    if (p >= P.batch) break;
+    const double* x0 = P.x0 + p * nx;
+    const double* xr = P.xref + (P.xref_bc ? 0 : p) * nx;
+    const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
+    double yd[ROWS];          // duals of the box rows (carried across SQP iterations)
+#pragma unroll
+    for (int i = 0; i < ROWS; i++) {
+      const int e = lane + 32 * i;
+      yd[i] = 0.0;
+      if (e < nz) {
+        double u0v;
+        if (P.warm_u) u0v = P.warm_u[p * nz + e];
+        else { const double r0 = ur[e % nu]; u0v = r0 < sLb[e] ? sLb[e] : (r0 > sUb[e] ? sUb[e] : r0); }
+        su[e] = u0v;
+        if (P.warm_y) yd[i] = P.warm_y[p * nz + e];
+      }
+    }
+    __syncwarp();
+
+    // forward rollout of the inputs in `uu` -> traj, returns the true cost J (all lanes)
+    auto rollout_cost = [&](const double* uu) -> double {
+      double J = 0.0;
+      for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
+      __syncwarp();
+      for (int k = 0; k <= H; k++) {
+        const double* W = (k == H) ? sPt : sQ;
+        double part = 0.0;
+        for (int i = lane; i < nx; i += 32) {
+          double s = 0.0;
+          for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], xu[j] - xr[j], s);
+          part = fma(xu[i] - xr[i], s, part);
+        }
+        J += part;
+        if (k == H) break;
+        for (int i = lane; i < nu; i += 32) xu[nx + i] = uu[k * nu + i];
+        __syncwarp();
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, lane);
+        for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; }
+        __syncwarp();
+      }
+      double part = 0.0;                 // 1/2 du' Hc du
+      for (int e = lane; e < nz; e += 32) {
+        double s = 0.0;
+        for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], uu[j] - ur[j % nu], s);
+        part = fma(0.5 * (uu[e] - ur[e % nu]), s, part);
+      }
+      return warp_sum(J + part);
+    };
+
+    int status = -2, sqp_it = 0, inner_total = 0;
+    double step = 0.0, qp_rd = 0.0, Jcur = 0.0;
+    bool have_traj = false;
+    for (sqp_it = 1; sqp_it <= P.sqp_max_iter; sqp_it++) {
+      // ---------------------------------------------------------------- 1. linearise along the trajectory of u
+      for (int o = lane; o < nz * ldk; o += 32) { const int a = o / ldk, c = o - a * ldk; K[o] = c < nz ? sHc[a * nz + c] : 0.0; }   // Hc symmetric
+      for (int o = lane; o < nx * nz; o += 32) { G0[o] = 0.0; G1[o] = 0.0; }
+      for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
+      __syncwarp();
+      double J0 = 0.0;
+      {
+        double part = 0.0;
+        for (int e = lane; e < nz; e += 32) {
+          double s = 0.0;
+          for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], su[j] - ur[j % nu], s);
+          sg[e] = s;
+          part = fma(0.5 * (su[e] - ur[e % nu]), s, part);
+        }
+        for (int i = lane; i < nx; i += 32) {
+          double s = 0.0;
+          for (int j = 0; j < nx; j++) s = fma(sQ[j * nx + i], x0[j] - xr[j], s);
+          part = fma(x0[i] - xr[i], s, part);
+        }
+        J0 = part;
+      }
+      double* Gc = G0; double* Gn = G1;
+      for (int k = 0; k < H; k++) {
+        for (int i = lane; i < nu; i += 32) xu[nx + i] = su[k * nu + i];
+        __syncwarp();
+        nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, lane);
+        const int ncol = (k + 1) * nu;                 // non-zero columns of Gamma_{k+1}
+        // Gamma_{k+1} = A_k Gamma_k, block k = B_k            (stored [i][c], c fastest)
+        for (int o = lane; o < nx * ncol; o += 32) {
+          const int i = o / ncol, c = o - i * ncol;
+          double s;
+          if (c >= k * nu) s = AB[(nx + c - k * nu) * nx + i];
+          else { s = 0.0; for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * nz + c], s); }
+          Gn[i * nz + c] = s;
+        }
+        const double* W = (k + 1 == H) ? sPt : sQ;
+        for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; se[i] = v - xr[i]; }
+        __syncwarp();
+        for (int i = lane; i < nx; i += 32) {
+          double s = 0.0;
+          for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], se[j], s);
+          sWe[i] = s;
+          J0 = fma(se[i], s, J0);
+        }
+        // W Gamma into the idle buffer
+        for (int o = lane; o < nx * ncol; o += 32) {
+          const int i = o / ncol, c = o - i * ncol;
+          double s = 0.0;
+          for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], Gn[j * nz + c], s);
+          Gc[i * nz + c] = s;
+        }
+        __syncwarp();
+        // K += 2 Gamma' (W Gamma),  g += 2 Gamma' (W e)
+        for (int o = lane; o < ncol * ncol; o += 32) {
+          const int a = o / ncol, c = o - a * ncol;
+          double s = 0.0;
+          for (int i = 0; i < nx; i++) s = fma(Gn[i * nz + a], Gc[i * nz + c], s);
+          K[a * ldk + c] = fma(2.0, s, K[a * ldk + c]);
+        }
+        for (int a = lane; a < ncol; a += 32) {
+          double s = 0.0;
+          for (int i = 0; i < nx; i++) s = fma(Gn[i * nz + a], sWe[i], s);
+          sg[a] = fma(2.0, s, sg[a]);
+        }
+        __syncwarp();
+        // the buffer that held W Gamma must again read as Gamma_k = 0 beyond its columns for the next step: it is fully
+        // rewritten for c < ncol + nu next time and never read beyond, so no clearing is needed
+        double* tp = Gc; Gc = Gn; Gn = tp;
+      }
+      J0 = warp_sum(J0);
+      // ---------------------------------------------------------------- 2. q = g - K u ; K <- (K + (sigma + rho) I)^-1
+      for (int e = lane; e < nz; e += 32) {
+        double s = 0.0;
+        for (int j = 0; j < nz; j++) s = fma(K[j * ldk + e], su[j], s);
+        sq[e] = sg[e] - s;
+      }
+      __syncwarp();
+      for (int e = lane; e < nz; e += 32) K[e * ldk + e] += sig_rho;
+      __syncwarp();
+      for (int pv = 0; pv < nz; pv++) {
+        const double dinv = 1.0 / K[pv * ldk + pv];
+        for (int i = lane; i < nz; i += 32) scol[i] = K[i * ldk + pv];
+        __syncwarp();
+        for (int j = lane; j < nz; j += 32) K[pv * ldk + j] = (j == pv) ? dinv : K[pv * ldk + j] * dinv;
+        __syncwarp();
+        for (int o = lane; o < nz * nz; o += 32) {
+          const int i = o / nz, j = o - i * nz;
+          if (i == pv) continue;
+          const double fct = scol[i];
+          K[i * ldk + j] = (j == pv) ? -fct * dinv : fma(-fct, K[pv * ldk + j], K[i * ldk + j]);
+        }
+        __syncwarp();
+      }
+      // ---------------------------------------------------------------- 3. ADMM (box-only form of admm_onchip.cuh)
+      double c[ROWS], qv[ROWS], xs[ROWS], tlast[ROWS], ylast[ROWS];
+      double qn = 0.0;
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) {
+        const int e = lane + 32 * i;
+        c[i] = qv[i] = xs[i] = tlast[i] = ylast[i] = 0.0;
+        if (e < nz) {
+          const double u0v = su[e], ys0 = yd[i] / rho;
+          qv[i] = sq[e];
+          xs[i] = u0v;
+          c[i] = fma(oma, u0v, ys0);
+          sr[e] = fma(rho, u0v - ys0, fma(sigma, u0v, -qv[i]));
+          qn = fmax(qn, fabs(qv[i]));
+        }
+      }
+      qn = warp_max(qn);
+      __syncwarp();
+      int it = 0;
+      double rp = 0.0, rd = 0.0;
+      while (true) {
+        bool conv = false;
+        for (int ii = 0; ii < P.check_every; ii++) {
+          const bool chk = (ii == P.check_every - 1);
+          double t[ROWS];
+#pragma unroll
+          for (int i = 0; i < ROWS; i++) t[i] = 0.0;
+          for (int j = 0; j < nz; j++) {
+            const double rj = sr[j];
+#pragma unroll
+            for (int i = 0; i < ROWS; i++) {
+              const int e = lane + 32 * i;
+              if (e < nz) t[i] = fma(K[j * ldk + e], rj, t[i]);
+            }
+          }
+          __syncwarp();       // every lane has consumed sr
+          double nA = 0.0, nD = 0.0;
+          if (chk) { rp = 0.0; rd = 0.0; }
+#pragma unroll
+          for (int i = 0; i < ROWS; i++) {
+            const int e = lane + 32 * i;
+            if (e < nz) {
+              const double wv = fma(alpha, t[i], c[i]);
+              const double lo = sLb[e], hi = sUb[e];
+              const double zn = wv < lo ? lo : (wv > hi ? hi : wv);
+              if (chk) {
+                const double pc = fma(-sig_rho, t[i], sr[e]);
+                const double ybv = rho * (wv - zn);
+                rp = fmax(rp, fabs(t[i] - zn));
+                rd = fmax(rd, fabs(pc + qv[i] + ybv));
+                nA = fmax(nA, fmax(fabs(t[i]), fabs(zn)));
+                nD = fmax(nD, fmax(fabs(pc), fabs(ybv)));
+                tlast[i] = t[i]; ylast[i] = ybv;
+              }
+              c[i] = fma(-alpha, zn, wv);
+              xs[i] = fma(alpha, t[i], oma * xs[i]);
+              sr[e] = fma(rho, fma(2.0, zn, -wv), fma(sigma, xs[i], -qv[i]));
+            }
+          }
+          __syncwarp();
+          if (chk) {
+            rp = warp_max(rp); rd = warp_max(rd); nA = warp_max(nA); nD = warp_max(nD);
+            conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * fmax(nD, qn));
+          }
+        }
+        it += P.check_every;
+        if (conv || it >= max_iter) break;
+      }
+      inner_total += it;
+      qp_rd = rd;
+      // ---------------------------------------------------------------- 4. step, acceptance, line search
+      double dmax = 0.0, gd = 0.0;
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) {
+        const int e = lane + 32 * i;
+        if (e < nz) {
+          const double d = tlast[i] - su[e];
+          dmax = fmax(dmax, fabs(d));
+          gd = fma(sg[e], d, gd);
+          sv[e] = tlast[i];
+          yd[i] = ylast[i];
+        }
+      }
+      dmax = warp_max(dmax); gd = warp_sum(gd);
+      step = dmax;
+      __syncwarp();
+      if (dmax <= P.sqp_tol) {           // converged: take the full step
+        for (int e = lane; e < nz; e += 32) su[e] = sv[e];
+        __syncwarp();
+        status = 1; have_traj = false;
+        break;
+      }
+      bool ok = false;
+      double tls = 1.0;
+      for (int ls = 0; ls <= P.ls_max; ls++) {
+#pragma unroll
+        for (int i = 0; i < ROWS; i++) {
+          const int e = lane + 32 * i;
+          if (e < nz) sv[e] = fma(tls, tlast[i] - su[e], su[e]);
+        }
+        __syncwarp();
+        const double Jc = rollout_cost(sv);
+        if (Jc <= J0 + P.ls_c1 * tls * gd + P.ls_noise * fmax(1.0, fabs(J0))) { ok = true; Jcur = Jc; break; }
+        tls *= 0.5;
+      }
+      if (!ok) { status = 2; have_traj = false; break; }       // stalled at a kink: keep u
+      for (int e = lane; e < nz; e += 32) su[e] = sv[e];
+      __syncwarp();
+      have_traj = true;
+    }
+    if (sqp_it > P.sqp_max_iter) sqp_it = P.sqp_max_iter;
+    if (!have_traj) Jcur = rollout_cost(su);
+    // ------------------------------------------------------------------ outputs
+    for (int e = lane; e < nz; e += 32) {
+      const double uv = su[e], ev = uv - ur[e % nu];
+      if (P.u) P.u[p * nz + e] = uv;
+      if (P.e_u) P.e_u[p * nz + e] = ev;
+      if (P.u0 && e < nu) P.u0[p * nu + e] = uv;
+    }
+    if (P.y) {
+#pragma unroll
+      for (int i = 0; i < ROWS; i++) { const int e = lane + 32 * i; if (e < nz) P.y[p * nz + e] = yd[i]; }
+    }
+    for (int o = lane; o < (H + 1) * nx; o += 32) {
+      const double xv = traj[o];
+      if (P.x) P.x[p * (H + 1) * nx + o] = xv;
+      if (P.e_x) P.e_x[p * (H + 1) * nx + o] = xv - xr[o % nx];
+    }
+    if (lane == 0) {
+      if (P.objective) P.objective[p] = Jcur;
+      P.status[p] = status; P.iters[p] = sqp_it;
+      if (P.inner_iters) P.inner_iters[p] = inner_total;
+      if (P.step) P.step[p] = step;
+      if (P.qp_dres) P.qp_dres[p] = qp_rd;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace mpcb

@@ -1,0 +1,406 @@
+// C ABI of the nonlinear path (include/mpcb200.h, section "Nonlinear path"): network upload, batched rollout /
+// Jacobian entry points, NMPC controller design (linearisation at the design reference on the GPU, DARE + rho on the
+// host) and the batched SQP solve.  No CPU fallback: every compute entry needs an sm_100 device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpcb200.h"
+#include "api_common.hpp"
+#include "host_design.hpp"
+#include "nmpc.cuh"
+
+using mpcb::api_fail;
+using mpcb::DevBuf;
+using mpcb::PinBuf;
+
+struct mpcb_nn {
+  int device = 0;
+  int sm_count = 0;
+  mpcb::NetDev net{};
+  DevBuf<double> weights;
+  cudaStream_t stream = nullptr;
+  DevBuf<double> in0, in1, out0, out1, out2;   // staging for the host-pointer entry points
+  size_t smem_set[2] = {0, 0};
+};
+
+struct mpcb_nmpc {
+  mpcb_nn* nn = nullptr;
+  mpcb_nmpc_settings st{};
+  int H = 0, nz = 0, rows = 0, warps = 0;
+  double rho = 0.0;
+  mpcb::Mat A, B, P;
+  DevBuf<double> Q, Pt, Hc, lb, ub;
+  DevBuf<unsigned long long> counter;
+  // host-entry workspaces
+  DevBuf<double> x0, xref, uref, warm_u, warm_y, u, e_u, x, e_x, u0, obj, y, step, dres;
+  DevBuf<int32_t> status, iters, inner;
+  PinBuf<int32_t> stage_int;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  mpcb_timing timing{};
+  size_t smem_set = 0;
+};
+
+namespace {
+
+int check_device(int device, int* sm_count) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return api_fail(MPCB_ERR_NO_DEVICE, "no CUDA device visible: libmpcb200 has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return api_fail(MPCB_ERR_INVALID, "device out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return api_fail(MPCB_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: this library is built for B200 only");
+  *sm_count = prop.multiProcessorCount;
+  return MPCB_OK;
+}
+
+int validate_nn(const mpcb_nn_desc* d) {
+  if (!d) return api_fail(MPCB_ERR_INVALID, "null network description");
+  if (d->arch != MPCB_NN_FNN && d->arch != MPCB_NN_RESNET) return api_fail(MPCB_ERR_INVALID, "unknown network architecture (fnn and resnet are supported)");
+  if (d->activation < MPCB_ACT_RELU || d->activation > MPCB_ACT_IDENTITY) return api_fail(MPCB_ERR_INVALID, "unknown activation id");
+  if (d->nx <= 0 || d->nu <= 0 || d->n_neurons <= 0 || d->n_hidden < 0) return api_fail(MPCB_ERR_INVALID, "bad network sizes");
+  if (!d->W_in || !d->W_out || (d->n_hidden > 0 && (!d->W_hidden || !d->b_hidden))) return api_fail(MPCB_ERR_INVALID, "null weight pointer");
+  return MPCB_OK;
+}
+
+template <bool JAC>
+int launch_nn_batch(mpcb_nn* n, const mpcb::NnBatchParams& P, cudaStream_t st) {
+  const size_t smem = mpcb::nn_batch_smem_bytes(n->net, JAC);
+  if (smem > 200 * 1024) return api_fail(MPCB_ERR_INVALID, "network too large for the shared-memory resident kernels");
+  auto kern = mpcb::nn_batch_kernel<JAC>;
+  if (smem > 48 * 1024 && smem > n->smem_set[JAC ? 1 : 0]) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    n->smem_set[JAC ? 1 : 0] = smem;
+  }
+  const long long blocks = (P.batch + mpcb::NN_WARPS - 1) / mpcb::NN_WARPS;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * 8));
+  kern<<<grid, mpcb::NN_THREADS, smem, st>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  return MPCB_OK;
+}
+
+int jacobian_device(mpcb_nn* n, int64_t batch, const double* x, const double* u, double* f, double* A, double* B, cudaStream_t st) {
+  mpcb::NnBatchParams P{};
+  P.net = n->net; P.batch = batch; P.H = 1; P.x0 = x; P.u = u; P.x = f; P.A = A; P.B = B;
+  return launch_nn_batch<true>(n, P, st);
+}
+
+template <int ROWS>
+cudaError_t launch_sqp_rows(const mpcb::NmpcParams& P, unsigned grid, int threads, size_t smem, size_t* smem_set, cudaStream_t st) {
+  auto kern = mpcb::nmpc_sqp_kernel<ROWS>;
+  if (smem > 48 * 1024 && smem > *smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    *smem_set = smem;
+  }
+  kern<<<grid, threads, smem, st>>>(P);
+  return cudaGetLastError();
+}
+
+int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
+  mpcb_nn* n = h->nn;
+  const long long Bn = io.batch;
+  if (Bn <= 0) return api_fail(MPCB_ERR_INVALID, "batch must be positive");
+  if (!io.x0 || !io.xref || !io.uref) return api_fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  int32_t* d_status = io.status; int32_t* d_iters = io.iters;
+  if (!d_status) { CUDA_TRY(h->status.ensure(Bn)); d_status = h->status.p; }
+  if (!d_iters) { CUDA_TRY(h->iters.ensure(Bn)); d_iters = h->iters.p; }
+  CUDA_TRY(h->counter.ensure(1));
+  CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), st));
+  mpcb::NmpcParams P{};
+  P.net = n->net; P.Q = h->Q.p; P.Pt = h->Pt.p; P.Hc = h->Hc.p; P.lb = h->lb.p; P.ub = h->ub.p; P.H = h->H; P.nz = h->nz;
+  const mpcb_settings& q = h->st.qp;
+  P.rho = h->rho; P.sigma = q.sigma; P.alpha = q.alpha; P.eps_abs = q.eps_abs; P.eps_rel = q.eps_rel; P.max_iter = q.max_iter; P.check_every = q.check_every;
+  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
+  P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
+  P.warm_u = io.warm_u; P.warm_y = io.warm_y;
+  P.u = io.u; P.e_u = io.e_u; P.x = io.x; P.e_x = io.e_x; P.u0 = io.u0; P.objective = io.objective; P.y = io.y;
+  P.status = d_status; P.iters = d_iters; P.inner_iters = io.inner_iters; P.step = io.prim_res; P.qp_dres = io.dual_res;
+  P.counter = h->counter.p;
+  const int threads = h->warps * 32;
+  const size_t smem = mpcb::nmpc_smem_bytes(n->net, h->H, h->nz, h->warps);
+  const long long blocks = (Bn + h->warps - 1) / h->warps;
+  const int per_sm = std::max<int>(1, (int)((220 * 1024) / smem));
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * per_sm));
+  cudaError_t e;
+  switch (h->rows) {
+    case 1: e = launch_sqp_rows<1>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 2: e = launch_sqp_rows<2>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 3: e = launch_sqp_rows<3>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 4: e = launch_sqp_rows<4>(P, grid, threads, smem, &h->smem_set, st); break;
+    default: return api_fail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
+  }
+  if (e != cudaSuccess) return api_fail(MPCB_ERR_CUDA, std::string("nmpc_sqp_kernel launch: ") + cudaGetErrorString(e));
+  h->timing.kernel_launches = 1;
+  h->timing.batch = Bn;
+  return MPCB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpcb_create_nn(const mpcb_nn_desc* d, int32_t device, mpcb_nn** out) {
+  if (!out) return api_fail(MPCB_ERR_INVALID, "mpcb_create_nn: null output");
+  *out = nullptr;
+  int rc = validate_nn(d);
+  if (rc != MPCB_OK) return rc;
+  int sms = 0;
+  rc = check_device(device, &sms);
+  if (rc != MPCB_OK) return rc;
+  mpcb_nn* n = new mpcb_nn();
+  n->device = device; n->sm_count = sms;
+  mpcb::NetDev& N = n->net;
+  N.arch = d->arch; N.act = d->activation; N.nx = d->nx; N.nu = d->nu; N.nn = d->n_neurons; N.nh = d->n_hidden; N.nin = d->nx + d->nu;
+  const size_t n1 = (size_t)N.nn * N.nin, n2 = (size_t)N.nh * N.nn * N.nn, n3 = (size_t)N.nh * N.nn, n4 = (size_t)N.nx * N.nn;
+  std::vector<double> w(n1 + n2 + n3 + n4);
+  std::memcpy(w.data(), d->W_in, n1 * sizeof(double));
+  if (n2) std::memcpy(w.data() + n1, d->W_hidden, n2 * sizeof(double));
+  if (n3) std::memcpy(w.data() + n1 + n2, d->b_hidden, n3 * sizeof(double));
+  std::memcpy(w.data() + n1 + n2 + n3, d->W_out, n4 * sizeof(double));
+  for (double v : w)
+    if (!std::isfinite(v)) { delete n; return api_fail(MPCB_ERR_INVALID, "network weights contain non-finite values"); }
+  if (mpcb::upload(n->weights, w.data(), w.size()) != cudaSuccess) { cudaGetLastError(); delete n; return api_fail(MPCB_ERR_CUDA, "weight upload failed"); }
+  N.W_in = n->weights.p; N.W_h = N.W_in + n1; N.b_h = N.W_h + n2; N.W_out = N.b_h + n3;
+  if (cudaStreamCreateWithFlags(&n->stream, cudaStreamNonBlocking) != cudaSuccess) { n->weights.release(); delete n; return api_fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
+  *out = n;
+  return MPCB_OK;
+}
+
+void mpcb_destroy_nn(mpcb_nn* n) {
+  if (!n) return;
+  cudaSetDevice(n->device);
+  if (n->stream) { cudaStreamSynchronize(n->stream); cudaStreamDestroy(n->stream); }
+  n->weights.release(); n->in0.release(); n->in1.release(); n->out0.release(); n->out1.release(); n->out2.release();
+  delete n;
+}
+
+int mpcb_nn_rollout_batch_device(mpcb_nn* n, int64_t batch, int32_t horizon, const double* x0, const double* u, double* x, void* cuda_stream) {
+  if (!n || !x0 || !u || !x) return api_fail(MPCB_ERR_INVALID, "null argument");
+  if (batch <= 0 || horizon <= 0) return api_fail(MPCB_ERR_INVALID, "batch and horizon must be positive");
+  CUDA_TRY(cudaSetDevice(n->device));
+  mpcb::NnBatchParams P{};
+  P.net = n->net; P.batch = batch; P.H = horizon; P.x0 = x0; P.u = u; P.x = x;
+  return launch_nn_batch<false>(n, P, (cudaStream_t)cuda_stream);
+}
+
+int mpcb_nn_rollout_batch(mpcb_nn* n, int64_t batch, int32_t horizon, const double* x0, const double* u, double* x) {
+  if (!n || !x0 || !u || !x) return api_fail(MPCB_ERR_INVALID, "null argument");
+  if (batch <= 0 || horizon <= 0) return api_fail(MPCB_ERR_INVALID, "batch and horizon must be positive");
+  CUDA_TRY(cudaSetDevice(n->device));
+  const size_t nx = n->net.nx, nu = n->net.nu, B = (size_t)batch, H = (size_t)horizon;
+  CUDA_TRY(n->in0.ensure(nx * B)); CUDA_TRY(n->in1.ensure(nu * H * B)); CUDA_TRY(n->out0.ensure(nx * (H + 1) * B));
+  CUDA_TRY(cudaMemcpyAsync(n->in0.p, x0, nx * B * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  CUDA_TRY(cudaMemcpyAsync(n->in1.p, u, nu * H * B * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  int rc = mpcb_nn_rollout_batch_device(n, batch, horizon, n->in0.p, n->in1.p, n->out0.p, n->stream);
+  if (rc != MPCB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(x, n->out0.p, nx * (H + 1) * B * sizeof(double), cudaMemcpyDeviceToHost, n->stream));
+  CUDA_TRY(cudaStreamSynchronize(n->stream));
+  return MPCB_OK;
+}
+
+int mpcb_nn_jacobian_batch_device(mpcb_nn* n, int64_t batch, const double* x, const double* u, double* f, double* A, double* B, void* cuda_stream) {
+  if (!n || !x || !u || !A || !B) return api_fail(MPCB_ERR_INVALID, "null argument");
+  if (batch <= 0) return api_fail(MPCB_ERR_INVALID, "batch must be positive");
+  CUDA_TRY(cudaSetDevice(n->device));
+  return jacobian_device(n, batch, x, u, f, A, B, (cudaStream_t)cuda_stream);
+}
+
+int mpcb_nn_jacobian_batch(mpcb_nn* n, int64_t batch, const double* x, const double* u, double* f, double* A, double* B) {
+  if (!n || !x || !u || !A || !B) return api_fail(MPCB_ERR_INVALID, "null argument");
+  if (batch <= 0) return api_fail(MPCB_ERR_INVALID, "batch must be positive");
+  CUDA_TRY(cudaSetDevice(n->device));
+  const size_t nx = n->net.nx, nu = n->net.nu, Bn = (size_t)batch;
+  CUDA_TRY(n->in0.ensure(nx * Bn)); CUDA_TRY(n->in1.ensure(nu * Bn));
+  CUDA_TRY(n->out0.ensure(nx * Bn)); CUDA_TRY(n->out1.ensure(nx * nx * Bn)); CUDA_TRY(n->out2.ensure(nx * nu * Bn));
+  CUDA_TRY(cudaMemcpyAsync(n->in0.p, x, nx * Bn * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  CUDA_TRY(cudaMemcpyAsync(n->in1.p, u, nu * Bn * sizeof(double), cudaMemcpyHostToDevice, n->stream));
+  int rc = jacobian_device(n, batch, n->in0.p, n->in1.p, n->out0.p, n->out1.p, n->out2.p, n->stream);
+  if (rc != MPCB_OK) return rc;
+  if (f) CUDA_TRY(cudaMemcpyAsync(f, n->out0.p, nx * Bn * sizeof(double), cudaMemcpyDeviceToHost, n->stream));
+  CUDA_TRY(cudaMemcpyAsync(A, n->out1.p, nx * nx * Bn * sizeof(double), cudaMemcpyDeviceToHost, n->stream));
+  CUDA_TRY(cudaMemcpyAsync(B, n->out2.p, nx * nu * Bn * sizeof(double), cudaMemcpyDeviceToHost, n->stream));
+  CUDA_TRY(cudaStreamSynchronize(n->stream));
+  return MPCB_OK;
+}
+
+void mpcb_default_nmpc_settings(mpcb_nmpc_settings* s) {
+  if (!s) return;
+  std::memset(s, 0, sizeof(*s));
+  mpcb_default_settings(&s->qp);
+  s->qp.eps_abs = 1e-9; s->qp.eps_rel = 0.0; s->qp.check_every = 5; s->qp.sigma = 0.0;
+  s->sqp_tol = 1e-6; s->ls_armijo = 1e-4; s->ls_noise = 1e-10; s->sqp_max_iter = 20; s->ls_max_halvings = 12;
+}
+
+int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings, mpcb_nmpc** out) {
+  if (!d || !out) return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: null argument");
+  *out = nullptr;
+  mpcb_nmpc_settings st;
+  if (settings) st = *settings; else mpcb_default_nmpc_settings(&st);
+  const mpcb_settings& q = st.qp;
+  if (q.check_every <= 0 || q.max_iter <= 0 || !(q.alpha > 0 && q.alpha < 2) || !(q.sigma >= 0) || !(q.eps_abs >= 0) || !(q.eps_rel >= 0) ||
+      st.sqp_max_iter <= 0 || st.ls_max_halvings < 0 || !(st.sqp_tol >= 0) || !(st.ls_armijo > 0 && st.ls_armijo < 1) || !(st.ls_noise >= 0))
+    return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: invalid settings");
+  if (d->terminal_mode != MPCB_TERMINAL_NONE)
+    return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: only terminal ingredient 'none' is supported on the nonlinear path");
+  if (d->horizon <= 0 || !d->Q || !d->R || !d->umin || !d->umax || !d->xref || !d->uref) return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: bad arguments");
+  mpcb_nn* n = nullptr;
+  int rc = mpcb_create_nn(d->nn, q.device, &n);
+  if (rc != MPCB_OK) return rc;
+  const int nx = n->net.nx, nu = n->net.nu, H = d->horizon, nz = nu * H;
+  mpcb_nmpc* h = new mpcb_nmpc();
+  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32;
+  auto bail = [&](int code, const std::string& msg) { mpcb_destroy_nmpc(h); return api_fail(code, msg); };
+  if (h->rows > 4) return bail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
+  h->warps = 0;
+  for (int w = mpcb::NN_WARPS; w >= 1; w--)
+    if (mpcb::nmpc_smem_bytes(n->net, H, nz, w) <= 110 * 1024 || (w == 1 && mpcb::nmpc_smem_bytes(n->net, H, nz, 1) <= 220 * 1024)) { h->warps = w; break; }
+  if (h->warps == 0) return bail(MPCB_ERR_INVALID, "NMPC problem too large for the shared-memory resident SQP kernel");
+
+  // linearise at the design reference ON THE GPU (the reference: proceed_system_linearization, design_mpc.jl:319-323)
+  {
+    DevBuf<double> dx, du, dA, dB;
+    if (mpcb::upload(dx, d->xref, nx) != cudaSuccess || mpcb::upload(du, d->uref, nu) != cudaSuccess || dA.ensure((size_t)nx * nx) != cudaSuccess ||
+        dB.ensure((size_t)nx * nu) != cudaSuccess) { cudaGetLastError(); return bail(MPCB_ERR_CUDA, "linearisation buffers"); }
+    rc = jacobian_device(n, 1, dx.p, du.p, nullptr, dA.p, dB.p, n->stream);
+    h->A = mpcb::Mat(nx, nx); h->B = mpcb::Mat(nx, nu);
+    cudaError_t e1 = cudaMemcpyAsync(h->A.a.data(), dA.p, sizeof(double) * nx * nx, cudaMemcpyDeviceToHost, n->stream);
+    cudaError_t e2 = cudaMemcpyAsync(h->B.a.data(), dB.p, sizeof(double) * nx * nu, cudaMemcpyDeviceToHost, n->stream);
+    cudaError_t e3 = cudaStreamSynchronize(n->stream);
+    dx.release(); du.release(); dA.release(); dB.release();
+    if (rc != MPCB_OK) { std::string keep = mpcb_last_error(); return bail(rc, keep); }
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cudaGetLastError(); return bail(MPCB_ERR_CUDA, "linearisation at the design reference failed"); }
+  }
+  // host design on the linearisation: P (if absent), rho = sqrt(lmin lmax) of the condensed Hessian
+  mpcb_linear_desc ld{};
+  ld.nx = nx; ld.nu = nu; ld.horizon = H; ld.A = h->A.a.data(); ld.B = h->B.a.data(); ld.Q = d->Q; ld.R = d->R; ld.S = d->S; ld.P = d->P;
+  ld.umin = d->umin; ld.umax = d->umax; ld.xmin = nullptr; ld.xmax = nullptr; ld.state_constraint = 0; ld.terminal_mode = MPCB_TERMINAL_NONE;
+  mpcb::Design D;
+  std::string err;
+  rc = mpcb::build_design(ld, q, D, err);
+  if (rc != MPCB_OK) return bail(rc, "design at the reference linearisation: " + err);
+  h->rho = D.rho; h->P = D.P;
+  // constant Hessian part Hc = 2 (I (x) R) + 2 D'(I (x) S) D with the reference's switches (design_mpc.jl:436-447)
+  std::vector<double> Hc((size_t)nz * nz, 0.0), lb(nz), ub(nz);
+  if (D.use_R) {
+    for (int k = 0; k < H; k++)
+      for (int i = 0; i < nu; i++)
+        for (int j = 0; j < nu; j++) Hc[(size_t)(k * nu + j) * nz + k * nu + i] += 2.0 * D.R(i, j);
+    if (D.use_S)
+      for (int k = 0; k + 1 < H; k++)
+        for (int i = 0; i < nu; i++)
+          for (int j = 0; j < nu; j++) {
+            const double s2 = 2.0 * D.S(i, j);
+            const int a0 = k * nu + i, a1 = (k + 1) * nu + i, b0 = k * nu + j, b1 = (k + 1) * nu + j;
+            Hc[(size_t)b0 * nz + a0] += s2; Hc[(size_t)b1 * nz + a1] += s2; Hc[(size_t)b1 * nz + a0] -= s2; Hc[(size_t)b0 * nz + a1] -= s2;
+          }
+  }
+  for (int e = 0; e < nz; e++) { lb[e] = d->umin[e % nu]; ub[e] = d->umax[e % nu]; if (!(lb[e] <= ub[e])) return bail(MPCB_ERR_INVALID, "umin > umax"); }
+  if (mpcb::upload(h->Q, D.Q.a.data(), D.Q.a.size()) != cudaSuccess || mpcb::upload(h->Pt, D.P.a.data(), D.P.a.size()) != cudaSuccess ||
+      mpcb::upload(h->Hc, Hc.data(), Hc.size()) != cudaSuccess || mpcb::upload(h->lb, lb.data(), nz) != cudaSuccess ||
+      mpcb::upload(h->ub, ub.data(), nz) != cudaSuccess) { cudaGetLastError(); return bail(MPCB_ERR_CUDA, "constant upload failed"); }
+  for (auto& e : h->ev)
+    if (cudaEventCreate(&e) != cudaSuccess) return bail(MPCB_ERR_CUDA, "cudaEventCreate failed");
+  *out = h;
+  return MPCB_OK;
+}
+
+void mpcb_destroy_nmpc(mpcb_nmpc* h) {
+  if (!h) return;
+  if (h->nn) { cudaSetDevice(h->nn->device); if (h->nn->stream) cudaStreamSynchronize(h->nn->stream); }
+  for (DevBuf<double>* b : {&h->Q, &h->Pt, &h->Hc, &h->lb, &h->ub, &h->x0, &h->xref, &h->uref, &h->warm_u, &h->warm_y, &h->u, &h->e_u, &h->x, &h->e_x, &h->u0,
+                            &h->obj, &h->y, &h->step, &h->dres})
+    b->release();
+  h->status.release(); h->iters.release(); h->inner.release(); h->counter.release(); h->stage_int.release();
+  for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  mpcb_destroy_nn(h->nn);
+  delete h;
+}
+
+int mpcb_nmpc_get_design(const mpcb_nmpc* h, double* rho, double* A, double* B, double* P) {
+  if (!h) return api_fail(MPCB_ERR_INVALID, "null handle");
+  if (rho) *rho = h->rho;
+  if (A) std::memcpy(A, h->A.a.data(), sizeof(double) * h->A.a.size());
+  if (B) std::memcpy(B, h->B.a.data(), sizeof(double) * h->B.a.size());
+  if (P) std::memcpy(P, h->P.a.data(), sizeof(double) * h->P.a.size());
+  return MPCB_OK;
+}
+
+int mpcb_nmpc_get_timing(const mpcb_nmpc* h, mpcb_timing* t) {
+  if (!h || !t) return api_fail(MPCB_ERR_INVALID, "null argument");
+  *t = h->timing;
+  return MPCB_OK;
+}
+
+int mpcb_solve_nmpc_batch_device(mpcb_nmpc* h, const mpcb_batch_io* io, void* cuda_stream) {
+  if (!h || !io) return api_fail(MPCB_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->nn->device));
+  return enqueue_nmpc(h, *io, (cudaStream_t)cuda_stream);
+}
+
+int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) {
+  if (!h || !hio) return api_fail(MPCB_ERR_INVALID, "null argument");
+  const long long Bn = hio->batch;
+  if (Bn <= 0) return api_fail(MPCB_ERR_INVALID, "batch must be positive");
+  if (!hio->x0 || !hio->xref || !hio->uref) return api_fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  mpcb_nn* n = h->nn;
+  CUDA_TRY(cudaSetDevice(n->device));
+  cudaStream_t st = n->stream;
+  const size_t nx = n->net.nx, nu = n->net.nu, H = h->H, nz = h->nz, B = (size_t)Bn;
+  const size_t n_xref = hio->xref_broadcast ? nx : nx * B, n_uref = hio->uref_broadcast ? nu : nu * B;
+  struct In { const double* src; DevBuf<double>* dst; size_t n; };
+  In ins[5] = {{hio->x0, &h->x0, nx * B}, {hio->xref, &h->xref, n_xref}, {hio->uref, &h->uref, n_uref}, {hio->warm_u, &h->warm_u, nz * B}, {hio->warm_y, &h->warm_y, nz * B}};
+  CUDA_TRY(cudaEventRecord(h->ev[0], st));
+  for (auto& in : ins) {
+    if (!in.src) continue;
+    CUDA_TRY(in.dst->ensure(in.n));
+    CUDA_TRY(cudaMemcpyAsync(in.dst->p, in.src, in.n * sizeof(double), cudaMemcpyHostToDevice, st));   // pageable sources are staged by the driver
+  }
+  CUDA_TRY(cudaEventRecord(h->ev[1], st));
+  mpcb_batch_io dio = *hio;
+  dio.x0 = h->x0.p; dio.xref = h->xref.p; dio.uref = h->uref.p;
+  dio.warm_u = hio->warm_u ? h->warm_u.p : nullptr; dio.warm_y = hio->warm_y ? h->warm_y.p : nullptr;
+  struct Out { double* host; DevBuf<double>* dev; size_t n; double** slot; };
+  Out outs[9] = {{hio->u, &h->u, nz * B, &dio.u}, {hio->e_u, &h->e_u, nz * B, &dio.e_u}, {hio->x, &h->x, nx * (H + 1) * B, &dio.x},
+                 {hio->e_x, &h->e_x, nx * (H + 1) * B, &dio.e_x}, {hio->u0, &h->u0, nu * B, &dio.u0}, {hio->prim_res, &h->step, B, &dio.prim_res},
+                 {hio->dual_res, &h->dres, B, &dio.dual_res}, {hio->objective, &h->obj, B, &dio.objective}, {hio->y, &h->y, nz * B, &dio.y}};
+  for (auto& o : outs) {
+    if (!o.host) { *o.slot = nullptr; continue; }
+    CUDA_TRY(o.dev->ensure(o.n));
+    *o.slot = o.dev->p;
+  }
+  CUDA_TRY(h->status.ensure(B)); CUDA_TRY(h->iters.ensure(B)); CUDA_TRY(h->inner.ensure(B));
+  dio.status = h->status.p; dio.iters = h->iters.p; dio.inner_iters = h->inner.p;
+  int rc = enqueue_nmpc(h, dio, st);
+  if (rc != MPCB_OK) return rc;
+  CUDA_TRY(cudaEventRecord(h->ev[2], st));
+  for (auto& o : outs)
+    if (o.host) CUDA_TRY(cudaMemcpyAsync(o.host, o.dev->p, o.n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h->stage_int.ensure(3 * B));
+  CUDA_TRY(cudaMemcpyAsync(h->stage_int.p, h->status.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->stage_int.p + B, h->iters.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h->stage_int.p + 2 * B, h->inner.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(h->ev[3], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (hio->status) std::memcpy(hio->status, h->stage_int.p, B * sizeof(int32_t));
+  if (hio->iters) std::memcpy(hio->iters, h->stage_int.p + B, B * sizeof(int32_t));
+  if (hio->inner_iters) std::memcpy(hio->inner_iters, h->stage_int.p + 2 * B, B * sizeof(int32_t));
+  long long tot = 0;
+  for (size_t i = 0; i < B; i++) tot += h->stage_int.p[2 * B + i];
+  h->timing.total_iterations = tot;
+  cudaEventElapsedTime(&h->timing.h2d_ms, h->ev[0], h->ev[1]);
+  cudaEventElapsedTime(&h->timing.solve_ms, h->ev[1], h->ev[2]);
+  h->timing.recover_ms = 0.f;
+  cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[2], h->ev[3]);
+  cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[3]);
+  return MPCB_OK;
+}
+
+}  // extern "C"

@@ -100,7 +100,8 @@ def _model_predictive_control_design(system, horizon: int, sample_time: int, ref
     elif isinstance(method, NonLinearProgramming):
         from .nmpc import B200NonlinearModeler
         modeler = B200NonlinearModeler(nn, weights.Q, weights.R, weights.S, P, umin, umax, xmin, xmax, horizon,
-                                       state_constraint=state_constraint, terminal=terminal, settings=settings, kws=kws)
+                                       references.x[:, -1], references.u[:, -1], state_constraint=state_constraint,
+                                       terminal=terminal, kws=kws)
     else:
         raise NotImplementedError("mixed-integer / fuzzy programming is outside the B200 path (SURVEY.md section 2)")
     tuning = ModelPredictiveControlTuning(modeler, references, horizon, weights, TerminalIngredient(terminal, P),

@@ -1,0 +1,95 @@
+"""B200NonlinearModeler: what `tuning.modeler` holds for `mpc_programming_type = "non_linear"` with `mpc_solver = "b200"`
+-- the NL modeler of the reference (fnn.jl:63-189, resnet.jl:62-188) + Ipopt, replaced by the batched SQP kernel."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_NMPC_SETTING_KEYS = {"mpc_b200_sqp_tol": "sqp_tol", "mpc_b200_sqp_max_iter": "sqp_max_iter", "mpc_b200_ls_armijo": "ls_armijo", "mpc_b200_ls_noise": "ls_noise",
+                      "mpc_b200_ls_max_halvings": "ls_max_halvings", "mpc_b200_eps_abs": "eps_abs", "mpc_b200_eps_rel": "eps_rel",
+                      "mpc_b200_rho": "rho", "mpc_b200_max_iter": "max_iter", "mpc_b200_check_every": "check_every", "mpc_b200_device": "device",
+                      "mpc_b200_alpha": "alpha", "mpc_b200_sigma": "sigma"}
+
+
+class B200NonlinearModeler:
+    def __init__(self, nn, Q, R, S, P, umin, umax, xmin, xmax, horizon, xref, uref, state_constraint=False, terminal="none", kws=None):
+        if terminal != "none":
+            raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported on the nonlinear b200 path (only 'none')")
+        if state_constraint:
+            raise _lib.MpcbError("mpc_state_constraint is not supported on the nonlinear b200 path yet")
+        kws = kws or {}
+        self.nn = nn
+        self.nx, self.nu, self.horizon = nn.nx, nn.nu, int(horizon)
+        self.settings = _lib.default_nmpc_settings(**{v: kws[k] for k, v in _NMPC_SETTING_KEYS.items() if k in kws})
+        nd, keep_nn = nn.desc()
+        f = lambda a: None if a is None else np.asfortranarray(np.asarray(a, np.float64))
+        keep = [f(Q), f(R), f(S), f(P), f(umin), f(umax), f(xref), f(uref)]
+        p = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+        d = _lib.NmpcDesc(C.pointer(nd), self.horizon, *[p(a) for a in keep], _lib.TERMINAL_NONE)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().mpcb_create_nmpc(C.byref(d), C.byref(self.settings), C.byref(self._h)), "mpcb_create_nmpc")
+        del keep_nn
+        self.nz = self.nu * self.horizon
+        self.x0 = self.xref = self.uref = None
+        self.warm = None
+
+    def design(self):
+        rho = C.c_double(); A = np.zeros((self.nx, self.nx), order="F"); B = np.zeros((self.nx, self.nu), order="F"); P = np.zeros((self.nx, self.nx), order="F")
+        p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        _lib.check(_lib.lib().mpcb_nmpc_get_design(self._h, C.byref(rho), p(A), p(B), p(P)), "mpcb_nmpc_get_design")
+        return {"rho": rho.value, "A": np.ascontiguousarray(A), "B": np.ascontiguousarray(B), "P": np.ascontiguousarray(P)}
+
+    def timing(self):
+        t = _lib.Timing()
+        _lib.check(_lib.lib().mpcb_nmpc_get_timing(self._h, C.byref(t)), "mpcb_nmpc_get_timing")
+        return {k: getattr(t, k) for k, _ in t._fields_}
+
+    def solve_batch(self, x0, xref, uref, want=("u", "e_u", "x", "e_x", "u0", "objective"), warm=None, out=None):
+        """Host-array entry (mpcb_solve_nmpc_batch).  warm = (u_init or None, y_init or None)."""
+        x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, np.float64)))
+        Bn = x0.shape[0]
+        if x0.shape[1] != self.nx: raise ValueError("x0 must be (batch, nx)")
+        xref = np.ascontiguousarray(np.asarray(xref, np.float64)); uref = np.ascontiguousarray(np.asarray(uref, np.float64))
+        xb = xref.ndim == 1 or xref.shape[0] == 1 and Bn != 1
+        ub = uref.ndim == 1 or uref.shape[0] == 1 and Bn != 1
+        if xref.size != (self.nx if xb else self.nx * Bn) or uref.size != (self.nu if ub else self.nu * Bn):
+            raise ValueError("reference shapes do not match the batch")
+        H = self.horizon
+        shapes = {"u": (Bn, H, self.nu), "e_u": (Bn, H, self.nu), "x": (Bn, H + 1, self.nx), "e_x": (Bn, H + 1, self.nx), "u0": (Bn, self.nu),
+                  "objective": (Bn,), "prim_res": (Bn,), "dual_res": (Bn,), "y": (Bn, self.nz)}
+        res = {} if out is None else out
+        for k in tuple(want) + ("prim_res", "dual_res"):
+            if k not in res: res[k] = np.empty(shapes[k], np.float64)
+        for k in ("status", "iters", "inner_iters"):
+            if k not in res: res[k] = np.empty(Bn, np.int32)
+        io = _lib.BatchIO()
+        io.batch = Bn; io.x0 = x0.ctypes.data; io.xref = xref.ctypes.data; io.uref = uref.ctypes.data
+        io.xref_broadcast = int(xb); io.uref_broadcast = int(ub)
+        keep = []
+        if warm is not None:
+            if warm[0] is not None:
+                wu = np.ascontiguousarray(warm[0], np.float64); keep.append(wu)
+                if wu.size != Bn * self.nz: raise ValueError("warm start shapes")
+                io.warm_u = wu.ctypes.data
+            if warm[1] is not None:
+                wy = np.ascontiguousarray(warm[1], np.float64); keep.append(wy)
+                if wy.size != Bn * self.nz: raise ValueError("warm start shapes")
+                io.warm_y = wy.ctypes.data
+        for k in ("u", "e_u", "x", "e_x", "u0", "objective", "prim_res", "dual_res", "y", "status", "iters", "inner_iters"):
+            if k in res: setattr(io, k, res[k].ctypes.data)
+        _lib.check(_lib.lib().mpcb_solve_nmpc_batch(self._h, C.byref(io)), "mpcb_solve_nmpc_batch")
+        return res
+
+    def solve_batch_device(self, io: _lib.BatchIO, stream=None):
+        _lib.check(_lib.lib().mpcb_solve_nmpc_batch_device(self._h, C.byref(io), C.c_void_p(stream or 0)), "mpcb_solve_nmpc_batch_device")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().mpcb_destroy_nmpc(self._h); self._h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass

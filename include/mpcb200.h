@@ -37,6 +37,7 @@ extern "C" {
 
 /* per-problem status, OSQP's codes (what JuMP.termination_status would be derived from) */
 #define MPCB_STATUS_SOLVED 1
+#define MPCB_STATUS_SOLVED_INACCURATE 2 /* NMPC only: the SQP line search found no further descent (kink of a relu network) */
 #define MPCB_STATUS_MAX_ITER -2
 #define MPCB_STATUS_PRIMAL_INFEASIBLE -3
 #define MPCB_STATUS_UNSOLVED -10
@@ -141,6 +142,7 @@ typedef struct {
   double* dual_res;
   double* objective; /* the reference's J (design_mpc.jl:449-456), constants included */
   double* y;
+  int32_t* inner_iters; /* NMPC only: total ADMM iterations over all SQP iterations (NULL = skip) */
 } mpcb_batch_io;
 
 /* CUDA-event timings of the last solve call on this handle, milliseconds. */
@@ -181,6 +183,96 @@ int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* dev_io, 
  * copy that pageable memory needs (Julia: unsafe_wrap the pointer; Python: numpy.frombuffer). */
 void* mpcb_alloc_pinned(size_t bytes);
 void mpcb_free_pinned(void* p);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Nonlinear path: Flux neural dynamics (fnn / resnet) + NMPC.
+ *
+ * Replaces, for a batch, the reference's NonLinearProgramming modelers + Ipopt
+ *   src/sub/model_modeler_implementation/fnn/mpc_modeler_implementation_fnn.jl:63-189
+ *   src/sub/model_modeler_implementation/resnet/mpc_modeler_implementation_resnet.jl:62-188
+ *   src/sub/solver_selection.jl:100-106 (Ipopt, no attributes)
+ * and the linearisation `AutomationLabsSystems.proceed_system_linearization` the LinearProgramming method applies to
+ * black-box models (fnn.jl:37-46, resnet.jl:37-46; terminal cost: design_mpc.jl:312-327).
+ * The network is described exactly as those modelers parse `Flux.params(system.f)` (fnn.jl:88-107):
+ *   params[1] = W_in (n_neurons x (nx+nu), NO bias); then n_hidden pairs (W_j, b_j); params[end] = W_out (nx x n_neurons,
+ *   NO bias).  fnn:  y_j = act(W_j y_{j-1} + b_j);  resnet:  y_j = y_{j-1} + act(W_j y_{j-1} + b_j);  x+ = W_out y_end.
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define MPCB_NN_FNN 0
+#define MPCB_NN_RESNET 1
+
+#define MPCB_ACT_RELU 0
+#define MPCB_ACT_TANH 1
+#define MPCB_ACT_SIGMOID 2
+#define MPCB_ACT_SWISH 3
+#define MPCB_ACT_IDENTITY 4
+
+typedef struct mpcb_nn mpcb_nn;
+typedef struct mpcb_nmpc mpcb_nmpc;
+
+typedef struct {
+  int32_t arch;       /* MPCB_NN_* */
+  int32_t activation; /* MPCB_ACT_*  (design_mpc.jl:472-496 reads it off the first hidden layer) */
+  int32_t nx, nu, n_neurons, n_hidden;
+  const double* W_in;     /* n_neurons x (nx+nu) column-major */
+  const double* W_hidden; /* n_hidden matrices n_neurons x n_neurons, back to back */
+  const double* b_hidden; /* n_hidden vectors of n_neurons, back to back */
+  const double* W_out;    /* nx x n_neurons */
+} mpcb_nn_desc;
+
+/* A network resident on `device`. */
+int mpcb_create_nn(const mpcb_nn_desc* desc, int32_t device, mpcb_nn** out);
+void mpcb_destroy_nn(mpcb_nn* n);
+
+/* Batched rollout x_{k+1} = f(x_k, u_k): x0 nx x batch, u nu x horizon x batch -> x nx x (horizon+1) x batch.
+ * HOST pointers; the *_device variants take device pointers and enqueue on `cuda_stream`. */
+int mpcb_nn_rollout_batch(mpcb_nn* n, int64_t batch, int32_t horizon, const double* x0, const double* u, double* x);
+int mpcb_nn_rollout_batch_device(mpcb_nn* n, int64_t batch, int32_t horizon, const double* x0, const double* u, double* x, void* cuda_stream);
+/* Batched forward-mode Jacobians at (x, u): x nx x batch, u nu x batch -> f nx x batch (may be NULL), A nx x nx x batch,
+ * B nx x nu x batch.  Replaces proceed_system_linearization (fnn.jl:42). */
+int mpcb_nn_jacobian_batch(mpcb_nn* n, int64_t batch, const double* x, const double* u, double* f, double* A, double* B);
+int mpcb_nn_jacobian_batch_device(mpcb_nn* n, int64_t batch, const double* x, const double* u, double* f, double* A, double* B, void* cuda_stream);
+
+/* NMPC controller = NL modeler + terminal ingredient + cost (design_mpc.jl:143-225).  xref/uref are the design references
+ * (constant over the horizon, main_mpc.jl:105-117): the network is linearised there for P = are(...) (design_mpc.jl:312-327,
+ * computed here when P is NULL) and for the ADMM step size rho. */
+typedef struct {
+  const mpcb_nn_desc* nn;
+  int32_t horizon;
+  const double* Q; /* nx x nx */
+  const double* R; /* nu x nu */
+  const double* S; /* nu x nu or NULL */
+  const double* P; /* nx x nx or NULL */
+  const double* umin;
+  const double* umax;
+  const double* xref; /* nx */
+  const double* uref; /* nu */
+  int32_t terminal_mode; /* MPCB_TERMINAL_NONE only */
+} mpcb_nmpc_desc;
+
+typedef struct {
+  mpcb_settings qp;        /* inner ADMM; defaults: eps_abs = 1e-9, eps_rel = 0 (|q| is the cost gradient, so a relative dual
+                              tolerance would be far looser than the SQP step tolerance), check_every = 5, sigma = 0, rest as OSQP */
+  double sqp_tol;          /* stop when the SQP step ||d||_inf <= sqp_tol          (1e-6) */
+  double ls_armijo;        /* sufficient-decrease constant                           (1e-4) */
+  double ls_noise;         /* round-off floor of a cost evaluation, relative to max(1,|J|): added to the Armijo bound (1e-10) */
+  int32_t sqp_max_iter;    /* (20) */
+  int32_t ls_max_halvings; /* (12) */
+} mpcb_nmpc_settings;
+
+void mpcb_default_nmpc_settings(mpcb_nmpc_settings* s);
+int mpcb_create_nmpc(const mpcb_nmpc_desc* desc, const mpcb_nmpc_settings* settings, mpcb_nmpc** out);
+void mpcb_destroy_nmpc(mpcb_nmpc* h);
+/* rho in use, and host copies of the design linearisation (any pointer may be NULL): A nx x nx, B nx x nu, P nx x nx */
+int mpcb_nmpc_get_design(const mpcb_nmpc* h, double* rho, double* A, double* B, double* P);
+int mpcb_nmpc_get_timing(const mpcb_nmpc* h, mpcb_timing* t);
+
+/* The hot path for the nonlinear method: update_initialization! + calculate! (computation_mpc.jl:17-55) for a batch.
+ * Uses mpcb_batch_io with these meanings: warm_u = initial guess of u (NULL: the reference input clipped to the box),
+ * warm_y = duals of the input box (nu*horizon per problem; may be NULL independently), y = those duals on exit,
+ * iters = SQP iterations, inner_iters = total ADMM iterations, prim_res = last SQP step ||d||_inf,
+ * dual_res = dual residual of the last QP, status = MPCB_STATUS_SOLVED / _SOLVED_INACCURATE / _MAX_ITER. */
+int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* host_io);
+int mpcb_solve_nmpc_batch_device(mpcb_nmpc* h, const mpcb_batch_io* dev_io, void* cuda_stream);
 
 #ifdef __cplusplus
 }

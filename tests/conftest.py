@@ -37,3 +37,21 @@ def qt_batch(qt, n, seed=0):
 def mpc():
     import almpc_b200
     return almpc_b200
+
+
+def load_nn_fixture(name):
+    """tests/golden/qt_fnn_model.json (decoded reference fixture) / qt_resnet_model.json (trained here): oracle model."""
+    from oracle import nn_oracle as no
+    g = json.loads((ROOT / "tests" / "golden" / name).read_text())
+    return no.NeuralModel(g["arch"], g["activation"], np.array(g["W_in"]), [np.array(w) for w in g["W_h"]], [np.array(b) for b in g["b_h"]],
+                          np.array(g["W_out"]))
+
+
+@pytest.fixture(scope="session")
+def fnn_model():
+    return load_nn_fixture("qt_fnn_model.json")
+
+
+@pytest.fixture(scope="session")
+def resnet_model():
+    return load_nn_fixture("qt_resnet_model.json")

@@ -1,0 +1,159 @@
+"""GPU parity tests of the nonlinear path: CUDA network rollout / Jacobians and the batched SQP kernel (through the C ABI)
+against oracle/nn_oracle.py on the same seeded inputs."""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from conftest import load_nn_fixture
+from oracle import mpc_oracle as mo
+from oracle import nn_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+U0_TOL, OBJ_TOL = 1e-4, 1e-6        # north_star tolerances
+
+
+def to_chain(mpc, m):
+    cls = mpc.ResNet if m.arch == "resnet" else mpc.Fnn
+    return cls(m.W_in, list(zip(m.W_h, m.b_h)), m.W_out, activation=m.activation)
+
+
+def make_system(mpc, qt, m):
+    return mpc.ConstrainedBlackBoxControlDiscreteSystem(to_chain(mpc, m), 4, 2, mpc.Hyperrectangle(qt["xmin"], qt["xmax"]),
+                                                        mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+
+
+def scenario(qt, n, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(qt["xmin"], qt["xmax"], (n, 4)), rng.uniform(0.4, 1.0, (n, 4)), qt["u_ref"].copy()
+
+
+@pytest.mark.parametrize("activation", ["relu", "tanh", "sigmoid", "swish", "identity"])
+def test_rollout_and_jacobian_match_oracle(mpc, fnn_model, resnet_model, activation):
+    rng = np.random.default_rng(7)
+    for base in (fnn_model, resnet_model):
+        m = dataclasses.replace(base, activation=activation)
+        f = to_chain(mpc, m)
+        n, H = 517, 9                                      # ragged: not a multiple of the CTA's 4 warps
+        x0 = rng.uniform(0.2, 1.3, (n, 4)); u = rng.uniform(0, 4, (n, H, 2))
+        x = f.rollout(x0, u)
+        xo = no.rollout(m, x0, u)
+        assert np.abs(x - xo).max() < 1e-13 * max(1.0, np.abs(xo).max())
+        fx, A, B = f.jacobian(x0, u[:, 0])
+        fo, Ao, Bo = no.jacobian(m, x0, u[:, 0])
+        assert np.abs(fx - fo).max() < 1e-13 and np.abs(A - Ao).max() < 1e-13 and np.abs(B - Bo).max() < 1e-13
+        assert np.allclose(f(np.concatenate([x0[0], u[0, 0]])), fo[0], atol=1e-13)      # system.f([x; u])
+
+
+def test_deeper_wider_network(mpc):
+    """Generic sizes: nx = 3, nu = 2, 40 neurons (more than one warp), 3 hidden layers."""
+    rng = np.random.default_rng(11)
+    for arch in ("fnn", "resnet"):
+        m = no.NeuralModel(arch, "tanh", 0.3 * rng.standard_normal((40, 5)), [0.2 * rng.standard_normal((40, 40)) for _ in range(3)],
+                           [0.1 * rng.standard_normal(40) for _ in range(3)], 0.2 * rng.standard_normal((3, 40)))
+        f = to_chain(mpc, m)
+        x0 = rng.standard_normal((33, 3)); u = rng.standard_normal((33, 6, 2))
+        assert np.abs(f.rollout(x0, u) - no.rollout(m, x0, u)).max() < 1e-12
+        _, A, B = f.jacobian(x0, u[:, 0]); _, Ao, Bo = no.jacobian(m, x0, u[:, 0])
+        assert np.abs(A - Ao).max() < 1e-13 and np.abs(B - Bo).max() < 1e-13
+
+
+def test_linear_method_on_blackbox_model(mpc, qt, fnn_model):
+    """fnn.jl:37-55: LinearProgramming on a black-box model = Jacobian linearisation at the reference + the linear modeler;
+    P from the linearisation at the last reference column (design_mpc.jl:312-327)."""
+    sys_ = make_system(mpc, qt, fnn_model)
+    C = mpc.proceed_controller(sys_, "model_predictive_control", 5, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="linear", mpc_b200_eps_abs=1e-8, mpc_b200_eps_rel=1e-8, mpc_b200_check_every=5)
+    _, A, B = no.jacobian(fnn_model, qt["x_ref"][None], qt["u_ref"][None])
+    P = mo.dare(A[0], B[0], qt["Q"], qt["R"])
+    assert np.abs(C.tuning.terminal_ingredient.P - P).max() < 1e-6 * np.abs(P).max()
+    d = C.tuning.modeler.design()
+    c = mo.condense(A[0], B[0], qt["Q"], qt["R"], qt["S"], C.tuning.terminal_ingredient.P, 5, qt["umin"], qt["umax"])
+    assert np.allclose(d["Pc"], c.Pc, rtol=1e-10, atol=1e-9)
+    mpc.update_initialization(C, qt["x0"]); mpc.calculate(C)
+    v, _ = mo.qp_exact(c, mo.pack_params(qt["x0"], qt["x_ref"], qt["u_ref"])[0])
+    assert mo.u0_metric(C.computation_results.u[:, 0], v[:2], qt["umin"], qt["umax"]) < U0_TOL
+
+
+@pytest.mark.parametrize("fixture,H", [("qt_resnet_model.json", 20), ("qt_fnn_tanh_model.json", 20), ("qt_resnet_swish_model.json", 20), ("qt_fnn_tanh_model.json", 7),
+                                       ("qt_resnet_swish_model.json", 33)])
+def test_sqp_matches_twin_and_independent_solve(mpc, qt, fixture, H):
+    m = load_nn_fixture(fixture)
+    n = 300
+    C = mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="non_linear")
+    mod = C.tuning.modeler
+    x0, xref, uref = scenario(qt, n)
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    # design parity
+    d = mod.design()
+    _, A, B = no.jacobian(m, qt["x_ref"][None], qt["u_ref"][None])
+    P = mo.dare(A[0], B[0], qt["Q"], qt["R"])
+    assert np.abs(d["A"] - A[0]).max() < 1e-13 and np.abs(d["B"] - B[0]).max() < 1e-13 and np.abs(d["P"] - P).max() < 1e-6 * np.abs(P).max()
+    # twin: same algorithm, same settings
+    tw = no.nmpc_sqp(m, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0, xref, np.tile(uref, (n, 1)), d["rho"])
+    assert (res["status"] == 1).all() and (tw["status"] == 1).all()
+    assert (res["iters"] == tw["iters"]).mean() > 0.9
+    assert np.abs(res["u"] - tw["u"]).max() < 5e-6            # both stop at ||step|| <= 1e-6 of the same fixed point
+    assert np.abs(res["objective"] - tw["objective"]).max() <= 1e-9 * np.abs(tw["objective"]).max()
+    # outputs are consistent with the reference's variables: x = rollout(u), e_x = x - x_ref, e_u = u - u_ref
+    assert np.abs(res["x"] - no.rollout(m, x0, res["u"])).max() < 1e-12 and no.reference_nl_residual(m, res["x"], res["u"]) < 1e-12
+    assert np.abs(res["e_x"] - (res["x"] - xref[:, None, :])).max() < 1e-15 and np.abs(res["e_u"] - (res["u"] - uref)).max() < 1e-15
+    assert np.abs(res["u0"] - res["u"][:, 0]).max() == 0.0 and np.abs(C.computation_results.u - res["u"][0].T).max() == 0.0
+    assert (res["u"] >= qt["umin"] - 2e-9).all() and (res["u"] <= qt["umax"] + 2e-9).all()       # x~ of the last QP: within eps_abs of the box
+    # independent solve (Ipopt stand-in) + KKT certificate
+    for i in range(5):
+        u, J, k = no.nmpc_local_opt(m, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0[i], xref[i], uref, u_init=res["u"][i])
+        assert k < 1e-5
+        assert mo.u0_metric(res["u0"][i], u[0], qt["umin"], qt["umax"]) < U0_TOL
+        assert abs(J - res["objective"][i]) <= OBJ_TOL * abs(J)
+
+
+def test_relu_fnn_fixture_statuses_and_reference_relation(mpc, qt, fnn_model):
+    """The reference's own fixture (relu FNN): nonsmooth NLP.  Statuses equal the twin's; solved problems match it; and the
+    one numeric relation the reference's tests state holds (|x_linear - x_nl| <= 0.5 at H = 5 from x0 = 0.6,
+    test/computation_mpc_test.jl:152,163)."""
+    sys_ = make_system(mpc, qt, fnn_model)
+    H, n = 20, 256
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_programming_type="non_linear")
+    x0, xref, uref = scenario(qt, n)
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    d = C.tuning.modeler.design()
+    tw = no.nmpc_sqp(fnn_model, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0, xref, np.tile(uref, (n, 1)), d["rho"])
+    assert set(np.unique(res["status"])) <= {1, 2, -2} and (res["status"] == 1).mean() > 0.8
+    same = (res["status"] == tw["status"]) & (res["iters"] == tw["iters"])
+    assert same.mean() > 0.9
+    ok = same & (res["status"] == 1)
+    assert np.abs(res["u"][ok] - tw["u"][ok]).max() < 5e-6
+    Hc = no.constant_hessian(2, H, qt["R"], qt["S"])
+    J_init, _ = no.objective(fnn_model, qt["Q"], d["P"], Hc, np.tile(uref, (n, H, 1)), x0, xref, np.tile(uref, (n, 1)))
+    assert (res["objective"] <= J_init + 1e-9).all()
+    # reference relation at H = 5
+    Cl = mpc.proceed_controller(sys_, "model_predictive_control", 5, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_programming_type="linear")
+    Cn = mpc.proceed_controller(sys_, "model_predictive_control", 5, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_programming_type="non_linear")
+    for Cx in (Cl, Cn):
+        mpc.update_initialization(Cx, qt["x0"]); mpc.calculate(Cx)
+    assert np.abs(Cl.computation_results.x - Cn.computation_results.x).max() < 0.5
+    assert np.abs(Cl.computation_results.e_x - Cn.computation_results.e_x).max() < 0.5
+
+
+def test_sqp_warm_start_and_ragged_batches(mpc, qt, resnet_model):
+    m = load_nn_fixture("qt_fnn_tanh_model.json")
+    C = mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", 20, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="non_linear")
+    mod = C.tuning.modeler
+    x0, xref, uref = scenario(qt, 131)
+    full = mod.solve_batch(x0, xref, uref, want=("u", "u0", "objective", "y"))
+    for nb in (1, 3, 130):
+        part = mod.solve_batch(x0[:nb], xref[:nb], uref, want=("u", "objective"))
+        assert np.array_equal(part["u"], full["u"][:nb]) and np.array_equal(part["iters"], full["iters"][:nb])     # per-problem results do not depend on the batch
+    warm = mod.solve_batch(x0, xref, uref, want=("u", "objective"), warm=(full["u"], full["y"]))
+    assert (warm["iters"] == 1).all() and (warm["status"] == 1).all() and np.abs(warm["u"] - full["u"]).max() < 2e-6
+    assert warm["inner_iters"].mean() < 0.2 * full["inner_iters"].mean()
+    # unsupported configurations are refused, not approximated
+    with pytest.raises(mpc.MpcbError):
+        mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", 20, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="non_linear", mpc_terminal_ingredient="equality")

@@ -13,7 +13,7 @@ def test_library_exports_every_declared_symbol(mpc):
     hdr = (ROOT / "include" / "mpcb200.h").read_text()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     declared = sorted(set(re.findall(r"\b(mpcb_[a-z0-9_]+)\s*\(", hdr)))
-    assert len(declared) >= 14
+    assert len(declared) >= 27
     L = mpc._lib.lib()
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
@@ -27,7 +27,12 @@ def test_struct_layouts_match_header(mpc):
     assert ctypes.sizeof(L.Settings) == 7 * 8 + 8 * 4
     assert ctypes.sizeof(L.LinearDesc) == 3 * 4 + 4 + 10 * 8 + 2 * 4
     assert ctypes.sizeof(L.Info) == 10 * 4 + 3 * 8
-    assert ctypes.sizeof(L.BatchIO) == 8 + 3 * 8 + 2 * 4 + 13 * 8
+    assert ctypes.sizeof(L.BatchIO) == 8 + 3 * 8 + 2 * 4 + 14 * 8
+    assert ctypes.sizeof(L.NnDesc) == 6 * 4 + 4 * 8
+    assert ctypes.sizeof(L.NmpcDesc) == 8 + 4 + 4 + 8 * 8 + 4 + 4
+    assert ctypes.sizeof(L.NmpcSettings) == ctypes.sizeof(L.Settings) + 3 * 8 + 2 * 4
+    n = L.default_nmpc_settings()
+    assert (n.qp.eps_abs, n.qp.eps_rel, n.qp.check_every, n.qp.sigma, n.sqp_tol, n.ls_armijo, n.ls_noise, n.sqp_max_iter, n.ls_max_halvings) == (1e-9, 0.0, 5, 0.0, 1e-6, 1e-4, 1e-10, 20, 12)
     s = L.default_settings()
     assert (s.eps_abs, s.eps_rel, s.sigma, s.alpha, s.max_iter, s.check_every, s.rho_eq_scale) == (1e-3, 1e-3, 1e-6, 1.6, 4000, 25, 1e3)
 

@@ -1,0 +1,146 @@
+"""CPU tests of the nonlinear-path oracle (oracle/nn_oracle.py): pinned to the decoded reference FNN fixture, to the layer
+equations of the reference's NL modelers, and cross-checked three ways (forward-mode vs finite differences vs adjoint; twin
+SQP vs an independent L-BFGS-B solve with a KKT certificate)."""
+import dataclasses
+import json
+import pathlib
+
+import numpy as np
+import pytest
+
+from conftest import load_nn_fixture
+from oracle import mpc_oracle as mo
+from oracle import nn_oracle as no
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+def _scenario(qt, n, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(qt["xmin"], qt["xmax"], (n, 4)), rng.uniform(0.4, 1.0, (n, 4)), np.tile(qt["u_ref"], (n, 1))
+
+
+def _design(m, qt, H):
+    _, A, B = no.jacobian(m, qt["x_ref"][None], qt["u_ref"][None])
+    P = mo.dare(A[0], B[0], qt["Q"], qt["R"])
+    c = mo.condense(A[0], B[0], qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"])
+    return A[0], B[0], P, mo.auto_rho(c.Pc), c
+
+
+def test_fnn_fixture_is_the_reference_layout(fnn_model):
+    """fnn.jl:88-107: W_in 13x6 (no bias), one hidden (W 13x13, b 13), W_out 4x13; Float32 values promoted exactly."""
+    g = json.loads((ROOT / "tests" / "golden" / "qt_fnn_model.json").read_text())
+    m = fnn_model
+    assert (m.nx, m.nu, m.n_neur, m.n_hid, m.activation, m.arch) == (4, 2, 13, 1, "relu", "fnn")
+    for a in (m.W_in, m.W_h[0], m.b_h[0], m.W_out):
+        assert np.array_equal(a, a.astype(np.float32).astype(np.float64))
+    assert g["offsets"] == ["0x19ebd7", "0x19ed25", "0x19efd0", "0x19f010"]
+    # the decoded chain is a one-step model of the quadruple tank: it nearly fixes the tests' operating point
+    f = no.forward(m, np.full((1, 4), 0.65), np.full((1, 2), 1.2))[0]
+    assert np.abs(f - 0.65).max() < 0.012
+    assert no.reference_nl_variable_count(m, 15) == 3 * 4 * 16 + 3 * 2 * 15 + 13 * 2 * 15      # fnn.jl:111-119 at the tests' horizon 15
+
+
+def test_layer_equations_match_reference_modelers(fnn_model, resnet_model):
+    """Spell the reference's per-neuron constraints (fnn.jl:126-143, resnet.jl:125-142) out with Python loops."""
+    rng = np.random.default_rng(3)
+    for m in (fnn_model, resnet_model):
+        x, u = rng.uniform(0.2, 1.3, 4), rng.uniform(0, 3, 2)
+        xu = np.concatenate([x, u])
+        y = np.zeros((m.n_neur, m.n_hid + 1))
+        for i in range(m.n_neur):
+            y[i, 0] = m.W_in[i, :] @ xu
+        for j in range(1, m.n_hid + 1):
+            for i in range(m.n_neur):
+                a = max(m.W_h[j - 1][i, :] @ y[:, j - 1] + m.b_h[j - 1][i], 0.0)
+                y[i, j] = (y[i, j - 1] + a) if m.arch == "resnet" else a
+        assert np.allclose(m.W_out @ y[:, -1], no.forward(m, x[None], u[None])[0], rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("activation", ["relu", "tanh", "sigmoid", "swish", "identity"])
+def test_jacobian_forward_mode_vs_finite_differences(fnn_model, resnet_model, activation):
+    rng = np.random.default_rng(5)
+    for base in (fnn_model, resnet_model):
+        m = dataclasses.replace(base, activation=activation)
+        x, u = rng.uniform(0.2, 1.3, (8, 4)), rng.uniform(0, 3, (8, 2))
+        f, A, B = no.jacobian(m, x, u)
+        assert np.allclose(f, no.forward(m, x, u))
+        h = 1e-6
+        for i in range(4):
+            d = np.zeros(4); d[i] = h
+            assert np.allclose((no.forward(m, x + d, u) - no.forward(m, x - d, u)) / (2 * h), A[:, :, i], atol=2e-7)
+        for i in range(2):
+            d = np.zeros(2); d[i] = h
+            assert np.allclose((no.forward(m, x, u + d) - no.forward(m, x, u - d)) / (2 * h), B[:, :, i], atol=2e-7)
+
+
+def test_gradient_forward_sensitivities_equal_adjoint(qt, fnn_model):
+    m = dataclasses.replace(fnn_model, activation="tanh")
+    H, n = 12, 16
+    _, _, P, _, _ = _design(m, qt, H)
+    x0, xref, uref = _scenario(qt, n)
+    rng = np.random.default_rng(1)
+    u = rng.uniform(qt["umin"], qt["umax"], (n, H, 2))
+    Hc = no.constant_hessian(2, H, qt["R"], 3.0 * np.eye(2))
+    J1, g1, Pc, x = no.linearize_trajectory(m, qt["Q"], P, Hc, u, x0, xref, uref)
+    J2, g2 = no.grad_adjoint(m, qt["Q"], P, Hc, u, x0, xref, uref)
+    J3, x3 = no.objective(m, qt["Q"], P, Hc, u, x0, xref, uref)
+    assert np.allclose(J1, J2, rtol=1e-13) and np.allclose(J1, J3, rtol=1e-13) and np.allclose(x, x3)
+    assert np.allclose(g1, g2, rtol=1e-10, atol=1e-9)
+    assert np.abs(Pc - Pc.transpose(0, 2, 1)).max() < 1e-9 and np.linalg.eigvalsh(Pc).min() > 0
+    assert no.reference_nl_residual(m, x, u) == 0.0
+
+
+@pytest.mark.parametrize("fixture", ["qt_resnet_model.json", "qt_fnn_tanh_model.json", "qt_resnet_swish_model.json"])
+def test_twin_sqp_matches_independent_solve(qt, fixture):
+    """Acceptance ladder for the NL path: the twin's answer is a certified KKT point and equals an independent L-BFGS-B solve
+    of the same NLP to the north-star tolerances (u0 within 1e-4 relative, objective within 1e-6 relative)."""
+    m = load_nn_fixture(fixture)
+    H, n = 20, 24
+    _, _, P, rho, _ = _design(m, qt, H)
+    x0, xref, uref = _scenario(qt, n)
+    r = no.nmpc_sqp(m, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0, xref, uref, rho)
+    assert (r["status"] == 1).all() and r["iters"].max() <= 16
+    Hc = no.constant_hessian(2, H, qt["R"], qt["S"])
+    _, g = no.grad_adjoint(m, qt["Q"], P, Hc, r["u"], x0, xref, uref)
+    lb, ub = np.tile(qt["umin"], H), np.tile(qt["umax"], H)
+    assert no.kkt_residual(g, r["u"].reshape(n, -1), lb, ub, tol=1e-7).max() < 5e-5 * np.abs(g).max()
+    for i in range(6):
+        u, J, k = no.nmpc_local_opt(m, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0[i], xref[i], uref[i], u_init=r["u"][i])
+        assert k < 1e-5
+        assert mo.u0_metric(r["u"][i, 0], u[0], qt["umin"], qt["umax"]) < 1e-4
+        assert abs(J - r["objective"][i]) <= 1e-6 * abs(J)
+        uc, Jc, _ = no.nmpc_local_opt(m, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0[i], xref[i], uref[i])     # cold start
+        assert Jc >= r["objective"][i] * (1 - 1e-6) - 1e-9       # nothing better is found from the reference input either
+
+
+def test_relu_fnn_fixture_kinks_are_flagged_not_hidden(qt, fnn_model):
+    """The decoded relu FNN has kinks inside the operating box, so the NLP is piecewise quadratic and NONSMOOTH (the reason
+    the reference also ships MILP modelers; its own NL-vs-MILP comparisons are `broken = true`,
+    test/computation_mpc_test.jl:153-169).  Most problems end at a certified smooth KKT point that an independent solver
+    confirms; the rest stop at a kink with the 'inaccurate' / max-iter status -- flagged, never reported as solved -- and
+    still improve on the initial guess."""
+    H, n = 20, 64
+    _, _, P, rho, _ = _design(fnn_model, qt, H)
+    x0, xref, uref = _scenario(qt, n)
+    r = no.nmpc_sqp(fnn_model, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0, xref, uref, rho)
+    ok = r["status"] == 1
+    assert ok.mean() > 0.8 and set(np.unique(r["status"])) <= {1, 2, -2}
+    Hc = no.constant_hessian(2, H, qt["R"], qt["S"])
+    J_init, _ = no.objective(fnn_model, qt["Q"], P, Hc, np.tile(uref[:, None, :], (1, H, 1)), x0, xref, uref)
+    assert (r["objective"] <= J_init + 1e-9).all()
+    for i in np.flatnonzero(ok)[:5]:
+        u, J, k = no.nmpc_local_opt(fnn_model, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0[i], xref[i], uref[i], u_init=r["u"][i])
+        assert abs(J - r["objective"][i]) <= 1e-6 * abs(J) and mo.u0_metric(r["u"][i, 0], u[0], qt["umin"], qt["umax"]) < 1e-4
+
+
+def test_reference_relation_linear_vs_nonlinear(qt, fnn_model):
+    """The one numeric statement the reference's tests make about this path (test/computation_mpc_test.jl:152,163): for the
+    FNN model at horizon 5 from x0 = 0.6, the linear-method and NL-method state predictions agree within 0.5."""
+    H = 5
+    A, B, P, rho, c = _design(fnn_model, qt, H)
+    p = mo.pack_params(qt["x0"], qt["x_ref"], qt["u_ref"])
+    v, _ = mo.qp_exact(c, p[0])
+    lin = mo.recover(c, v[None], p)
+    nl = no.nmpc_sqp(fnn_model, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], qt["x0"][None], qt["x_ref"][None], qt["u_ref"][None], rho)
+    assert np.abs(lin["x"] - nl["x"]).max() < 0.5 and np.abs(lin["e_x"] - nl["e_x"]).max() < 0.5
