@@ -5,8 +5,8 @@
 //     OUT[b][:] = R[b][:] * T          (T symmetric, cached per system, L2 resident)
 // with the ADMM elementwise step (relaxation, box projection, dual update, next right-hand side, residual partials)
 // fused into the epilogue, so the state is read and written exactly once per iteration.  Operand tiles are staged into
-// padded shared-memory rows by the TMA engine (cp.async.bulk, one 128-byte row per copy, mbarrier complete_tx) four
-// stages deep; the MMA is DMMA.8x8x4 (FP64 has no tcgen05 kind) with 32x32 per-warp register tiles.
+// padded shared-memory rows with 16-byte cp.async copies, STAGES deep; the MMA is DMMA.8x8x4 (FP64 has no tcgen05 kind)
+// with 32x32 per-warp register tiles.
 // Terminated problems are written out and the active rows are compacted so the GEMM shrinks with the batch.
 #include "admm_stream.cuh"
 
@@ -18,9 +18,9 @@ namespace mpcb {
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 16, LDS_ = 20, STAGES = 4, THREADS = 256;
+constexpr int BM = 128, BN = 64, BK = 16, LDS_ = 20, STAGES = 3, THREADS = 256;
 constexpr int STAGE_DOUBLES = (BM + BN) * LDS_;
-constexpr size_t SMEM_BYTES = sizeof(double) * STAGE_DOUBLES * STAGES + 64;
+constexpr size_t SMEM_BYTES = sizeof(double) * STAGE_DOUBLES * STAGES;
 
 enum : int { MODE_NORMAL = 0, MODE_SAVE_YP = 1, MODE_CHECK = 2 };
 
@@ -42,23 +42,6 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-               "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ double dmaxf(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dclamp(double w, double lo, double hi) { const double t = w < lo ? lo : w; return t > hi ? hi : t; }
 __device__ __forceinline__ void atomic_max_nn(unsigned long long* addr, double v) {   // v >= 0: bit patterns order like the values
@@ -66,8 +49,22 @@ __device__ __forceinline__ void atomic_max_nn(unsigned long long* addr, double v
 }
 
 // Tiled GEMM core: acc[mt][nt2][2] for the warp's 32x32 tile of OUT = In * M (M symmetric, row-major == column-major).
+// Operand tiles [rows][BK] are staged with 16-byte cp.async (LDGSTS, L2 -> shared memory without a register round trip)
+// into rows padded to LDS_ doubles, so that the 64-bit fragment loads of every half-warp hit 32 distinct banks.  One
+// __syncthreads per k-tile: it publishes the tile that just landed and retires the stage the next prefetch overwrites.
+// (History: the first version staged these tiles with per-row cp.async.bulk + mbarrier copies of 128 bytes; ncu showed the
+// DMMA pipe 17 % active with the warps parked on the barrier behind the TMA queue -- 192 tiny bulk copies per k-tile --
+// see profiles/r01/prof_stream_lti_r01a.txt.  FP64 mma.sync fragments need padded rows, which the tensor-map TMA cannot
+// produce, so the copy engine of choice here is LDGSTS.)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ In, const double* __restrict__ M, int rows, int NTp, int bm0, int bn0,
-                                          double (&acc)[4][4][2], double* smem, uint64_t* full) {
+                                          double (&acc)[4][4][2], double* smem) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, l4 = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   const int KT = NTp / BK;
@@ -76,33 +73,36 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ In, const d
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  auto issue = [&](int kt) {   // warp 0 only
-    const int s = kt % STAGES;
-    double* sA = smem + s * STAGE_DOUBLES;
-    double* sB = sA + BM * LDS_;
-    if (lane == 0) mbar_expect_tx(&full[s], (BM + BN) * BK * sizeof(double));
-    __syncwarp();
+  // this thread's 16-byte chunks of a stage: (BM + BN) rows x (BK / 2) chunks, THREADS chunks per pass
+  constexpr int CPR = BK / 2;                                  // chunks per row
+  constexpr int PASSES = (BM + BN) * CPR / THREADS;
+  static_assert((BM + BN) * CPR % THREADS == 0, "tile must divide evenly over the CTA");
+  const double* src[PASSES];
+  int dst[PASSES];
 #pragma unroll
-    for (int i = 0; i < BM / 32; i++) {
-      const int rloc = lane + 32 * i;
-      const int row = min(bm0 + rloc, rows - 1);      // tail tile: re-read the last row, masked in the epilogue
-      bulk_g2s(sA + rloc * LDS_, In + (size_t)row * NTp + kt * BK, BK * sizeof(double), &full[s]);
-    }
+  for (int q = 0; q < PASSES; q++) {
+    const int c = tid + q * THREADS, r = c / CPR, cc = c % CPR;
+    if (r < BM) src[q] = In + (size_t)min(bm0 + r, rows - 1) * NTp + cc * 2;      // tail tile: re-read the last row, masked in the epilogue
+    else src[q] = M + (size_t)(bn0 + r - BM) * NTp + cc * 2;
+    dst[q] = r * LDS_ + cc * 2;
+  }
+  auto issue = [&](int kt) {
+    double* st = smem + (kt % STAGES) * STAGE_DOUBLES;
 #pragma unroll
-    for (int i = 0; i < BN / 32; i++) {
-      const int rloc = lane + 32 * i;
-      bulk_g2s(sB + rloc * LDS_, M + (size_t)(bn0 + rloc) * NTp + kt * BK, BK * sizeof(double), &full[s]);
-    }
+    for (int q = 0; q < PASSES; q++) cp_async16(st + dst[q], src[q] + kt * BK);
   };
-
-  if (warp == 0)
-    for (int kt = 0; kt < STAGES && kt < KT; kt++) issue(kt);
-
+#pragma unroll
+  for (int kt = 0; kt < STAGES - 1; kt++) {
+    if (kt < KT) issue(kt);
+    cp_async_commit();
+  }
   for (int kt = 0; kt < KT; kt++) {
-    const int s = kt % STAGES;
-    mbar_wait(&full[s], (kt / STAGES) & 1);
-    const double* sA = smem + s * STAGE_DOUBLES + (wm * 32 + g) * LDS_ + l4;
-    const double* sB = smem + s * STAGE_DOUBLES + BM * LDS_ + (wn * 32 + g) * LDS_ + l4;
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
+    cp_async_commit();
+    const double* sA = smem + (kt % STAGES) * STAGE_DOUBLES + (wm * 32 + g) * LDS_ + l4;
+    const double* sB = smem + (kt % STAGES) * STAGE_DOUBLES + BM * LDS_ + (wn * 32 + g) * LDS_ + l4;
 #pragma unroll
     for (int k4 = 0; k4 < BK / 4; k4++) {
       double a[4], b[4];
@@ -115,23 +115,15 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ In, const d
 #pragma unroll
         for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
-    __syncthreads();   // every warp is done with stage s: hand it back to the TMA producer
-    if (warp == 0 && kt + STAGES < KT) issue(kt + STAGES);
   }
+  cp_async_wait<0>();
 }
 
-__global__ void __launch_bounds__(THREADS, 1) stream_iter_kernel(const IterParams P) {
-  extern __shared__ __align__(128) double smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGE_DOUBLES * STAGES);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(THREADS, 2) stream_iter_kernel(const IterParams P) {
+  extern __shared__ __align__(16) double smem[];
   const int bn0 = blockIdx.x * BN, bm0 = blockIdx.y * BM;
   double acc[4][4][2];
-  gemm_tile(P.Rin, P.T, P.rows, P.NTp, bm0, bn0, acc, smem, full);
+  gemm_tile(P.Rin, P.T, P.rows, P.NTp, bm0, bn0, acc, smem);
 
   // ---- fused ADMM step on the accumulator fragments: row b = problem, columns n, n+1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
@@ -221,18 +213,11 @@ struct CheckParams {
   double* Out;        // optional: raw product (used for A' dy of the certificate), may be null
   int rows, NTp, nz, mode;   // mode 0: dual residual reductions ; 1: store product only
 };
-__global__ void __launch_bounds__(THREADS, 1) stream_check_kernel(const CheckParams P) {
-  extern __shared__ __align__(128) double smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGE_DOUBLES * STAGES);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  __syncthreads();
+__global__ void __launch_bounds__(THREADS, 2) stream_check_kernel(const CheckParams P) {
+  extern __shared__ __align__(16) double smem[];
   const int bn0 = blockIdx.x * BN, bm0 = blockIdx.y * BM;
   double acc[4][4][2];
-  gemm_tile(P.In, P.C, P.rows, P.NTp, bm0, bn0, acc, smem, full);
+  gemm_tile(P.In, P.C, P.rows, P.NTp, bm0, bn0, acc, smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
 #pragma unroll

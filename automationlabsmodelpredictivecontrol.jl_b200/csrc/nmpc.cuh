@@ -310,11 +310,14 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         __syncwarp();
       }
       double part = 0.0;                 // 1/2 du' Hc du
+      for (int e = lane; e < nz; e += 32) scol[e] = uu[e] - ur[e % nu];
+      __syncwarp();
       for (int e = lane; e < nz; e += 32) {
         double s = 0.0;
-        for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], uu[j] - ur[j % nu], s);
-        part = fma(0.5 * (uu[e] - ur[e % nu]), s, part);
+        for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
+        part = fma(0.5 * scol[e], s, part);
       }
+      __syncwarp();
       return warp_sum(J + part);
     };
 
@@ -323,19 +326,23 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
     bool have_traj = false;
     for (sqp_it = 1; sqp_it <= P.sqp_max_iter; sqp_it++) {
       // ---------------------------------------------------------------- 1. linearise along the trajectory of u
-      for (int o = lane; o < nz * ldk; o += 32) { const int a = o / ldk, c = o - a * ldk; K[o] = c < nz ? sHc[a * nz + c] : 0.0; }   // Hc symmetric
+      for (int a = 0; a < nz; a++)
+        for (int c = lane; c < ldk; c += 32) K[a * ldk + c] = c < nz ? sHc[a * nz + c] : 0.0;
       for (int o = lane; o < nx * nz; o += 32) { G0[o] = 0.0; G1[o] = 0.0; }
       for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
       __syncwarp();
       double J0 = 0.0;
       {
         double part = 0.0;
+        for (int e = lane; e < nz; e += 32) scol[e] = su[e] - ur[e % nu];
+        __syncwarp();
         for (int e = lane; e < nz; e += 32) {
           double s = 0.0;
-          for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], su[j] - ur[j % nu], s);
+          for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
           sg[e] = s;
-          part = fma(0.5 * (su[e] - ur[e % nu]), s, part);
+          part = fma(0.5 * scol[e], s, part);
         }
+        __syncwarp();
         for (int i = lane; i < nx; i += 32) {
           double s = 0.0;
           for (int j = 0; j < nx; j++) s = fma(sQ[j * nx + i], x0[j] - xr[j], s);
@@ -350,13 +357,13 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, lane);
         const int ncol = (k + 1) * nu;                 // non-zero columns of Gamma_{k+1}
         // Gamma_{k+1} = A_k Gamma_k, block k = B_k            (stored [i][c], c fastest)
-        for (int o = lane; o < nx * ncol; o += 32) {
-          const int i = o / ncol, c = o - i * ncol;
-          double s;
-          if (c >= k * nu) s = AB[(nx + c - k * nu) * nx + i];
-          else { s = 0.0; for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * nz + c], s); }
-          Gn[i * nz + c] = s;
-        }
+        for (int i = 0; i < nx; i++)
+          for (int c = lane; c < ncol; c += 32) {
+            double s;
+            if (c >= k * nu) s = AB[(nx + c - k * nu) * nx + i];
+            else { s = 0.0; for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * nz + c], s); }
+            Gn[i * nz + c] = s;
+          }
         const double* W = (k + 1 == H) ? sPt : sQ;
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; se[i] = v - xr[i]; }
         __syncwarp();
@@ -367,19 +374,21 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
           J0 = fma(se[i], s, J0);
         }
         // W Gamma into the idle buffer
-        for (int o = lane; o < nx * ncol; o += 32) {
-          const int i = o / ncol, c = o - i * ncol;
-          double s = 0.0;
-          for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], Gn[j * nz + c], s);
-          Gc[i * nz + c] = s;
-        }
+        for (int i = 0; i < nx; i++)
+          for (int c = lane; c < ncol; c += 32) {
+            double s = 0.0;
+            for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], Gn[j * nz + c], s);
+            Gc[i * nz + c] = s;
+          }
         __syncwarp();
         // K += 2 Gamma' (W Gamma),  g += 2 Gamma' (W e)
-        for (int o = lane; o < ncol * ncol; o += 32) {
-          const int a = o / ncol, c = o - a * ncol;
-          double s = 0.0;
-          for (int i = 0; i < nx; i++) s = fma(Gn[i * nz + a], Gc[i * nz + c], s);
-          K[a * ldk + c] = fma(2.0, s, K[a * ldk + c]);
+        for (int a = 0; a < ncol; a++) {
+          double* Ka = K + a * ldk;
+          for (int c = lane; c < ncol; c += 32) {
+            double s = 0.0;
+            for (int i = 0; i < nx; i++) s = fma(Gn[i * nz + a], Gc[i * nz + c], s);
+            Ka[c] = fma(2.0, s, Ka[c]);
+          }
         }
         for (int a = lane; a < ncol; a += 32) {
           double s = 0.0;
@@ -407,11 +416,12 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         __syncwarp();
         for (int j = lane; j < nz; j += 32) K[pv * ldk + j] = (j == pv) ? dinv : K[pv * ldk + j] * dinv;
         __syncwarp();
-        for (int o = lane; o < nz * nz; o += 32) {
-          const int i = o / nz, j = o - i * nz;
+        for (int i = 0; i < nz; i++) {              // rows one by one, the row spread over the lanes (no index division)
           if (i == pv) continue;
           const double fct = scol[i];
-          K[i * ldk + j] = (j == pv) ? -fct * dinv : fma(-fct, K[pv * ldk + j], K[i * ldk + j]);
+          double* Ki = K + i * ldk;
+          const double* Kp = K + pv * ldk;
+          for (int j = lane; j < nz; j += 32) Ki[j] = (j == pv) ? -fct * dinv : fma(-fct, Kp[j], Ki[j]);
         }
         __syncwarp();
       }

@@ -79,6 +79,39 @@ def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="eq
                       "solves_per_s": round(n / ms * 1e3), "tflops_active_rows": round(fl / ms / 1e9, 2), "launches": m.timing()["kernel_launches"]}), flush=True)
 
 
+def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
+    """NMPC with a neural dynamics model, SQP kernel."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    from conftest import load_nn_fixture
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
+    m = load_nn_fixture(fixture)
+    cls = mpc.ResNet if m.arch == "resnet" else mpc.Fnn
+    f = cls(m.W_in, list(zip(m.W_h, m.b_h)), m.W_out, activation=m.activation)
+    sys_ = mpc.ConstrainedBlackBoxControlDiscreteSystem(f, 4, 2, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_programming_type="non_linear", **kw)
+    mod = C.tuning.modeler
+    x0_h, xref_h, uref_h = bench.make_batch(n, 0)
+    dev = torch.device("cuda", 0)
+    x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
+    status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev); inner = torch.empty(n, dtype=torch.int32, device=dev)
+    u = torch.empty((n, H, 2), dtype=torch.float64, device=dev); x = torch.empty((n, H + 1, 4), dtype=torch.float64, device=dev)
+    eu = torch.empty_like(u); ex = torch.empty_like(x); obj = torch.empty(n, dtype=torch.float64, device=dev)
+    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 1
+    io.status = status.data_ptr(); io.iters = iters.data_ptr(); io.inner_iters = inner.data_ptr()
+    io.u = u.data_ptr(); io.x = x.data_ptr(); io.e_u = eu.data_ptr(); io.e_x = ex.data_ptr(); io.objective = obj.data_ptr()
+    st = torch.cuda.current_stream().cuda_stream
+    mod.solve_batch_device(io, st); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); mod.solve_batch_device(io, st); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    it = iters.cpu().numpy(); inn = inner.cpu().numpy(); stt = status.cpu().numpy()
+    ms = min(ts)
+    print(json.dumps({"cfg": "nmpc", "fixture": fixture, "H": H, "n": n, "ms": round(ms, 3), "solves_per_s": round(n / ms * 1e3), "sqp_iters_mean": round(float(it.mean()), 2),
+                      "sqp_iters_max": int(it.max()), "inner_mean": round(float(inn.mean()), 1), "solved": float((stt == 1).mean()), "stalled": float((stt == 2).mean()),
+                      "maxiter": float((stt == -2).mean()), "rho": round(mod.design()["rho"], 4)}), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--set", default="qt")
     a = ap.parse_args()
@@ -96,6 +129,16 @@ if __name__ == "__main__":
     elif a.set == "hsweep":
         for H in (10, 20, 30, 50, 75, 100, 150, 200):
             run(H, 16384, 1e-7, 5, 0.0, reps=2)
+    elif a.set == "nmpc":
+        for fx in ("qt_resnet_model.json", "qt_fnn_tanh_model.json", "qt_resnet_swish_model.json", "qt_fnn_model.json"):
+            run_nmpc(fx)
+        run_nmpc("qt_resnet_model.json", n=65536)
+    elif a.set == "nmpc1":
+        run_nmpc("qt_fnn_tanh_model.json", reps=1)
+    elif a.set == "lti1":
+        run_lti(scale=1.0, reps=1)
+    elif a.set == "h50":
+        run(50, 16384, 1e-7, 5, 0.0, reps=1)
     elif a.set == "lti":
         for scale in (0.1, 0.3, 1.0):
             run_lti(scale=scale)
