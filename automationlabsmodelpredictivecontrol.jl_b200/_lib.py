@@ -48,7 +48,7 @@ class BatchIO(C.Structure):
 
 class Timing(C.Structure):
     _fields_ = [("h2d_ms", C.c_float), ("solve_ms", C.c_float), ("recover_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("total_ms", C.c_float), ("batch", C.c_int64), ("total_iterations", C.c_int64), ("kernel_launches", C.c_int32)]
+                ("total_ms", C.c_float), ("batch", C.c_int64), ("total_iterations", C.c_int64), ("kernel_launches", C.c_int32), ("chunks", C.c_int32)]
 
 
 class NnDesc(C.Structure):

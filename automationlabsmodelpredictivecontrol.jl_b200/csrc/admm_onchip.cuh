@@ -53,7 +53,8 @@ struct OnchipParams {
   int32_t* iters;
   double* pres;
   double* dres;
-  unsigned long long* counter;  // work queue head (zeroed before launch)
+  unsigned long long* counter;  // [0] work queue head, [1] CTAs that have drained it; both zero at launch, the last CTA to
+                                // finish re-zeroes them so that back-to-back launches need no memset in between
 };
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
@@ -405,6 +406,12 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
       }
       pi = -1;
     }
+  }
+  // every warp of this CTA has seen the queue empty: the last CTA of the grid re-arms the queue for the next launch
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long prev = atomicAdd(P.counter + 1, 1ULL);
+    if (prev == (unsigned long long)gridDim.x - 1ULL) { P.counter[0] = 0ULL; P.counter[1] = 0ULL; }
   }
 }
 

@@ -43,7 +43,9 @@ struct mpcb_handle {
   mpcb_timing timing;
   int NT = 0;  // padded operator size of the on-chip kernel
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // device-to-host leg of the pipelined host entry
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t chunk_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // per-system constants
   DevBuf<double> Tfrag, Cfrag, Lt, lo, hi, rho, rinv, A, B, Q, R, S, P;
   DevBuf<unsigned long long> counter;
@@ -55,6 +57,7 @@ struct mpcb_handle {
   // pinned staging for pageable user memory
   PinBuf<double> stage_in, stage_out;
   PinBuf<int32_t> stage_int;
+  PinBuf<double> small_io;     // small batches: inputs and outputs live in one page-locked block the kernels access directly
   int onchip_blocks_per_sm = 0;
   size_t recover_smem_set = 0;
 };
@@ -126,7 +129,8 @@ int upload_design(mpcb_handle* h) {
   CUDA_TRY(upload(h->R, D.R.a.data(), D.R.a.size()));
   CUDA_TRY(upload(h->S, D.S.a.data(), D.S.a.size()));
   CUDA_TRY(upload(h->P, D.P.a.data(), D.P.a.size()));
-  CUDA_TRY(h->counter.ensure(1));
+  CUDA_TRY(h->counter.ensure(2));
+  CUDA_TRY(cudaMemset(h->counter.p, 0, 2 * sizeof(unsigned long long)));   // once: the on-chip kernel re-arms it itself
   if (h->info.kernel == MPCB_KERNEL_ONCHIP) {
     const int NT = h->NT, nt = D.nt, np = D.np;
     std::vector<double> tf = to_fragments(D.T, nt, NT), cf = to_fragments(D.C, nt, NT);
@@ -166,7 +170,6 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
   if (!d_dres) { CUDA_TRY(h->dres.ensure(Bn)); d_dres = h->dres.p; }
   int launches = 0;
   if (h->info.kernel == MPCB_KERNEL_ONCHIP) {
-    CUDA_TRY(cudaMemsetAsync(h->counter.p, 0, sizeof(unsigned long long), st));
     OnchipParams P;
     P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
     P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu;
@@ -290,8 +293,11 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   h->NT = (kernel == MPCB_KERNEL_ONCHIP) ? ((D.nt + 7) / 8) * 8 : mpcb::stream_padded(D.nt);
   h->info.nt_pad = h->NT;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
+  if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
   for (auto& e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
+  for (auto& e : h->chunk_ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
   rc = upload_design(h);
   if (rc != MPCB_OK) { std::string keep = g_err; mpcb_destroy(h); return fail(rc, keep); }
   *out = h;
@@ -308,8 +314,10 @@ void mpcb_destroy(mpcb_handle* h) {
     b->release();
   h->status.release(); h->iters.release(); h->counter.release();
   mpcb::stream_release(h->sc, h->sw);
-  h->stage_in.release(); h->stage_out.release(); h->stage_int.release();
+  h->stage_in.release(); h->stage_out.release(); h->stage_int.release(); h->small_io.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+  if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -354,6 +362,120 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
   cudaStream_t st = h->stream;
   const size_t nx = D.nx, nu = D.nu, H = D.H, nz = D.nz, nt = D.nt;
   const size_t n_xref = hio->xref_broadcast ? nx : nx * Bn, n_uref = hio->uref_broadcast ? nu : nu * Bn;
+
+  // ---- small batches (the closed-loop, one-problem-at-a-time use of update_initialization! / calculate!): no copy
+  // engine at all.  Inputs are placed in one page-locked block that the kernels read over PCIe directly, the results are
+  // written by the kernels straight into the same block (zero-copy), so a call is two kernel launches and one
+  // synchronisation instead of ~14 DMA operations of a few hundred bytes each.
+  {
+    struct Seg { const double* src; double* dst; size_t n; };
+    const size_t n_in[5] = {nx * (size_t)Bn, n_xref, n_uref, hio->warm_u ? nz * (size_t)Bn : 0, hio->warm_y ? nt * (size_t)Bn : 0};
+    const size_t n_out[9] = {hio->u ? nz * (size_t)Bn : 0, hio->e_u ? nz * (size_t)Bn : 0, hio->x ? nx * (H + 1) * (size_t)Bn : 0,
+                             hio->e_x ? nx * (H + 1) * (size_t)Bn : 0, hio->u0 ? nu * (size_t)Bn : 0, (size_t)Bn, (size_t)Bn,
+                             hio->objective ? (size_t)Bn : 0, hio->y ? nt * (size_t)Bn : 0};
+    size_t total = 2 * (size_t)Bn;   // status + iters as int32 pairs -> Bn doubles, rounded up
+    for (size_t n : n_in) total += (n + 1) & ~(size_t)1;
+    for (size_t n : n_out) total += (n + 1) & ~(size_t)1;
+    if (total * sizeof(double) <= 96 * 1024) {
+      CUDA_TRY(h->small_io.ensure(total));
+      double* base = h->small_io.p;
+      size_t off = 0;
+      auto take = [&](size_t n) { double* q = base + off; off += (n + 1) & ~(size_t)1; return q; };
+      const double* srcs[5] = {hio->x0, hio->xref, hio->uref, hio->warm_u, hio->warm_y};
+      double* in_p[5];
+      for (int i = 0; i < 5; i++) {
+        in_p[i] = n_in[i] ? take(n_in[i]) : nullptr;
+        if (n_in[i]) std::memcpy(in_p[i], srcs[i], n_in[i] * sizeof(double));
+      }
+      double* out_p[9];
+      for (int i = 0; i < 9; i++) out_p[i] = n_out[i] ? take(n_out[i]) : nullptr;
+      int32_t* ints = reinterpret_cast<int32_t*>(take((size_t)Bn));
+      mpcb_batch_io dio = *hio;
+      dio.x0 = in_p[0]; dio.xref = in_p[1]; dio.uref = in_p[2]; dio.warm_u = in_p[3]; dio.warm_y = in_p[4];
+      dio.u = out_p[0]; dio.e_u = out_p[1]; dio.x = out_p[2]; dio.e_x = out_p[3]; dio.u0 = out_p[4];
+      dio.prim_res = out_p[5]; dio.dual_res = out_p[6]; dio.objective = out_p[7]; dio.y = out_p[8];
+      dio.status = ints; dio.iters = ints + Bn;
+      int rc = enqueue_device(h, dio, st, nullptr);
+      if (rc != MPCB_OK) return rc;
+      CUDA_TRY(cudaStreamSynchronize(st));
+      double* dsts[9] = {hio->u, hio->e_u, hio->x, hio->e_x, hio->u0, hio->prim_res, hio->dual_res, hio->objective, hio->y};
+      for (int i = 0; i < 9; i++)
+        if (dsts[i] && n_out[i]) std::memcpy(dsts[i], out_p[i], n_out[i] * sizeof(double));
+      if (hio->status) std::memcpy(hio->status, ints, Bn * sizeof(int32_t));
+      if (hio->iters) std::memcpy(hio->iters, ints + Bn, Bn * sizeof(int32_t));
+      long long tot = 0;
+      for (long long i = 0; i < Bn; i++) tot += ints[Bn + i];
+      h->timing.total_iterations = tot;
+      h->timing.h2d_ms = h->timing.solve_ms = h->timing.recover_ms = h->timing.d2h_ms = h->timing.total_ms = 0.f;   // no events on this path
+      h->timing.chunks = 1;
+      return MPCB_OK;
+    }
+  }
+
+  // ---- large batches in page-locked user memory: the result download (PCIe, ~2 KB per quadruple-tank problem) dwarfs the
+  // solve, so the batch is cut into chunks and chunk c's download (copy stream) overlaps chunk c+1's upload + solve +
+  // recover (compute stream).  Per-problem results do not depend on the chunking.
+  {
+    const double* in_ptrs[5] = {hio->x0, hio->xref, hio->uref, hio->warm_u, hio->warm_y};
+    double* out_ptrs[9] = {hio->u, hio->e_u, hio->x, hio->e_x, hio->u0, hio->prim_res, hio->dual_res, hio->objective, hio->y};
+    const size_t per_out[9] = {nz, nz, nx * (H + 1), nx * (H + 1), nu, 1, 1, 1, nt};
+    size_t out_bytes = 0;
+    bool pinned = (hio->status == nullptr || is_pinned_or_device(hio->status)) && (hio->iters == nullptr || is_pinned_or_device(hio->iters));
+    for (const double* q : in_ptrs) if (q && !is_pinned_or_device(q)) pinned = false;
+    for (int i = 0; i < 9; i++)
+      if (out_ptrs[i]) { out_bytes += per_out[i] * (size_t)Bn * sizeof(double); if (!is_pinned_or_device(out_ptrs[i])) pinned = false; }
+    if (pinned && h->info.kernel == MPCB_KERNEL_ONCHIP && out_bytes >= ((size_t)32 << 20) && Bn >= 4096) {
+      const int nch = (int)std::min<size_t>(8, std::max<size_t>(2, out_bytes / ((size_t)16 << 20)));
+      const long long Bc = (Bn + nch - 1) / nch;
+      DevBuf<double>* in_dev[5] = {&h->x0, &h->xref, &h->uref, &h->warm_v, &h->warm_y};
+      const size_t per_in[5] = {nx, hio->xref_broadcast ? 0 : nx, hio->uref_broadcast ? 0 : nu, nz, nt};
+      const size_t n_in[5] = {nx * (size_t)Bn, n_xref, n_uref, nz * (size_t)Bn, nt * (size_t)Bn};
+      for (int i = 0; i < 5; i++) if (in_ptrs[i]) CUDA_TRY(in_dev[i]->ensure(n_in[i]));
+      DevBuf<double>* out_dev[9] = {&h->u, &h->e_u, &h->x, &h->e_x, &h->u0, &h->pres, &h->dres, &h->obj, &h->y};
+      for (int i = 0; i < 9; i++) if (out_ptrs[i]) CUDA_TRY(out_dev[i]->ensure(per_out[i] * (size_t)Bn));
+      CUDA_TRY(h->status.ensure(Bn)); CUDA_TRY(h->iters.ensure(Bn)); CUDA_TRY(h->stage_int.ensure(2 * (size_t)Bn));
+      CUDA_TRY(cudaEventRecord(h->ev[0], st));
+      for (int i = 1; i < 3; i++)          // broadcast references: once
+        if (per_in[i] == 0) CUDA_TRY(cudaMemcpyAsync(in_dev[i]->p, in_ptrs[i], n_in[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+      int launches = 0;
+      for (int c = 0; c < nch; c++) {
+        const long long b0 = c * Bc, bn = std::min<long long>(Bc, Bn - b0);
+        if (bn <= 0) break;
+        for (int i = 0; i < 5; i++)
+          if (in_ptrs[i] && per_in[i])
+            CUDA_TRY(cudaMemcpyAsync(in_dev[i]->p + b0 * per_in[i], in_ptrs[i] + b0 * per_in[i], bn * per_in[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+        mpcb_batch_io dio = *hio;
+        dio.batch = bn;
+        dio.x0 = h->x0.p + b0 * nx; dio.xref = h->xref.p + b0 * per_in[1]; dio.uref = h->uref.p + b0 * per_in[2];
+        dio.warm_u = hio->warm_u ? h->warm_v.p + b0 * nz : nullptr; dio.warm_y = hio->warm_y ? h->warm_y.p + b0 * nt : nullptr;
+        double** slots[9] = {&dio.u, &dio.e_u, &dio.x, &dio.e_x, &dio.u0, &dio.prim_res, &dio.dual_res, &dio.objective, &dio.y};
+        for (int i = 0; i < 9; i++) *slots[i] = out_ptrs[i] ? out_dev[i]->p + b0 * per_out[i] : nullptr;
+        dio.status = h->status.p + b0; dio.iters = h->iters.p + b0;
+        int rc = enqueue_device(h, dio, st, nullptr);
+        if (rc != MPCB_OK) return rc;
+        launches += h->timing.kernel_launches;
+        CUDA_TRY(cudaEventRecord(h->chunk_ev[c], st));
+        CUDA_TRY(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[c], 0));
+        for (int i = 0; i < 9; i++)
+          if (out_ptrs[i])
+            CUDA_TRY(cudaMemcpyAsync(out_ptrs[i] + b0 * per_out[i], out_dev[i]->p + b0 * per_out[i], bn * per_out[i] * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(h->stage_int.p + b0, h->status.p + b0, bn * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(h->stage_int.p + Bn + b0, h->iters.p + b0, bn * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+      }
+      CUDA_TRY(cudaEventRecord(h->ev[4], h->copy_stream));
+      CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      if (hio->status) std::memcpy(hio->status, h->stage_int.p, Bn * sizeof(int32_t));
+      if (hio->iters) std::memcpy(hio->iters, h->stage_int.p + Bn, Bn * sizeof(int32_t));
+      long long tot = 0;
+      for (long long i = 0; i < Bn; i++) tot += h->stage_int.p[Bn + i];
+      h->timing.total_iterations = tot; h->timing.batch = Bn; h->timing.kernel_launches = launches; h->timing.chunks = nch;
+      h->timing.h2d_ms = h->timing.solve_ms = h->timing.recover_ms = h->timing.d2h_ms = 0.f;   // the phases overlap: only the total is meaningful
+      cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[4]);
+      return MPCB_OK;
+    }
+  }
+  h->timing.chunks = 1;
 
   // ---- inputs: pageable user memory goes through one pinned staging buffer, pinned memory is copied directly
   struct In { const double* src; DevBuf<double>* dst; size_t n; };

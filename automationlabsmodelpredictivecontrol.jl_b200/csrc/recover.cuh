@@ -128,7 +128,9 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
 
 // Register-resident specialisation for small systems (the quadruple tank is NX=4, NU=2): the deviation state, the
 // references and the weights' rows live in registers, every result column leaves as 16-byte stores that fill whole
-// 32-byte sectors, and the per-problem input row is fetched with 16-byte loads.
+// 32-byte sectors, and the per-problem input row is fetched with 16-byte loads.  The rollout is a dependent chain, so the
+// inputs are prefetched RCH steps at a time, one chunk ahead of the chunk being rolled: the loads of chunk c+1 are in
+// flight while chunk c computes and stores (ncu on the first version: 24 long-scoreboard stall cycles per issue).
 template <int NX, int NU>
 __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const RecoverParams P) {
   __shared__ double sA[NX * NX], sB[NX * NU], sQ[NX * NX], sPt[NX * NX], sR[NU * NU], sS[NU * NU];
@@ -139,38 +141,54 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const Re
   __syncthreads();
   const long long p = (long long)blockIdx.x * RECOVER_THREADS + tid;
   if (p >= P.batch) return;
-  double e[NX], xr[NX], ur[NU], eu[NU], up[NU];
+  constexpr int NM = NX > NU ? NX : NU;
+  constexpr int RCH = 4;
+  double e[NX], xr[NX], ur[NU], up[NU];
 #pragma unroll
   for (int i = 0; i < NX; i++) { xr[i] = P.xref[(P.xref_bc ? 0 : p) * NX + i]; e[i] = P.x0[p * NX + i] - xr[i]; }
 #pragma unroll
   for (int i = 0; i < NU; i++) { ur[i] = P.uref[(P.uref_bc ? 0 : p) * NU + i]; up[i] = 0.0; }
-  const double* v = P.v + p * (long long)NU * H;
-  auto store_run = [](double* dst, const double (&val)[NX > NU ? NX : NU], int n) {
+  const double* __restrict__ v = P.v + p * (long long)NU * H;
+  double* __restrict__ o_u = P.u ? P.u + p * (long long)H * NU : nullptr;
+  double* __restrict__ o_eu = P.e_u ? P.e_u + p * (long long)H * NU : nullptr;
+  double* __restrict__ o_x = P.x ? P.x + p * (long long)(H + 1) * NX : nullptr;
+  double* __restrict__ o_ex = P.e_x ? P.e_x + p * (long long)(H + 1) * NX : nullptr;
+  const bool vec_in = (NU & 1) == 0 && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
+  auto load_chunk = [&](int c, double (&dst)[RCH * NU]) {
+    const int k0 = c * RCH;
+    if (vec_in && k0 + RCH <= H) {
+#pragma unroll
+      for (int i = 0; i < RCH * NU; i += 2) { const double2 t = *reinterpret_cast<const double2*>(v + k0 * NU + i); dst[i] = t.x; dst[i + 1] = t.y; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RCH * NU; i++) dst[i] = (k0 * NU + i < H * NU) ? v[k0 * NU + i] : 0.0;
+    }
+  };
+  auto store_run = [](double* dst, const double (&val)[NM], int n) {
     if ((n & 1) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-      for (int i = 0; i < (NX > NU ? NX : NU); i += 2)
+      for (int i = 0; i < NM; i += 2)
         if (i < n) *reinterpret_cast<double2*>(dst + i) = make_double2(val[i], val[i + 1]);
     } else {
 #pragma unroll
-      for (int i = 0; i < (NX > NU ? NX : NU); i++)
+      for (int i = 0; i < NM; i++)
         if (i < n) dst[i] = val[i];
     }
   };
-  constexpr int NM = NX > NU ? NX : NU;
   double J = 0.0;
-  for (int k = 0; k <= H; k++) {
+  // writes x_k, e_x_k and returns e' W e
+  auto emit_state = [&](int k, const double* W) {
     double tmp[NM];
-    if (P.e_x) {
+    if (o_ex) {
 #pragma unroll
       for (int i = 0; i < NX; i++) tmp[i] = e[i];
-      store_run(P.e_x + (p * (H + 1) + k) * NX, tmp, NX);
+      store_run(o_ex + k * NX, tmp, NX);
     }
-    if (P.x) {
+    if (o_x) {
 #pragma unroll
       for (int i = 0; i < NX; i++) tmp[i] = e[i] + xr[i];
-      store_run(P.x + (p * (H + 1) + k) * NX, tmp, NX);
+      store_run(o_x + k * NX, tmp, NX);
     }
-    const double* W = (k == H) ? sPt : sQ;
     double quad = 0.0;
 #pragma unroll
     for (int i = 0; i < NX; i++) {
@@ -179,57 +197,68 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const Re
       for (int j = 0; j < NX; j++) s = fma(W[j * NX + i], e[j], s);
       quad = fma(e[i], s, quad);
     }
-    J += quad;
-    if (k == H) break;
-    double uk[NM];
+    return quad;
+  };
+  double cur[RCH * NU], nxt[RCH * NU];
+  load_chunk(0, cur);
+  const int nchunks = (H + RCH - 1) / RCH;
+  for (int c = 0; c < nchunks; c++) {
+    if (c + 1 < nchunks) load_chunk(c + 1, nxt);
 #pragma unroll
-    for (int i = 0; i < NU; i++) { uk[i] = v[k * NU + i]; eu[i] = uk[i] - ur[i]; }
-    if (P.u) store_run(P.u + (p * H + k) * NU, uk, NU);
-    if (P.e_u) {
+    for (int q = 0; q < RCH; q++) {
+      const int k = c * RCH + q;
+      if (k < H) {
+        J += emit_state(k, sQ);
+        double uk[NM], eu[NM];
 #pragma unroll
-      for (int i = 0; i < NU; i++) tmp[i] = eu[i];
-      store_run(P.e_u + (p * H + k) * NU, tmp, NU);
-    }
-    if (k == 0 && P.u0) store_run(P.u0 + p * NU, uk, NU);
-    if (P.use_R) {
-      double quadr = 0.0;
-#pragma unroll
-      for (int i = 0; i < NU; i++) {
-        double s = 0.0;
-#pragma unroll
-        for (int j = 0; j < NU; j++) s = fma(sR[j * NU + i], eu[j], s);
-        quadr = fma(eu[i], s, quadr);
-      }
-      J += quadr;
-      if (P.use_S) {
-        if (k > 0) {
-          double quads = 0.0;
+        for (int i = 0; i < NU; i++) { uk[i] = cur[q * NU + i]; eu[i] = uk[i] - ur[i]; }
+        if (o_u) store_run(o_u + k * NU, uk, NU);
+        if (o_eu) store_run(o_eu + k * NU, eu, NU);
+        if (k == 0 && P.u0) store_run(P.u0 + p * NU, uk, NU);
+        if (P.use_R) {
+          double quadr = 0.0;
 #pragma unroll
           for (int i = 0; i < NU; i++) {
             double s = 0.0;
 #pragma unroll
-            for (int j = 0; j < NU; j++) s = fma(sS[j * NU + i], up[j] - uk[j], s);
-            quads = fma(up[i] - uk[i], s, quads);
+            for (int j = 0; j < NU; j++) s = fma(sR[j * NU + i], eu[j], s);
+            quadr = fma(eu[i], s, quadr);
           }
-          J += quads;
+          J += quadr;
+          if (P.use_S) {
+            if (k > 0) {        // delta_u_{k-1} = u_{k-1} - u_k  (design_mpc.jl:429-432)
+              double quads = 0.0;
+#pragma unroll
+              for (int i = 0; i < NU; i++) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < NU; j++) s = fma(sS[j * NU + i], up[j] - uk[j], s);
+                quads = fma(up[i] - uk[i], s, quads);
+              }
+              J += quads;
+            }
+#pragma unroll
+            for (int i = 0; i < NU; i++) up[i] = uk[i];
+          }
+        }
+        double en[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < NX; j++) s = fma(sA[j * NX + i], e[j], s);
+#pragma unroll
+          for (int j = 0; j < NU; j++) s = fma(sB[j * NX + i], eu[j], s);
+          en[i] = s;
         }
 #pragma unroll
-        for (int i = 0; i < NU; i++) up[i] = uk[i];
+        for (int i = 0; i < NX; i++) e[i] = en[i];
       }
     }
-    double en[NX];
 #pragma unroll
-    for (int i = 0; i < NX; i++) {
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; j++) s = fma(sA[j * NX + i], e[j], s);
-#pragma unroll
-      for (int j = 0; j < NU; j++) s = fma(sB[j * NX + i], eu[j], s);
-      en[i] = s;
-    }
-#pragma unroll
-    for (int i = 0; i < NX; i++) e[i] = en[i];
+    for (int i = 0; i < RCH * NU; i++) cur[i] = nxt[i];
   }
+  J += emit_state(H, sPt);
   if (P.objective) P.objective[p] = J;
 }
 

@@ -44,6 +44,26 @@ struct MpcbBatchIO
     u::Ptr{Cdouble}; e_u::Ptr{Cdouble}; x::Ptr{Cdouble}; e_x::Ptr{Cdouble}; u0::Ptr{Cdouble}
     status::Ptr{Int32}; iters::Ptr{Int32}
     prim_res::Ptr{Cdouble}; dual_res::Ptr{Cdouble}; objective::Ptr{Cdouble}; y::Ptr{Cdouble}
+    inner_iters::Ptr{Int32}
+end
+
+# nonlinear path (include/mpcb200.h, section "Nonlinear path")
+struct MpcbNnDesc
+    arch::Int32; activation::Int32; nx::Int32; nu::Int32; n_neurons::Int32; n_hidden::Int32
+    W_in::Ptr{Cdouble}; W_hidden::Ptr{Cdouble}; b_hidden::Ptr{Cdouble}; W_out::Ptr{Cdouble}
+end
+
+struct MpcbNmpcDesc
+    nn::Ptr{MpcbNnDesc}; horizon::Int32
+    Q::Ptr{Cdouble}; R::Ptr{Cdouble}; S::Ptr{Cdouble}; P::Ptr{Cdouble}
+    umin::Ptr{Cdouble}; umax::Ptr{Cdouble}; xref::Ptr{Cdouble}; uref::Ptr{Cdouble}
+    terminal_mode::Int32
+end
+
+struct MpcbNmpcSettings
+    qp::MpcbSettings
+    sqp_tol::Cdouble; ls_armijo::Cdouble; ls_noise::Cdouble
+    sqp_max_iter::Int32; ls_max_halvings::Int32
 end
 
 last_error() = unsafe_string(ccall((:mpcb_last_error, libmpcb200), Cstring, ()))
@@ -126,10 +146,98 @@ function calculate!(m::B200Modeler)
         io = MpcbBatchIO(batch, pointer(m.X0), pointer(m.xref), pointer(m.uref), size(m.xref, 2) == 1 ? 1 : 0,
                          size(m.uref, 2) == 1 ? 1 : 0, C_NULL, C_NULL, pointer(m.u), pointer(m.e_u), pointer(m.x), pointer(m.e_x),
                          C_NULL, pointer(m.status), pointer(m.iterations), pointer(m.prim_res), pointer(m.dual_res),
-                         pointer(m.objective), C_NULL)
+                         pointer(m.objective), C_NULL, C_NULL)
         check(ccall((:mpcb_solve_linear_batch, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbBatchIO}), m.handle, io), "mpcb_solve_linear_batch")
     end
     return m
+end
+
+# ---- nonlinear path: Flux chain -> mpcb_nn_desc, NL modeler + Ipopt -> mpcb_create_nmpc / mpcb_solve_nmpc_batch -----
+const _ACTIVATION_IDS = Dict("relu" => 0, "tanh" => 1, "sigmoid" => 2, "σ" => 2, "swish" => 3, "identity" => 4)
+
+"""
+    nn_arrays(params, arch, activation)
+
+`params = collect(Flux.params(system.f))` parsed exactly as the reference's NL modelers do (fnn.jl:88-107): params[1] = W_in,
+then (W_j, b_j) pairs, params[end] = W_out.  Returns Float64 copies (Flux stores Float32) and the descriptor fields.
+"""
+function nn_arrays(params::Vector, arch::Symbol, activation::String)
+    W_in = Matrix{Float64}(params[1]); W_out = Matrix{Float64}(params[end])
+    n_hidden = (length(params) - 2) ÷ 2
+    W_h = n_hidden == 0 ? zeros(1) : vcat((vec(Matrix{Float64}(params[i])) for i in 2:2:length(params)-1)...)
+    b_h = n_hidden == 0 ? zeros(1) : vcat((Vector{Float64}(params[i+1]) for i in 2:2:length(params)-1)...)
+    nx = size(W_out, 1); nu = size(W_in, 2) - nx
+    return (W_in, W_h, b_h, W_out), (Int32(arch == :resnet ? 1 : 0), Int32(_ACTIVATION_IDS[activation]), Int32(nx), Int32(nu),
+                                       Int32(size(W_in, 1)), Int32(n_hidden))
+end
+
+mutable struct B200NonlinearModeler
+    handle::Ptr{Cvoid}
+    nx::Int; nu::Int; horizon::Int
+    X0::Matrix{Float64}; xref::Matrix{Float64}; uref::Matrix{Float64}
+    u::Array{Float64,3}; e_u::Array{Float64,3}; x::Array{Float64,3}; e_x::Array{Float64,3}
+    status::Vector{Int32}; iterations::Vector{Int32}; inner_iterations::Vector{Int32}
+    step::Vector{Float64}; objective::Vector{Float64}
+end
+
+"Replaces `_model_predictive_control_modeler_implementation(::NonLinearProgramming, ::Fnn | ::ResNet, ...)` (fnn.jl:63-189,
+resnet.jl:62-188) + `_JuMP_model_definition(::NonLinearProgramming, ::ipopt_solver_def)`."
+function B200NonlinearModeler(params::Vector, arch::Symbol, activation::String, Q, R, S, P, umin, umax, horizon::Int, xref, uref;
+                              settings::Union{Nothing,MpcbNmpcSettings}=nothing)
+    arrs, f = nn_arrays(params, arch, activation)
+    mats = map(M -> Matrix{Float64}(M), (Q, R, S, P)); vecs = map(v -> Vector{Float64}(v), (umin, umax, xref, uref))
+    st = Ref{MpcbNmpcSettings}()
+    settings === nothing ? ccall((:mpcb_default_nmpc_settings, libmpcb200), Cvoid, (Ref{MpcbNmpcSettings},), st) : (st[] = settings)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve arrs mats vecs begin
+        nd = Ref(MpcbNnDesc(f..., map(pointer, arrs)...))
+        GC.@preserve nd begin
+            d = MpcbNmpcDesc(Base.unsafe_convert(Ptr{MpcbNnDesc}, nd), horizon, map(pointer, mats)..., map(pointer, vecs)..., 0)
+            check(ccall((:mpcb_create_nmpc, libmpcb200), Cint, (Ref{MpcbNmpcDesc}, Ref{MpcbNmpcSettings}, Ref{Ptr{Cvoid}}), d, st, h), "mpcb_create_nmpc")
+        end
+    end
+    nx, nu = Int(f[3]), Int(f[4])
+    m = B200NonlinearModeler(h[], nx, nu, horizon, zeros(nx, 0), zeros(nx, 1), zeros(nu, 1), zeros(nu, horizon, 0), zeros(nu, horizon, 0),
+                             zeros(nx, horizon + 1, 0), zeros(nx, horizon + 1, 0), Int32[], Int32[], Int32[], Float64[], Float64[])
+    finalizer(m -> ccall((:mpcb_destroy_nmpc, libmpcb200), Cvoid, (Ptr{Cvoid},), m.handle), m)
+    return m
+end
+
+function update_initialization!(m::B200NonlinearModeler, X0::AbstractMatrix; xref::AbstractMatrix, uref::AbstractMatrix)
+    m.X0 = Matrix{Float64}(X0); m.xref = Matrix{Float64}(xref); m.uref = Matrix{Float64}(uref)
+end
+
+function calculate!(m::B200NonlinearModeler)
+    nx, nu, H = m.nx, m.nu, m.horizon
+    batch = size(m.X0, 2)
+    batch > 0 || error("calculate!: call update_initialization! first")
+    m.u = Array{Float64}(undef, nu, H, batch); m.e_u = similar(m.u); m.x = Array{Float64}(undef, nx, H + 1, batch); m.e_x = similar(m.x)
+    m.status = Vector{Int32}(undef, batch); m.iterations = similar(m.status); m.inner_iterations = similar(m.status)
+    m.step = Vector{Float64}(undef, batch); m.objective = similar(m.step)
+    GC.@preserve m begin
+        io = MpcbBatchIO(batch, pointer(m.X0), pointer(m.xref), pointer(m.uref), size(m.xref, 2) == 1 ? 1 : 0, size(m.uref, 2) == 1 ? 1 : 0,
+                         C_NULL, C_NULL, pointer(m.u), pointer(m.e_u), pointer(m.x), pointer(m.e_x), C_NULL, pointer(m.status),
+                         pointer(m.iterations), pointer(m.step), C_NULL, pointer(m.objective), C_NULL, pointer(m.inner_iterations))
+        check(ccall((:mpcb_solve_nmpc_batch, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbBatchIO}), m.handle, io), "mpcb_solve_nmpc_batch")
+    end
+    return m
+end
+
+"AutomationLabsSystems.proceed_system_linearization for a Flux chain (fnn.jl:42, design_mpc.jl:319-323) on the GPU."
+function linearize(params::Vector, arch::Symbol, activation::String, x::Vector{Float64}, u::Vector{Float64}; device::Integer=0)
+    arrs, f = nn_arrays(params, arch, activation)
+    nx, nu = Int(f[3]), Int(f[4])
+    A = Matrix{Float64}(undef, nx, nx); B = Matrix{Float64}(undef, nx, nu)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve arrs begin
+        nd = MpcbNnDesc(f..., map(pointer, arrs)...)
+        check(ccall((:mpcb_create_nn, libmpcb200), Cint, (Ref{MpcbNnDesc}, Int32, Ref{Ptr{Cvoid}}), nd, device, h), "mpcb_create_nn")
+    end
+    rc = ccall((:mpcb_nn_jacobian_batch, libmpcb200), Cint, (Ptr{Cvoid}, Int64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+               h[], 1, x, u, C_NULL, A, B)
+    ccall((:mpcb_destroy_nn, libmpcb200), Cvoid, (Ptr{Cvoid},), h[])
+    check(rc, "mpcb_nn_jacobian_batch")
+    return A, B
 end
 
 # In AutomationLabsModelPredictiveControl (computation_mpc.jl) the two new methods read:

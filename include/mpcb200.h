@@ -145,12 +145,14 @@ typedef struct {
   int32_t* inner_iters; /* NMPC only: total ADMM iterations over all SQP iterations (NULL = skip) */
 } mpcb_batch_io;
 
-/* CUDA-event timings of the last solve call on this handle, milliseconds. */
+/* CUDA-event timings of the last solve call on this handle, milliseconds (all 0 on the zero-copy small-batch path). */
 typedef struct {
   float h2d_ms, solve_ms, recover_ms, d2h_ms, total_ms;
   int64_t batch;
   int64_t total_iterations; /* sum over problems of ADMM iterations */
   int32_t kernel_launches;  /* kernels of this library launched by the call */
+  int32_t chunks;           /* > 1: the host entry pipelined the batch in this many chunks (download of chunk c overlaps the
+                               solve of chunk c+1); the per-phase times are then 0 and only total_ms is meaningful */
 } mpcb_timing;
 
 int mpcb_version(void);

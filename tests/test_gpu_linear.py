@@ -262,3 +262,41 @@ def test_random_lti_generic_recover(mpc):
     assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
     ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in range(48)])
     assert mo.u0_metric(res["u0"][:48], ex[:, :nu], -np.ones(nu), np.ones(nu)).max() < U0_TOL
+
+
+def test_pipelined_host_entry_equals_plain(mpc, qt):
+    """Large batches in page-locked memory take the chunked, download-overlapped path of mpcb_solve_linear_batch; the
+    per-problem results must be bit-identical to the plain path (pageable arrays), and the one-problem zero-copy path
+    must agree with both."""
+    import ctypes
+    n, H = 20000, 20
+    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=1e-7, mpc_b200_eps_rel=1e-7, mpc_b200_check_every=5, mpc_b200_sigma=0.0)
+    m = C.tuning.modeler
+    x0, xref, uref = qt_batch(qt, n)
+    plain = m.solve_batch(x0, xref, uref)
+    assert m.timing()["chunks"] == 1
+    L = mpc._lib.lib()
+    shapes = {"u": (n, H, 2), "e_u": (n, H, 2), "x": (n, H + 1, 4), "e_x": (n, H + 1, 4), "u0": (n, 2), "objective": (n,), "prim_res": (n,), "dual_res": (n,)}
+    ptrs = []
+
+    def pinned(shape, dtype=np.float64):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = L.mpcb_alloc_pinned(nbytes); assert p
+        ptrs.append(p)
+        return np.frombuffer((ctypes.c_char * nbytes).from_address(p), dtype=dtype).reshape(shape)
+
+    try:
+        out = {k: pinned(s) for k, s in shapes.items()}
+        out["status"] = pinned((n,), np.int32); out["iters"] = pinned((n,), np.int32)
+        px0 = pinned(x0.shape); px0[:] = x0
+        pxr = pinned(xref.shape); pxr[:] = xref
+        pur = pinned(uref.shape); pur[:] = uref
+        m.solve_batch(px0, pxr, pur, out=out)
+        assert m.timing()["chunks"] > 1
+        for k in list(shapes) + ["status", "iters"]:
+            assert np.array_equal(out[k], plain[k]), k
+        one = m.solve_batch(x0[:3], xref[:3], uref)          # zero-copy small path
+        for k in ("u", "x", "objective", "iters"):
+            assert np.array_equal(one[k], plain[k][:3]), k
+    finally:
+        for p in ptrs: L.mpcb_free_pinned(p)
