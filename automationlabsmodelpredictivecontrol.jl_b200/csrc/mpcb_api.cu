@@ -421,7 +421,8 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
     const size_t per_out[9] = {nz, nz, nx * (H + 1), nx * (H + 1), nu, 1, 1, 1, nt};
     size_t out_bytes = 0;
     bool pinned = (hio->status == nullptr || is_pinned_or_device(hio->status)) && (hio->iters == nullptr || is_pinned_or_device(hio->iters));
-    for (const double* q : in_ptrs) if (q && !is_pinned_or_device(q)) pinned = false;
+    const bool bc_in[5] = {false, hio->xref_broadcast != 0, hio->uref_broadcast != 0, false, false};
+    for (int i = 0; i < 5; i++) if (in_ptrs[i] && !bc_in[i] && !is_pinned_or_device(in_ptrs[i])) pinned = false;   // broadcast references are tiny: staged below
     for (int i = 0; i < 9; i++)
       if (out_ptrs[i]) { out_bytes += per_out[i] * (size_t)Bn * sizeof(double); if (!is_pinned_or_device(out_ptrs[i])) pinned = false; }
     if (pinned && h->info.kernel == MPCB_KERNEL_ONCHIP && out_bytes >= ((size_t)32 << 20) && Bn >= 4096) {
@@ -435,8 +436,13 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
       for (int i = 0; i < 9; i++) if (out_ptrs[i]) CUDA_TRY(out_dev[i]->ensure(per_out[i] * (size_t)Bn));
       CUDA_TRY(h->status.ensure(Bn)); CUDA_TRY(h->iters.ensure(Bn)); CUDA_TRY(h->stage_int.ensure(2 * (size_t)Bn));
       CUDA_TRY(cudaEventRecord(h->ev[0], st));
-      for (int i = 1; i < 3; i++)          // broadcast references: once
-        if (per_in[i] == 0) CUDA_TRY(cudaMemcpyAsync(in_dev[i]->p, in_ptrs[i], n_in[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(h->stage_in.ensure(nx + nu));
+      for (int i = 1; i < 3; i++)          // broadcast references: once, through the handle's page-locked staging block
+        if (per_in[i] == 0) {
+          double* stg = h->stage_in.p + (i == 1 ? 0 : nx);
+          std::memcpy(stg, in_ptrs[i], n_in[i] * sizeof(double));
+          CUDA_TRY(cudaMemcpyAsync(in_dev[i]->p, stg, n_in[i] * sizeof(double), cudaMemcpyHostToDevice, st));
+        }
       int launches = 0;
       for (int c = 0; c < nch; c++) {
         const long long b0 = c * Bc, bn = std::min<long long>(Bc, Bn - b0);

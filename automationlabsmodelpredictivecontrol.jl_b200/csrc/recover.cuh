@@ -126,95 +126,101 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
   if (P.objective) P.objective[p] = J;
 }
 
-// Register-resident specialisation for small systems (the quadruple tank is NX=4, NU=2): the deviation state, the
-// references and the weights' rows live in registers, every result column leaves as 16-byte stores that fill whole
-// 32-byte sectors, and the per-problem input row is fetched with 16-byte loads.  The rollout is a dependent chain, so the
-// inputs are prefetched RCH steps at a time, one chunk ahead of the chunk being rolled: the loads of chunk c+1 are in
-// flight while chunk c computes and stores (ncu on the first version: 24 long-scoreboard stall cycles per issue).
+// Specialisation for small systems (the quadruple tank is NX=4, NU=2): one lane per problem rolls the deviation dynamics
+// in registers; everything that touches HBM goes through a per-warp shared-memory tile so that the global accesses are
+// WARP-COOPERATIVE: a chunk of RCH steps of 32 problems is staged (inputs in, results out) and moved with 16-byte
+// accesses in which consecutive lanes cover consecutive bytes of one problem's row (128-byte runs for x / e_x, 64-byte
+// runs for u / e_u at NX=4, NU=2).  History (profiles/r01/recover_qt_h20_ncu_full*.txt): with per-lane 16-byte stores
+// every store instruction touched 32 different 128-byte lines, the kernel sat on lg/mio-throttle and long-scoreboard
+// stalls and reached 1.5 TB/s.
+constexpr int RECOVER_RCH = 4;
+template <int NX, int NU>
+__host__ __device__ constexpr int recover_small_warp_doubles() {
+  return 32 * (2 * (RECOVER_RCH * NX + 2) + 3 * (RECOVER_RCH * NU + 2));
+}
+
+// moves a [32 problems][n doubles] tile (pitch `pitch`) between shared memory and rows of global memory that are
+// `gstride` doubles apart; 16-byte accesses when the row geometry allows it
+template <bool STORE>
+__device__ __forceinline__ void warp_tile_copy(double* tile, int pitch, double* gbase, long long gstride, int n, int nvalid, int lane, bool vec_ok) {
+  if (vec_ok) {
+    const int cpr = n >> 1;                                   // 16-byte chunks per row
+    for (int idx = lane; idx < nvalid * cpr; idx += 32) {
+      const int r = idx / cpr, c = idx - r * cpr;
+      double2* g = reinterpret_cast<double2*>(gbase + r * gstride) + c;
+      double2* t = reinterpret_cast<double2*>(tile + r * pitch) + c;
+      if (STORE) *g = *t; else *t = *g;
+    }
+  } else {
+    for (int idx = lane; idx < nvalid * n; idx += 32) {
+      const int r = idx / n, c = idx - r * n;
+      if (STORE) gbase[r * gstride + c] = tile[r * pitch + c]; else tile[r * pitch + c] = gbase[r * gstride + c];
+    }
+  }
+}
+
 template <int NX, int NU>
 __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const RecoverParams P) {
   __shared__ double sA[NX * NX], sB[NX * NU], sQ[NX * NX], sPt[NX * NX], sR[NU * NU], sS[NU * NU];
-  const int tid = threadIdx.x, H = P.H;
+  extern __shared__ __align__(16) double tiles[];
+  constexpr int RCH = RECOVER_RCH, PX = RCH * NX + 2, PU = RCH * NU + 2;
+  const int tid = threadIdx.x, H = P.H, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < NX * NX; i += RECOVER_THREADS) { sA[i] = P.A[i]; sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
   for (int i = tid; i < NX * NU; i += RECOVER_THREADS) sB[i] = P.B[i];
   for (int i = tid; i < NU * NU; i += RECOVER_THREADS) { sR[i] = P.R[i]; sS[i] = P.S ? P.S[i] : 0.0; }
   __syncthreads();
-  const long long p = (long long)blockIdx.x * RECOVER_THREADS + tid;
-  if (p >= P.batch) return;
-  constexpr int NM = NX > NU ? NX : NU;
-  constexpr int RCH = 4;
+  double* tX = tiles + warp * recover_small_warp_doubles<NX, NU>();
+  double* tEX = tX + 32 * PX;
+  double* tV = tEX + 32 * PX;
+  double* tU = tV + 32 * PU;
+  double* tEU = tU + 32 * PU;
+  const long long pbase = ((long long)blockIdx.x * (RECOVER_THREADS / 32) + warp) * 32;
+  if (pbase >= P.batch) return;
+  const int nvalid = (int)((P.batch - pbase) < 32 ? (P.batch - pbase) : 32);
+  const bool active = lane < nvalid;
+  const long long p = pbase + (active ? lane : 0);
+  // 16-byte accesses need even row lengths and 16-byte aligned bases (cudaMalloc'ed arrays are; offsets into them may not be)
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vx = (NX % 2 == 0) && ((((long long)(H + 1) * NX) & 1) == 0) && al16(P.x) && al16(P.e_x);
+  const bool vu = (NU % 2 == 0) && ((((long long)H * NU) & 1) == 0) && al16(P.u) && al16(P.e_u) && al16(P.v);
   double e[NX], xr[NX], ur[NU], up[NU];
 #pragma unroll
   for (int i = 0; i < NX; i++) { xr[i] = P.xref[(P.xref_bc ? 0 : p) * NX + i]; e[i] = P.x0[p * NX + i] - xr[i]; }
 #pragma unroll
   for (int i = 0; i < NU; i++) { ur[i] = P.uref[(P.uref_bc ? 0 : p) * NU + i]; up[i] = 0.0; }
-  const double* __restrict__ v = P.v + p * (long long)NU * H;
-  double* __restrict__ o_u = P.u ? P.u + p * (long long)H * NU : nullptr;
-  double* __restrict__ o_eu = P.e_u ? P.e_u + p * (long long)H * NU : nullptr;
-  double* __restrict__ o_x = P.x ? P.x + p * (long long)(H + 1) * NX : nullptr;
-  double* __restrict__ o_ex = P.e_x ? P.e_x + p * (long long)(H + 1) * NX : nullptr;
-  const bool vec_in = (NU & 1) == 0 && ((reinterpret_cast<uintptr_t>(v) & 15) == 0);
-  auto load_chunk = [&](int c, double (&dst)[RCH * NU]) {
-    const int k0 = c * RCH;
-    if (vec_in && k0 + RCH <= H) {
-#pragma unroll
-      for (int i = 0; i < RCH * NU; i += 2) { const double2 t = *reinterpret_cast<const double2*>(v + k0 * NU + i); dst[i] = t.x; dst[i + 1] = t.y; }
-    } else {
-#pragma unroll
-      for (int i = 0; i < RCH * NU; i++) dst[i] = (k0 * NU + i < H * NU) ? v[k0 * NU + i] : 0.0;
-    }
-  };
-  auto store_run = [](double* dst, const double (&val)[NM], int n) {
-    if ((n & 1) == 0 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-      for (int i = 0; i < NM; i += 2)
-        if (i < n) *reinterpret_cast<double2*>(dst + i) = make_double2(val[i], val[i + 1]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < NM; i++)
-        if (i < n) dst[i] = val[i];
-    }
-  };
   double J = 0.0;
-  // writes x_k, e_x_k and returns e' W e
-  auto emit_state = [&](int k, const double* W) {
-    double tmp[NM];
-    if (o_ex) {
-#pragma unroll
-      for (int i = 0; i < NX; i++) tmp[i] = e[i];
-      store_run(o_ex + k * NX, tmp, NX);
-    }
-    if (o_x) {
-#pragma unroll
-      for (int i = 0; i < NX; i++) tmp[i] = e[i] + xr[i];
-      store_run(o_x + k * NX, tmp, NX);
-    }
-    double quad = 0.0;
-#pragma unroll
-    for (int i = 0; i < NX; i++) {
-      double s = 0.0;
-#pragma unroll
-      for (int j = 0; j < NX; j++) s = fma(W[j * NX + i], e[j], s);
-      quad = fma(e[i], s, quad);
-    }
-    return quad;
-  };
-  double cur[RCH * NU], nxt[RCH * NU];
-  load_chunk(0, cur);
-  const int nchunks = (H + RCH - 1) / RCH;
+  const int nchunks = (H + 1 + RCH - 1) / RCH;
   for (int c = 0; c < nchunks; c++) {
-    if (c + 1 < nchunks) load_chunk(c + 1, nxt);
+    const int k0 = c * RCH;
+    const int ns_x = (H + 1 - k0) < RCH ? (H + 1 - k0) : RCH;        // states k0 .. k0 + ns_x - 1
+    const int ns_u = (H - k0) < RCH ? (H - k0 > 0 ? H - k0 : 0) : RCH;
+    if (ns_u > 0) warp_tile_copy<false>(tV, PU, const_cast<double*>(P.v) + pbase * (long long)NU * H + k0 * NU, (long long)NU * H, ns_u * NU, nvalid, lane, vu);
+    __syncwarp();
 #pragma unroll
     for (int q = 0; q < RCH; q++) {
-      const int k = c * RCH + q;
-      if (k < H) {
-        J += emit_state(k, sQ);
-        double uk[NM], eu[NM];
+      const int k = k0 + q;
+      if (k <= H) {
+        const double* W = (k == H) ? sPt : sQ;
+        double quad = 0.0;
 #pragma unroll
-        for (int i = 0; i < NU; i++) { uk[i] = cur[q * NU + i]; eu[i] = uk[i] - ur[i]; }
-        if (o_u) store_run(o_u + k * NU, uk, NU);
-        if (o_eu) store_run(o_eu + k * NU, eu, NU);
-        if (k == 0 && P.u0) store_run(P.u0 + p * NU, uk, NU);
+        for (int i = 0; i < NX; i++) {
+          tEX[lane * PX + q * NX + i] = e[i];
+          tX[lane * PX + q * NX + i] = e[i] + xr[i];
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < NX; j++) s = fma(W[j * NX + i], e[j], s);
+          quad = fma(e[i], s, quad);
+        }
+        J += quad;
+      }
+      if (k < H) {
+        double uk[NU], eu[NU];
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+          uk[i] = tV[lane * PU + q * NU + i]; eu[i] = uk[i] - ur[i];
+          tU[lane * PU + q * NU + i] = uk[i]; tEU[lane * PU + q * NU + i] = eu[i];
+          if (k == 0 && P.u0 && active) P.u0[p * NU + i] = uk[i];
+        }
         if (P.use_R) {
           double quadr = 0.0;
 #pragma unroll
@@ -255,18 +261,33 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const Re
         for (int i = 0; i < NX; i++) e[i] = en[i];
       }
     }
-#pragma unroll
-    for (int i = 0; i < RCH * NU; i++) cur[i] = nxt[i];
+    __syncwarp();
+    const long long gx = pbase * (long long)(H + 1) * NX + (long long)k0 * NX, gu = pbase * (long long)H * NU + (long long)k0 * NU;
+    if (P.x) warp_tile_copy<true>(tX, PX, P.x + gx, (long long)(H + 1) * NX, ns_x * NX, nvalid, lane, vx);
+    if (P.e_x) warp_tile_copy<true>(tEX, PX, P.e_x + gx, (long long)(H + 1) * NX, ns_x * NX, nvalid, lane, vx);
+    if (ns_u > 0) {
+      if (P.u) warp_tile_copy<true>(tU, PU, P.u + gu, (long long)H * NU, ns_u * NU, nvalid, lane, vu);
+      if (P.e_u) warp_tile_copy<true>(tEU, PU, P.e_u + gu, (long long)H * NU, ns_u * NU, nvalid, lane, vu);
+    }
+    __syncwarp();
   }
-  J += emit_state(H, sPt);
-  if (P.objective) P.objective[p] = J;
+  if (P.objective && active) P.objective[p] = J;
 }
 
 // returns false when no specialisation exists (caller falls back to recover_kernel)
 inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
   const unsigned grid = (unsigned)((R.batch + RECOVER_THREADS - 1) / RECOVER_THREADS);
 #define MPCB_RS(NX_, NU_) \
-  if (R.nx == NX_ && R.nu == NU_) { recover_small_kernel<NX_, NU_><<<grid, RECOVER_THREADS, 0, st>>>(R); return true; }
+  if (R.nx == NX_ && R.nu == NU_) {                                                                                       \
+    constexpr size_t smem = sizeof(double) * (RECOVER_THREADS / 32) * recover_small_warp_doubles<NX_, NU_>();              \
+    static bool attr_set = false;                                                                                       \
+    if (smem > 48 * 1024 && !attr_set) {                                                                                \
+      cudaFuncSetAttribute(recover_small_kernel<NX_, NU_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+      attr_set = true;                                                                                                  \
+    }                                                                                                                   \
+    recover_small_kernel<NX_, NU_><<<grid, RECOVER_THREADS, smem, st>>>(R);                                             \
+    return true;                                                                                                        \
+  }
   MPCB_RS(2, 1) MPCB_RS(2, 2) MPCB_RS(3, 1) MPCB_RS(3, 2) MPCB_RS(4, 1) MPCB_RS(4, 2) MPCB_RS(4, 4) MPCB_RS(6, 2) MPCB_RS(6, 3)
   MPCB_RS(8, 2) MPCB_RS(8, 4)
 #undef MPCB_RS

@@ -1,0 +1,8 @@
+#!/bin/bash
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_linear.py -m gpu -x -q -k "pipelined or warm or ragged" > gpurun_out/pytest_gpu_f.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_f.log
+tail -15 gpurun_out/pytest_gpu_f.log
+python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_r01_f.json 2> gpurun_out/bench_f_err.log
+cat gpurun_out/bench_r01_f.json; tail -5 gpurun_out/bench_f_err.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:recover -s 3 -c 1 -o gpurun_out/prof_recover_r01e -f python tools/dev_bench.py --set onefull > gpurun_out/ncu_e2.log 2>&1
