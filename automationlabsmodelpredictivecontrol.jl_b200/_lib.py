@@ -51,6 +51,12 @@ class Timing(C.Structure):
                 ("total_ms", C.c_float), ("batch", C.c_int64), ("total_iterations", C.c_int64), ("kernel_launches", C.c_int32), ("chunks", C.c_int32)]
 
 
+class ClosedLoopIO(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("steps", C.c_int32), ("warm_start", C.c_int32), ("x0", C.c_void_p), ("xref", C.c_void_p),
+                ("uref", C.c_void_p), ("xref_broadcast", C.c_int32), ("uref_broadcast", C.c_int32), ("x_traj", C.c_void_p),
+                ("u_traj", C.c_void_p), ("iters_total", C.c_void_p), ("unsolved_steps", C.c_void_p)]
+
+
 class NnDesc(C.Structure):
     _fields_ = [("arch", C.c_int32), ("activation", C.c_int32), ("nx", C.c_int32), ("nu", C.c_int32), ("n_neurons", C.c_int32),
                 ("n_hidden", C.c_int32), ("W_in", _dp), ("W_hidden", _dp), ("b_hidden", _dp), ("W_out", _dp)]
@@ -70,7 +76,7 @@ class NmpcSettings(C.Structure):
 EXPORTED_SYMBOLS = (
     "mpcb_version", "mpcb_device_count", "mpcb_last_error", "mpcb_default_settings", "mpcb_dare", "mpcb_create_linear",
     "mpcb_destroy", "mpcb_get_info", "mpcb_get_timing", "mpcb_get_design", "mpcb_solve_linear_batch",
-    "mpcb_solve_linear_batch_device", "mpcb_alloc_pinned", "mpcb_free_pinned",
+    "mpcb_solve_linear_batch_device", "mpcb_alloc_pinned", "mpcb_free_pinned", "mpcb_closed_loop_linear_batch",
     "mpcb_create_nn", "mpcb_destroy_nn", "mpcb_nn_rollout_batch", "mpcb_nn_rollout_batch_device", "mpcb_nn_jacobian_batch",
     "mpcb_nn_jacobian_batch_device", "mpcb_default_nmpc_settings", "mpcb_create_nmpc", "mpcb_destroy_nmpc", "mpcb_nmpc_get_design",
     "mpcb_nmpc_get_timing", "mpcb_solve_nmpc_batch", "mpcb_solve_nmpc_batch_device",
@@ -100,6 +106,7 @@ def lib():
         L.mpcb_get_design.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _dp]
         L.mpcb_solve_linear_batch.argtypes = [C.c_void_p, C.POINTER(BatchIO)]
         L.mpcb_solve_linear_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIO), C.c_void_p]
+        L.mpcb_closed_loop_linear_batch.argtypes = [C.c_void_p, C.POINTER(ClosedLoopIO)]
         L.mpcb_dare.argtypes = [C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]
         L.mpcb_alloc_pinned.argtypes = [C.c_size_t]
         L.mpcb_alloc_pinned.restype = C.c_void_p

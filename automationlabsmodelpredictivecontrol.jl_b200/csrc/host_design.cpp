@@ -320,9 +320,15 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
   // rho
   if (!sym_extreme_eigs(D.Pc, D.lmin, D.lmax)) { err = "condensed Hessian is not positive definite (need R != 0 or full-rank Q)"; return MPCB_ERR_NUMERIC; }
   D.rho = s.rho > 0 ? s.rho : std::sqrt(D.lmin * D.lmax);
+  // General rows get rho / |G_i|^2: the per-row step size that row equilibration (OSQP's Ruiz scaling of A) would give.
+  // The rows of Gamma_k are tiny for slow plants (quadruple tank: |G_i|^2 ~ 1e-4..1e-3), and with a common rho the state
+  // box / terminal equality rows converge 10-200x slower (oracle experiment recorded in DESIGN.md section 3).
   D.rho_vec.assign(D.nt, D.rho);
-  for (int i = 0; i < mg; i++)
-    if (D.is_eq[nz + i]) D.rho_vec[nz + i] = s.rho_eq_scale * D.rho;
+  for (int i = 0; i < mg; i++) {
+    double rn = 0.0;
+    for (int j = 0; j < nz; j++) rn += D.G(i, j) * D.G(i, j);
+    D.rho_vec[nz + i] = (D.is_eq[nz + i] ? s.rho_eq_scale * D.rho : D.rho) / std::max(rn, 1e-12);
+  }
   // K = Pc + (sigma + rho) I + G' diag(rho_g) G ;  T = [I;G] K^-1 [I,G'] ;  C = [[Pc,G'],[G,0]]
   Mat K = D.Pc;
   for (int i = 0; i < nz; i++) K(i, i) += s.sigma + D.rho;

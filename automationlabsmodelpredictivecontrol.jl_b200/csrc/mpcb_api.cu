@@ -14,6 +14,7 @@
 #include "api_common.hpp"
 #include "admm_onchip.cuh"
 #include "admm_stream.cuh"
+#include "closed_loop.cuh"
 #include "host_design.hpp"
 #include "recover.cuh"
 
@@ -156,13 +157,15 @@ int upload_design(mpcb_handle* h) {
 }
 
 // Enqueue solve + recover on `st` with device-resident io.  Internal scratch is used for anything the caller skipped.
-int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cudaEvent_t ev_mid) {
+// `v_keep` (optional): device buffer [batch][nz] that receives the absolute inputs instead of the handle's scratch.
+int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cudaEvent_t ev_mid, double* v_keep = nullptr) {
   const mpcb::Design& D = h->D;
   const long long Bn = io.batch;
   if (Bn <= 0) return fail(MPCB_ERR_INVALID, "batch must be positive");
   if (!io.x0 || !io.xref || !io.uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
   if ((io.warm_u == nullptr) != (io.warm_y == nullptr)) return fail(MPCB_ERR_INVALID, "warm_u and warm_y must be given together");
-  CUDA_TRY(h->v.ensure((size_t)Bn * D.nz));
+  double* v_buf = v_keep;
+  if (!v_buf) { CUDA_TRY(h->v.ensure((size_t)Bn * D.nz)); v_buf = h->v.p; }
   int32_t* d_status = io.status; int32_t* d_iters = io.iters; double* d_pres = io.prim_res; double* d_dres = io.dual_res;
   if (!d_status) { CUDA_TRY(h->status.ensure(Bn)); d_status = h->status.p; }
   if (!d_iters) { CUDA_TRY(h->iters.ensure(Bn)); d_iters = h->iters.p; }
@@ -176,7 +179,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     P.rho_box = D.rho; P.sigma = h->st.sigma; P.alpha = h->st.alpha; P.eps_abs = h->st.eps_abs; P.eps_rel = h->st.eps_rel;
     P.eps_pinf = h->st.eps_prim_inf; P.max_iter = h->st.max_iter; P.check_every = h->st.check_every;
     P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
-    P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = h->v.p; P.y_out = io.y;
+    P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = v_buf; P.y_out = io.y;
     P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres; P.counter = h->counter.p;
     cudaError_t e = launch_onchip(h->NT, D.mg > 0, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
@@ -185,7 +188,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     std::string err;
     mpcb::StreamBatch sb;
     sb.batch = Bn; sb.x0 = io.x0; sb.xref = io.xref; sb.uref = io.uref; sb.xref_bc = io.xref_broadcast; sb.uref_bc = io.uref_broadcast;
-    sb.warm_v = io.warm_u; sb.warm_y = io.warm_y; sb.v_out = h->v.p; sb.y_out = io.y;
+    sb.warm_v = io.warm_u; sb.warm_y = io.warm_y; sb.v_out = v_buf; sb.y_out = io.y;
     sb.status = d_status; sb.iters = d_iters; sb.pres = d_pres; sb.dres = d_dres;
     int nl = 0;
     cudaError_t e = mpcb::stream_solve(h->D, h->st, h->sc, h->sw, sb, h->info.sm_count, st, &nl, err);
@@ -198,7 +201,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     R.A = h->A.p; R.B = h->B.p; R.Q = h->Q.p; R.R = h->R.p; R.S = h->S.p; R.Pt = h->P.p;
     R.nx = D.nx; R.nu = D.nu; R.H = D.H; R.use_R = D.use_R; R.use_S = D.use_S; R.batch = Bn;
     R.x0 = io.x0; R.xref = io.xref; R.uref = io.uref; R.xref_bc = io.xref_broadcast; R.uref_bc = io.uref_broadcast;
-    R.v = h->v.p; R.u = io.u; R.e_u = io.e_u; R.x = io.x; R.e_x = io.e_x; R.u0 = io.u0; R.objective = io.objective;
+    R.v = v_buf; R.u = io.u; R.e_u = io.e_u; R.x = io.x; R.e_x = io.e_x; R.u0 = io.u0; R.objective = io.objective;
     if (!mpcb::launch_recover_small(R, st)) {
       const int rt = mpcb::recover_threads_for(D.nx, D.nu);
       if (rt == 0) return fail(MPCB_ERR_INVALID, "result recovery: system too wide for the generic kernel (nx, nu)");
@@ -559,6 +562,72 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
   cudaEventElapsedTime(&h->timing.recover_ms, h->ev[2], h->ev[3]);
   cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[3], h->ev[4]);
   cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[4]);
+  return MPCB_OK;
+}
+
+int mpcb_closed_loop_linear_batch(mpcb_handle* h, const mpcb_closed_loop_io* cio) {
+  if (!h || !cio) return fail(MPCB_ERR_INVALID, "null argument");
+  const mpcb::Design& D = h->D;
+  const long long Bn = cio->batch;
+  const int T = cio->steps;
+  if (Bn <= 0 || T <= 0) return fail(MPCB_ERR_INVALID, "batch and steps must be positive");
+  if (!cio->x0 || !cio->xref || !cio->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  if (cio->warm_start && h->info.kernel != MPCB_KERNEL_ONCHIP) return fail(MPCB_ERR_INVALID, "warm-started closed loop needs the on-chip kernel (nz + mg <= 64)");
+  CUDA_TRY(cudaSetDevice(h->st.device));
+  cudaStream_t st = h->stream;
+  const size_t nx = D.nx, nu = D.nu, nz = D.nz, nt = D.nt, B = (size_t)Bn;
+  const size_t n_xref = cio->xref_broadcast ? nx : nx * B, n_uref = cio->uref_broadcast ? nu : nu * B;
+  // state ping-pong in x0 / warm_v's neighbours: dedicated buffers keep this independent of the batch entry's workspaces
+  DevBuf<double> xa, xb, va, vb, ya, yb, xtraj, utraj;
+  DevBuf<int32_t> itot, unsol;
+  auto cleanup = [&]() { xa.release(); xb.release(); va.release(); vb.release(); ya.release(); yb.release(); xtraj.release(); utraj.release(); itot.release(); unsol.release(); };
+#define CL_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return fail(MPCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  CL_TRY(xa.ensure(nx * B)); CL_TRY(xb.ensure(nx * B)); CL_TRY(va.ensure(nz * B)); CL_TRY(vb.ensure(nz * B)); CL_TRY(ya.ensure(nt * B)); CL_TRY(yb.ensure(nt * B));
+  CL_TRY(h->xref.ensure(n_xref)); CL_TRY(h->uref.ensure(n_uref)); CL_TRY(h->status.ensure(B)); CL_TRY(h->iters.ensure(B));
+  if (cio->x_traj) CL_TRY(xtraj.ensure(nx * (size_t)(T + 1) * B));
+  if (cio->u_traj) CL_TRY(utraj.ensure(nu * (size_t)T * B));
+  if (cio->iters_total) CL_TRY(itot.ensure(B));
+  if (cio->unsolved_steps) CL_TRY(unsol.ensure(B));
+  CL_TRY(cudaMemcpyAsync(xa.p, cio->x0, nx * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  CL_TRY(cudaMemcpyAsync(h->xref.p, cio->xref, n_xref * sizeof(double), cudaMemcpyHostToDevice, st));
+  CL_TRY(cudaMemcpyAsync(h->uref.p, cio->uref, n_uref * sizeof(double), cudaMemcpyHostToDevice, st));
+  CL_TRY(cudaEventRecord(h->ev[0], st));
+  int launches = 0;
+  double *xc = xa.p, *xn = xb.p, *vc = va.p, *vp = vb.p, *yc = ya.p, *yp = yb.p;
+  for (int t = 0; t < T; t++) {
+    mpcb_batch_io dio;
+    std::memset(&dio, 0, sizeof(dio));
+    dio.batch = Bn; dio.x0 = xc; dio.xref = h->xref.p; dio.uref = h->uref.p; dio.xref_broadcast = cio->xref_broadcast; dio.uref_broadcast = cio->uref_broadcast;
+    if (cio->warm_start && t > 0) { dio.warm_u = vp; dio.warm_y = yp; }
+    dio.status = h->status.p; dio.iters = h->iters.p;
+    dio.y = cio->warm_start ? yc : nullptr;
+    int rc = enqueue_device(h, dio, st, nullptr, vc);      // the absolute inputs land in vc: u0 for the plant, warm start for t+1
+    if (rc != MPCB_OK) { cleanup(); return rc; }
+    launches += h->timing.kernel_launches;
+    mpcb::PlantStepParams Pp;
+    Pp.A = h->A.p; Pp.B = h->B.p; Pp.nx = D.nx; Pp.nu = D.nu; Pp.nz = D.nz; Pp.t = t; Pp.steps = T; Pp.batch = Bn;
+    Pp.xref = h->xref.p; Pp.uref = h->uref.p; Pp.xref_bc = cio->xref_broadcast; Pp.uref_bc = cio->uref_broadcast;
+    Pp.v = vc; Pp.status = h->status.p; Pp.iters = h->iters.p; Pp.x_in = xc; Pp.x_out = xn;
+    Pp.x_traj = cio->x_traj ? xtraj.p : nullptr; Pp.u_traj = cio->u_traj ? utraj.p : nullptr;
+    Pp.iters_total = cio->iters_total ? itot.p : nullptr; Pp.unsolved = cio->unsolved_steps ? unsol.p : nullptr;
+    mpcb::plant_step_kernel<<<(unsigned)((Bn + 127) / 128), 128, 0, st>>>(Pp);
+    CL_TRY(cudaGetLastError());
+    launches += 1;
+    std::swap(xc, xn); std::swap(vc, vp); std::swap(yc, yp);
+  }
+  CL_TRY(cudaEventRecord(h->ev[3], st));
+  if (cio->x_traj) CL_TRY(cudaMemcpyAsync(cio->x_traj, xtraj.p, nx * (size_t)(T + 1) * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (cio->u_traj) CL_TRY(cudaMemcpyAsync(cio->u_traj, utraj.p, nu * (size_t)T * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (cio->iters_total) CL_TRY(cudaMemcpyAsync(cio->iters_total, itot.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (cio->unsolved_steps) CL_TRY(cudaMemcpyAsync(cio->unsolved_steps, unsol.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CL_TRY(cudaEventRecord(h->ev[4], st));
+  CL_TRY(cudaStreamSynchronize(st));
+#undef CL_TRY
+  cudaEventElapsedTime(&h->timing.solve_ms, h->ev[0], h->ev[3]);
+  cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[3], h->ev[4]);
+  h->timing.h2d_ms = 0.f; h->timing.recover_ms = 0.f; h->timing.total_ms = h->timing.solve_ms + h->timing.d2h_ms;
+  h->timing.batch = Bn; h->timing.kernel_launches = launches; h->timing.chunks = 1; h->timing.total_iterations = 0;
+  cleanup();
   return MPCB_OK;
 }
 

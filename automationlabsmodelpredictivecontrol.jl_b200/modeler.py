@@ -96,6 +96,23 @@ class B200Modeler:
         _lib.check(_lib.lib().mpcb_solve_linear_batch_device(self._h, C.byref(io), C.c_void_p(stream or 0)),
                    "mpcb_solve_linear_batch_device")
 
+    def closed_loop(self, x0, xref, uref, steps, warm_start=True):
+        """GPU-resident closed loop (mpcb_closed_loop_linear_batch): x0 (B, nx) -> x_traj (B, steps+1, nx), u_traj (B, steps, nu),
+        iters_total (B,), unsolved_steps (B,)."""
+        i = self.info
+        x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, np.float64))); Bn = x0.shape[0]
+        xref = np.ascontiguousarray(np.asarray(xref, np.float64)); uref = np.ascontiguousarray(np.asarray(uref, np.float64))
+        xb = xref.ndim == 1 or xref.shape[0] == 1 and Bn != 1
+        ub = uref.ndim == 1 or uref.shape[0] == 1 and Bn != 1
+        if x0.shape[1] != i.nx or xref.size != (i.nx if xb else i.nx * Bn) or uref.size != (i.nu if ub else i.nu * Bn):
+            raise ValueError("closed_loop: shapes")
+        out = {"x_traj": np.empty((Bn, steps + 1, i.nx)), "u_traj": np.empty((Bn, steps, i.nu)), "iters_total": np.empty(Bn, np.int32),
+               "unsolved_steps": np.empty(Bn, np.int32)}
+        io = _lib.ClosedLoopIO(Bn, int(steps), int(bool(warm_start)), x0.ctypes.data, xref.ctypes.data, uref.ctypes.data, int(xb), int(ub),
+                               out["x_traj"].ctypes.data, out["u_traj"].ctypes.data, out["iters_total"].ctypes.data, out["unsolved_steps"].ctypes.data)
+        _lib.check(_lib.lib().mpcb_closed_loop_linear_batch(self._h, C.byref(io)), "mpcb_closed_loop_linear_batch")
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().mpcb_destroy(self._h); self._h = None

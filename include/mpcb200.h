@@ -181,6 +181,29 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* host_io);
  * stream).  Asynchronous: returns after enqueueing. */
 int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* dev_io, void* cuda_stream);
 
+/* Closed-loop batched simulation, resident on the GPU: repeats { solve from the current state (warm-started from the
+ * previous step's solution and duals when warm_start != 0, as OSQP does inside one JuMP model); apply the first input;
+ * advance the controller's own deviation model  x+ = x_ref + A (x - x_ref) + B (u0 - u_ref)  (linear.jl:59) } `steps`
+ * times without leaving the device -- the update_initialization! / calculate! loop a user of the reference writes
+ * (computation_mpc.jl:17-55; pattern of test/computation_mpc_test.jl:94-103) for a whole batch of plants.
+ * HOST pointers.  x0 nx x batch; x_traj nx x (steps+1) x batch (column 1 = x0); u_traj nu x steps x batch; any output
+ * may be NULL.  Only for controllers on the on-chip kernel when warm_start != 0. */
+typedef struct {
+  int64_t batch;
+  int32_t steps;
+  int32_t warm_start;
+  const double* x0;
+  const double* xref;
+  const double* uref;
+  int32_t xref_broadcast;
+  int32_t uref_broadcast;
+  double* x_traj;
+  double* u_traj;
+  int32_t* iters_total;    /* per plant: ADMM iterations summed over the steps */
+  int32_t* unsolved_steps; /* per plant: steps whose solve did not end with MPCB_STATUS_SOLVED */
+} mpcb_closed_loop_io;
+int mpcb_closed_loop_linear_batch(mpcb_handle* h, const mpcb_closed_loop_io* host_io);
+
 /* Page-locked host memory helpers: arrays allocated here are copied to/from the device without the extra staging
  * copy that pageable memory needs (Julia: unsafe_wrap the pointer; Python: numpy.frombuffer). */
 void* mpcb_alloc_pinned(size_t bytes);

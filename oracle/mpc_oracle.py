@@ -321,10 +321,11 @@ def auto_rho(Pc):
 
 def admm_matrices(c: CondensedQP, s: AdmmSettings):
     """Stacked operator T = [I;G] K^-1 [I,G'] with K = Pc + sigma I + rho I + G' diag(rho_g) G and the check
-    operator C = [[Pc, G'],[G, 0]]  (DESIGN.md section 3)."""
+    operator C = [[Pc, G'],[G, 0]]  (DESIGN.md section 3).  rho_g,i = rho (x rho_eq_scale on equality rows) / |G_i|^2: what
+    OSQP's row equilibration of the constraint matrix amounts to for a per-row step size."""
     nz, mg = c.nz, c.mg
     rho = s.rho if s.rho > 0 else auto_rho(c.Pc)
-    rho_g = np.where(c.eq_mask, s.rho_eq_scale * rho, rho)
+    rho_g = np.where(c.eq_mask, s.rho_eq_scale * rho, rho) / np.maximum((c.G ** 2).sum(1), 1e-12)   # row-equilibrated step sizes
     K = c.Pc + (s.sigma + rho) * np.eye(nz) + c.G.T @ (rho_g[:, None] * c.G)
     Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.T)
     Ac = np.vstack([np.eye(nz), c.G])

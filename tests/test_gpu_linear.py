@@ -300,3 +300,71 @@ def test_pipelined_host_entry_equals_plain(mpc, qt):
             assert np.array_equal(one[k], plain[k][:3]), k
     finally:
         for p in ptrs: L.mpcb_free_pinned(p)
+
+
+@pytest.mark.parametrize("H", [10, 20])
+def test_state_constraint_rows(mpc, qt, H):
+    """kw `mpc_state_constraint` (linear.jl:62-70): state-box rows on x[:,2..H+1] become general inequality rows
+    (H = 10: nt = 60, on-chip kernel with general rows; H = 20: nt = 120, streamed kernel).  The box is tightened to
+    [0.55, 0.75] and the references sit partly beyond it, so the optimal trajectories press against the state bounds.
+    CUDA vs the condensed twin, and vs the OSQP port run on the reference's own sparse formulation (independent encoding
+    and solver) at tight tolerance."""
+    from oracle import osqp_ref as orf
+    n, eps = 256, 1e-7
+    xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_state_constraint=True,
+                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    m = C.tuning.modeler
+    assert m.info.mg == 4 * H and m.info.kernel == (1 if H == 10 else 2)
+    rng = np.random.default_rng(5)
+    xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
+    res = mpc.calculate(C)
+    P = C.tuning.terminal_ingredient.P
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], xmin, xmax, state_constraint=True)
+    p = mo.pack_params(x0, xref, qt["u_ref"])
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000))
+    assert (res["status"] == 1).all() and (tw["status"] == 1).all()
+    assert (res["iters"] == tw["iters"]).mean() > 0.97 and res["iters"].max() < 2000
+    assert np.abs(res["u"].reshape(n, -1) - tw["v"]).max() < 1e-7
+    xs = res["x"]
+    touching = (xs[:, 1:] > xmax - 1e-6).any(axis=(1, 2))
+    assert touching.sum() >= n // 4                                   # the rows are really exercised
+    assert (xs[:, 1:] <= xmax + 1e-5).all() and (xs[:, 1:] >= xmin - 1e-5).all()
+    for i in np.flatnonzero(touching)[:4]:                            # independent check on the reference's sparse model
+        qp = mo.build_reference_qp(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, xref[i], qt["u_ref"], x0[i], qt["umin"], qt["umax"], xmin, xmax,
+                                   state_constraint=True)
+        w = orf.Workspace(orf.Problem(qp.P, qp.q, qp.A, qp.l, qp.u), orf.default_settings(eps_abs=1e-8, eps_rel=1e-8, max_iter=200000))
+        r = w.solve(cold_start=True)
+        assert r["status"] == 1
+        u_sparse = r["x"][qp.idx["u"].T.ravel()]
+        assert mo.u0_metric(res["u0"][i], u_sparse[:2], qt["umin"], qt["umax"]) < U0_TOL
+        assert abs(r["obj"] - res["objective"][i]) <= 1e-5 * max(1.0, abs(r["obj"]))
+
+
+def test_closed_loop_on_gpu_equals_host_loop(mpc, qt):
+    """the update_initialization! -> calculate! -> apply u[:,1] loop kept on the device for a batch of plants
+    must reproduce the same loop driven from the host (one batched calculate! per step, warm-started the same way)."""
+    H, n, steps = 20, 300, 12
+    C = make_controller(mpc, qt, H, mpc_b200_eps_abs=1e-7, mpc_b200_eps_rel=1e-7, mpc_b200_check_every=5, mpc_b200_sigma=0.0)
+    m = C.tuning.modeler
+    x0, xref, uref = qt_batch(qt, n)
+    for warm in (True, False):
+        dev = m.closed_loop(x0, xref, uref, steps, warm_start=warm)
+        x = x0.copy(); m.warm = None
+        xs, us, its = [x.copy()], [], np.zeros(n, np.int64)
+        for t in range(steps):
+            mpc.update_initialization(C, x, references=(xref, uref))
+            r = mpc.calculate(C, warm_start=warm, want=("u", "u0"))
+            assert (r["status"] == 1).all()
+            its += r["iters"]
+            x = xref + (x - xref) @ qt["A"].T + (r["u0"] - uref) @ qt["B"].T
+            xs.append(x.copy()); us.append(r["u0"].copy())
+        xs = np.stack(xs, 1); us = np.stack(us, 1)
+        assert np.abs(dev["x_traj"] - xs).max() < 1e-9 and np.abs(dev["u_traj"] - us).max() < 1e-8
+        assert (dev["unsolved_steps"] == 0).all() and np.abs(dev["iters_total"] - its).max() <= 5 * 2      # a borderline check may flip on 1e-16 differences
+        if warm: it_warm = dev["iters_total"].mean()
+        else: assert it_warm < dev["iters_total"].mean()                      # the (unshifted, OSQP-style) warm start pays
+    # the regulated plants approach their references
+    assert np.abs(dev["x_traj"][:, -1] - xref).max() < np.abs(x0 - xref).max()
