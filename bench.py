@@ -36,6 +36,7 @@ BATCH = 65536
 EPS = 1e-7
 CHECK = 5
 SIGMA = 0.0    # OSQP's sigma only regularises a semidefinite P; the condensed K = Pc + rho I is positive definite without it
+NCU_DRAM_BYTES_PER_LAUNCH = 4257024   # profiles/r01/onchip_qt_h20_ncu_full.txt
 FP64_PEAK_TFLOPS = 37.1   # DMMA.8x8x4 peak measured on this pool's B200 (profiles/micro/fp64_peak_r01.jsonl);
                           # MEASURED_PEAKS.json has no FP64 entry (cuBLAS DGEMM 8192^3 measured 35.5 in the same run)
 
@@ -223,7 +224,9 @@ def run_ours(args):
                     "phases_ms": {k: round(v, 4) for k, v in tim.items() if k.endswith("_ms")}},
             "gpu_launches": int(2 * args.steps),
             "roofline": {"bound": "tensor", "kernel": "admm_onchip_kernel<40,false,false,3>", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, ncu --set full capture "
+                                           "profiles/r01/onchip_qt_h20_ncu_full.txt (4.26 MB read, 0 written: outputs stay in L2 until recover reads them)",
                          "peak_source": "FP64 DMMA peak measured by profiles/micro/fp64_peak.cu on this pool (MEASURED_PEAKS.json has no FP64 number)",
                          "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops, "mean_iters": float(it_np.mean())},
             "solver": {"mean_iters": float(it_np.mean()), "max_iters": int(it_np.max()), "solved_frac": float((st_np == 1).mean())},
