@@ -66,13 +66,16 @@ __device__ __forceinline__ void act_eval(int id, double h, double& a, double& da
 }
 
 // Warp-cooperative network evaluation.  xu[nin] (shared) -> f[nx] (shared).  Scratch: ya, yb [nn].  With JAC also
-// AB[nin][nx] (column-major nx x nin: d f / d [x;u]) using Ja, Jb [nin][nn].  Ends with a __syncwarp().
+// AB[nin][nx] (column-major nx x nin: d f / d [x;u]) using Ja, Jb [nin][nn] and sd [nn] (activation derivatives).
+// The Jacobian products run over flattened (input, neuron) pairs so that all 32 lanes work even for 13-neuron layers,
+// two pairs per lane and pass for instruction-level parallelism.  Ends with a __syncwarp().
 template <bool JAC>
 __device__ __forceinline__ void nn_eval_warp(const NetSm& N, const double* xu, double* f, double* ya, double* yb, double* Ja, double* Jb,
-                                             double* AB, int lane) {
+                                             double* AB, double* sd, int lane) {
   const int nn = N.nn, nin = N.nin, nx = N.nx;
   for (int i = lane; i < nn; i += 32) {
     double s = 0.0;
+#pragma unroll 6
     for (int j = 0; j < nin; j++) s = fma(N.W_in[j * nn + i], xu[j], s);
     ya[i] = s;
   }
@@ -81,36 +84,54 @@ __device__ __forceinline__ void nn_eval_warp(const NetSm& N, const double* xu, d
   __syncwarp();
   double *yc = ya, *yn = yb, *Jc = Ja, *Jn = Jb;
   for (int l = 0; l < N.nh; l++) {
-    const double* W = N.W_h + (size_t)l * nn * nn;
-    const double* b = N.b_h + l * nn;
+    const double* __restrict__ W = N.W_h + (size_t)l * nn * nn;
+    const double* __restrict__ b = N.b_h + l * nn;
     for (int i = lane; i < nn; i += 32) {
       double s = b[i];
+#pragma unroll 8
       for (int j = 0; j < nn; j++) s = fma(W[j * nn + i], yc[j], s);
       double a, da;
       act_eval(N.act, s, a, da);
       yn[i] = N.arch == NN_RESNET ? a + yc[i] : a;
-      if (JAC) {                                    // d y_new[i] / d in[c] = da * (W Jc)[i][c] (+ Jc[i][c])
-        for (int c = 0; c < nin; c++) {
-          double t = 0.0;
-          for (int j = 0; j < nn; j++) t = fma(W[j * nn + i], Jc[c * nn + j], t);
-          t *= da;
-          Jn[c * nn + i] = N.arch == NN_RESNET ? t + Jc[c * nn + i] : t;
-        }
-      }
+      if (JAC) sd[i] = da;
     }
     __syncwarp();
+    if (JAC) {                                      // d y_new[i] / d in[c] = da[i] * (W Jc)[i][c] (+ Jc[i][c])
+      const double* __restrict__ Jr = Jc;
+      double* __restrict__ Jw = Jn;
+      const int tot = nn * nin;
+      for (int o0 = lane; o0 < tot; o0 += 64) {
+        const int o1 = o0 + 32;
+        const bool has1 = o1 < tot;
+        const int c0 = o0 / nn, i0 = o0 - c0 * nn;
+        const int c1 = has1 ? o1 / nn : c0, i1 = has1 ? o1 - c1 * nn : i0;
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll 4
+        for (int j = 0; j < nn; j++) {
+          t0 = fma(W[j * nn + i0], Jr[c0 * nn + j], t0);
+          t1 = fma(W[j * nn + i1], Jr[c1 * nn + j], t1);
+        }
+        t0 *= sd[i0]; t1 *= sd[i1];
+        if (N.arch == NN_RESNET) { t0 += Jr[o0]; if (has1) t1 += Jr[o1]; }
+        Jw[o0] = t0;
+        if (has1) Jw[o1] = t1;
+      }
+      __syncwarp();
+    }
     double* tp = yc; yc = yn; yn = tp;
     if (JAC) { tp = Jc; Jc = Jn; Jn = tp; }
   }
   for (int i = lane; i < nx; i += 32) {
     double s = 0.0;
+#pragma unroll 8
     for (int j = 0; j < nn; j++) s = fma(N.W_out[j * nx + i], yc[j], s);
     f[i] = s;
   }
   if (JAC)
     for (int o = lane; o < nx * nin; o += 32) {
-      const int i = o % nx, c = o / nx;
+      const int c = o / nx, i = o - c * nx;
       double s = 0.0;
+#pragma unroll 8
       for (int j = 0; j < nn; j++) s = fma(N.W_out[j * nx + i], Jc[c * nn + j], s);
       AB[o] = s;
     }
@@ -127,6 +148,16 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// Phase profiling for development (-DMPCB_NMPC_PROF): per-phase clock64() totals of lane 0, accumulated in a global array.
+#ifdef MPCB_NMPC_PROF
+__device__ unsigned long long g_nmpc_prof[8];
+#define NMPC_PROF_DECL long long _pt = clock64();
+#define NMPC_PROF(slot) do { const long long _n = clock64(); if (lane == 0) atomicAdd(&g_nmpc_prof[slot], (unsigned long long)(_n - _pt)); _pt = _n; } while (0)
+#else
+#define NMPC_PROF_DECL
+#define NMPC_PROF(slot)
+#endif
 
 constexpr int NN_WARPS = 4;
 constexpr int NN_THREADS = NN_WARPS * 32;
@@ -146,7 +177,7 @@ struct NnBatchParams {
 };
 
 __host__ __device__ inline size_t nn_eval_scratch_doubles(const NetDev& N, bool jac) {
-  return (size_t)N.nin + N.nx + 2 * N.nn + (jac ? (size_t)2 * N.nn * N.nin + (size_t)N.nx * N.nin : 0);
+  return (size_t)N.nin + N.nx + 2 * N.nn + (jac ? (size_t)2 * N.nn * N.nin + (size_t)N.nx * N.nin + N.nn : 0);
 }
 __host__ __device__ inline size_t nn_batch_smem_bytes(const NetDev& N, bool jac) {
   return sizeof(double) * (N.weight_count() + NN_WARPS * nn_eval_scratch_doubles(N, jac));
@@ -161,13 +192,13 @@ __global__ void __launch_bounds__(NN_THREADS) nn_batch_kernel(const NnBatchParam
   const int nx = N.nx, nu = N.nu, nin = N.nin, nn = N.nn;
   double* w = sm + P.net.weight_count() + warp * nn_eval_scratch_doubles(P.net, JAC);
   double* xu = w; double* f = xu + nin; double* ya = f + nx; double* yb = ya + nn;
-  double* Ja = yb + nn; double* Jb = Ja + (JAC ? nn * nin : 0); double* AB = Jb + (JAC ? nn * nin : 0);
+  double* Ja = yb + nn; double* Jb = Ja + (JAC ? nn * nin : 0); double* AB = Jb + (JAC ? nn * nin : 0); double* sd = AB + (JAC ? nx * nin : 0);
   for (long long p = (long long)blockIdx.x * NN_WARPS + warp; p < P.batch; p += (long long)gridDim.x * NN_WARPS) {
     if (JAC) {
       for (int i = lane; i < nx; i += 32) xu[i] = P.x0[p * nx + i];
       for (int i = lane; i < nu; i += 32) xu[nx + i] = P.u[p * nu + i];
       __syncwarp();
-      nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, lane);
+      nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
       if (P.x) for (int i = lane; i < nx; i += 32) P.x[p * nx + i] = f[i];
       for (int o = lane; o < nx * nx; o += 32) P.A[p * nx * nx + o] = AB[o];
       for (int o = lane; o < nx * nu; o += 32) P.B[p * nx * nu + o] = AB[nx * nx + o];
@@ -177,7 +208,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_batch_kernel(const NnBatchParam
       for (int k = 0; k < P.H; k++) {
         for (int i = lane; i < nu; i += 32) xu[nx + i] = P.u[(p * P.H + k) * nu + i];
         __syncwarp();
-        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, lane);
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, nullptr, lane);
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; P.x[(p * (P.H + 1) + k + 1) * nx + i] = v; }
         __syncwarp();
       }
@@ -229,8 +260,9 @@ __host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz
 }
 
 // ROWS = ceil(nz / 32): decision-variable rows owned by each lane (row e = lane + 32 * i)
+constexpr int NMPC_MAX_WARPS = 10;      // CTA width is chosen at design time to maximise resident warps per SM (shared-memory bound)
 template <int ROWS>
-__global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P) {
+__global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const NmpcParams P) {
   extern __shared__ __align__(16) double sm[];
   const int nwarps = blockDim.x >> 5;
   const NetSm N = stage_network(P.net, sm, threadIdx.x, blockDim.x);
@@ -260,7 +292,7 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
   double* se = w;                        w += nx;
   double* sWe = w;                       w += nx;
   double* xu = w; double* f = xu + nin; double* ya = f + nx; double* yb = ya + nn;
-  double* Ja = yb + nn; double* Jb = Ja + nn * nin; double* AB = Jb + nn * nin;
+  double* Ja = yb + nn; double* Jb = Ja + nn * nin; double* AB = Jb + nn * nin; double* sd = AB + nx * nin;
 
   const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha, sig_rho = P.sigma + P.rho;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
@@ -305,7 +337,7 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         if (k == H) break;
         for (int i = lane; i < nu; i += 32) xu[nx + i] = uu[k * nu + i];
         __syncwarp();
-        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, lane);
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, nullptr, lane);
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; }
         __syncwarp();
       }
@@ -314,6 +346,7 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
       __syncwarp();
       for (int e = lane; e < nz; e += 32) {
         double s = 0.0;
+#pragma unroll 8
         for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
         part = fma(0.5 * scol[e], s, part);
       }
@@ -321,10 +354,12 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
       return warp_sum(J + part);
     };
 
+    NMPC_PROF_DECL
     int status = -2, sqp_it = 0, inner_total = 0;
     double step = 0.0, qp_rd = 0.0, Jcur = 0.0;
     bool have_traj = false;
     for (sqp_it = 1; sqp_it <= P.sqp_max_iter; sqp_it++) {
+      NMPC_PROF(4);
       // ---------------------------------------------------------------- 1. linearise along the trajectory of u
       for (int a = 0; a < nz; a++)
         for (int c = lane; c < ldk; c += 32) K[a * ldk + c] = c < nz ? sHc[a * nz + c] : 0.0;
@@ -338,7 +373,8 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         __syncwarp();
         for (int e = lane; e < nz; e += 32) {
           double s = 0.0;
-          for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
+  #pragma unroll 8
+        for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
           sg[e] = s;
           part = fma(0.5 * scol[e], s, part);
         }
@@ -354,14 +390,20 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
       for (int k = 0; k < H; k++) {
         for (int i = lane; i < nu; i += 32) xu[nx + i] = su[k * nu + i];
         __syncwarp();
-        nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, lane);
+        NMPC_PROF(0);
+        nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
+        NMPC_PROF(5);
         const int ncol = (k + 1) * nu;                 // non-zero columns of Gamma_{k+1}
         // Gamma_{k+1} = A_k Gamma_k, block k = B_k            (stored [i][c], c fastest)
         for (int i = 0; i < nx; i++)
           for (int c = lane; c < ncol; c += 32) {
             double s;
             if (c >= k * nu) s = AB[(nx + c - k * nu) * nx + i];
-            else { s = 0.0; for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * nz + c], s); }
+            else {
+              s = 0.0;
+#pragma unroll 4
+              for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * nz + c], s);
+            }
             Gn[i * nz + c] = s;
           }
         const double* W = (k + 1 == H) ? sPt : sQ;
@@ -377,18 +419,40 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         for (int i = 0; i < nx; i++)
           for (int c = lane; c < ncol; c += 32) {
             double s = 0.0;
+#pragma unroll 4
             for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], Gn[j * nz + c], s);
             Gc[i * nz + c] = s;
           }
         __syncwarp();
-        // K += 2 Gamma' (W Gamma),  g += 2 Gamma' (W e)
-        for (int a = 0; a < ncol; a++) {
-          double* Ka = K + a * ldk;
-          for (int c = lane; c < ncol; c += 32) {
-            double s = 0.0;
-            for (int i = 0; i < nx; i++) s = fma(Gn[i * nz + a], Gc[i * nz + c], s);
-            Ka[c] = fma(2.0, s, Ka[c]);
+        NMPC_PROF(6);
+        // K += 2 Gamma' (W Gamma),  g += 2 Gamma' (W e).  Each lane owns the columns c = lane + 32 r of K; four rows a are
+        // processed per pass with all loads issued before the dependent FMAs (the rows are independent, but K, Gamma and
+        // W Gamma share one shared-memory allocation, so the compiler must be told by construction).
+        for (int a0 = 0; a0 < ncol; a0 += 4) {
+          double acc[4][ROWS];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) acc[u][r] = 0.0;
+#pragma unroll 2
+          for (int i = 0; i < nx; i++) {
+            double ga[4], gc[ROWS];
+#pragma unroll
+            for (int u = 0; u < 4; u++) ga[u] = (a0 + u < ncol) ? Gn[i * nz + a0 + u] : 0.0;
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) { const int c = lane + 32 * r; gc[r] = (c < ncol) ? Gc[i * nz + c] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int r = 0; r < ROWS; r++) acc[u][r] = fma(ga[u], gc[r], acc[u][r]);
           }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              const int c = lane + 32 * r;
+              if (a0 + u < ncol && c < ncol) K[(a0 + u) * ldk + c] = fma(2.0, acc[u][r], K[(a0 + u) * ldk + c]);
+            }
         }
         for (int a = lane; a < ncol; a += 32) {
           double s = 0.0;
@@ -396,35 +460,62 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
           sg[a] = fma(2.0, s, sg[a]);
         }
         __syncwarp();
+        NMPC_PROF(7);
         // the buffer that held W Gamma must again read as Gamma_k = 0 beyond its columns for the next step: it is fully
         // rewritten for c < ncol + nu next time and never read beyond, so no clearing is needed
         double* tp = Gc; Gc = Gn; Gn = tp;
       }
       J0 = warp_sum(J0);
+      NMPC_PROF(0);
       // ---------------------------------------------------------------- 2. q = g - K u ; K <- (K + (sigma + rho) I)^-1
       for (int e = lane; e < nz; e += 32) {
         double s = 0.0;
+#pragma unroll 8
         for (int j = 0; j < nz; j++) s = fma(K[j * ldk + e], su[j], s);
         sq[e] = sg[e] - s;
       }
       __syncwarp();
       for (int e = lane; e < nz; e += 32) K[e * ldk + e] += sig_rho;
       __syncwarp();
+      // In-place Gauss-Jordan inverse of the SPD matrix K (no pivoting).  Each lane owns the columns j = lane + 32 r; per
+      // pivot the scaled pivot row sits in registers and the rows are swept four at a time, loads first (rows are
+      // independent; see the note on aliasing above).
       for (int pv = 0; pv < nz; pv++) {
         const double dinv = 1.0 / K[pv * ldk + pv];
         for (int i = lane; i < nz; i += 32) scol[i] = K[i * ldk + pv];
         __syncwarp();
-        for (int j = lane; j < nz; j += 32) K[pv * ldk + j] = (j == pv) ? dinv : K[pv * ldk + j] * dinv;
-        __syncwarp();
-        for (int i = 0; i < nz; i++) {              // rows one by one, the row spread over the lanes (no index division)
-          if (i == pv) continue;
-          const double fct = scol[i];
-          double* Ki = K + i * ldk;
-          const double* Kp = K + pv * ldk;
-          for (int j = lane; j < nz; j += 32) Ki[j] = (j == pv) ? -fct * dinv : fma(-fct, Kp[j], Ki[j]);
+        double kp[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) {
+          const int j = lane + 32 * r;
+          kp[r] = 0.0;
+          if (j < nz) {
+            kp[r] = (j == pv) ? dinv : K[pv * ldk + j] * dinv;      // with K[i][pv] read as 0 below, kp[pv] = dinv yields -f dinv
+            K[pv * ldk + j] = kp[r];
+          }
+        }
+        for (int i0 = 0; i0 < nz; i0 += 4) {
+          double fct[4], kv[4][ROWS];
+#pragma unroll
+          for (int u = 0; u < 4; u++) { const int i = i0 + u; fct[u] = (i < nz && i != pv) ? scol[i] : 0.0; }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              const int i = i0 + u, j = lane + 32 * r;
+              kv[u][r] = (i < nz && j < nz && j != pv) ? K[i * ldk + j] : 0.0;
+            }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              const int i = i0 + u, j = lane + 32 * r;
+              if (i < nz && i != pv && j < nz) K[i * ldk + j] = fma(-fct[u], kp[r], kv[u][r]);
+            }
         }
         __syncwarp();
       }
+      NMPC_PROF(1);
       // ---------------------------------------------------------------- 3. ADMM (box-only form of admm_onchip.cuh)
       double c[ROWS], qv[ROWS], xs[ROWS], tlast[ROWS], ylast[ROWS];
       double qn = 0.0;
@@ -452,13 +543,12 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
           double t[ROWS];
 #pragma unroll
           for (int i = 0; i < ROWS; i++) t[i] = 0.0;
+          // lanes beyond nz in the last row group read the (finite) padding / next row of K and discard the result below
+#pragma unroll 8
           for (int j = 0; j < nz; j++) {
             const double rj = sr[j];
 #pragma unroll
-            for (int i = 0; i < ROWS; i++) {
-              const int e = lane + 32 * i;
-              if (e < nz) t[i] = fma(K[j * ldk + e], rj, t[i]);
-            }
+            for (int i = 0; i < ROWS; i++) t[i] = fma(K[j * ldk + ((lane + 32 * i) < nz ? (lane + 32 * i) : 0)], rj, t[i]);
           }
           __syncwarp();       // every lane has consumed sr
           double nA = 0.0, nD = 0.0;
@@ -494,6 +584,7 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
         if (conv || it >= max_iter) break;
       }
       inner_total += it;
+      NMPC_PROF(2);
       qp_rd = rd;
       // ---------------------------------------------------------------- 4. step, acceptance, line search
       double dmax = 0.0, gd = 0.0;
@@ -536,6 +627,7 @@ __global__ void __launch_bounds__(NN_THREADS) nmpc_sqp_kernel(const NmpcParams P
       have_traj = true;
     }
     if (sqp_it > P.sqp_max_iter) sqp_it = P.sqp_max_iter;
+    NMPC_PROF(3);
     if (!have_traj) Jcur = rollout_cost(su);
     // ------------------------------------------------------------------ outputs
     for (int e = lane; e < nz; e += 32) {

@@ -127,7 +127,7 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
   const int threads = h->warps * 32;
   const size_t smem = mpcb::nmpc_smem_bytes(n->net, h->H, h->nz, h->warps);
   const long long blocks = (Bn + h->warps - 1) / h->warps;
-  const int per_sm = std::max<int>(1, (int)((220 * 1024) / smem));
+  const int per_sm = std::max<int>(1, (int)((226 * 1024) / smem));
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * per_sm));
   cudaError_t e;
   switch (h->rows) {
@@ -144,6 +144,15 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
 }
 
 }  // namespace
+
+#ifdef MPCB_NMPC_PROF
+extern "C" int mpcb_debug_nmpc_prof(unsigned long long* out8, int reset) {   // development builds only (not in the header)
+  cudaDeviceSynchronize();
+  if (out8) cudaMemcpyFromSymbol(out8, mpcb::g_nmpc_prof, 8 * sizeof(unsigned long long));
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(mpcb::g_nmpc_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif
 
 extern "C" {
 
@@ -259,9 +268,16 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32;
   auto bail = [&](int code, const std::string& msg) { mpcb_destroy_nmpc(h); return api_fail(code, msg); };
   if (h->rows > 4) return bail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
+  // CTA width: the kernel is latency bound and shared-memory limited (one K matrix per warp), so pick the width that puts
+  // the most warps on an SM (227 KB); ties go to the narrower CTA.
   h->warps = 0;
-  for (int w = mpcb::NN_WARPS; w >= 1; w--)
-    if (mpcb::nmpc_smem_bytes(n->net, H, nz, w) <= 110 * 1024 || (w == 1 && mpcb::nmpc_smem_bytes(n->net, H, nz, 1) <= 220 * 1024)) { h->warps = w; break; }
+  int best = 0;
+  for (int w = 1; w <= mpcb::NMPC_MAX_WARPS; w++) {
+    const size_t sm = mpcb::nmpc_smem_bytes(n->net, H, nz, w);
+    if (sm > 226 * 1024) break;
+    const int resident = (int)((226 * 1024) / sm) * w;
+    if (resident > best) { best = resident; h->warps = w; }
+  }
   if (h->warps == 0) return bail(MPCB_ERR_INVALID, "NMPC problem too large for the shared-memory resident SQP kernel");
 
   // linearise at the design reference ON THE GPU (the reference: proceed_system_linearization, design_mpc.jl:319-323)

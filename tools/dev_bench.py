@@ -107,6 +107,14 @@ def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
         a.record(); mod.solve_batch_device(io, st); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     it = iters.cpu().numpy(); inn = inner.cpu().numpy(); stt = status.cpu().numpy()
     ms = min(ts)
+    L = _lib.lib()
+    if hasattr(L, "mpcb_debug_nmpc_prof"):      # development build with -DMPCB_NMPC_PROF
+        import ctypes
+        buf = (ctypes.c_ulonglong * 8)()
+        L.mpcb_debug_nmpc_prof(buf, 1)
+        tot = sum(buf) or 1
+        names = ["linearise-other", "q+inverse", "admm", "final accept", "line search/init", "nn_eval+jac", "gamma+Wgamma", "K,g accumulate"]
+        print(json.dumps({"nmpc_phase_share": {nm: round(buf[i] / tot, 3) for i, nm in enumerate(names)}, "cycles_per_problem_per_launch": round(tot / n / (reps + 1))}), flush=True)
     print(json.dumps({"cfg": "nmpc", "fixture": fixture, "H": H, "n": n, "ms": round(ms, 3), "solves_per_s": round(n / ms * 1e3), "sqp_iters_mean": round(float(it.mean()), 2),
                       "sqp_iters_max": int(it.max()), "inner_mean": round(float(inn.mean()), 1), "solved": float((stt == 1).mean()), "stalled": float((stt == 2).mean()),
                       "maxiter": float((stt == -2).mean()), "rho": round(mod.design()["rho"], 4)}), flush=True)
@@ -140,6 +148,6 @@ if __name__ == "__main__":
     elif a.set == "h50":
         run(50, 16384, 1e-7, 5, 0.0, reps=1)
     elif a.set == "lti":
-        for scale in (0.1, 0.3, 1.0):
+        for scale in (1.0, 3.0, 10.0, 30.0):
             run_lti(scale=scale)
         run_lti(scale=0.3, terminal="none")
