@@ -257,8 +257,32 @@ def closed_loop_latency(mpc, Cn, steps=200):
         if k >= 20: ts.append(dt)
         u0 = Cn.computation_results.u[:, 0]
         x = x_ref + A @ (x - x_ref) + B @ (u0 - u_ref)
-    return {"p50_us": statistics.median(ts) * 1e6, "p99_us": float(np.percentile(ts, 99)) * 1e6, "steps": steps,
-            "what": "update_initialization!+calculate! B=1 warm start, host wall clock incl. H2D/D2H"}
+    out = {"p50_us": statistics.median(ts) * 1e6, "p99_us": float(np.percentile(ts, 99)) * 1e6, "steps": steps,
+           "what": "update_initialization!+calculate! B=1 warm start through the Python host mirror, host wall clock incl. transfers"}
+    # the same closed loop straight through the C ABI with a prebuilt mpcb_batch_io (what a Julia ccall pays: no Python
+    # object churn between the measurement points except one ctypes call)
+    from almpc_b200 import _lib
+    m = Cn.tuning.modeler; i = m.info; L = _lib.lib()
+    xb = np.array(x0, np.float64)[None].copy(); xr = np.array(x_ref, np.float64); ur = np.array(u_ref, np.float64)
+    bufs = {"u": np.empty((1, i.horizon, i.nu)), "e_u": np.empty((1, i.horizon, i.nu)), "x": np.empty((1, i.horizon + 1, i.nx)),
+            "e_x": np.empty((1, i.horizon + 1, i.nx)), "y": np.empty((1, i.nt)), "prim_res": np.empty(1), "dual_res": np.empty(1)}
+    wu = np.zeros((1, i.nz)); wy = np.zeros((1, i.nt)); st = np.empty(1, np.int32); it = np.empty(1, np.int32)
+    io = _lib.BatchIO(); io.batch = 1; io.x0 = xb.ctypes.data; io.xref = xr.ctypes.data; io.uref = ur.ctypes.data; io.xref_broadcast = 1; io.uref_broadcast = 1
+    for k, v in bufs.items(): setattr(io, k, v.ctypes.data)
+    io.status = st.ctypes.data; io.iters = it.ctypes.data
+    ref = C.byref(io); h = m._h; f = L.mpcb_solve_linear_batch
+    tc = []
+    for k in range(steps + 20):
+        if k == 1: io.warm_u = wu.ctypes.data; io.warm_y = wy.ctypes.data
+        t0 = time.perf_counter()
+        rc = f(h, ref)
+        dt = time.perf_counter() - t0
+        assert rc == 0 and st[0] == 1
+        if k >= 20: tc.append(dt)
+        wu[:] = bufs["u"].reshape(1, -1); wy[:] = bufs["y"]
+        xb[0] = x_ref + A @ (xb[0] - x_ref) + B @ (bufs["u"][0, 0] - u_ref)
+    out["c_abi_p50_us"] = statistics.median(tc) * 1e6; out["c_abi_p99_us"] = float(np.percentile(tc, 99)) * 1e6
+    return out
 
 
 def _reference_problem():
