@@ -230,12 +230,13 @@ struct NmpcParams {
   double rho, sigma, alpha, eps_abs, eps_rel;
   int max_iter, check_every;
   double sqp_tol, ls_c1, ls_noise;
+  double rho_eq_scale;   // terminal equality rows: rho_e,i = rho_eq_scale * rho / |Gamma_H,i|^2
   int sqp_max_iter, ls_max;
   long long batch;
   const double* x0; const double* xref; const double* uref;
   int xref_bc, uref_bc;
   const double* warm_u;   // [batch][nz] initial guess (null: the reference input clipped to the box)
-  const double* warm_y;   // [batch][nz] duals of the box rows (null: 0)
+  const double* warm_y;   // [batch][nz (+ nx with the terminal equality)] duals of the box rows [and terminal rows] (null: 0)
   double *u, *e_u, *x, *e_x, *u0, *objective, *y;   // outputs, any may be null
   int32_t *status, *iters, *inner_iters;
   double *step, *qp_dres;
@@ -250,6 +251,7 @@ __host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int 
          + 6 * (size_t)nz                     // u, v, r, g, q, col
          + (size_t)(H + 1) * N.nx             // trajectory
          + 2 * (size_t)N.nx                   // e, We
+         + 8 * (size_t)N.nx                   // terminal equality rows: rho_e, b, z_g, ys_g, m, n, t_g, y_g
          + nn_eval_scratch_doubles(N, true);
 }
 __host__ __device__ inline size_t nmpc_const_doubles(const NetDev& N, int nz) {
@@ -261,8 +263,9 @@ __host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz
 
 // ROWS = ceil(nz / 32): decision-variable rows owned by each lane (row e = lane + 32 * i)
 constexpr int NMPC_MAX_WARPS = 10;      // CTA width is chosen at design time to maximise resident warps per SM (shared-memory bound)
-template <int ROWS>
-__global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const NmpcParams P) {
+// EQ: terminal equality e_x[:,end] == 0 (design_mpc.jl:330-331) as nx linearised rows Gamma_H v = Gamma_H u - e_H(u).
+template <int ROWS, bool EQ>
+__global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const NmpcParams P) {
   extern __shared__ __align__(16) double sm[];
   const int nwarps = blockDim.x >> 5;
   const NetSm N = stage_network(P.net, sm, threadIdx.x, blockDim.x);
@@ -291,6 +294,14 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
   double* traj = w;                      w += (size_t)(H + 1) * nx;
   double* se = w;                        w += nx;
   double* sWe = w;                       w += nx;
+  double* srhoe = w;                     w += nx;     // EQ only: per-row step size
+  double* sb = w;                        w += nx;     // right-hand side of the linearised terminal rows
+  double* szg = w;                       w += nx;     // z of the terminal rows
+  double* sysg = w;                      w += nx;     // y / rho_e of the terminal rows
+  double* ssm = w;                       w += nx;     // rho_e (z_g - ys_g): operand of the G' product in the right-hand side
+  double* ssn = w;                       w += nx;     // rho_e (ys_g+ - t_g): operand of the G' product in the dual residual
+  double* stg = w;                       w += nx;     // G x~
+  double* syg = w;                       w += nx;     // multipliers of the terminal rows (carried across SQP iterations)
   double* xu = w; double* f = xu + nin; double* ya = f + nx; double* yb = ya + nn;
   double* Ja = yb + nn; double* Jb = Ja + nn * nin; double* AB = Jb + nn * nin; double* sd = AB + nx * nin;
 
@@ -306,6 +317,9 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
     const double* xr = P.xref + (P.xref_bc ? 0 : p) * nx;
     const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
     double yd[ROWS];          // duals of the box rows (carried across SQP iterations)
+    double mu = 0.0;          // l1 merit weight of the terminal rows
+    const int ny = EQ ? nz + nx : nz;
+    if (EQ) { for (int i = lane; i < nx; i += 32) syg[i] = P.warm_y ? P.warm_y[p * ny + nz + i] : 0.0; }
 #pragma unroll
     for (int i = 0; i < ROWS; i++) {
       const int e = lane + 32 * i;
@@ -315,7 +329,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
         if (P.warm_u) u0v = P.warm_u[p * nz + e];
         else { const double r0 = ur[e % nu]; u0v = r0 < sLb[e] ? sLb[e] : (r0 > sUb[e] ? sUb[e] : r0); }
         su[e] = u0v;
-        if (P.warm_y) yd[i] = P.warm_y[p * nz + e];
+        if (P.warm_y) yd[i] = P.warm_y[p * ny + e];
       }
     }
     __syncwarp();
@@ -476,6 +490,32 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
       }
       __syncwarp();
       for (int e = lane; e < nz; e += 32) K[e * ldk + e] += sig_rho;
+      const double* GH = Gc;               // Gamma_H: the buffer the last linearisation step left current
+      double cviol = 0.0;                  // |e_H|_1
+      if (EQ) {
+        for (int i = 0; i < nx; i++) {     // per terminal row: |G_i|^2, G_i u  (warp reductions)
+          double n2 = 0.0, gu = 0.0;
+          for (int cidx = lane; cidx < nz; cidx += 32) { const double gv = GH[i * nz + cidx]; n2 = fma(gv, gv, n2); gu = fma(gv, su[cidx], gu); }
+          n2 = warp_sum(n2); gu = warp_sum(gu);
+          const double eh = se[i];
+          cviol += fabs(eh);
+          if (lane == 0) {
+            const double re = P.rho_eq_scale * rho / fmax(n2, 1e-12);
+            srhoe[i] = re; sb[i] = gu - eh; szg[i] = gu; sysg[i] = syg[i] / re;     // OSQP warm start: z = A x, y kept
+          }
+        }
+        __syncwarp();
+        for (int a = 0; a < nz; a++) {     // K += G' diag(rho_e) G
+          for (int i = 0; i < nx; i++) {
+            const double gai = srhoe[i] * GH[i * nz + a];
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+              const int cidx = lane + 32 * r;
+              if (cidx < nz) K[a * ldk + cidx] = fma(gai, GH[i * nz + cidx], K[a * ldk + cidx]);
+            }
+          }
+        }
+      }
       __syncwarp();
       // In-place Gauss-Jordan inverse of the SPD matrix K (no pivoting).  Each lane owns the columns j = lane + 32 r; per
       // pivot the scaled pivot row sits in registers and the rows are swept four at a time, loads first (rows are
@@ -536,10 +576,21 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
       __syncwarp();
       int it = 0;
       double rp = 0.0, rd = 0.0;
+      bool qp_conv = false;
       while (true) {
         bool conv = false;
         for (int ii = 0; ii < P.check_every; ii++) {
           const bool chk = (ii == P.check_every - 1);
+          if (EQ) {            // right-hand side += G' (rho_e (z_g - ys_g))
+            for (int i = lane; i < nx; i += 32) ssm[i] = srhoe[i] * (szg[i] - sysg[i]);
+            __syncwarp();
+            for (int e = lane; e < nz; e += 32) {
+              double a = sr[e];
+              for (int i = 0; i < nx; i++) a = fma(GH[i * nz + e], ssm[i], a);
+              sr[e] = a;
+            }
+            __syncwarp();
+          }
           double t[ROWS];
 #pragma unroll
           for (int i = 0; i < ROWS; i++) t[i] = 0.0;
@@ -553,6 +604,19 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
           __syncwarp();       // every lane has consumed sr
           double nA = 0.0, nD = 0.0;
           if (chk) { rp = 0.0; rd = 0.0; }
+          if (EQ) {            // terminal rows: t_g = G x~ ; z_g+ = b ; ys_g+ = alpha t_g + (1 - alpha) z_g + ys_g - b
+            for (int i = 0; i < nx; i++) {
+              double part = 0.0;
+#pragma unroll
+              for (int r = 0; r < ROWS; r++) { const int e = lane + 32 * r; if (e < nz) part = fma(GH[i * nz + e], t[r], part); }
+              const double zg_old = szg[i], ysg_old = sysg[i], bi = sb[i], re = srhoe[i];     // read before the reduction (a convergence point) ...
+              const double tgi = warp_sum(part);
+              const double ysgn = fma(alpha, tgi, fma(oma, zg_old, ysg_old)) - bi;
+              if (chk) { rp = fmax(rp, fabs(tgi - bi)); nA = fmax(nA, fmax(fabs(tgi), fabs(bi))); }
+              if (lane == 0) { szg[i] = bi; sysg[i] = ysgn; ssn[i] = re * (ysgn - tgi); stg[i] = tgi; }   // ... written after it
+            }
+            __syncwarp();
+          }
 #pragma unroll
           for (int i = 0; i < ROWS; i++) {
             const int e = lane + 32 * i;
@@ -561,7 +625,8 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
               const double lo = sLb[e], hi = sUb[e];
               const double zn = wv < lo ? lo : (wv > hi ? hi : wv);
               if (chk) {
-                const double pc = fma(-sig_rho, t[i], sr[e]);
+                double pc = fma(-sig_rho, t[i], sr[e]);
+                if (EQ) for (int k2 = 0; k2 < nx; k2++) pc = fma(GH[k2 * nz + e], ssn[k2], pc);     // Kgn x~ + G' y_g from the cached factor
                 const double ybv = rho * (wv - zn);
                 rp = fmax(rp, fabs(t[i] - zn));
                 rd = fmax(rd, fabs(pc + qv[i] + ybv));
@@ -581,11 +646,20 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
           }
         }
         it += P.check_every;
-        if (conv || it >= max_iter) break;
+        if (conv) { qp_conv = true; break; }
+        if (it >= max_iter) break;
       }
       inner_total += it;
       NMPC_PROF(2);
       qp_rd = rd;
+      bool qp_failed = false;
+      if (EQ) {
+        double ymax = 0.0;
+        for (int i = 0; i < nx; i++) { const double yv = srhoe[i] * sysg[i]; ymax = fmax(ymax, fabs(yv)); if (lane == 0) syg[i] = yv; }
+        mu = fmax(mu, 1.1 * ymax);
+        qp_failed = !qp_conv;          // linearised terminal rows + input box not solvable within the inner cap
+        __syncwarp();
+      }
       // ---------------------------------------------------------------- 4. step, acceptance, line search
       double dmax = 0.0, gd = 0.0;
 #pragma unroll
@@ -602,6 +676,11 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
       dmax = warp_max(dmax); gd = warp_sum(gd);
       step = dmax;
       __syncwarp();
+      if (EQ) {
+        if (qp_failed) { status = -3; have_traj = false; break; }
+        gd -= mu * cviol;                // directional derivative of the l1 merit (the full step zeroes the linearised rows)
+        J0 += mu * cviol;
+      }
       if (dmax <= P.sqp_tol) {           // converged: take the full step
         for (int e = lane; e < nz; e += 32) su[e] = sv[e];
         __syncwarp();
@@ -618,7 +697,13 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
         }
         __syncwarp();
         const double Jc = rollout_cost(sv);
-        if (Jc <= J0 + P.ls_c1 * tls * gd + P.ls_noise * fmax(1.0, fabs(J0))) { ok = true; Jcur = Jc; break; }
+        double merit = Jc;
+        if (EQ) {
+          double cv = 0.0;
+          for (int i = 0; i < nx; i++) cv += fabs(traj[H * nx + i] - xr[i]);
+          merit = fma(mu, cv, Jc);
+        }
+        if (merit <= J0 + P.ls_c1 * tls * gd + P.ls_noise * fmax(1.0, fabs(J0))) { ok = true; Jcur = Jc; break; }
         tls *= 0.5;
       }
       if (!ok) { status = 2; have_traj = false; break; }       // stalled at a kink: keep u
@@ -638,7 +723,8 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32) nmpc_sqp_kernel(const Nmp
     }
     if (P.y) {
 #pragma unroll
-      for (int i = 0; i < ROWS; i++) { const int e = lane + 32 * i; if (e < nz) P.y[p * nz + e] = yd[i]; }
+      for (int i = 0; i < ROWS; i++) { const int e = lane + 32 * i; if (e < nz) P.y[p * ny + e] = yd[i]; }
+      if (EQ) for (int i = lane; i < nx; i += 32) P.y[p * ny + nz + i] = syg[i];
     }
     for (int o = lane; o < (H + 1) * nx; o += 32) {
       const double xv = traj[o];

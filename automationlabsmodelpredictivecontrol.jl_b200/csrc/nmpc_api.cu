@@ -31,6 +31,7 @@ struct mpcb_nmpc {
   mpcb_nn* nn = nullptr;
   mpcb_nmpc_settings st{};
   int H = 0, nz = 0, rows = 0, warps = 0;
+  bool terminal_eq = false;
   double rho = 0.0;
   mpcb::Mat A, B, P;
   DevBuf<double> Q, Pt, Hc, lb, ub;
@@ -92,9 +93,9 @@ int jacobian_device(mpcb_nn* n, int64_t batch, const double* x, const double* u,
   return launch_nn_batch<true>(n, P, st);
 }
 
-template <int ROWS>
+template <int ROWS, bool EQ>
 cudaError_t launch_sqp_rows(const mpcb::NmpcParams& P, unsigned grid, int threads, size_t smem, size_t* smem_set, cudaStream_t st) {
-  auto kern = mpcb::nmpc_sqp_kernel<ROWS>;
+  auto kern = mpcb::nmpc_sqp_kernel<ROWS, EQ>;
   if (smem > 48 * 1024 && smem > *smem_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -118,7 +119,7 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
   P.net = n->net; P.Q = h->Q.p; P.Pt = h->Pt.p; P.Hc = h->Hc.p; P.lb = h->lb.p; P.ub = h->ub.p; P.H = h->H; P.nz = h->nz;
   const mpcb_settings& q = h->st.qp;
   P.rho = h->rho; P.sigma = q.sigma; P.alpha = q.alpha; P.eps_abs = q.eps_abs; P.eps_rel = q.eps_rel; P.max_iter = q.max_iter; P.check_every = q.check_every;
-  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
+  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.rho_eq_scale = q.rho_eq_scale; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
   P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
   P.warm_u = io.warm_u; P.warm_y = io.warm_y;
   P.u = io.u; P.e_u = io.e_u; P.x = io.x; P.e_x = io.e_x; P.u0 = io.u0; P.objective = io.objective; P.y = io.y;
@@ -130,11 +131,12 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
   const int per_sm = std::max<int>(1, (int)((226 * 1024) / smem));
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * per_sm));
   cudaError_t e;
+  const bool eq = h->terminal_eq;
   switch (h->rows) {
-    case 1: e = launch_sqp_rows<1>(P, grid, threads, smem, &h->smem_set, st); break;
-    case 2: e = launch_sqp_rows<2>(P, grid, threads, smem, &h->smem_set, st); break;
-    case 3: e = launch_sqp_rows<3>(P, grid, threads, smem, &h->smem_set, st); break;
-    case 4: e = launch_sqp_rows<4>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 1: e = eq ? launch_sqp_rows<1, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<1, false>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 2: e = eq ? launch_sqp_rows<2, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<2, false>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 3: e = eq ? launch_sqp_rows<3, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<3, false>(P, grid, threads, smem, &h->smem_set, st); break;
+    case 4: e = eq ? launch_sqp_rows<4, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<4, false>(P, grid, threads, smem, &h->smem_set, st); break;
     default: return api_fail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
   }
   if (e != cudaSuccess) return api_fail(MPCB_ERR_CUDA, std::string("nmpc_sqp_kernel launch: ") + cudaGetErrorString(e));
@@ -257,15 +259,15 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   if (q.check_every <= 0 || q.max_iter <= 0 || !(q.alpha > 0 && q.alpha < 2) || !(q.sigma >= 0) || !(q.eps_abs >= 0) || !(q.eps_rel >= 0) ||
       st.sqp_max_iter <= 0 || st.ls_max_halvings < 0 || !(st.sqp_tol >= 0) || !(st.ls_armijo > 0 && st.ls_armijo < 1) || !(st.ls_noise >= 0))
     return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: invalid settings");
-  if (d->terminal_mode != MPCB_TERMINAL_NONE)
-    return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: only terminal ingredient 'none' is supported on the nonlinear path");
+  if (d->terminal_mode != MPCB_TERMINAL_NONE && d->terminal_mode != MPCB_TERMINAL_EQUALITY)
+    return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: terminal ingredient must be 'none' or 'equality'");
   if (d->horizon <= 0 || !d->Q || !d->R || !d->umin || !d->umax || !d->xref || !d->uref) return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: bad arguments");
   mpcb_nn* n = nullptr;
   int rc = mpcb_create_nn(d->nn, q.device, &n);
   if (rc != MPCB_OK) return rc;
   const int nx = n->net.nx, nu = n->net.nu, H = d->horizon, nz = nu * H;
   mpcb_nmpc* h = new mpcb_nmpc();
-  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32;
+  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32; h->terminal_eq = d->terminal_mode == MPCB_TERMINAL_EQUALITY;
   auto bail = [&](int code, const std::string& msg) { mpcb_destroy_nmpc(h); return api_fail(code, msg); };
   if (h->rows > 4) return bail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
   // CTA width: the kernel is latency bound and shared-memory limited (one K matrix per warp), so pick the width that puts
@@ -369,10 +371,10 @@ int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) {
   mpcb_nn* n = h->nn;
   CUDA_TRY(cudaSetDevice(n->device));
   cudaStream_t st = n->stream;
-  const size_t nx = n->net.nx, nu = n->net.nu, H = h->H, nz = h->nz, B = (size_t)Bn;
+  const size_t nx = n->net.nx, nu = n->net.nu, H = h->H, nz = h->nz, B = (size_t)Bn, ny = nz + (h->terminal_eq ? nx : 0);
   const size_t n_xref = hio->xref_broadcast ? nx : nx * B, n_uref = hio->uref_broadcast ? nu : nu * B;
   struct In { const double* src; DevBuf<double>* dst; size_t n; };
-  In ins[5] = {{hio->x0, &h->x0, nx * B}, {hio->xref, &h->xref, n_xref}, {hio->uref, &h->uref, n_uref}, {hio->warm_u, &h->warm_u, nz * B}, {hio->warm_y, &h->warm_y, nz * B}};
+  In ins[5] = {{hio->x0, &h->x0, nx * B}, {hio->xref, &h->xref, n_xref}, {hio->uref, &h->uref, n_uref}, {hio->warm_u, &h->warm_u, nz * B}, {hio->warm_y, &h->warm_y, ny * B}};
   CUDA_TRY(cudaEventRecord(h->ev[0], st));
   for (auto& in : ins) {
     if (!in.src) continue;
@@ -386,7 +388,7 @@ int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) {
   struct Out { double* host; DevBuf<double>* dev; size_t n; double** slot; };
   Out outs[9] = {{hio->u, &h->u, nz * B, &dio.u}, {hio->e_u, &h->e_u, nz * B, &dio.e_u}, {hio->x, &h->x, nx * (H + 1) * B, &dio.x},
                  {hio->e_x, &h->e_x, nx * (H + 1) * B, &dio.e_x}, {hio->u0, &h->u0, nu * B, &dio.u0}, {hio->prim_res, &h->step, B, &dio.prim_res},
-                 {hio->dual_res, &h->dres, B, &dio.dual_res}, {hio->objective, &h->obj, B, &dio.objective}, {hio->y, &h->y, nz * B, &dio.y}};
+                 {hio->dual_res, &h->dres, B, &dio.dual_res}, {hio->objective, &h->obj, B, &dio.objective}, {hio->y, &h->y, ny * B, &dio.y}};
   for (auto& o : outs) {
     if (!o.host) { *o.slot = nullptr; continue; }
     CUDA_TRY(o.dev->ensure(o.n));

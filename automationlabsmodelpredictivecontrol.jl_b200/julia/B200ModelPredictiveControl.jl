@@ -183,7 +183,8 @@ end
 "Replaces `_model_predictive_control_modeler_implementation(::NonLinearProgramming, ::Fnn | ::ResNet, ...)` (fnn.jl:63-189,
 resnet.jl:62-188) + `_JuMP_model_definition(::NonLinearProgramming, ::ipopt_solver_def)`."
 function B200NonlinearModeler(params::Vector, arch::Symbol, activation::String, Q, R, S, P, umin, umax, horizon::Int, xref, uref;
-                              settings::Union{Nothing,MpcbNmpcSettings}=nothing)
+                              terminal::String="none", settings::Union{Nothing,MpcbNmpcSettings}=nothing)
+    terminal in ("none", "equality") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\" and \"equality\" only")
     arrs, f = nn_arrays(params, arch, activation)
     mats = map(M -> Matrix{Float64}(M), (Q, R, S, P)); vecs = map(v -> Vector{Float64}(v), (umin, umax, xref, uref))
     st = Ref{MpcbNmpcSettings}()
@@ -192,7 +193,8 @@ function B200NonlinearModeler(params::Vector, arch::Symbol, activation::String, 
     GC.@preserve arrs mats vecs begin
         nd = Ref(MpcbNnDesc(f..., map(pointer, arrs)...))
         GC.@preserve nd begin
-            d = MpcbNmpcDesc(Base.unsafe_convert(Ptr{MpcbNnDesc}, nd), horizon, map(pointer, mats)..., map(pointer, vecs)..., 0)
+            d = MpcbNmpcDesc(Base.unsafe_convert(Ptr{MpcbNnDesc}, nd), horizon, map(pointer, mats)..., map(pointer, vecs)...,
+                             terminal == "equality" ? 1 : 0)
             check(ccall((:mpcb_create_nmpc, libmpcb200), Cint, (Ref{MpcbNmpcDesc}, Ref{MpcbNmpcSettings}, Ref{Ptr{Cvoid}}), d, st, h), "mpcb_create_nmpc")
         end
     end

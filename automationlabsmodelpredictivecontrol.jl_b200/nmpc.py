@@ -16,8 +16,8 @@ _NMPC_SETTING_KEYS = {"mpc_b200_sqp_tol": "sqp_tol", "mpc_b200_sqp_max_iter": "s
 
 class B200NonlinearModeler:
     def __init__(self, nn, Q, R, S, P, umin, umax, xmin, xmax, horizon, xref, uref, state_constraint=False, terminal="none", kws=None):
-        if terminal != "none":
-            raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported on the nonlinear b200 path (only 'none')")
+        if terminal not in ("none", "equality"):
+            raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported by mpc_solver='b200' (only 'none' and 'equality')")
         if state_constraint:
             raise _lib.MpcbError("mpc_state_constraint is not supported on the nonlinear b200 path yet")
         kws = kws or {}
@@ -28,11 +28,14 @@ class B200NonlinearModeler:
         f = lambda a: None if a is None else np.asfortranarray(np.asarray(a, np.float64))
         keep = [f(Q), f(R), f(S), f(P), f(umin), f(umax), f(xref), f(uref)]
         p = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
-        d = _lib.NmpcDesc(C.pointer(nd), self.horizon, *[p(a) for a in keep], _lib.TERMINAL_NONE)
+        self.terminal = terminal
+        d = _lib.NmpcDesc(C.pointer(nd), self.horizon, *[p(a) for a in keep],
+                          _lib.TERMINAL_EQUALITY if terminal == "equality" else _lib.TERMINAL_NONE)
         self._h = C.c_void_p()
         _lib.check(_lib.lib().mpcb_create_nmpc(C.byref(d), C.byref(self.settings), C.byref(self._h)), "mpcb_create_nmpc")
         del keep_nn
         self.nz = self.nu * self.horizon
+        self.ny = self.nz + (self.nx if terminal == "equality" else 0)      # duals: input box rows [+ terminal rows]
         self.x0 = self.xref = self.uref = None
         self.warm = None
 
@@ -59,7 +62,7 @@ class B200NonlinearModeler:
             raise ValueError("reference shapes do not match the batch")
         H = self.horizon
         shapes = {"u": (Bn, H, self.nu), "e_u": (Bn, H, self.nu), "x": (Bn, H + 1, self.nx), "e_x": (Bn, H + 1, self.nx), "u0": (Bn, self.nu),
-                  "objective": (Bn,), "prim_res": (Bn,), "dual_res": (Bn,), "y": (Bn, self.nz)}
+                  "objective": (Bn,), "prim_res": (Bn,), "dual_res": (Bn,), "y": (Bn, self.ny)}
         res = {} if out is None else out
         for k in tuple(want) + ("prim_res", "dual_res"):
             if k not in res: res[k] = np.empty(shapes[k], np.float64)
@@ -76,7 +79,7 @@ class B200NonlinearModeler:
                 io.warm_u = wu.ctypes.data
             if warm[1] is not None:
                 wy = np.ascontiguousarray(warm[1], np.float64); keep.append(wy)
-                if wy.size != Bn * self.nz: raise ValueError("warm start shapes")
+                if wy.size != Bn * self.ny: raise ValueError("warm start shapes")
                 io.warm_y = wy.ctypes.data
         for k in ("u", "e_u", "x", "e_x", "u0", "objective", "prim_res", "dual_res", "y", "status", "iters", "inner_iters"):
             if k in res: setattr(io, k, res[k].ctypes.data)

@@ -149,7 +149,8 @@ def objective(m, Q, P, Hc, u, x0, xref, uref):
 
 
 def linearize_trajectory(m, Q, P, Hc, u, x0, xref, uref):
-    """One Gauss-Newton linearisation: J, gradient g (B, nz), GN Hessian Pc (B, nz, nz) (incl. Hc) and the trajectory."""
+    """One Gauss-Newton linearisation: J, gradient g (B, nz), GN Hessian Pc (B, nz, nz) (incl. Hc), the trajectory and the
+    terminal sensitivity Gamma_H = d x_H / d u (B, nx, nz)."""
     Bn, H, nu = u.shape; nx = m.nx; nz = nu * H
     x = np.zeros((Bn, H + 1, nx)); x[:, 0] = x0
     Gam = np.zeros((Bn, nx, nz))
@@ -169,7 +170,7 @@ def linearize_trajectory(m, Q, P, Hc, u, x0, xref, uref):
         Pc += 2.0 * np.einsum("bia,bic->bac", Gam, WG)
         g += 2.0 * np.einsum("bia,ij,bj->ba", Gam, W, e)
         J += np.einsum("bi,ij,bj->b", e, W, e)
-    return J, g, Pc, x
+    return J, g, Pc, x, Gam
 
 
 @dataclasses.dataclass
@@ -214,10 +215,53 @@ def admm_box_per_problem(Kinv, q, lb, ub, s: mo.AdmmSettings, rho, x0, y0):
     return xo, yo, iters, status, pres, dres
 
 
-def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: SqpSettings = None, u_init=None, y_init=None):
+def admm_box_eq_per_problem(Kinv, q, lb, ub, G, b, rho_e, s: mo.AdmmSettings, rho, x0, y0, yg0):
+    """As admm_box_per_problem plus nx EQUALITY rows  G v = b  (the linearised terminal constraint), per-row step sizes
+    rho_e; Kinv is the inverse of  Kgn + (sigma + rho) I + G' diag(rho_e) G.  Returns the box and row multipliers."""
+    Bn, nz = q.shape
+    x = x0.copy(); z = x0.copy(); ys = y0 / rho
+    zg = np.einsum("bij,bj->bi", G, x0); ysg = yg0 / rho_e
+    max_iter = -(-s.max_iter // s.check_every) * s.check_every
+    iters = np.zeros(Bn, np.int32); status = np.full(Bn, mo.STATUS_MAX_ITER, np.int32)
+    xo = np.zeros((Bn, nz)); yo = np.zeros((Bn, nz)); ygo = np.zeros_like(b); pres = np.zeros(Bn); dres = np.zeros(Bn)
+    active = np.ones(Bn, bool); qn = np.abs(q).max(1)
+    for it in range(1, max_iter + 1):
+        r = rho * (z - ys) + s.sigma * x - q + np.einsum("bij,bi->bj", G, rho_e * (zg - ysg))
+        t = np.einsum("bij,bj->bi", Kinv, r)
+        tg = np.einsum("bij,bj->bi", G, t)
+        w = s.alpha * t + (1 - s.alpha) * z + ys
+        zn = np.minimum(np.maximum(w, lb), ub)
+        ysn = w - zn
+        wg = s.alpha * tg + (1 - s.alpha) * zg + ysg
+        ysgn = wg - b
+        x = s.alpha * t + (1 - s.alpha) * x
+        z, ys, zg, ysg = zn, ysn, b.copy(), ysgn
+        if it % s.check_every == 0:
+            y = rho * ys; yg = rho_e * ysg
+            kt = r - (s.sigma + rho) * t - np.einsum("bij,bi->bj", G, rho_e * tg)      # Kgn x~ from the cached factor
+            gs = kt + np.einsum("bij,bi->bj", G, yg)
+            rp = np.maximum(np.abs(t - z).max(1), np.abs(tg - b).max(1))
+            rd = np.abs(gs + q + y).max(1)
+            ep = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(t).max(1), np.abs(z).max(1)), np.maximum(np.abs(tg).max(1), np.abs(b).max(1)))
+            ed = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(gs).max(1), np.abs(y).max(1)), qn)
+            conv = (rp <= ep) & (rd <= ed)
+            fin = active & (conv | (it >= max_iter))
+            status[active & conv] = mo.STATUS_SOLVED
+            iters[fin] = it; xo[fin] = t[fin]; yo[fin] = y[fin]; ygo[fin] = yg[fin]; pres[fin] = rp[fin]; dres[fin] = rd[fin]
+            active &= ~fin
+            if not active.any(): break
+    return xo, yo, ygo, iters, status, pres, dres
+
+
+def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: SqpSettings = None, u_init=None, y_init=None,
+             terminal="none", rho_eq_scale=1e3):
     """Twin of the CUDA kernel `nmpc_sqp_kernel`: per problem, repeat { rollout + Jacobians -> GN condensed QP in absolute
     inputs v (box umin <= v <= umax) -> ADMM warm-started at (u, y) -> step d = v - u -> Armijo backtracking on J } until
-    ||d||_inf <= sqp_tol (status 1) or sqp_max_iter (status -2); a failed line search ends with status -2 as well."""
+    ||d||_inf <= sqp_tol (status 1) or sqp_max_iter (status -2); a failed line search ends with status 2.
+    terminal="equality" (design_mpc.jl:330-331, e_x[:,end] == 0): the QP carries the linearised rows
+    Gamma_H v = Gamma_H u - e_H(u) with row-equilibrated step sizes, the line search runs on the l1 merit
+    J + mu |e_H|_1 with mu = max(mu, 1.1 |multipliers|_inf), and a QP that does not converge within the inner cap is
+    reported as primal infeasible (-3)."""
     s = s or SqpSettings()
     x0 = np.atleast_2d(np.asarray(x0, float)); Bn = x0.shape[0]; nx, nu = m.nx, m.nu; nz = nu * H
     xref = np.broadcast_to(np.atleast_2d(np.asarray(xref, float)), (Bn, nx)); uref = np.broadcast_to(np.atleast_2d(np.asarray(uref, float)), (Bn, nu))
@@ -227,26 +271,45 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
     y = np.zeros((Bn, nz)) if y_init is None else np.array(y_init, float).reshape(Bn, nz)
     status = np.full(Bn, mo.STATUS_MAX_ITER, np.int32); sqp_iters = np.zeros(Bn, np.int32); inner = np.zeros(Bn, np.int64)
     step = np.zeros(Bn); qp_dres = np.zeros(Bn)
+    eq = terminal == "equality"
+    yg = np.zeros((Bn, nx)); mu = np.zeros(Bn)
     act_ = np.ones(Bn, bool)
     for it in range(1, s.sqp_max_iter + 1):
         idx = np.flatnonzero(act_)
         if idx.size == 0: break
         ua = u[idx]
-        J0, g, Pc, _ = linearize_trajectory(m, Q, P, Hc, ua.reshape(-1, H, nu), x0[idx], xref[idx], uref[idx])
-        K = Pc + (s.qp.sigma + rho) * np.eye(nz)
-        Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.transpose(0, 2, 1))
+        J0, g, Pc, xa, GH = linearize_trajectory(m, Q, P, Hc, ua.reshape(-1, H, nu), x0[idx], xref[idx], uref[idx])
         q = g - np.einsum("bij,bj->bi", Pc, ua)
-        v, yn, its, _st, _pr, dr = admm_box_per_problem(Kinv, q, lb, ub, s.qp, rho, ua, y[idx])
+        qp_failed = np.zeros(idx.size, bool)
+        if eq:
+            eH = xa[:, H] - xref[idx]
+            rho_e = rho_eq_scale * rho / np.maximum((GH ** 2).sum(2), 1e-12)
+            K = Pc + (s.qp.sigma + rho) * np.eye(nz) + np.einsum("bia,bi,bic->bac", GH, rho_e, GH)
+            Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.transpose(0, 2, 1))
+            bq = np.einsum("bij,bj->bi", GH, ua) - eH
+            v, yn, ygn, its, st_qp, _pr, dr = admm_box_eq_per_problem(Kinv, q, lb, ub, GH, bq, rho_e, s.qp, rho, ua, y[idx], yg[idx])
+            qp_failed = st_qp != mo.STATUS_SOLVED
+            yg[idx] = ygn
+            mu[idx] = np.maximum(mu[idx], 1.1 * np.abs(ygn).max(1))
+            c0 = np.abs(eH).sum(1)
+        else:
+            K = Pc + (s.qp.sigma + rho) * np.eye(nz)
+            Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.transpose(0, 2, 1))
+            v, yn, its, _st, _pr, dr = admm_box_per_problem(Kinv, q, lb, ub, s.qp, rho, ua, y[idx])
+            c0 = np.zeros(idx.size)
         d = v - ua
-        gd = np.einsum("bi,bi->b", g, d)
+        gd = np.einsum("bi,bi->b", g, d) - mu[idx] * c0          # directional derivative of the l1 merit (the step zeroes the linearised rows)
+        J0 = J0 + mu[idx] * c0
         stp = np.abs(d).max(1)
         small = stp <= s.sqp_tol                      # converged: take the full step, no line search
-        t = np.ones(idx.size); ok = small.copy(); un = np.where(small[:, None], v, ua)
+        small &= ~qp_failed
+        t = np.ones(idx.size); ok = small | qp_failed; un = np.where(small[:, None], v, ua)
         for _ in range(s.ls_max + 1):
             todo = ~ok
             if not todo.any(): break
             cand = ua[todo] + t[todo, None] * d[todo]
-            Jc, _ = objective(m, Q, P, Hc, cand.reshape(-1, H, nu), x0[idx][todo], xref[idx][todo], uref[idx][todo])
+            Jc, xc = objective(m, Q, P, Hc, cand.reshape(-1, H, nu), x0[idx][todo], xref[idx][todo], uref[idx][todo])
+            if eq: Jc = Jc + mu[idx][todo] * np.abs(xc[:, H] - xref[idx][todo]).sum(1)
             good = Jc <= J0[todo] + s.ls_c1 * t[todo] * gd[todo] + s.ls_noise * np.maximum(1.0, np.abs(J0[todo]))
             tt = np.flatnonzero(todo)
             un[tt[good]] = cand[good]; ok[tt[good]] = True
@@ -255,10 +318,11 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
         sqp_iters[idx] = it; inner[idx] += its; step[idx] = stp; qp_dres[idx] = dr
         status[idx[small]] = mo.STATUS_SOLVED
         status[idx[~ok]] = STATUS_STALLED             # no Armijo decrease along the SQP direction (kink of a relu network)
-        act_[idx[small | ~ok]] = False
+        status[idx[qp_failed]] = mo.STATUS_PRIMAL_INF  # linearised terminal rows + input box not solvable within the inner cap
+        act_[idx[small | ~ok | qp_failed]] = False
     uu = u.reshape(Bn, H, nu)
     J, x = objective(m, Q, P, Hc, uu, x0, xref, uref)
-    return {"u": uu, "x": x, "e_x": x - xref[:, None, :], "e_u": uu - uref[:, None, :], "objective": J, "y": y, "status": status,
+    return {"u": uu, "x": x, "e_x": x - xref[:, None, :], "e_u": uu - uref[:, None, :], "objective": J, "y": y, "y_terminal": yg, "status": status,
             "iters": sqp_iters, "inner_iters": inner, "step": step, "qp_dual_res": qp_dres}
 
 

@@ -154,6 +154,41 @@ def test_sqp_warm_start_and_ragged_batches(mpc, qt, resnet_model):
     assert (warm["iters"] == 1).all() and (warm["status"] == 1).all() and np.abs(warm["u"] - full["u"]).max() < 2e-6
     assert warm["inner_iters"].mean() < 0.2 * full["inner_iters"].mean()
     # unsupported configurations are refused, not approximated
-    with pytest.raises(mpc.MpcbError):
-        mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", 20, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+    for kw in ({"mpc_terminal_ingredient": "contractive"}, {"mpc_state_constraint": True}):
+        with pytest.raises(mpc.MpcbError):
+            mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", 20, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                                   mpc_programming_type="non_linear", **kw)
+
+
+@pytest.mark.parametrize("fixture", ["qt_resnet_model.json", "qt_fnn_tanh_model.json"])
+def test_sqp_terminal_equality(mpc, qt, fixture):
+    """mpc_terminal_ingredient = "equality" on an NL model (design_mpc.jl:330-331: e_x[:,end] == 0 added to the NL modeler's
+    problem).  CUDA vs twin; solved problems reach the reference exactly and match an independent SLSQP solve of the same
+    NLP; problems whose terminal state is unreachable under the input box are flagged -3 by both."""
+    from scipy.optimize import minimize
+    m = load_nn_fixture(fixture)
+    H, n = 20, 96
+    C = mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
                                mpc_programming_type="non_linear", mpc_terminal_ingredient="equality")
+    mod = C.tuning.modeler
+    rng = np.random.default_rng(4)
+    xref = np.tile(qt["x_ref"], (n, 1)); x0 = xref + 0.02 * rng.standard_normal((n, 4)); uref = qt["u_ref"].copy()
+    res = mod.solve_batch(x0, xref, uref, want=("u", "u0", "x", "e_x", "objective", "y"))
+    d = mod.design()
+    tw = no.nmpc_sqp(m, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0, xref, np.tile(uref, (n, 1)), d["rho"], terminal="equality")
+    assert set(np.unique(res["status"])) <= {1, -3, 2, -2}
+    assert (res["status"] == tw["status"]).mean() > 0.95
+    ok = (res["status"] == 1) & (tw["status"] == 1)
+    assert ok.sum() >= n // 3 and (res["status"] == -3).sum() == (tw["status"] == -3).sum()
+    assert np.abs(res["e_x"][ok][:, H]).max() < 1e-9                       # the terminal state IS the reference
+    assert np.abs(res["u"][ok] - tw["u"][ok]).max() < 5e-6 and np.abs(res["objective"][ok] - tw["objective"][ok]).max() <= 1e-8 * np.abs(tw["objective"][ok]).max()
+    assert np.abs(res["y"][ok][:, 2 * H:] - tw["y_terminal"][ok]).max() <= 1e-4 * max(1.0, np.abs(tw["y_terminal"][ok]).max())
+    Hc = no.constant_hessian(2, H, qt["R"], qt["S"])
+    lb, ub = np.tile(qt["umin"], H), np.tile(qt["umax"], H)
+    for i in np.flatnonzero(ok)[:4]:
+        fg = lambda v: tuple(a[0] for a in no.grad_adjoint(m, qt["Q"], d["P"], Hc, v.reshape(1, H, 2), x0[i:i + 1], xref[i:i + 1], uref[None]))
+        cons = lambda v: no.rollout(m, x0[i:i + 1], v.reshape(1, H, 2))[0, H] - xref[i]
+        r = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), res["u"][i].ravel(), jac=True, method="SLSQP", bounds=list(zip(lb, ub)),
+                     constraints=[{"type": "eq", "fun": cons}], options={"maxiter": 500, "ftol": 1e-15})
+        assert np.abs(cons(r.x)).max() < 1e-9
+        assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL and abs(r.fun - res["objective"][i]) <= OBJ_TOL * abs(r.fun)

@@ -82,7 +82,7 @@ def test_gradient_forward_sensitivities_equal_adjoint(qt, fnn_model):
     rng = np.random.default_rng(1)
     u = rng.uniform(qt["umin"], qt["umax"], (n, H, 2))
     Hc = no.constant_hessian(2, H, qt["R"], 3.0 * np.eye(2))
-    J1, g1, Pc, x = no.linearize_trajectory(m, qt["Q"], P, Hc, u, x0, xref, uref)
+    J1, g1, Pc, x, _GH = no.linearize_trajectory(m, qt["Q"], P, Hc, u, x0, xref, uref)
     J2, g2 = no.grad_adjoint(m, qt["Q"], P, Hc, u, x0, xref, uref)
     J3, x3 = no.objective(m, qt["Q"], P, Hc, u, x0, xref, uref)
     assert np.allclose(J1, J2, rtol=1e-13) and np.allclose(J1, J3, rtol=1e-13) and np.allclose(x, x3)
@@ -144,3 +144,30 @@ def test_reference_relation_linear_vs_nonlinear(qt, fnn_model):
     lin = mo.recover(c, v[None], p)
     nl = no.nmpc_sqp(fnn_model, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], qt["x0"][None], qt["x_ref"][None], qt["u_ref"][None], rho)
     assert np.abs(lin["x"] - nl["x"]).max() < 0.5 and np.abs(lin["e_x"] - nl["e_x"]).max() < 0.5
+
+
+def test_twin_terminal_equality_vs_slsqp(qt):
+    """NL model + terminal equality: the twin's solved problems satisfy e_H = 0 and match an independent SLSQP solve; the
+    problems it flags infeasible cannot reach the reference at all (a pure feasibility search confirms)."""
+    from scipy.optimize import minimize
+    m = load_nn_fixture("qt_resnet_model.json")
+    H, n = 20, 32
+    _, _, P, rho, _ = _design(m, qt, H)
+    rng = np.random.default_rng(4)
+    xref = np.tile(qt["x_ref"], (n, 1)); x0 = xref + 0.03 * rng.standard_normal((n, 4)); uref = np.tile(qt["u_ref"], (n, 1))
+    r = no.nmpc_sqp(m, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0, xref, uref, rho, terminal="equality")
+    ok = r["status"] == 1; bad = r["status"] == -3
+    assert ok.sum() >= 8 and bad.sum() >= 1 and (ok | bad).all()
+    assert np.abs(r["e_x"][ok][:, H]).max() < 1e-9
+    Hc = no.constant_hessian(2, H, qt["R"], qt["S"]); lb, ub = np.tile(qt["umin"], H), np.tile(qt["umax"], H)
+    for i in np.flatnonzero(ok)[:3]:
+        fg = lambda v: tuple(a[0] for a in no.grad_adjoint(m, qt["Q"], P, Hc, v.reshape(1, H, 2), x0[i:i + 1], xref[i:i + 1], uref[i:i + 1]))
+        cons = lambda v: no.rollout(m, x0[i:i + 1], v.reshape(1, H, 2))[0, H] - xref[i]
+        s_ = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), r["u"][i].ravel(), jac=True, method="SLSQP", bounds=list(zip(lb, ub)),
+                      constraints=[{"type": "eq", "fun": cons}], options={"maxiter": 500, "ftol": 1e-15})
+        assert np.abs(s_.x[:2] - r["u"][i, 0]).max() < 1e-4 * 4 and abs(s_.fun - r["objective"][i]) <= 1e-6 * abs(s_.fun)
+    for i in np.flatnonzero(bad)[:2]:
+        cons = lambda v: no.rollout(m, x0[i:i + 1], v.reshape(1, H, 2))[0, H] - xref[i]
+        f_ = minimize(lambda v: float((cons(v) ** 2).sum()), np.tile(qt["u_ref"], H), method="L-BFGS-B", bounds=list(zip(lb, ub)),
+                      options={"maxiter": 2000, "ftol": 1e-20, "gtol": 1e-14})
+        assert np.sqrt(f_.fun) > 1e-5
