@@ -10,7 +10,7 @@ _PKG = pathlib.Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmpcb200.so"
 
 MPCB_OK = 0
-KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED = 0, 1, 2
+KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED, KERNEL_ONCHIP_SMEM = 0, 1, 2, 3
 TERMINAL_NONE, TERMINAL_EQUALITY = 0, 1
 STATUS_SOLVED, STATUS_SOLVED_INACCURATE, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE = 1, 2, -2, -3
 NN_FNN, NN_RESNET = 0, 1

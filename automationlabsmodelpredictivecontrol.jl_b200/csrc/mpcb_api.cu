@@ -18,6 +18,12 @@
 #include "host_design.hpp"
 #include "recover.cuh"
 
+namespace mpcb {
+// admm_smem.cu (own translation unit: 14 kernel instantiations compile in parallel with this file)
+size_t smemk_bytes_host(int NT, int np, bool sig);
+cudaError_t launch_smemk(int NT, const OnchipParams& P, int sm_count, int* attr_set, cudaStream_t st);
+}  // namespace mpcb
+
 namespace {
 thread_local std::string g_err;
 }  // namespace
@@ -132,7 +138,7 @@ int upload_design(mpcb_handle* h) {
   CUDA_TRY(upload(h->P, D.P.a.data(), D.P.a.size()));
   CUDA_TRY(h->counter.ensure(2));
   CUDA_TRY(cudaMemset(h->counter.p, 0, 2 * sizeof(unsigned long long)));   // once: the on-chip kernel re-arms it itself
-  if (h->info.kernel == MPCB_KERNEL_ONCHIP) {
+  if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     const int NT = h->NT, nt = D.nt, np = D.np;
     std::vector<double> tf = to_fragments(D.T, nt, NT), cf = to_fragments(D.C, nt, NT);
     std::vector<double> Lt((size_t)np * NT, 0.0), lo(NT, 0.0), hi(NT, 0.0), rho(NT, 1.0), rinv(NT, 1.0);
@@ -172,7 +178,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
   if (!d_pres) { CUDA_TRY(h->pres.ensure(Bn)); d_pres = h->pres.p; }
   if (!d_dres) { CUDA_TRY(h->dres.ensure(Bn)); d_dres = h->dres.p; }
   int launches = 0;
-  if (h->info.kernel == MPCB_KERNEL_ONCHIP) {
+  if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     OnchipParams P;
     P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
     P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu;
@@ -181,7 +187,8 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
     P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = v_buf; P.y_out = io.y;
     P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres; P.counter = h->counter.p;
-    cudaError_t e = launch_onchip(h->NT, D.mg > 0, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+    cudaError_t e = h->info.kernel == MPCB_KERNEL_ONCHIP ? launch_onchip(h->NT, D.mg > 0, P, h->info.sm_count, &h->onchip_blocks_per_sm, st)
+                                                         : mpcb::launch_smemk(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
     launches += 1;
   } else {
@@ -289,11 +296,14 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   h->info.rho = D.rho; h->info.lambda_min = D.lmin; h->info.lambda_max = D.lmax;
   h->info.device = st.device; h->info.sm_count = prop.multiProcessorCount;
   int kernel = st.kernel;
-  if (kernel == MPCB_KERNEL_AUTO) kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : MPCB_KERNEL_STREAMED;
+  const int nt8 = ((D.nt + 7) / 8) * 8;
+  const bool smem_ok = D.mg == 0 && nt8 > 64 && nt8 <= 120 && mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) <= (size_t)prop.sharedMemPerBlockOptin;
+  if (kernel == MPCB_KERNEL_AUTO) kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : MPCB_KERNEL_STREAMED);
   if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
-  if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
+  if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs a box-only problem with 64 < nz <= 120 that fits 227 KB"); }
+  if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;
-  h->NT = (kernel == MPCB_KERNEL_ONCHIP) ? ((D.nt + 7) / 8) * 8 : mpcb::stream_padded(D.nt);
+  h->NT = (kernel == MPCB_KERNEL_STREAMED) ? mpcb::stream_padded(D.nt) : nt8;
   h->info.nt_pad = h->NT;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
@@ -428,7 +438,7 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
     for (int i = 0; i < 5; i++) if (in_ptrs[i] && !bc_in[i] && !is_pinned_or_device(in_ptrs[i])) pinned = false;   // broadcast references are tiny: staged below
     for (int i = 0; i < 9; i++)
       if (out_ptrs[i]) { out_bytes += per_out[i] * (size_t)Bn * sizeof(double); if (!is_pinned_or_device(out_ptrs[i])) pinned = false; }
-    if (pinned && h->info.kernel == MPCB_KERNEL_ONCHIP && out_bytes >= ((size_t)32 << 20) && Bn >= 4096) {
+    if (pinned && h->info.kernel != MPCB_KERNEL_STREAMED && out_bytes >= ((size_t)32 << 20) && Bn >= 4096) {
       const int nch = (int)std::min<size_t>(8, std::max<size_t>(2, out_bytes / ((size_t)16 << 20)));
       const long long Bc = (Bn + nch - 1) / nch;
       DevBuf<double>* in_dev[5] = {&h->x0, &h->xref, &h->uref, &h->warm_v, &h->warm_y};
@@ -572,7 +582,7 @@ int mpcb_closed_loop_linear_batch(mpcb_handle* h, const mpcb_closed_loop_io* cio
   const int T = cio->steps;
   if (Bn <= 0 || T <= 0) return fail(MPCB_ERR_INVALID, "batch and steps must be positive");
   if (!cio->x0 || !cio->xref || !cio->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
-  if (cio->warm_start && h->info.kernel != MPCB_KERNEL_ONCHIP) return fail(MPCB_ERR_INVALID, "warm-started closed loop needs the on-chip kernel (nz + mg <= 64)");
+  if (cio->warm_start && h->info.kernel == MPCB_KERNEL_STREAMED) return fail(MPCB_ERR_INVALID, "warm-started closed loop needs an on-chip kernel (the streamed kernel has no warm start yet)");
   CUDA_TRY(cudaSetDevice(h->st.device));
   cudaStream_t st = h->stream;
   const size_t nx = D.nx, nu = D.nu, nz = D.nz, nt = D.nt, B = (size_t)Bn;

@@ -51,6 +51,7 @@ extern "C" {
 #define MPCB_KERNEL_AUTO 0
 #define MPCB_KERNEL_ONCHIP 1   /* register/shared-memory resident DMMA ADMM (nz + m_g <= 64) */
 #define MPCB_KERNEL_STREAMED 2 /* per-iteration FP64 tensor GEMM over HBM/L2-resident state */
+#define MPCB_KERNEL_ONCHIP_SMEM 3 /* shared-memory resident DMMA ADMM: box-only problems, 64 < nz <= ~120 */
 
 typedef struct mpcb_handle mpcb_handle;
 

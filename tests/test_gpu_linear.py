@@ -176,13 +176,16 @@ def test_empty_and_ragged_batches(mpc, qt):
 # ------------------------------------------------------------------------------------------------------------------
 # streamed kernel (nt > 64, or forced with mpc_b200_kernel = 2)
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("H,force,sigma", [(20, 2, 0.0), (20, 2, 1e-6), (50, 0, 0.0), (35, 0, 1e-6)])
-def test_streamed_matches_twin_and_exact(mpc, qt, H, force, sigma):
+@pytest.mark.parametrize("H,force,sigma,expect", [(20, 2, 0.0, 2), (20, 2, 1e-6, 2), (50, 2, 0.0, 2), (35, 2, 1e-6, 2), (70, 0, 0.0, 2),
+                                                   # shared-memory resident kernel (box-only, 64 < nz <= 120 and the state fits 227 KB):
+                                                   # picked automatically; nz = 120 with sigma > 0 (4 state arrays) does not fit -> streamed
+                                                   (50, 0, 0.0, 3), (35, 0, 1e-6, 3), (33, 3, 0.0, 3), (60, 0, 0.0, 3), (60, 0, 1e-6, 2), (47, 0, 1e-6, 3)])
+def test_streamed_matches_twin_and_exact(mpc, qt, H, force, sigma, expect):
     n, eps, check = 700, 1e-7, 5          # 700: not a multiple of the 128-row GEMM tile
     C = make_controller(mpc, qt, H, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma,
                         mpc_b200_kernel=force)
     m = C.tuning.modeler
-    assert m.info.kernel == 2
+    assert m.info.kernel == expect
     x0, xref, uref = qt_batch(qt, n, seed=21)
     mpc.update_initialization(C, x0, references=(xref, uref))
     res = mpc.calculate(C)
@@ -211,6 +214,19 @@ def test_streamed_equals_onchip(mpc, qt):
     assert (out[0]["iters"] == out[1]["iters"]).mean() > 0.995
     same = out[0]["iters"] == out[1]["iters"]
     assert np.abs(out[0]["u"][same] - out[1]["u"][same]).max() < 1e-10
+    # and the shared-memory kernel against the streamed one at a horizon both accept, incl. duals and a warm-started second solve
+    res = []
+    for kern in (3, 2):
+        C = make_controller(mpc, qt, 40, mpc_b200_eps_abs=1e-7, mpc_b200_eps_rel=1e-7, mpc_b200_check_every=5, mpc_b200_kernel=kern)
+        m = C.tuning.modeler
+        r = m.solve_batch(x0, xref, uref, want=("u", "u0", "objective", "y"))
+        res.append(r)
+        if kern == 3:
+            w = m.solve_batch(x0, xref, uref, want=("u",), warm=(r["u"], r["y"]))
+            assert (w["status"] == 1).all() and w["iters"].max() <= 10 and np.abs(w["u"] - r["u"]).max() < 2e-5       # both within eps of the optimum
+    same = res[0]["iters"] == res[1]["iters"]
+    assert same.mean() > 0.995 and np.abs(res[0]["u"][same] - res[1]["u"][same]).max() < 1e-10
+    assert np.abs(res[0]["y"][same] - res[1]["y"][same]).max() < 1e-8
 
 
 def test_streamed_terminal_equality(mpc, qt):
