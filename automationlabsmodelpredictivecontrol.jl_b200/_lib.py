@@ -64,7 +64,8 @@ class NnDesc(C.Structure):
 
 class NmpcDesc(C.Structure):
     _fields_ = [("nn", C.POINTER(NnDesc)), ("horizon", C.c_int32), ("Q", _dp), ("R", _dp), ("S", _dp), ("P", _dp), ("umin", _dp),
-                ("umax", _dp), ("xref", _dp), ("uref", _dp), ("terminal_mode", C.c_int32)]
+                ("umax", _dp), ("xref", _dp), ("uref", _dp), ("terminal_mode", C.c_int32), ("state_constraint", C.c_int32),
+                ("xmin", _dp), ("xmax", _dp)]
 
 
 class NmpcSettings(C.Structure):

@@ -231,6 +231,8 @@ struct NmpcParams {
   int max_iter, check_every;
   double sqp_tol, ls_c1, ls_noise;
   double rho_eq_scale;   // terminal equality rows: rho_e,i = rho_eq_scale * rho / |Gamma_H,i|^2
+  const double* xmin;    // nx, state box (SB kernels only)
+  const double* xmax;
   int sqp_max_iter, ls_max;
   long long batch;
   const double* x0; const double* xref; const double* uref;
@@ -245,9 +247,12 @@ struct NmpcParams {
 
 __host__ __device__ inline int nmpc_ldk(int nz) { return nz | 1; }
 // per-warp shared memory (doubles)
-__host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int nz) {
+__host__ __device__ inline int nmpc_ldg(int nz, bool sb) { return sb ? (nz | 1) : nz; }   // odd pitch: row-per-lane dot products are conflict-free
+__host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int nz, bool sb) {
   return (size_t)nz * nmpc_ldk(nz)            // K
-         + 2 * (size_t)N.nx * nz              // Gamma double buffer (the idle one holds W Gamma)
+         + (sb ? (size_t)(H + 1) * N.nx * nmpc_ldg(nz, true)      // all Gamma_k (state-box rows) + W Gamma scratch
+               : 2 * (size_t)N.nx * nz)       // Gamma double buffer (the idle one holds W Gamma)
+         + (sb ? 8 * (size_t)H * N.nx : 0)    // state-box rows: rho_g, lo, hi, z_g, ys_g, m, n, y_g
          + 6 * (size_t)nz                     // u, v, r, g, q, col
          + (size_t)(H + 1) * N.nx             // trajectory
          + 2 * (size_t)N.nx                   // e, We
@@ -255,36 +260,48 @@ __host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int 
          + nn_eval_scratch_doubles(N, true);
 }
 __host__ __device__ inline size_t nmpc_const_doubles(const NetDev& N, int nz) {
-  return N.weight_count() + 2 * (size_t)N.nx * N.nx + (size_t)nz * nz + 2 * (size_t)nz;
+  return N.weight_count() + 2 * (size_t)N.nx * N.nx + (size_t)nz * nz + 2 * (size_t)nz + 2 * (size_t)N.nx;
 }
-__host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz, int warps) {
-  return sizeof(double) * (nmpc_const_doubles(N, nz) + (size_t)warps * nmpc_warp_doubles(N, H, nz));
+__host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz, int warps, bool sb) {
+  return sizeof(double) * (nmpc_const_doubles(N, nz) + (size_t)warps * nmpc_warp_doubles(N, H, nz, sb));
 }
 
 // ROWS = ceil(nz / 32): decision-variable rows owned by each lane (row e = lane + 32 * i)
 constexpr int NMPC_MAX_WARPS = 10;      // CTA width is chosen at design time to maximise resident warps per SM (shared-memory bound)
 // EQ: terminal equality e_x[:,end] == 0 (design_mpc.jl:330-331) as nx linearised rows Gamma_H v = Gamma_H u - e_H(u).
-template <int ROWS, bool EQ>
+// SB: state box xmin <= x[:,k] <= xmax for k = 2..H+1 (fnn.jl:146-154) as nx*H linearised inequality rows.
+template <int ROWS, bool EQ, bool SB>
 __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const NmpcParams P) {
   extern __shared__ __align__(16) double sm[];
   const int nwarps = blockDim.x >> 5;
   const NetSm N = stage_network(P.net, sm, threadIdx.x, blockDim.x);
-  const int nx = N.nx, nu = N.nu, nin = N.nin, nn = N.nn, H = P.H, nz = P.nz, ldk = nmpc_ldk(nz);
+  const int nx = N.nx, nu = N.nu, nin = N.nin, nn = N.nn, H = P.H, nz = P.nz, ldk = nmpc_ldk(nz), ldg = nmpc_ldg(nz, SB), ms = SB ? nx * H : 0;
   double* sQ = sm + P.net.weight_count();
   double* sPt = sQ + nx * nx;
   double* sHc = sPt + nx * nx;
   double* sLb = sHc + (size_t)nz * nz;
   double* sUb = sLb + nz;
+  double* sXmin = sUb + nz;
+  double* sXmax = sXmin + nx;
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) { sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
   for (int i = threadIdx.x; i < nz * nz; i += blockDim.x) sHc[i] = P.Hc[i];
   for (int i = threadIdx.x; i < nz; i += blockDim.x) { sLb[i] = P.lb[i]; sUb[i] = P.ub[i]; }
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) { sXmin[i] = SB ? P.xmin[i] : 0.0; sXmax[i] = SB ? P.xmax[i] : 0.0; }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)nwarps;
-  double* w = sUb + nz + (size_t)warp * nmpc_warp_doubles(P.net, H, nz);
+  double* w = sXmax + nx + (size_t)warp * nmpc_warp_doubles(P.net, H, nz, SB);
   double* K = w;                         w += (size_t)nz * ldk;
-  double* G0 = w;                        w += (size_t)nx * nz;
-  double* G1 = w;                        w += (size_t)nx * nz;
+  double* G0 = w;                        w += SB ? (size_t)H * nx * ldg : (size_t)nx * nz;   // SB: Gamma_1 .. Gamma_H, one block of nx rows each
+  double* G1 = w;                        w += SB ? (size_t)nx * ldg : (size_t)nx * nz;       // SB: W Gamma scratch
+  double* grho = w;                      w += ms;     // SB only, per state-box row: step size
+  double* glo = w;                       w += ms;     //   bounds of the linearised row
+  double* ghi = w;                       w += ms;
+  double* gz = w;                        w += ms;     //   z
+  double* gys = w;                       w += ms;     //   y / rho
+  double* gm = w;                        w += ms;     //   rho (z - ys)
+  double* gn = w;                        w += ms;     //   rho (ys+ - t_g)
+  double* gy = w;                        w += ms;     //   multipliers carried across SQP iterations
   double* su = w;                        w += nz;     // current iterate u
   double* sv = w;                        w += nz;     // QP solution / line-search candidate
   double* sr = w;                        w += nz;     // ADMM right-hand side
@@ -318,8 +335,9 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
     const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
     double yd[ROWS];          // duals of the box rows (carried across SQP iterations)
     double mu = 0.0;          // l1 merit weight of the terminal rows
-    const int ny = EQ ? nz + nx : nz;
-    if (EQ) { for (int i = lane; i < nx; i += 32) syg[i] = P.warm_y ? P.warm_y[p * ny + nz + i] : 0.0; }
+    const int ny = nz + ms + (EQ ? nx : 0);       // duals: [input box | state-box rows | terminal rows]
+    if (SB) { for (int r = lane; r < ms; r += 32) gy[r] = P.warm_y ? P.warm_y[p * ny + nz + r] : 0.0; }
+    if (EQ) { for (int i = lane; i < nx; i += 32) syg[i] = P.warm_y ? P.warm_y[p * ny + nz + ms + i] : 0.0; }
 #pragma unroll
     for (int i = 0; i < ROWS; i++) {
       const int e = lane + 32 * i;
@@ -377,7 +395,8 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       // ---------------------------------------------------------------- 1. linearise along the trajectory of u
       for (int a = 0; a < nz; a++)
         for (int c = lane; c < ldk; c += 32) K[a * ldk + c] = c < nz ? sHc[a * nz + c] : 0.0;
-      for (int o = lane; o < nx * nz; o += 32) { G0[o] = 0.0; G1[o] = 0.0; }
+      if (SB) { for (int o = lane; o < H * nx * ldg; o += 32) G0[o] = 0.0; }      // columns beyond the current stage must read as zero in the row products
+      else { for (int o = lane; o < nx * nz; o += 32) { G0[o] = 0.0; G1[o] = 0.0; } }
       for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
       __syncwarp();
       double J0 = 0.0;
@@ -402,6 +421,8 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       }
       double* Gc = G0; double* Gn = G1;
       for (int k = 0; k < H; k++) {
+        double* GW = Gc;                               // W Gamma goes to the idle buffer ...
+        if (SB) { Gc = G0 + (size_t)(k > 0 ? k - 1 : 0) * nx * ldg; Gn = G0 + (size_t)k * nx * ldg; GW = G1; }   // ... or, with all Gamma_k kept, to the scratch block
         for (int i = lane; i < nu; i += 32) xu[nx + i] = su[k * nu + i];
         __syncwarp();
         NMPC_PROF(0);
@@ -416,9 +437,9 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
             else {
               s = 0.0;
 #pragma unroll 4
-              for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * nz + c], s);
+              for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * ldg + c], s);
             }
-            Gn[i * nz + c] = s;
+            Gn[i * ldg + c] = s;
           }
         const double* W = (k + 1 == H) ? sPt : sQ;
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; se[i] = v - xr[i]; }
@@ -434,8 +455,8 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
           for (int c = lane; c < ncol; c += 32) {
             double s = 0.0;
 #pragma unroll 4
-            for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], Gn[j * nz + c], s);
-            Gc[i * nz + c] = s;
+            for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], Gn[j * ldg + c], s);
+            GW[i * ldg + c] = s;
           }
         __syncwarp();
         NMPC_PROF(6);
@@ -452,9 +473,9 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
           for (int i = 0; i < nx; i++) {
             double ga[4], gc[ROWS];
 #pragma unroll
-            for (int u = 0; u < 4; u++) ga[u] = (a0 + u < ncol) ? Gn[i * nz + a0 + u] : 0.0;
+            for (int u = 0; u < 4; u++) ga[u] = (a0 + u < ncol) ? Gn[i * ldg + a0 + u] : 0.0;
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) { const int c = lane + 32 * r; gc[r] = (c < ncol) ? Gc[i * nz + c] : 0.0; }
+            for (int r = 0; r < ROWS; r++) { const int c = lane + 32 * r; gc[r] = (c < ncol) ? GW[i * ldg + c] : 0.0; }
 #pragma unroll
             for (int u = 0; u < 4; u++)
 #pragma unroll
@@ -470,14 +491,14 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         }
         for (int a = lane; a < ncol; a += 32) {
           double s = 0.0;
-          for (int i = 0; i < nx; i++) s = fma(Gn[i * nz + a], sWe[i], s);
+          for (int i = 0; i < nx; i++) s = fma(Gn[i * ldg + a], sWe[i], s);
           sg[a] = fma(2.0, s, sg[a]);
         }
         __syncwarp();
         NMPC_PROF(7);
         // the buffer that held W Gamma must again read as Gamma_k = 0 beyond its columns for the next step: it is fully
         // rewritten for c < ncol + nu next time and never read beyond, so no clearing is needed
-        double* tp = Gc; Gc = Gn; Gn = tp;
+        if (!SB) { double* tp = Gc; Gc = Gn; Gn = tp; }
       }
       J0 = warp_sum(J0);
       NMPC_PROF(0);
@@ -490,12 +511,13 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       }
       __syncwarp();
       for (int e = lane; e < nz; e += 32) K[e * ldk + e] += sig_rho;
-      const double* GH = Gc;               // Gamma_H: the buffer the last linearisation step left current
-      double cviol = 0.0;                  // |e_H|_1
+      const double* GH = SB ? G0 + (size_t)(H - 1) * nx * ldg : Gc;      // Gamma_H
+      double cviol = 0.0;                  // l1 violation of the nonlinear constraints at u: |e_H|_1 (all lanes) + state-box part (per-lane partial, reduced below)
+      double cviol_sb = 0.0;
       if (EQ) {
         for (int i = 0; i < nx; i++) {     // per terminal row: |G_i|^2, G_i u  (warp reductions)
           double n2 = 0.0, gu = 0.0;
-          for (int cidx = lane; cidx < nz; cidx += 32) { const double gv = GH[i * nz + cidx]; n2 = fma(gv, gv, n2); gu = fma(gv, su[cidx], gu); }
+          for (int cidx = lane; cidx < nz; cidx += 32) { const double gv = GH[i * ldg + cidx]; n2 = fma(gv, gv, n2); gu = fma(gv, su[cidx], gu); }
           n2 = warp_sum(n2); gu = warp_sum(gu);
           const double eh = se[i];
           cviol += fabs(eh);
@@ -507,13 +529,56 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         __syncwarp();
         for (int a = 0; a < nz; a++) {     // K += G' diag(rho_e) G
           for (int i = 0; i < nx; i++) {
-            const double gai = srhoe[i] * GH[i * nz + a];
+            const double gai = srhoe[i] * GH[i * ldg + a];
 #pragma unroll
             for (int r = 0; r < ROWS; r++) {
               const int cidx = lane + 32 * r;
-              if (cidx < nz) K[a * ldk + cidx] = fma(gai, GH[i * nz + cidx], K[a * ldk + cidx]);
+              if (cidx < nz) K[a * ldk + cidx] = fma(gai, GH[i * ldg + cidx], K[a * ldk + cidx]);
             }
           }
+        }
+      }
+      if (SB) {
+        // per state-box row r = (k-1) nx + i (k = 1..H): step size, linearised bounds, OSQP warm start z = G u
+        for (int r = lane; r < ms; r += 32) {
+          const double* Gr = G0 + (size_t)r * ldg;
+          double n2 = 0.0, gu = 0.0;
+#pragma unroll 4
+          for (int cidx = 0; cidx < nz; cidx++) { const double gv = Gr[cidx]; n2 = fma(gv, gv, n2); gu = fma(gv, su[cidx], gu); }
+          const int i = r % nx;
+          const double xk = traj[nx + r];                   // x_k[i] of the current trajectory (traj holds k = 0..H)
+          const double re = rho / fmax(n2, 1e-12);
+          grho[r] = re; glo[r] = sXmin[i] - xk + gu; ghi[r] = sXmax[i] - xk + gu; gz[r] = gu; gys[r] = gy[r] / re;
+          cviol_sb += fmax(xk - sXmax[i], 0.0) + fmax(sXmin[i] - xk, 0.0);
+        }
+        __syncwarp();
+        // K += G' diag(rho_g) G : each lane owns the columns c = lane + 32 r of K, four rows a per pass
+        for (int a0 = 0; a0 < nz; a0 += 4) {
+          double acc[4][ROWS];
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int r2 = 0; r2 < ROWS; r2++) acc[u][r2] = 0.0;
+          for (int r = 0; r < ms; r++) {
+            const double* Gr = G0 + (size_t)r * ldg;
+            const double rg = grho[r];
+            double ga[4], gc[ROWS];
+#pragma unroll
+            for (int u = 0; u < 4; u++) ga[u] = (a0 + u < nz) ? rg * Gr[a0 + u] : 0.0;
+#pragma unroll
+            for (int r2 = 0; r2 < ROWS; r2++) { const int c = lane + 32 * r2; gc[r2] = (c < nz) ? Gr[c] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+              for (int r2 = 0; r2 < ROWS; r2++) acc[u][r2] = fma(ga[u], gc[r2], acc[u][r2]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int r2 = 0; r2 < ROWS; r2++) {
+              const int c = lane + 32 * r2;
+              if (a0 + u < nz && c < nz) K[(a0 + u) * ldk + c] += acc[u][r2];
+            }
         }
       }
       __syncwarp();
@@ -581,12 +646,23 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         bool conv = false;
         for (int ii = 0; ii < P.check_every; ii++) {
           const bool chk = (ii == P.check_every - 1);
+          if (SB) {            // right-hand side += G' (rho_g (z_g - ys_g)) over the state-box rows
+            for (int r = lane; r < ms; r += 32) gm[r] = grho[r] * (gz[r] - gys[r]);
+            __syncwarp();
+            for (int e = lane; e < nz; e += 32) {
+              double a = sr[e];
+#pragma unroll 4
+              for (int r = 0; r < ms; r++) a = fma(G0[(size_t)r * ldg + e], gm[r], a);
+              sr[e] = a;
+            }
+            __syncwarp();
+          }
           if (EQ) {            // right-hand side += G' (rho_e (z_g - ys_g))
             for (int i = lane; i < nx; i += 32) ssm[i] = srhoe[i] * (szg[i] - sysg[i]);
             __syncwarp();
             for (int e = lane; e < nz; e += 32) {
               double a = sr[e];
-              for (int i = 0; i < nx; i++) a = fma(GH[i * nz + e], ssm[i], a);
+              for (int i = 0; i < nx; i++) a = fma(GH[i * ldg + e], ssm[i], a);
               sr[e] = a;
             }
             __syncwarp();
@@ -604,11 +680,29 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
           __syncwarp();       // every lane has consumed sr
           double nA = 0.0, nD = 0.0;
           if (chk) { rp = 0.0; rd = 0.0; }
+          if (SB) {            // state-box rows: t_g = G x~ ; z_g+ = clip(alpha t_g + (1 - alpha) z_g + ys_g) ; ys_g+ = w_g - z_g+
+#pragma unroll
+            for (int r2 = 0; r2 < ROWS; r2++) { const int e = lane + 32 * r2; if (e < nz) sv[e] = t[r2]; }
+            __syncwarp();
+            for (int r = lane; r < ms; r += 32) {
+              const double* Gr = G0 + (size_t)r * ldg;
+              double tg = 0.0;
+#pragma unroll 4
+              for (int cidx = 0; cidx < nz; cidx++) tg = fma(Gr[cidx], sv[cidx], tg);
+              const double wg = fma(alpha, tg, fma(oma, gz[r], gys[r]));
+              const double lo = glo[r], hi = ghi[r];
+              const double zg = wg < lo ? lo : (wg > hi ? hi : wg);
+              const double ysn = wg - zg;
+              if (chk) { rp = fmax(rp, fabs(tg - zg)); nA = fmax(nA, fmax(fabs(tg), fabs(zg))); }
+              gz[r] = zg; gys[r] = ysn; gn[r] = grho[r] * (ysn - tg);
+            }
+            __syncwarp();
+          }
           if (EQ) {            // terminal rows: t_g = G x~ ; z_g+ = b ; ys_g+ = alpha t_g + (1 - alpha) z_g + ys_g - b
             for (int i = 0; i < nx; i++) {
               double part = 0.0;
 #pragma unroll
-              for (int r = 0; r < ROWS; r++) { const int e = lane + 32 * r; if (e < nz) part = fma(GH[i * nz + e], t[r], part); }
+              for (int r = 0; r < ROWS; r++) { const int e = lane + 32 * r; if (e < nz) part = fma(GH[i * ldg + e], t[r], part); }
               const double zg_old = szg[i], ysg_old = sysg[i], bi = sb[i], re = srhoe[i];     // read before the reduction (a convergence point) ...
               const double tgi = warp_sum(part);
               const double ysgn = fma(alpha, tgi, fma(oma, zg_old, ysg_old)) - bi;
@@ -626,7 +720,11 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
               const double zn = wv < lo ? lo : (wv > hi ? hi : wv);
               if (chk) {
                 double pc = fma(-sig_rho, t[i], sr[e]);
-                if (EQ) for (int k2 = 0; k2 < nx; k2++) pc = fma(GH[k2 * nz + e], ssn[k2], pc);     // Kgn x~ + G' y_g from the cached factor
+                if (EQ) for (int k2 = 0; k2 < nx; k2++) pc = fma(GH[k2 * ldg + e], ssn[k2], pc);     // Kgn x~ + G' y_g from the cached factor
+                if (SB) {
+#pragma unroll 4
+                  for (int r = 0; r < ms; r++) pc = fma(G0[(size_t)r * ldg + e], gn[r], pc);
+                }
                 const double ybv = rho * (wv - zn);
                 rp = fmax(rp, fabs(t[i] - zn));
                 rd = fmax(rd, fabs(pc + qv[i] + ybv));
@@ -653,11 +751,19 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       NMPC_PROF(2);
       qp_rd = rd;
       bool qp_failed = false;
+      if (SB) {
+        double ymax = 0.0;
+        for (int r = lane; r < ms; r += 32) { const double yv = grho[r] * gys[r]; gy[r] = yv; ymax = fmax(ymax, fabs(yv)); }
+        mu = fmax(mu, 1.1 * warp_max(ymax));
+        cviol += warp_sum(cviol_sb);
+        qp_failed = !qp_conv;
+        __syncwarp();
+      }
       if (EQ) {
         double ymax = 0.0;
         for (int i = 0; i < nx; i++) { const double yv = srhoe[i] * sysg[i]; ymax = fmax(ymax, fabs(yv)); if (lane == 0) syg[i] = yv; }
         mu = fmax(mu, 1.1 * ymax);
-        qp_failed = !qp_conv;          // linearised terminal rows + input box not solvable within the inner cap
+        qp_failed = qp_failed || !qp_conv;          // linearised rows + input box not solvable within the inner cap
         __syncwarp();
       }
       // ---------------------------------------------------------------- 4. step, acceptance, line search
@@ -676,7 +782,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       dmax = warp_max(dmax); gd = warp_sum(gd);
       step = dmax;
       __syncwarp();
-      if (EQ) {
+      if (EQ || SB) {
         if (qp_failed) { status = -3; have_traj = false; break; }
         gd -= mu * cviol;                // directional derivative of the l1 merit (the full step zeroes the linearised rows)
         J0 += mu * cviol;
@@ -698,9 +804,14 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         __syncwarp();
         const double Jc = rollout_cost(sv);
         double merit = Jc;
-        if (EQ) {
+        if (EQ || SB) {
           double cv = 0.0;
-          for (int i = 0; i < nx; i++) cv += fabs(traj[H * nx + i] - xr[i]);
+          if (EQ) for (int i = 0; i < nx; i++) cv += fabs(traj[H * nx + i] - xr[i]);
+          if (SB) {
+            double part = 0.0;
+            for (int r = lane; r < ms; r += 32) { const double xk = traj[nx + r]; const int i = r % nx; part += fmax(xk - sXmax[i], 0.0) + fmax(sXmin[i] - xk, 0.0); }
+            cv += warp_sum(part);
+          }
           merit = fma(mu, cv, Jc);
         }
         if (merit <= J0 + P.ls_c1 * tls * gd + P.ls_noise * fmax(1.0, fabs(J0))) { ok = true; Jcur = Jc; break; }
@@ -724,7 +835,8 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
     if (P.y) {
 #pragma unroll
       for (int i = 0; i < ROWS; i++) { const int e = lane + 32 * i; if (e < nz) P.y[p * ny + e] = yd[i]; }
-      if (EQ) for (int i = lane; i < nx; i += 32) P.y[p * ny + nz + i] = syg[i];
+      if (SB) for (int r = lane; r < ms; r += 32) P.y[p * ny + nz + r] = gy[r];
+      if (EQ) for (int i = lane; i < nx; i += 32) P.y[p * ny + nz + ms + i] = syg[i];
     }
     for (int o = lane; o < (H + 1) * nx; o += 32) {
       const double xv = traj[o];

@@ -12,6 +12,7 @@
 #include "api_common.hpp"
 #include "host_design.hpp"
 #include "nmpc.cuh"
+#include "nmpc_launch.hpp"
 
 using mpcb::api_fail;
 using mpcb::DevBuf;
@@ -31,10 +32,10 @@ struct mpcb_nmpc {
   mpcb_nn* nn = nullptr;
   mpcb_nmpc_settings st{};
   int H = 0, nz = 0, rows = 0, warps = 0;
-  bool terminal_eq = false;
+  bool terminal_eq = false, state_box = false;
   double rho = 0.0;
   mpcb::Mat A, B, P;
-  DevBuf<double> Q, Pt, Hc, lb, ub;
+  DevBuf<double> Q, Pt, Hc, lb, ub, xmin, xmax;
   DevBuf<unsigned long long> counter;
   // host-entry workspaces
   DevBuf<double> x0, xref, uref, warm_u, warm_y, u, e_u, x, e_x, u0, obj, y, step, dres;
@@ -93,18 +94,6 @@ int jacobian_device(mpcb_nn* n, int64_t batch, const double* x, const double* u,
   return launch_nn_batch<true>(n, P, st);
 }
 
-template <int ROWS, bool EQ>
-cudaError_t launch_sqp_rows(const mpcb::NmpcParams& P, unsigned grid, int threads, size_t smem, size_t* smem_set, cudaStream_t st) {
-  auto kern = mpcb::nmpc_sqp_kernel<ROWS, EQ>;
-  if (smem > 48 * 1024 && smem > *smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    *smem_set = smem;
-  }
-  kern<<<grid, threads, smem, st>>>(P);
-  return cudaGetLastError();
-}
-
 int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
   mpcb_nn* n = h->nn;
   const long long Bn = io.batch;
@@ -119,26 +108,20 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
   P.net = n->net; P.Q = h->Q.p; P.Pt = h->Pt.p; P.Hc = h->Hc.p; P.lb = h->lb.p; P.ub = h->ub.p; P.H = h->H; P.nz = h->nz;
   const mpcb_settings& q = h->st.qp;
   P.rho = h->rho; P.sigma = q.sigma; P.alpha = q.alpha; P.eps_abs = q.eps_abs; P.eps_rel = q.eps_rel; P.max_iter = q.max_iter; P.check_every = q.check_every;
-  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.rho_eq_scale = q.rho_eq_scale; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
+  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.rho_eq_scale = q.rho_eq_scale; P.xmin = h->xmin.p; P.xmax = h->xmax.p; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
   P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
   P.warm_u = io.warm_u; P.warm_y = io.warm_y;
   P.u = io.u; P.e_u = io.e_u; P.x = io.x; P.e_x = io.e_x; P.u0 = io.u0; P.objective = io.objective; P.y = io.y;
   P.status = d_status; P.iters = d_iters; P.inner_iters = io.inner_iters; P.step = io.prim_res; P.qp_dres = io.dual_res;
   P.counter = h->counter.p;
   const int threads = h->warps * 32;
-  const size_t smem = mpcb::nmpc_smem_bytes(n->net, h->H, h->nz, h->warps);
+  const size_t smem = mpcb::nmpc_smem_bytes(n->net, h->H, h->nz, h->warps, h->state_box);
   const long long blocks = (Bn + h->warps - 1) / h->warps;
   const int per_sm = std::max<int>(1, (int)((226 * 1024) / smem));
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * per_sm));
   cudaError_t e;
-  const bool eq = h->terminal_eq;
-  switch (h->rows) {
-    case 1: e = eq ? launch_sqp_rows<1, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<1, false>(P, grid, threads, smem, &h->smem_set, st); break;
-    case 2: e = eq ? launch_sqp_rows<2, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<2, false>(P, grid, threads, smem, &h->smem_set, st); break;
-    case 3: e = eq ? launch_sqp_rows<3, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<3, false>(P, grid, threads, smem, &h->smem_set, st); break;
-    case 4: e = eq ? launch_sqp_rows<4, true>(P, grid, threads, smem, &h->smem_set, st) : launch_sqp_rows<4, false>(P, grid, threads, smem, &h->smem_set, st); break;
-    default: return api_fail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
-  }
+  if (h->rows < 1 || h->rows > 4) return api_fail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
+  e = mpcb::launch_sqp(h->terminal_eq, h->state_box, h->rows, P, grid, threads, smem, &h->smem_set, st);
   if (e != cudaSuccess) return api_fail(MPCB_ERR_CUDA, std::string("nmpc_sqp_kernel launch: ") + cudaGetErrorString(e));
   h->timing.kernel_launches = 1;
   h->timing.batch = Bn;
@@ -267,7 +250,8 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   if (rc != MPCB_OK) return rc;
   const int nx = n->net.nx, nu = n->net.nu, H = d->horizon, nz = nu * H;
   mpcb_nmpc* h = new mpcb_nmpc();
-  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32; h->terminal_eq = d->terminal_mode == MPCB_TERMINAL_EQUALITY;
+  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32; h->terminal_eq = d->terminal_mode == MPCB_TERMINAL_EQUALITY; h->state_box = d->state_constraint != 0;
+  if (h->state_box && (!d->xmin || !d->xmax)) { mpcb_destroy_nmpc(h); return api_fail(MPCB_ERR_INVALID, "state_constraint needs xmin and xmax"); }
   auto bail = [&](int code, const std::string& msg) { mpcb_destroy_nmpc(h); return api_fail(code, msg); };
   if (h->rows > 4) return bail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
   // CTA width: the kernel is latency bound and shared-memory limited (one K matrix per warp), so pick the width that puts
@@ -275,7 +259,7 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   h->warps = 0;
   int best = 0;
   for (int w = 1; w <= mpcb::NMPC_MAX_WARPS; w++) {
-    const size_t sm = mpcb::nmpc_smem_bytes(n->net, H, nz, w);
+    const size_t sm = mpcb::nmpc_smem_bytes(n->net, H, nz, w, h->state_box);
     if (sm > 226 * 1024) break;
     const int resident = (int)((226 * 1024) / sm) * w;
     if (resident > best) { best = resident; h->warps = w; }
@@ -324,6 +308,10 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   if (mpcb::upload(h->Q, D.Q.a.data(), D.Q.a.size()) != cudaSuccess || mpcb::upload(h->Pt, D.P.a.data(), D.P.a.size()) != cudaSuccess ||
       mpcb::upload(h->Hc, Hc.data(), Hc.size()) != cudaSuccess || mpcb::upload(h->lb, lb.data(), nz) != cudaSuccess ||
       mpcb::upload(h->ub, ub.data(), nz) != cudaSuccess) { cudaGetLastError(); return bail(MPCB_ERR_CUDA, "constant upload failed"); }
+  if (h->state_box) {
+    for (int i = 0; i < nx; i++) if (!(d->xmin[i] <= d->xmax[i])) return bail(MPCB_ERR_INVALID, "xmin > xmax");
+    if (mpcb::upload(h->xmin, d->xmin, nx) != cudaSuccess || mpcb::upload(h->xmax, d->xmax, nx) != cudaSuccess) { cudaGetLastError(); return bail(MPCB_ERR_CUDA, "constant upload failed"); }
+  }
   for (auto& e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(MPCB_ERR_CUDA, "cudaEventCreate failed");
   *out = h;
@@ -333,7 +321,7 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
 void mpcb_destroy_nmpc(mpcb_nmpc* h) {
   if (!h) return;
   if (h->nn) { cudaSetDevice(h->nn->device); if (h->nn->stream) cudaStreamSynchronize(h->nn->stream); }
-  for (DevBuf<double>* b : {&h->Q, &h->Pt, &h->Hc, &h->lb, &h->ub, &h->x0, &h->xref, &h->uref, &h->warm_u, &h->warm_y, &h->u, &h->e_u, &h->x, &h->e_x, &h->u0,
+  for (DevBuf<double>* b : {&h->Q, &h->Pt, &h->Hc, &h->lb, &h->ub, &h->xmin, &h->xmax, &h->x0, &h->xref, &h->uref, &h->warm_u, &h->warm_y, &h->u, &h->e_u, &h->x, &h->e_x, &h->u0,
                             &h->obj, &h->y, &h->step, &h->dres})
     b->release();
   h->status.release(); h->iters.release(); h->inner.release(); h->counter.release(); h->stage_int.release();
@@ -371,7 +359,7 @@ int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) {
   mpcb_nn* n = h->nn;
   CUDA_TRY(cudaSetDevice(n->device));
   cudaStream_t st = n->stream;
-  const size_t nx = n->net.nx, nu = n->net.nu, H = h->H, nz = h->nz, B = (size_t)Bn, ny = nz + (h->terminal_eq ? nx : 0);
+  const size_t nx = n->net.nx, nu = n->net.nu, H = h->H, nz = h->nz, B = (size_t)Bn, ny = nz + (h->state_box ? nx * H : 0) + (h->terminal_eq ? nx : 0);
   const size_t n_xref = hio->xref_broadcast ? nx : nx * B, n_uref = hio->uref_broadcast ? nu : nu * B;
   struct In { const double* src; DevBuf<double>* dst; size_t n; };
   In ins[5] = {{hio->x0, &h->x0, nx * B}, {hio->xref, &h->xref, n_xref}, {hio->uref, &h->uref, n_uref}, {hio->warm_u, &h->warm_u, nz * B}, {hio->warm_y, &h->warm_y, ny * B}};

@@ -1,0 +1,4 @@
+#define NMPC_EQ true
+#define NMPC_SB true
+#define NMPC_LAUNCHER launch_sqp_11
+#include "nmpc_variant.inc"

@@ -57,7 +57,8 @@ struct MpcbNmpcDesc
     nn::Ptr{MpcbNnDesc}; horizon::Int32
     Q::Ptr{Cdouble}; R::Ptr{Cdouble}; S::Ptr{Cdouble}; P::Ptr{Cdouble}
     umin::Ptr{Cdouble}; umax::Ptr{Cdouble}; xref::Ptr{Cdouble}; uref::Ptr{Cdouble}
-    terminal_mode::Int32
+    terminal_mode::Int32; state_constraint::Int32
+    xmin::Ptr{Cdouble}; xmax::Ptr{Cdouble}
 end
 
 struct MpcbNmpcSettings
@@ -183,18 +184,21 @@ end
 "Replaces `_model_predictive_control_modeler_implementation(::NonLinearProgramming, ::Fnn | ::ResNet, ...)` (fnn.jl:63-189,
 resnet.jl:62-188) + `_JuMP_model_definition(::NonLinearProgramming, ::ipopt_solver_def)`."
 function B200NonlinearModeler(params::Vector, arch::Symbol, activation::String, Q, R, S, P, umin, umax, horizon::Int, xref, uref;
-                              terminal::String="none", settings::Union{Nothing,MpcbNmpcSettings}=nothing)
+                              terminal::String="none", state_constraint::Bool=false, xmin=zeros(0), xmax=zeros(0),
+                              settings::Union{Nothing,MpcbNmpcSettings}=nothing)
     terminal in ("none", "equality") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\" and \"equality\" only")
     arrs, f = nn_arrays(params, arch, activation)
     mats = map(M -> Matrix{Float64}(M), (Q, R, S, P)); vecs = map(v -> Vector{Float64}(v), (umin, umax, xref, uref))
+    xb = (Vector{Float64}(xmin), Vector{Float64}(xmax))
     st = Ref{MpcbNmpcSettings}()
     settings === nothing ? ccall((:mpcb_default_nmpc_settings, libmpcb200), Cvoid, (Ref{MpcbNmpcSettings},), st) : (st[] = settings)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve arrs mats vecs begin
+    GC.@preserve arrs mats vecs xb begin
         nd = Ref(MpcbNnDesc(f..., map(pointer, arrs)...))
         GC.@preserve nd begin
             d = MpcbNmpcDesc(Base.unsafe_convert(Ptr{MpcbNnDesc}, nd), horizon, map(pointer, mats)..., map(pointer, vecs)...,
-                             terminal == "equality" ? 1 : 0)
+                             terminal == "equality" ? 1 : 0, state_constraint ? 1 : 0,
+                             state_constraint ? pointer(xb[1]) : C_NULL, state_constraint ? pointer(xb[2]) : C_NULL)
             check(ccall((:mpcb_create_nmpc, libmpcb200), Cint, (Ref{MpcbNmpcDesc}, Ref{MpcbNmpcSettings}, Ref{Ptr{Cvoid}}), d, st, h), "mpcb_create_nmpc")
         end
     end

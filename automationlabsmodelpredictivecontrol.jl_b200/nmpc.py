@@ -18,8 +18,6 @@ class B200NonlinearModeler:
     def __init__(self, nn, Q, R, S, P, umin, umax, xmin, xmax, horizon, xref, uref, state_constraint=False, terminal="none", kws=None):
         if terminal not in ("none", "equality"):
             raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported by mpc_solver='b200' (only 'none' and 'equality')")
-        if state_constraint:
-            raise _lib.MpcbError("mpc_state_constraint is not supported on the nonlinear b200 path yet")
         kws = kws or {}
         self.nn = nn
         self.nx, self.nu, self.horizon = nn.nx, nn.nu, int(horizon)
@@ -29,13 +27,17 @@ class B200NonlinearModeler:
         keep = [f(Q), f(R), f(S), f(P), f(umin), f(umax), f(xref), f(uref)]
         p = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
         self.terminal = terminal
+        keep_x = [f(xmin), f(xmax)]
         d = _lib.NmpcDesc(C.pointer(nd), self.horizon, *[p(a) for a in keep],
-                          _lib.TERMINAL_EQUALITY if terminal == "equality" else _lib.TERMINAL_NONE)
+                          _lib.TERMINAL_EQUALITY if terminal == "equality" else _lib.TERMINAL_NONE, 1 if state_constraint else 0,
+                          p(keep_x[0]), p(keep_x[1]))
         self._h = C.c_void_p()
         _lib.check(_lib.lib().mpcb_create_nmpc(C.byref(d), C.byref(self.settings), C.byref(self._h)), "mpcb_create_nmpc")
         del keep_nn
         self.nz = self.nu * self.horizon
-        self.ny = self.nz + (self.nx if terminal == "equality" else 0)      # duals: input box rows [+ terminal rows]
+        self.state_constraint = bool(state_constraint)
+        # duals: input box rows [+ state-box rows] [+ terminal rows]
+        self.ny = self.nz + (self.nx * self.horizon if state_constraint else 0) + (self.nx if terminal == "equality" else 0)
         self.x0 = self.xref = self.uref = None
         self.warm = None
 

@@ -273,6 +273,9 @@ typedef struct {
   const double* xref; /* nx */
   const double* uref; /* nu */
   int32_t terminal_mode; /* MPCB_TERMINAL_NONE | MPCB_TERMINAL_EQUALITY (e_x[:,end] == 0, design_mpc.jl:330-331) */
+  int32_t state_constraint; /* != 0: kw `mpc_state_constraint` present -> xmin <= x[:,k] <= xmax for k = 2..H+1 (fnn.jl:146-154) */
+  const double* xmin; /* nx, first / last vertex of system.X; read only when state_constraint != 0 */
+  const double* xmax;
 } mpcb_nmpc_desc;
 
 typedef struct {
@@ -294,8 +297,8 @@ int mpcb_nmpc_get_timing(const mpcb_nmpc* h, mpcb_timing* t);
 
 /* The hot path for the nonlinear method: update_initialization! + calculate! (computation_mpc.jl:17-55) for a batch.
  * Uses mpcb_batch_io with these meanings: warm_u = initial guess of u (NULL: the reference input clipped to the box),
- * warm_y = duals of the input box followed, with the terminal equality, by the nx duals of the terminal rows
- * (nu*horizon [+ nx] per problem; may be NULL independently), y = those duals on exit,
+ * warm_y = duals of [input box (nu*horizon) | state-box rows (nx*horizon, if state_constraint) | terminal rows (nx, with
+ * the terminal equality)] per problem (may be NULL independently), y = those duals on exit,
  * iters = SQP iterations, inner_iters = total ADMM iterations, prim_res = last SQP step ||d||_inf,
  * dual_res = dual residual of the last QP, status = MPCB_STATUS_SOLVED / _SOLVED_INACCURATE / _MAX_ITER /
  * _PRIMAL_INFEASIBLE (a linearised terminal constraint that the input box does not admit within the inner iteration cap). */

@@ -150,12 +150,13 @@ def objective(m, Q, P, Hc, u, x0, xref, uref):
 
 def linearize_trajectory(m, Q, P, Hc, u, x0, xref, uref):
     """One Gauss-Newton linearisation: J, gradient g (B, nz), GN Hessian Pc (B, nz, nz) (incl. Hc), the trajectory and the
-    terminal sensitivity Gamma_H = d x_H / d u (B, nx, nz)."""
+    sensitivities Gamma_k = d x_k / d u for k = 1..H, shape (B, H, nx, nz)."""
     Bn, H, nu = u.shape; nx = m.nx; nz = nu * H
     x = np.zeros((Bn, H + 1, nx)); x[:, 0] = x0
     Gam = np.zeros((Bn, nx, nz))
     du = (u - uref[:, None, :]).reshape(Bn, nz)
     Pc = np.broadcast_to(Hc, (Bn, nz, nz)).copy()
+    Gall = np.zeros((Bn, H, nx, nz))                       # Gamma_1 .. Gamma_H
     g = du @ Hc.T
     e0 = x[:, 0] - xref
     J = 0.5 * np.einsum("bi,bi->b", du, g) + np.einsum("bi,ij,bj->b", e0, Q, e0)
@@ -164,13 +165,14 @@ def linearize_trajectory(m, Q, P, Hc, u, x0, xref, uref):
         x[:, k + 1] = f
         Gam = A @ Gam
         Gam[:, :, k * nu:(k + 1) * nu] = Bm
+        Gall[:, k] = Gam
         W = P if k + 1 == H else Q
         e = f - xref
         WG = W @ Gam                                           # (B, nx, nz)
         Pc += 2.0 * np.einsum("bia,bic->bac", Gam, WG)
         g += 2.0 * np.einsum("bia,ij,bj->ba", Gam, W, e)
         J += np.einsum("bi,ij,bj->b", e, W, e)
-    return J, g, Pc, x, Gam
+    return J, g, Pc, x, Gall
 
 
 @dataclasses.dataclass
@@ -215,34 +217,36 @@ def admm_box_per_problem(Kinv, q, lb, ub, s: mo.AdmmSettings, rho, x0, y0):
     return xo, yo, iters, status, pres, dres
 
 
-def admm_box_eq_per_problem(Kinv, q, lb, ub, G, b, rho_e, s: mo.AdmmSettings, rho, x0, y0, yg0):
-    """As admm_box_per_problem plus nx EQUALITY rows  G v = b  (the linearised terminal constraint), per-row step sizes
-    rho_e; Kinv is the inverse of  Kgn + (sigma + rho) I + G' diag(rho_e) G.  Returns the box and row multipliers."""
+def admm_box_gen_per_problem(Kinv, q, lb, ub, G, lo_g, hi_g, rho_g, s: mo.AdmmSettings, rho, x0, y0, yg0):
+    """As admm_box_per_problem plus GENERAL rows  lo_g <= G v <= hi_g  (linearised state box and / or terminal equality,
+    lo = hi), per-row step sizes rho_g; Kinv is the inverse of  Kgn + (sigma + rho) I + G' diag(rho_g) G.  Returns the box
+    and row multipliers."""
     Bn, nz = q.shape
     x = x0.copy(); z = x0.copy(); ys = y0 / rho
-    zg = np.einsum("bij,bj->bi", G, x0); ysg = yg0 / rho_e
+    zg = np.einsum("bij,bj->bi", G, x0); ysg = yg0 / rho_g
     max_iter = -(-s.max_iter // s.check_every) * s.check_every
     iters = np.zeros(Bn, np.int32); status = np.full(Bn, mo.STATUS_MAX_ITER, np.int32)
-    xo = np.zeros((Bn, nz)); yo = np.zeros((Bn, nz)); ygo = np.zeros_like(b); pres = np.zeros(Bn); dres = np.zeros(Bn)
+    xo = np.zeros((Bn, nz)); yo = np.zeros((Bn, nz)); ygo = np.zeros_like(lo_g); pres = np.zeros(Bn); dres = np.zeros(Bn)
     active = np.ones(Bn, bool); qn = np.abs(q).max(1)
     for it in range(1, max_iter + 1):
-        r = rho * (z - ys) + s.sigma * x - q + np.einsum("bij,bi->bj", G, rho_e * (zg - ysg))
+        r = rho * (z - ys) + s.sigma * x - q + np.einsum("bij,bi->bj", G, rho_g * (zg - ysg))
         t = np.einsum("bij,bj->bi", Kinv, r)
         tg = np.einsum("bij,bj->bi", G, t)
         w = s.alpha * t + (1 - s.alpha) * z + ys
         zn = np.minimum(np.maximum(w, lb), ub)
         ysn = w - zn
         wg = s.alpha * tg + (1 - s.alpha) * zg + ysg
-        ysgn = wg - b
+        zgn = np.minimum(np.maximum(wg, lo_g), hi_g)
+        ysgn = wg - zgn
         x = s.alpha * t + (1 - s.alpha) * x
-        z, ys, zg, ysg = zn, ysn, b.copy(), ysgn
+        z, ys, zg, ysg = zn, ysn, zgn, ysgn
         if it % s.check_every == 0:
-            y = rho * ys; yg = rho_e * ysg
-            kt = r - (s.sigma + rho) * t - np.einsum("bij,bi->bj", G, rho_e * tg)      # Kgn x~ from the cached factor
+            y = rho * ys; yg = rho_g * ysg
+            kt = r - (s.sigma + rho) * t - np.einsum("bij,bi->bj", G, rho_g * tg)      # Kgn x~ from the cached factor
             gs = kt + np.einsum("bij,bi->bj", G, yg)
-            rp = np.maximum(np.abs(t - z).max(1), np.abs(tg - b).max(1))
+            rp = np.maximum(np.abs(t - z).max(1), np.abs(tg - zg).max(1))
             rd = np.abs(gs + q + y).max(1)
-            ep = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(t).max(1), np.abs(z).max(1)), np.maximum(np.abs(tg).max(1), np.abs(b).max(1)))
+            ep = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(t).max(1), np.abs(z).max(1)), np.maximum(np.abs(tg).max(1), np.abs(zg).max(1)))
             ed = s.eps_abs + s.eps_rel * np.maximum(np.maximum(np.abs(gs).max(1), np.abs(y).max(1)), qn)
             conv = (rp <= ep) & (rd <= ed)
             fin = active & (conv | (it >= max_iter))
@@ -254,14 +258,17 @@ def admm_box_eq_per_problem(Kinv, q, lb, ub, G, b, rho_e, s: mo.AdmmSettings, rh
 
 
 def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: SqpSettings = None, u_init=None, y_init=None,
-             terminal="none", rho_eq_scale=1e3):
+             terminal="none", rho_eq_scale=1e3, xmin=None, xmax=None, state_constraint=False):
     """Twin of the CUDA kernel `nmpc_sqp_kernel`: per problem, repeat { rollout + Jacobians -> GN condensed QP in absolute
     inputs v (box umin <= v <= umax) -> ADMM warm-started at (u, y) -> step d = v - u -> Armijo backtracking on J } until
     ||d||_inf <= sqp_tol (status 1) or sqp_max_iter (status -2); a failed line search ends with status 2.
     terminal="equality" (design_mpc.jl:330-331, e_x[:,end] == 0): the QP carries the linearised rows
     Gamma_H v = Gamma_H u - e_H(u) with row-equilibrated step sizes, the line search runs on the l1 merit
     J + mu |e_H|_1 with mu = max(mu, 1.1 |multipliers|_inf), and a QP that does not converge within the inner cap is
-    reported as primal infeasible (-3)."""
+    reported as primal infeasible (-3).
+    state_constraint (fnn.jl:146-154, `mpc_state_constraint` present): rows xmin <= x_k(u) + Gamma_k (v - u) <= xmax for
+    k = 1..H (the fixed column k = 0 is constant), row-equilibrated, violations enter the same merit.
+    General rows are ordered [state rows (k, i) ..., terminal rows]."""
     s = s or SqpSettings()
     x0 = np.atleast_2d(np.asarray(x0, float)); Bn = x0.shape[0]; nx, nu = m.nx, m.nu; nz = nu * H
     xref = np.broadcast_to(np.atleast_2d(np.asarray(xref, float)), (Bn, nx)); uref = np.broadcast_to(np.atleast_2d(np.asarray(uref, float)), (Bn, nu))
@@ -271,8 +278,19 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
     y = np.zeros((Bn, nz)) if y_init is None else np.array(y_init, float).reshape(Bn, nz)
     status = np.full(Bn, mo.STATUS_MAX_ITER, np.int32); sqp_iters = np.zeros(Bn, np.int32); inner = np.zeros(Bn, np.int64)
     step = np.zeros(Bn); qp_dres = np.zeros(Bn)
-    eq = terminal == "equality"
-    yg = np.zeros((Bn, nx)); mu = np.zeros(Bn)
+    eq = terminal == "equality"; sb = bool(state_constraint)
+    xmin_ = np.asarray(xmin, float) if sb else None; xmax_ = np.asarray(xmax, float) if sb else None
+    mg = (nx * H if sb else 0) + (nx if eq else 0)
+    yg = np.zeros((Bn, mg)); mu = np.zeros(Bn)
+
+    def violation(xt, sel=None):
+        """l1 measure of the nonlinear constraints along a trajectory (B', H+1, nx)."""
+        xr_ = xref[idx] if sel is None else xref[idx][sel]
+        c = np.zeros(xt.shape[0])
+        if sb: c += (np.maximum(xt[:, 1:] - xmax_, 0.0) + np.maximum(xmin_ - xt[:, 1:], 0.0)).sum((1, 2))
+        if eq: c += np.abs(xt[:, H] - xr_).sum(1)
+        return c
+
     act_ = np.ones(Bn, bool)
     for it in range(1, s.sqp_max_iter + 1):
         idx = np.flatnonzero(act_)
@@ -281,17 +299,28 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
         J0, g, Pc, xa, GH = linearize_trajectory(m, Q, P, Hc, ua.reshape(-1, H, nu), x0[idx], xref[idx], uref[idx])
         q = g - np.einsum("bij,bj->bi", Pc, ua)
         qp_failed = np.zeros(idx.size, bool)
-        if eq:
-            eH = xa[:, H] - xref[idx]
-            rho_e = rho_eq_scale * rho / np.maximum((GH ** 2).sum(2), 1e-12)
-            K = Pc + (s.qp.sigma + rho) * np.eye(nz) + np.einsum("bia,bi,bic->bac", GH, rho_e, GH)
+        if eq or sb:
+            Gs, los, his, rhos = [], [], [], []
+            if sb:
+                Gk = GH.reshape(idx.size, H * nx, nz)
+                gu = np.einsum("bij,bj->bi", Gk, ua)
+                xk = xa[:, 1:].reshape(idx.size, H * nx)
+                Gs.append(Gk); los.append(np.tile(xmin_, H) - xk + gu); his.append(np.tile(xmax_, H) - xk + gu)
+                rhos.append(rho / np.maximum((Gk ** 2).sum(2), 1e-12))
+            if eq:
+                GT = GH[:, H - 1]
+                eH = xa[:, H] - xref[idx]
+                bq = np.einsum("bij,bj->bi", GT, ua) - eH
+                Gs.append(GT); los.append(bq); his.append(bq)
+                rhos.append(rho_eq_scale * rho / np.maximum((GT ** 2).sum(2), 1e-12))
+            Gg = np.concatenate(Gs, 1); lo_g = np.concatenate(los, 1); hi_g = np.concatenate(his, 1); rho_g = np.concatenate(rhos, 1)
+            K = Pc + (s.qp.sigma + rho) * np.eye(nz) + np.einsum("bia,bi,bic->bac", Gg, rho_g, Gg)
             Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.transpose(0, 2, 1))
-            bq = np.einsum("bij,bj->bi", GH, ua) - eH
-            v, yn, ygn, its, st_qp, _pr, dr = admm_box_eq_per_problem(Kinv, q, lb, ub, GH, bq, rho_e, s.qp, rho, ua, y[idx], yg[idx])
+            v, yn, ygn, its, st_qp, _pr, dr = admm_box_gen_per_problem(Kinv, q, lb, ub, Gg, lo_g, hi_g, rho_g, s.qp, rho, ua, y[idx], yg[idx])
             qp_failed = st_qp != mo.STATUS_SOLVED
             yg[idx] = ygn
             mu[idx] = np.maximum(mu[idx], 1.1 * np.abs(ygn).max(1))
-            c0 = np.abs(eH).sum(1)
+            c0 = violation(xa)
         else:
             K = Pc + (s.qp.sigma + rho) * np.eye(nz)
             Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.transpose(0, 2, 1))
@@ -309,7 +338,7 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
             if not todo.any(): break
             cand = ua[todo] + t[todo, None] * d[todo]
             Jc, xc = objective(m, Q, P, Hc, cand.reshape(-1, H, nu), x0[idx][todo], xref[idx][todo], uref[idx][todo])
-            if eq: Jc = Jc + mu[idx][todo] * np.abs(xc[:, H] - xref[idx][todo]).sum(1)
+            if eq or sb: Jc = Jc + mu[idx][todo] * violation(xc, todo)
             good = Jc <= J0[todo] + s.ls_c1 * t[todo] * gd[todo] + s.ls_noise * np.maximum(1.0, np.abs(J0[todo]))
             tt = np.flatnonzero(todo)
             un[tt[good]] = cand[good]; ok[tt[good]] = True

@@ -154,7 +154,7 @@ def test_sqp_warm_start_and_ragged_batches(mpc, qt, resnet_model):
     assert (warm["iters"] == 1).all() and (warm["status"] == 1).all() and np.abs(warm["u"] - full["u"]).max() < 2e-6
     assert warm["inner_iters"].mean() < 0.2 * full["inner_iters"].mean()
     # unsupported configurations are refused, not approximated
-    for kw in ({"mpc_terminal_ingredient": "contractive"}, {"mpc_state_constraint": True}):
+    for kw in ({"mpc_terminal_ingredient": "contractive"}, {"mpc_terminal_ingredient": "neighborhood"}):
         with pytest.raises(mpc.MpcbError):
             mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", 20, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
                                    mpc_programming_type="non_linear", **kw)
@@ -191,4 +191,53 @@ def test_sqp_terminal_equality(mpc, qt, fixture):
         r = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), res["u"][i].ravel(), jac=True, method="SLSQP", bounds=list(zip(lb, ub)),
                      constraints=[{"type": "eq", "fun": cons}], options={"maxiter": 500, "ftol": 1e-15})
         assert np.abs(cons(r.x)).max() < 1e-9
+        assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL and abs(r.fun - res["objective"][i]) <= OBJ_TOL * abs(r.fun)
+
+
+
+@pytest.mark.parametrize("fixture,terminal", [("qt_resnet_model.json", "none"), ("qt_fnn_tanh_model.json", "none"), ("qt_resnet_model.json", "equality")])
+def test_sqp_state_constraint(mpc, qt, fixture, terminal):
+    """kw `mpc_state_constraint` on an NL model (fnn.jl:146-154 / resnet.jl:145-153): linearised state-box rows inside the SQP.
+    The box is tightened to [0.55, 0.75] with references partly beyond it so the rows are active.  CUDA vs twin, and vs an
+    independent SLSQP solve of the same NLP with the nonlinear state constraints."""
+    from scipy.optimize import minimize
+    m = load_nn_fixture(fixture)
+    H, n = 20, 96
+    xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
+    sys_ = mpc.ConstrainedBlackBoxControlDiscreteSystem(to_chain(mpc, m), 4, 2, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="non_linear", mpc_state_constraint=True, mpc_terminal_ingredient=terminal)
+    mod = C.tuning.modeler
+    rng = np.random.default_rng(5)
+    if terminal == "none":
+        xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    else:                                    # reachable terminal state: start near the design reference, upper bound just above it
+        xref = np.tile(qt["x_ref"], (n, 1)); x0 = xref + 0.01 * rng.standard_normal((n, 4))
+    uref = qt["u_ref"].copy()
+    res = mod.solve_batch(x0, xref, uref, want=("u", "u0", "x", "e_x", "objective", "y"))
+    d = mod.design()
+    tw = no.nmpc_sqp(m, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0, xref, np.tile(uref, (n, 1)), d["rho"], terminal=terminal,
+                     xmin=xmin, xmax=xmax, state_constraint=True)
+    assert res["y"].shape == (n, 2 * H + 4 * H + (4 if terminal == "equality" else 0))
+    assert (res["status"] == tw["status"]).mean() > 0.95
+    ok = (res["status"] == 1) & (tw["status"] == 1)
+    assert ok.mean() > (0.9 if terminal == "none" else 0.3)
+    assert np.abs(res["u"][ok] - tw["u"][ok]).max() < 5e-6 and np.abs(res["objective"][ok] - tw["objective"][ok]).max() <= 1e-8 * np.abs(tw["objective"][ok]).max()
+    xs = res["x"][ok]
+    assert (xs[:, 1:] <= xmax + 1e-8).all() and (xs[:, 1:] >= xmin - 1e-8).all()
+    if terminal == "none":
+        touching = (xs[:, 1:] > xmax - 1e-6).any(axis=(1, 2))
+        assert touching.sum() >= n // 2                                    # the rows are really active
+        pick = np.flatnonzero(ok)[np.flatnonzero(touching)[:3]]
+    else:
+        assert np.abs(res["e_x"][ok][:, H]).max() < 1e-9
+        pick = np.flatnonzero(ok)[:2]
+    Hc = no.constant_hessian(2, H, qt["R"], qt["S"]); lb, ub = np.tile(qt["umin"], H), np.tile(qt["umax"], H)
+    for i in pick:
+        fg = lambda v: tuple(a[0] for a in no.grad_adjoint(m, qt["Q"], d["P"], Hc, v.reshape(1, H, 2), x0[i:i + 1], xref[i:i + 1], uref[None]))
+        roll = lambda v: no.rollout(m, x0[i:i + 1], v.reshape(1, H, 2))[0]
+        cons = [{"type": "ineq", "fun": lambda v: np.concatenate([(xmax - roll(v)[1:]).ravel(), (roll(v)[1:] - xmin).ravel()])}]
+        if terminal == "equality": cons.append({"type": "eq", "fun": lambda v: roll(v)[H] - xref[i]})
+        r = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), res["u"][i].ravel(), jac=True, method="SLSQP", bounds=list(zip(lb, ub)), constraints=cons,
+                     options={"maxiter": 500, "ftol": 1e-15})
         assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL and abs(r.fun - res["objective"][i]) <= OBJ_TOL * abs(r.fun)

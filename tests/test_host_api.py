@@ -29,7 +29,7 @@ def test_struct_layouts_match_header(mpc):
     assert ctypes.sizeof(L.Info) == 10 * 4 + 3 * 8
     assert ctypes.sizeof(L.BatchIO) == 8 + 3 * 8 + 2 * 4 + 14 * 8
     assert ctypes.sizeof(L.NnDesc) == 6 * 4 + 4 * 8
-    assert ctypes.sizeof(L.NmpcDesc) == 8 + 4 + 4 + 8 * 8 + 4 + 4
+    assert ctypes.sizeof(L.NmpcDesc) == 8 + 4 + 4 + 8 * 8 + 4 + 4 + 2 * 8
     assert ctypes.sizeof(L.NmpcSettings) == ctypes.sizeof(L.Settings) + 3 * 8 + 2 * 4
     n = L.default_nmpc_settings()
     assert (n.qp.eps_abs, n.qp.eps_rel, n.qp.check_every, n.qp.sigma, n.sqp_tol, n.ls_armijo, n.ls_noise, n.sqp_max_iter, n.ls_max_halvings) == (1e-9, 0.0, 5, 0.0, 1e-6, 1e-4, 1e-10, 20, 12)

@@ -82,7 +82,7 @@ def test_gradient_forward_sensitivities_equal_adjoint(qt, fnn_model):
     rng = np.random.default_rng(1)
     u = rng.uniform(qt["umin"], qt["umax"], (n, H, 2))
     Hc = no.constant_hessian(2, H, qt["R"], 3.0 * np.eye(2))
-    J1, g1, Pc, x, _GH = no.linearize_trajectory(m, qt["Q"], P, Hc, u, x0, xref, uref)
+    J1, g1, Pc, x, _Gall = no.linearize_trajectory(m, qt["Q"], P, Hc, u, x0, xref, uref)
     J2, g2 = no.grad_adjoint(m, qt["Q"], P, Hc, u, x0, xref, uref)
     J3, x3 = no.objective(m, qt["Q"], P, Hc, u, x0, xref, uref)
     assert np.allclose(J1, J2, rtol=1e-13) and np.allclose(J1, J3, rtol=1e-13) and np.allclose(x, x3)
