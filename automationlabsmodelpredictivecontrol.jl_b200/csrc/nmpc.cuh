@@ -25,7 +25,7 @@
 
 namespace mpcb {
 
-enum : int { NN_FNN = 0, NN_RESNET = 1 };
+enum : int { NN_FNN = 0, NN_RESNET = 1, NN_POLYNET = 2 };
 enum : int { ACT_RELU = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_SWISH = 3, ACT_IDENTITY = 4 };
 
 struct NetDev {            // device pointers, Julia column-major
@@ -65,14 +65,43 @@ __device__ __forceinline__ void act_eval(int id, double h, double& a, double& da
   }
 }
 
-// Warp-cooperative network evaluation.  xu[nin] (shared) -> f[nx] (shared).  Scratch: ya, yb [nn].  With JAC also
-// AB[nin][nx] (column-major nx x nin: d f / d [x;u]) using Ja, Jb [nin][nn] and sd [nn] (activation derivatives).
-// The Jacobian products run over flattened (input, neuron) pairs so that all 32 lanes work even for 13-neuron layers,
-// two pairs per lane and pass for instruction-level parallelism.  Ends with a __syncwarp().
+// One layer of the forward-mode Jacobian:  Jw[c][i] = sdv[i] * sum_j W[i][j] Jr[c][j]  (+ addA[c][i]) (+ addB[c][i]),
+// over flattened (input c, neuron i) pairs so that all 32 lanes work even for 13-neuron layers, two pairs per lane and pass.
+__device__ __forceinline__ void jac_layer(const double* __restrict__ W, const double* __restrict__ Jr, double* __restrict__ Jw,
+                                          const double* __restrict__ sdv, const double* addA, const double* addB, int nn, int nin, int lane) {
+  const int tot = nn * nin;
+  for (int o0 = lane; o0 < tot; o0 += 64) {
+    const int o1 = o0 + 32;
+    const bool has1 = o1 < tot;
+    const int c0 = o0 / nn, i0 = o0 - c0 * nn;
+    const int c1 = has1 ? o1 / nn : c0, i1 = has1 ? o1 - c1 * nn : i0;
+    double t0 = 0.0, t1 = 0.0;
+#pragma unroll 4
+    for (int j = 0; j < nn; j++) {
+      t0 = fma(W[j * nn + i0], Jr[c0 * nn + j], t0);
+      t1 = fma(W[j * nn + i1], Jr[c1 * nn + j], t1);
+    }
+    t0 *= sdv[i0]; t1 *= sdv[i1];
+    if (addA) { t0 += addA[o0]; if (has1) t1 += addA[o1]; }
+    if (addB) { t0 += addB[o0]; if (has1) t1 += addB[o1]; }
+    Jw[o0] = t0;
+    if (has1) Jw[o1] = t1;
+  }
+}
+
+// Warp-cooperative network evaluation.  xu[nin] (shared) -> f[nx] (shared).  Scratch: ya, yb, yc3 [nn] (yc3: the PolyNet
+// branch).  With JAC also AB[nin][nx] (column-major nx x nin: d f / d [x;u]) using Ja, Jb, Jc3 [nin][nn] and sd, sd2 [nn]
+// (activation derivatives).  Ends with a __syncwarp().
+//   fnn     y+ = act(W y + b)                                     (fnn.jl:133-141)
+//   resnet  y+ = y + act(W y + b)                                 (resnet.jl:131-140)
+//   polynet br = act(W y + b);  y+ = y + br + act(W br + b)       (polynet.jl:132-149: both paths share W_j and b_j)
 template <bool JAC>
 __device__ __forceinline__ void nn_eval_warp(const NetSm& N, const double* xu, double* f, double* ya, double* yb, double* Ja, double* Jb,
                                              double* AB, double* sd, int lane) {
   const int nn = N.nn, nin = N.nin, nx = N.nx;
+  double* yc3 = sd + (JAC ? 2 * nn : 0);            // scratch layout: [sd | sd2 |] br [| Jbr]   (see nn_eval_scratch_doubles)
+  double* sd2 = sd + nn;
+  double* Jc3 = yc3 + nn;
   for (int i = lane; i < nn; i += 32) {
     double s = 0.0;
 #pragma unroll 6
@@ -92,30 +121,28 @@ __device__ __forceinline__ void nn_eval_warp(const NetSm& N, const double* xu, d
       for (int j = 0; j < nn; j++) s = fma(W[j * nn + i], yc[j], s);
       double a, da;
       act_eval(N.act, s, a, da);
-      yn[i] = N.arch == NN_RESNET ? a + yc[i] : a;
+      if (N.arch == NN_POLYNET) yc3[i] = a; else yn[i] = N.arch == NN_RESNET ? a + yc[i] : a;
       if (JAC) sd[i] = da;
     }
     __syncwarp();
-    if (JAC) {                                      // d y_new[i] / d in[c] = da[i] * (W Jc)[i][c] (+ Jc[i][c])
-      const double* __restrict__ Jr = Jc;
-      double* __restrict__ Jw = Jn;
-      const int tot = nn * nin;
-      for (int o0 = lane; o0 < tot; o0 += 64) {
-        const int o1 = o0 + 32;
-        const bool has1 = o1 < tot;
-        const int c0 = o0 / nn, i0 = o0 - c0 * nn;
-        const int c1 = has1 ? o1 / nn : c0, i1 = has1 ? o1 - c1 * nn : i0;
-        double t0 = 0.0, t1 = 0.0;
-#pragma unroll 4
-        for (int j = 0; j < nn; j++) {
-          t0 = fma(W[j * nn + i0], Jr[c0 * nn + j], t0);
-          t1 = fma(W[j * nn + i1], Jr[c1 * nn + j], t1);
-        }
-        t0 *= sd[i0]; t1 *= sd[i1];
-        if (N.arch == NN_RESNET) { t0 += Jr[o0]; if (has1) t1 += Jr[o1]; }
-        Jw[o0] = t0;
-        if (has1) Jw[o1] = t1;
+    if (N.arch == NN_POLYNET) {
+      for (int i = lane; i < nn; i += 32) {
+        double s = b[i];
+#pragma unroll 8
+        for (int j = 0; j < nn; j++) s = fma(W[j * nn + i], yc3[j], s);
+        double a, da;
+        act_eval(N.act, s, a, da);
+        yn[i] = yc[i] + yc3[i] + a;
+        if (JAC) sd2[i] = da;
       }
+      if (JAC) {
+        jac_layer(W, Jc, Jc3, sd, nullptr, nullptr, nn, nin, lane);      // J_br = D1 W J_y
+        __syncwarp();
+        jac_layer(W, Jc3, Jn, sd2, Jc, Jc3, nn, nin, lane);              // J_y+ = J_y + J_br + D2 W J_br
+      }
+      __syncwarp();
+    } else if (JAC) {
+      jac_layer(W, Jc, Jn, sd, N.arch == NN_RESNET ? Jc : nullptr, nullptr, nn, nin, lane);
       __syncwarp();
     }
     double* tp = yc; yc = yn; yn = tp;
@@ -177,7 +204,7 @@ struct NnBatchParams {
 };
 
 __host__ __device__ inline size_t nn_eval_scratch_doubles(const NetDev& N, bool jac) {
-  return (size_t)N.nin + N.nx + 2 * N.nn + (jac ? (size_t)2 * N.nn * N.nin + (size_t)N.nx * N.nin + N.nn : 0);
+  return (size_t)N.nin + N.nx + 3 * N.nn + (jac ? (size_t)3 * N.nn * N.nin + (size_t)N.nx * N.nin + 2 * N.nn : 0);
 }
 __host__ __device__ inline size_t nn_batch_smem_bytes(const NetDev& N, bool jac) {
   return sizeof(double) * (N.weight_count() + NN_WARPS * nn_eval_scratch_doubles(N, jac));
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(NN_THREADS) nn_batch_kernel(const NnBatchParam
       for (int k = 0; k < P.H; k++) {
         for (int i = lane; i < nu; i += 32) xu[nx + i] = P.u[(p * P.H + k) * nu + i];
         __syncwarp();
-        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, nullptr, lane);
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; P.x[(p * (P.H + 1) + k + 1) * nx + i] = v; }
         __syncwarp();
       }
@@ -369,7 +396,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         if (k == H) break;
         for (int i = lane; i < nu; i += 32) xu[nx + i] = uu[k * nu + i];
         __syncwarp();
-        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, nullptr, lane);
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; }
         __syncwarp();
       }

@@ -65,7 +65,8 @@ int check_device(int device, int* sm_count) {
 
 int validate_nn(const mpcb_nn_desc* d) {
   if (!d) return api_fail(MPCB_ERR_INVALID, "null network description");
-  if (d->arch != MPCB_NN_FNN && d->arch != MPCB_NN_RESNET) return api_fail(MPCB_ERR_INVALID, "unknown network architecture (fnn and resnet are supported)");
+  if (d->arch != MPCB_NN_FNN && d->arch != MPCB_NN_RESNET && d->arch != MPCB_NN_POLYNET)
+    return api_fail(MPCB_ERR_INVALID, "unknown network architecture (fnn, resnet and polynet are supported)");
   if (d->activation < MPCB_ACT_RELU || d->activation > MPCB_ACT_IDENTITY) return api_fail(MPCB_ERR_INVALID, "unknown activation id");
   if (d->nx <= 0 || d->nu <= 0 || d->n_neurons <= 0 || d->n_hidden < 0) return api_fail(MPCB_ERR_INVALID, "bad network sizes");
   if (!d->W_in || !d->W_out || (d->n_hidden > 0 && (!d->W_hidden || !d->b_hidden))) return api_fail(MPCB_ERR_INVALID, "null weight pointer");

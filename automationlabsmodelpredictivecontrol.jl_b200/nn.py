@@ -20,7 +20,7 @@ def _f(a):
 
 
 class _Chain:
-    arch = None      # "fnn" | "resnet"
+    arch = None      # "fnn" | "resnet" | "polynet"
 
     def __init__(self, W_in, hidden, W_out, activation="relu", device=0):
         """hidden: sequence of (W_j, b_j); layouts as Flux stores them (out x in)."""
@@ -51,7 +51,7 @@ class _Chain:
         bh = np.concatenate(self.b_h) if nh else np.zeros(1)
         keep = [self.W_in, Wh, bh, self.W_out]
         p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-        d = _lib.NnDesc(_lib.NN_RESNET if self.arch == "resnet" else _lib.NN_FNN, _lib.ACTIVATION_IDS[self.activation], self.nx, self.nu,
+        d = _lib.NnDesc({"fnn": _lib.NN_FNN, "resnet": _lib.NN_RESNET, "polynet": _lib.NN_POLYNET}[self.arch], _lib.ACTIVATION_IDS[self.activation], self.nx, self.nu,
                         self.n_neurons, nh, p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]))
         return d, keep
 
@@ -106,6 +106,11 @@ class Fnn(_Chain):
 class ResNet(_Chain):
     """AutomationLabsSystems.ResNet: y_j = y_{j-1} + act(W_j y_{j-1} + b_j)  (resnet.jl:131-140)."""
     arch = "resnet"
+
+
+class PolyNet(_Chain):
+    """AutomationLabsSystems.PolyNet: br = act(W_j y + b_j); y_j = y_{j-1} + br + act(W_j br + b_j)  (polynet.jl:132-149)."""
+    arch = "polynet"
 
 
 def linearize(nn: _Chain, x, u):

@@ -221,10 +221,12 @@ void mpcb_free_pinned(void* p);
  * black-box models (fnn.jl:37-46, resnet.jl:37-46; terminal cost: design_mpc.jl:312-327).
  * The network is described exactly as those modelers parse `Flux.params(system.f)` (fnn.jl:88-107):
  *   params[1] = W_in (n_neurons x (nx+nu), NO bias); then n_hidden pairs (W_j, b_j); params[end] = W_out (nx x n_neurons,
- *   NO bias).  fnn:  y_j = act(W_j y_{j-1} + b_j);  resnet:  y_j = y_{j-1} + act(W_j y_{j-1} + b_j);  x+ = W_out y_end.
+ *   NO bias).  fnn:  y_j = act(W_j y_{j-1} + b_j);  resnet:  y_j = y_{j-1} + act(W_j y_{j-1} + b_j);  polynet: see below;
+ *   x+ = W_out y_end.
  * ------------------------------------------------------------------------------------------------------------------ */
 #define MPCB_NN_FNN 0
 #define MPCB_NN_RESNET 1
+#define MPCB_NN_POLYNET 2 /* br = act(W y + b); y+ = y + br + act(W br + b)  (polynet/mpc_modeler_implementation_polynet.jl:132-149) */
 
 #define MPCB_ACT_RELU 0
 #define MPCB_ACT_TANH 1

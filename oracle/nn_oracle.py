@@ -47,7 +47,7 @@ def dact(name, h):
 @dataclasses.dataclass
 class NeuralModel:
     """`Flux.params(system.f)` as the reference parses it: params[1] = W_in, then (W_j, b_j) pairs, last = W_out."""
-    arch: str                 # "fnn" | "resnet"
+    arch: str                 # "fnn" | "resnet" | "polynet"
     activation: str
     W_in: np.ndarray          # (n_neur, nx + nu)
     W_h: list                 # n_hidden x (n_neur, n_neur)
@@ -71,8 +71,14 @@ def hidden_states(m: NeuralModel, x, u):
     ys = [xu @ m.W_in.T]; pre = []
     for W, b in zip(m.W_h, m.b_h):
         h = ys[-1] @ W.T + b
-        pre.append(h)
-        ys.append(act(m.activation, h) + (ys[-1] if m.arch == "resnet" else 0.0))
+        if m.arch == "polynet":        # polynet.jl:132-149: branch = act(W y + b); y+ = y + branch + act(W branch + b)  (same W, b)
+            br = act(m.activation, h)
+            h2 = br @ W.T + b
+            pre.append((h, h2))
+            ys.append(ys[-1] + br + act(m.activation, h2))
+        else:
+            pre.append(h)
+            ys.append(act(m.activation, h) + (ys[-1] if m.arch == "resnet" else 0.0))
     return ys, pre
 
 
@@ -88,6 +94,10 @@ def jacobian(m: NeuralModel, x, u):
     Bn = ys[0].shape[0]
     Jm = np.broadcast_to(m.W_in, (Bn,) + m.W_in.shape).copy()          # d y_1 / d [x;u]
     for W, h in zip(m.W_h, pre):
+        if m.arch == "polynet":
+            Jb = dact(m.activation, h[0])[:, :, None] * (W @ Jm)
+            Jm = Jm + Jb + dact(m.activation, h[1])[:, :, None] * (W @ Jb)
+            continue
         D = dact(m.activation, h)[:, :, None]
         Jn = D * (W @ Jm)
         Jm = Jn + Jm if m.arch == "resnet" else Jn

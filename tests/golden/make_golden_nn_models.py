@@ -38,7 +38,8 @@ def main():
                         "W_out": arr2(o4, 4, 13).tolist(), "offsets": [hex(o) for o in (o1, o2, o3, o4)]}
     out = {"source": "test/models_saved/fnn_train_result.jls (Float32 arrays promoted exactly to Float64)", "arch": "fnn", "activation": "relu",
            "chain": "b", **chains["b"], "other_chain": chains["a"]}
-    (HERE / "qt_fnn_model.json").write_text(json.dumps(out))
+    import sys
+    if not sys.argv[1:]: (HERE / "qt_fnn_model.json").write_text(json.dumps(out))
 
     import torch
     torch.manual_seed(2); torch.set_default_dtype(torch.float64); torch.set_num_threads(4)
@@ -66,9 +67,12 @@ def main():
     Xi = torch.from_numpy(np.hstack([X, U])); Yt = torch.from_numpy(Y)
     acts = {"relu": torch.relu, "tanh": torch.tanh, "swish": lambda h: h * torch.sigmoid(h)}
     fits = {}
-    # (2) the BASELINE config-5 surrogate, (3)+(4) smooth-activation surrogates for the parity tests of the SQP path
+    # (2) the BASELINE config-5 surrogate, (3)+(4) smooth-activation surrogates for the parity tests of the SQP path, (5) a PolyNet
+    import sys
+    only = set(sys.argv[1:])          # optional: regenerate only the named files (the others are kept bit for bit)
     for fname, arch, actname in (("qt_resnet_model.json", "resnet", "relu"), ("qt_fnn_tanh_model.json", "fnn", "tanh"),
-                                 ("qt_resnet_swish_model.json", "resnet", "swish")):
+                                 ("qt_resnet_swish_model.json", "resnet", "swish"), ("qt_polynet_tanh_model.json", "polynet", "tanh")):
+        if only and fname not in only: continue
         torch.manual_seed(2)
         W_in = (0.3 * torch.randn(13, 6)).requires_grad_(); W_h = (0.3 * torch.randn(13, 13)).requires_grad_()
         b_h = torch.zeros(13, requires_grad=True); W_out = (0.3 * torch.randn(4, 13)).requires_grad_()
@@ -78,6 +82,7 @@ def main():
         def net():
             y1 = Xi @ W_in.T
             a = sigma(y1 @ W_h.T + b_h)
+            if arch == "polynet": return (y1 + a + sigma(a @ W_h.T + b_h)) @ W_out.T      # polynet.jl:132-149
             return ((y1 + a) if arch == "resnet" else a) @ W_out.T
 
         loss_fn = lambda: (((net() - Yt) * 100.0) ** 2).mean()          # error in centimetres

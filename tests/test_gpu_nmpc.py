@@ -15,7 +15,7 @@ U0_TOL, OBJ_TOL = 1e-4, 1e-6        # north_star tolerances
 
 
 def to_chain(mpc, m):
-    cls = mpc.ResNet if m.arch == "resnet" else mpc.Fnn
+    cls = {"fnn": mpc.Fnn, "resnet": mpc.ResNet, "polynet": mpc.PolyNet}[m.arch]
     return cls(m.W_in, list(zip(m.W_h, m.b_h)), m.W_out, activation=m.activation)
 
 
@@ -32,7 +32,7 @@ def scenario(qt, n, seed=0):
 @pytest.mark.parametrize("activation", ["relu", "tanh", "sigmoid", "swish", "identity"])
 def test_rollout_and_jacobian_match_oracle(mpc, fnn_model, resnet_model, activation):
     rng = np.random.default_rng(7)
-    for base in (fnn_model, resnet_model):
+    for base in (fnn_model, resnet_model, dataclasses.replace(resnet_model, arch="polynet")):
         m = dataclasses.replace(base, activation=activation)
         f = to_chain(mpc, m)
         n, H = 517, 9                                      # ragged: not a multiple of the CTA's 4 warps
@@ -49,7 +49,7 @@ def test_rollout_and_jacobian_match_oracle(mpc, fnn_model, resnet_model, activat
 def test_deeper_wider_network(mpc):
     """Generic sizes: nx = 3, nu = 2, 40 neurons (more than one warp), 3 hidden layers."""
     rng = np.random.default_rng(11)
-    for arch in ("fnn", "resnet"):
+    for arch in ("fnn", "resnet", "polynet"):
         m = no.NeuralModel(arch, "tanh", 0.3 * rng.standard_normal((40, 5)), [0.2 * rng.standard_normal((40, 40)) for _ in range(3)],
                            [0.1 * rng.standard_normal(40) for _ in range(3)], 0.2 * rng.standard_normal((3, 40)))
         f = to_chain(mpc, m)
@@ -77,7 +77,7 @@ def test_linear_method_on_blackbox_model(mpc, qt, fnn_model):
 
 
 @pytest.mark.parametrize("fixture,H", [("qt_resnet_model.json", 20), ("qt_fnn_tanh_model.json", 20), ("qt_resnet_swish_model.json", 20), ("qt_fnn_tanh_model.json", 7),
-                                       ("qt_resnet_swish_model.json", 33)])
+                                       ("qt_resnet_swish_model.json", 33), ("qt_polynet_tanh_model.json", 20)])
 def test_sqp_matches_twin_and_independent_solve(mpc, qt, fixture, H):
     m = load_nn_fixture(fixture)
     n = 300
@@ -94,17 +94,19 @@ def test_sqp_matches_twin_and_independent_solve(mpc, qt, fixture, H):
     assert np.abs(d["A"] - A[0]).max() < 1e-13 and np.abs(d["B"] - B[0]).max() < 1e-13 and np.abs(d["P"] - P).max() < 1e-6 * np.abs(P).max()
     # twin: same algorithm, same settings
     tw = no.nmpc_sqp(m, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0, xref, np.tile(uref, (n, 1)), d["rho"])
-    assert (res["status"] == 1).all() and (tw["status"] == 1).all()
+    assert (res["status"] == tw["status"]).mean() > 0.98 and set(np.unique(res["status"])) <= {1, -2}
+    ok = (res["status"] == 1) & (tw["status"] == 1)
+    assert ok.all() if "polynet" not in fixture else ok.mean() > 0.9     # the PolyNet surrogate converges slowly on a few problems (cap of 20)
     assert (res["iters"] == tw["iters"]).mean() > 0.9
-    assert np.abs(res["u"] - tw["u"]).max() < 5e-6            # both stop at ||step|| <= 1e-6 of the same fixed point
-    assert np.abs(res["objective"] - tw["objective"]).max() <= 1e-9 * np.abs(tw["objective"]).max()
+    assert np.abs(res["u"][ok] - tw["u"][ok]).max() < 5e-6            # both stop at ||step|| <= 1e-6 of the same fixed point
+    assert np.abs(res["objective"][ok] - tw["objective"][ok]).max() <= 1e-9 * np.abs(tw["objective"]).max()
     # outputs are consistent with the reference's variables: x = rollout(u), e_x = x - x_ref, e_u = u - u_ref
     assert np.abs(res["x"] - no.rollout(m, x0, res["u"])).max() < 1e-12 and no.reference_nl_residual(m, res["x"], res["u"]) < 1e-12
     assert np.abs(res["e_x"] - (res["x"] - xref[:, None, :])).max() < 1e-15 and np.abs(res["e_u"] - (res["u"] - uref)).max() < 1e-15
     assert np.abs(res["u0"] - res["u"][:, 0]).max() == 0.0 and np.abs(C.computation_results.u - res["u"][0].T).max() == 0.0
     assert (res["u"] >= qt["umin"] - 2e-9).all() and (res["u"] <= qt["umax"] + 2e-9).all()       # x~ of the last QP: within eps_abs of the box
     # independent solve (Ipopt stand-in) + KKT certificate
-    for i in range(5):
+    for i in np.flatnonzero(ok)[:5]:
         u, J, k = no.nmpc_local_opt(m, qt["Q"], qt["R"], qt["S"], d["P"], H, qt["umin"], qt["umax"], x0[i], xref[i], uref, u_init=res["u"][i])
         assert k < 1e-5
         assert mo.u0_metric(res["u0"][i], u[0], qt["umin"], qt["umax"]) < U0_TOL

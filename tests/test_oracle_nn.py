@@ -44,23 +44,27 @@ def test_fnn_fixture_is_the_reference_layout(fnn_model):
 def test_layer_equations_match_reference_modelers(fnn_model, resnet_model):
     """Spell the reference's per-neuron constraints (fnn.jl:126-143, resnet.jl:125-142) out with Python loops."""
     rng = np.random.default_rng(3)
-    for m in (fnn_model, resnet_model):
+    for m in (fnn_model, resnet_model, dataclasses.replace(resnet_model, arch="polynet")):
         x, u = rng.uniform(0.2, 1.3, 4), rng.uniform(0, 3, 2)
         xu = np.concatenate([x, u])
-        y = np.zeros((m.n_neur, m.n_hid + 1))
+        y = np.zeros((m.n_neur, m.n_hid + 1)); branch = np.zeros((m.n_neur, m.n_hid))
         for i in range(m.n_neur):
             y[i, 0] = m.W_in[i, :] @ xu
         for j in range(1, m.n_hid + 1):
             for i in range(m.n_neur):
                 a = max(m.W_h[j - 1][i, :] @ y[:, j - 1] + m.b_h[j - 1][i], 0.0)
+                branch[i, j - 1] = a
                 y[i, j] = (y[i, j - 1] + a) if m.arch == "resnet" else a
+            if m.arch == "polynet":                                   # polynet.jl:132-149, second path through the same W_j, b_j
+                for i in range(m.n_neur):
+                    y[i, j] = y[i, j - 1] + branch[i, j - 1] + max(m.W_h[j - 1][i, :] @ branch[:, j - 1] + m.b_h[j - 1][i], 0.0)
         assert np.allclose(m.W_out @ y[:, -1], no.forward(m, x[None], u[None])[0], rtol=0, atol=1e-14)
 
 
 @pytest.mark.parametrize("activation", ["relu", "tanh", "sigmoid", "swish", "identity"])
 def test_jacobian_forward_mode_vs_finite_differences(fnn_model, resnet_model, activation):
     rng = np.random.default_rng(5)
-    for base in (fnn_model, resnet_model):
+    for base in (fnn_model, resnet_model, dataclasses.replace(resnet_model, arch="polynet")):
         m = dataclasses.replace(base, activation=activation)
         x, u = rng.uniform(0.2, 1.3, (8, 4)), rng.uniform(0, 3, (8, 2))
         f, A, B = no.jacobian(m, x, u)
