@@ -25,8 +25,11 @@ constexpr size_t SMEM_BYTES = sizeof(double) * STAGE_DOUBLES * STAGES;
 enum : int { MODE_NORMAL = 0, MODE_SAVE_YP = 1, MODE_CHECK = 2 };
 
 struct IterParams {
-  const double* Rin;   // [rows][NTp] MMA operand of this iteration
-  double* Rout;        // next operand
+  double* R0;          // [rows][NTp] MMA operand of the period's first iteration (iterations alternate R0 -> R1 -> R0 ...)
+  double* R1;
+  int iters;           // iterations fused into this launch (= check_every)
+  int* sched;          // device: [0] tile ticket counter, [1 + it * nrb + rb] column tiles of (iteration it, row block rb) finished
+  int nrb, ncb;
   const double* T;     // [NTp][NTp]
   double* Cst;         // c = (1-alpha) z + y/rho
   const double* QB;    // box cols: q ; general cols: bound offset b(p)
@@ -34,7 +37,7 @@ struct IterParams {
   const double* lo; const double* hi; const double* rho;   // [NTp]
   double* XT; double* YO; double* YP;                      // candidate x~ / y+ (check), y of the iteration before (certificate)
   unsigned long long* red;                                 // [rows][4]: rp, rd, nA, nD as bit patterns of non-negative doubles
-  int rows, NTp, nz, nt, mg, mode;
+  int rows, NTp, nz, nt, mg;
   double alpha, sigma;
 };
 
@@ -119,11 +122,42 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ In, const d
   cp_async_wait<0>();
 }
 
+// One launch = `iters` ADMM iterations.  A row block of iteration it+1 needs only the SAME row block of iteration it (all
+// of its column tiles), so there is no grid-wide barrier between iterations: CTAs draw (iteration, row block, column tile)
+// tickets in that order from a global counter and wait on a per-(iteration, row block) completion count.  This removes the
+// launch per iteration and, above all, the idle tail of every iteration's last partial wave (LTI64: 896 tiles on 296 CTA
+// slots = 3.03 waves, i.e. a quarter of the machine-time of each iteration was spent waiting for 8 tiles).
+// Deadlock-free: tickets are drawn in dependency order and every CTA that holds a ticket is resident.
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __global__ void __launch_bounds__(THREADS, 2) stream_iter_kernel(const IterParams P) {
   extern __shared__ __align__(16) double smem[];
-  const int bn0 = blockIdx.x * BN, bm0 = blockIdx.y * BM;
+  __shared__ int s_ticket;
+  const int tiles_per_iter = P.nrb * P.ncb, total = tiles_per_iter * P.iters;
+  for (;;) {
+  __syncthreads();                                   // the previous tile's epilogue no longer needs s_ticket / the pipeline buffers
+  if (threadIdx.x == 0) s_ticket = atomicAdd(P.sched, 1);
+  __syncthreads();
+  const int ticket = s_ticket;
+  if (ticket >= total) break;
+  const int it = ticket / tiles_per_iter, rem = ticket - it * tiles_per_iter, rb = rem / P.ncb, cb = rem - rb * P.ncb;
+  if (it > 0) {
+    if (threadIdx.x == 0) {
+      const int* flag = P.sched + 1 + (it - 1) * P.nrb + rb;
+      while (ld_acquire(flag) < P.ncb) __nanosleep(64);
+    }
+    __syncthreads();
+  }
+  const double* Rin = (it & 1) ? P.R1 : P.R0;
+  double* Rout = (it & 1) ? P.R0 : P.R1;
+  const int mode = (it == P.iters - 1) ? MODE_CHECK : ((P.mg > 0 && it == P.iters - 2) ? MODE_SAVE_YP : MODE_NORMAL);
+  const int bn0 = cb * BN, bm0 = rb * BM;
   double acc[4][4][2];
-  gemm_tile(P.Rin, P.T, P.rows, P.NTp, bm0, bn0, acc, smem);
+  gemm_tile(Rin, P.T, P.rows, P.NTp, bm0, bn0, acc, smem);
 
   // ---- fused ADMM step on the accumulator fragments: row b = problem, columns n, n+1
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
@@ -140,14 +174,14 @@ __global__ void __launch_bounds__(THREADS, 2) stream_iter_kernel(const IterParam
     for (int j = 0; j < 4; j++) {
       const int n = bn0 + wn * 32 + j * 8 + 2 * l4;
       const size_t off = (size_t)b * P.NTp + n;
-      const double2 c2 = *reinterpret_cast<const double2*>(P.Cst + off);
+      const double2 c2 = __ldcg(reinterpret_cast<const double2*>(P.Cst + off));      // written by another SM one iteration ago: bypass L1
       const double2 q2 = *reinterpret_cast<const double2*>(P.QB + off);
       const double2 lo2 = *reinterpret_cast<const double2*>(P.lo + n);
       const double2 hi2 = *reinterpret_cast<const double2*>(P.hi + n);
       const double2 rh2 = *reinterpret_cast<const double2*>(P.rho + n);
       double2 x2 = make_double2(0.0, 0.0), rin2 = make_double2(0.0, 0.0);
-      if (sig) x2 = *reinterpret_cast<const double2*>(P.X + off);
-      if (P.mode == MODE_CHECK && P.mg == 0) rin2 = *reinterpret_cast<const double2*>(P.Rin + off);
+      if (sig) x2 = __ldcg(reinterpret_cast<const double2*>(P.X + off));
+      if (mode == MODE_CHECK && P.mg == 0) rin2 = __ldcg(reinterpret_cast<const double2*>(Rin + off));
       double cn[2], rn[2], xn[2], xt[2], yo[2];
 #pragma unroll
       for (int jj = 0; jj < 2; jj++) {
@@ -160,7 +194,7 @@ __global__ void __launch_bounds__(THREADS, 2) stream_iter_kernel(const IterParam
         const double zn = dclamp(w, lo_e, hi_e);
         const double yb = rho_e * (w - zn);
         xt[jj] = t; yo[jj] = yb;
-        if (P.mode == MODE_CHECK) {
+        if (mode == MODE_CHECK) {
           rp = dmaxf(rp, fabs(t - zn));
           nA = dmaxf(nA, dmaxf(fabs(t), fabs(zn)));
           if (P.mg == 0) {   // closed-form dual residual: Pc x~ = r - (sigma + rho) x~
@@ -181,15 +215,15 @@ __global__ void __launch_bounds__(THREADS, 2) stream_iter_kernel(const IterParam
       }
       if (!valid) continue;
       *reinterpret_cast<double2*>(P.Cst + off) = make_double2(cn[0], cn[1]);
-      *reinterpret_cast<double2*>(P.Rout + off) = make_double2(rn[0], rn[1]);
+      *reinterpret_cast<double2*>(Rout + off) = make_double2(rn[0], rn[1]);
       if (sig) *reinterpret_cast<double2*>(P.X + off) = make_double2(xn[0], xn[1]);
-      if (P.mode == MODE_SAVE_YP) *reinterpret_cast<double2*>(P.YP + off) = make_double2(yo[0], yo[1]);
-      if (P.mode == MODE_CHECK) {
+      if (mode == MODE_SAVE_YP) *reinterpret_cast<double2*>(P.YP + off) = make_double2(yo[0], yo[1]);
+      if (mode == MODE_CHECK) {
         *reinterpret_cast<double2*>(P.XT + off) = make_double2(xt[0], xt[1]);
         *reinterpret_cast<double2*>(P.YO + off) = make_double2(yo[0], yo[1]);
       }
     }
-    if (P.mode == MODE_CHECK) {
+    if (mode == MODE_CHECK) {
       // the four lanes of a quad share row b: combine, then one atomic per quad
       for (int o = 1; o <= 2; o <<= 1) {
         rp = dmaxf(rp, __shfl_xor_sync(0xffffffffu, rp, o)); rd = dmaxf(rd, __shfl_xor_sync(0xffffffffu, rd, o));
@@ -202,6 +236,11 @@ __global__ void __launch_bounds__(THREADS, 2) stream_iter_kernel(const IterParam
       }
     }
   }
+  // publish this tile: every thread's stores are fenced, then one release increment of the row block's completion count
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(P.sched + 1 + it * P.nrb + rb, 1);
+  }   // ticket loop
 }
 
 // second operator pass of a check when general rows exist:  [Pc x~ + G' y_g ; G x~] = [x~; y_g] * C
@@ -443,8 +482,8 @@ cudaError_t stream_upload(const Design& D, StreamConsts& sc, std::string& err) {
   return cudaSuccess;
 }
 
-static cudaError_t ensure_work(StreamWork& sw, long long rows, int NTp) {
-  if (rows <= sw.cap && sw.NTp == NTp) return cudaSuccess;
+static cudaError_t ensure_work(StreamWork& sw, long long rows, int NTp, int check_every) {
+  if (rows <= sw.cap && sw.NTp == NTp && 1 + (size_t)check_every * ((rows + BM - 1) / BM) <= sw.sched_cap) return cudaSuccess;
   double** arrs[] = {&sw.X, &sw.Q, &sw.Z, &sw.YS, &sw.R0, &sw.R1, &sw.DY, &sw.X2, &sw.Q2, &sw.Z2, &sw.XT, &sw.YO, &sw.YP};
   for (auto a : arrs) { if (*a) cudaFree(*a); *a = nullptr; }
   for (auto a : arrs) { cudaError_t e = dev_alloc(a, (size_t)rows * NTp); if (e != cudaSuccess) return e; }
@@ -456,6 +495,15 @@ static cudaError_t ensure_work(StreamWork& sw, long long rows, int NTp) {
   cudaError_t e = cudaMalloc(&sw.red, std::max<size_t>(rows, 1) * 4 * sizeof(unsigned long long)); if (e != cudaSuccess) return e;
   e = cudaMalloc(&sw.red2, std::max<size_t>(rows, 1) * 4 * sizeof(unsigned long long)); if (e != cudaSuccess) return e;
   if (!sw.count) { e = cudaMalloc(&sw.count, 2 * sizeof(int)); if (e != cudaSuccess) return e; }
+  if (sw.sched) cudaFree(sw.sched);
+  sw.sched = nullptr; sw.sched_cap = 1 + (size_t)check_every * ((rows + BM - 1) / BM);
+  e = cudaMalloc(&sw.sched, sw.sched_cap * sizeof(int)); if (e != cudaSuccess) return e;
+  {
+    int occ = 0, dev = 0, sms = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stream_iter_kernel, THREADS, SMEM_BYTES); if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    sw.resident_ctas = std::max(1, occ) * sms;      // the ticket scheme needs every CTA of the grid resident
+  }
   if (!sw.h_count) { e = cudaMallocHost(&sw.h_count, 2 * sizeof(int)); if (e != cudaSuccess) return e; }
   sw.cap = rows; sw.NTp = NTp;
   return cudaSuccess;
@@ -467,7 +515,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
   const int NTp = sc.NTp, nz = D.nz, nt = D.nt, mg = D.mg;
   if (B.warm_v != nullptr) { err = "warm start is not supported by the streamed kernel yet"; return cudaErrorNotSupported; }
   if (B.batch > 0x7fffffffLL / 4) { err = "batch too large"; return cudaErrorInvalidValue; }
-  cudaError_t e = ensure_work(sw, B.batch, NTp);
+  cudaError_t e = ensure_work(sw, B.batch, NTp, st.check_every);
   if (e != cudaSuccess) { err = "workspace allocation"; return e; }
   int nl = 0;
   int rows = (int)B.batch;
@@ -487,15 +535,19 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
   const bool sig = st.sigma != 0.0;
   int it = 0, n_done_rows = 0;   // rows finished but not yet compacted away
   while (rows > 0 && it < max_iter) {
-    for (int ii = 0; ii < st.check_every; ii++) {
+    {
       IterParams P;
-      P.Rin = Rin; P.Rout = Rout; P.T = sc.T; P.Cst = Cst; P.QB = QB; P.X = X; P.lo = sc.lo; P.hi = sc.hi; P.rho = sc.rho;
+      P.R0 = Rin; P.R1 = Rout; P.iters = st.check_every; P.sched = sw.sched;
+      P.nrb = (rows + BM - 1) / BM; P.ncb = NTp / BN;
+      P.T = sc.T; P.Cst = Cst; P.QB = QB; P.X = X; P.lo = sc.lo; P.hi = sc.hi; P.rho = sc.rho;
       P.XT = sw.XT; P.YO = sw.YO; P.YP = sw.YP; P.red = red; P.rows = rows; P.NTp = NTp; P.nz = nz; P.nt = nt; P.mg = mg;
-      P.mode = (ii == st.check_every - 1) ? MODE_CHECK : ((mg > 0 && ii == st.check_every - 2) ? MODE_SAVE_YP : MODE_NORMAL);
       P.alpha = st.alpha; P.sigma = st.sigma;
-      dim3 grid(NTp / BN, (rows + BM - 1) / BM);
+      e = cudaMemsetAsync(sw.sched, 0, sizeof(int) * (1 + (size_t)st.check_every * P.nrb), stream);
+      if (e != cudaSuccess) { err = "memset"; return e; }
+      const int tiles = P.nrb * P.ncb;
+      const int grid = std::min(tiles * st.check_every, sw.resident_ctas);
       stream_iter_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(P); nl++;
-      std::swap(Rin, Rout);
+      if (st.check_every & 1) std::swap(Rin, Rout);      // the operand of the next period is where the last iteration wrote
     }
     it += st.check_every;
     if (mg > 0) {
@@ -554,7 +606,7 @@ void stream_release(StreamConsts& sc, StreamWork& sw) {
   for (auto p : cs) { if (*p) cudaFree(*p); *p = nullptr; }
   double** ws[] = {&sw.X, &sw.Q, &sw.Z, &sw.YS, &sw.R0, &sw.R1, &sw.DY, &sw.X2, &sw.Q2, &sw.Z2, &sw.XT, &sw.YO, &sw.YP, &sw.qn, &sw.qn2, &sw.cert};
   for (auto p : ws) { if (*p) cudaFree(*p); *p = nullptr; }
-  int** is[] = {&sw.idx, &sw.idx2, &sw.done, &sw.done2, &sw.newly, &sw.count};
+  int** is[] = {&sw.idx, &sw.idx2, &sw.done, &sw.done2, &sw.newly, &sw.count, &sw.sched};
   for (auto p : is) { if (*p) cudaFree(*p); *p = nullptr; }
   if (sw.red) cudaFree(sw.red); if (sw.red2) cudaFree(sw.red2); sw.red = sw.red2 = nullptr;
   if (sw.h_count) cudaFreeHost(sw.h_count); sw.h_count = nullptr;

@@ -31,6 +31,9 @@ struct StreamWork {
   int *idx = nullptr, *idx2 = nullptr, *done = nullptr, *done2 = nullptr, *newly = nullptr;
   int* count = nullptr;        // device: [0] active rows after a check, [1] compaction cursor
   int* h_count = nullptr;      // pinned mirror
+  int* sched = nullptr;        // device: ticket counter + per-(iteration, row block) completion counts of the fused-period kernel
+  size_t sched_cap = 0;
+  int resident_ctas = 0;       // CTAs of the iteration kernel that fit the device at once
   long long cap = 0;
   int NTp = 0;
 };
