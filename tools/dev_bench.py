@@ -81,12 +81,10 @@ def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="eq
 
 def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
     """NMPC with a neural dynamics model, SQP kernel."""
-    sys.path.insert(0, str(ROOT / "tests"))
-    from conftest import load_nn_fixture
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
-    m = load_nn_fixture(fixture)
-    cls = mpc.ResNet if m.arch == "resnet" else mpc.Fnn
-    f = cls(m.W_in, list(zip(m.W_h, m.b_h)), m.W_out, activation=m.activation)
+    g = json.loads((ROOT / "tests" / "golden" / fixture).read_text())          # the fixture weights, read directly (no oracle import here)
+    cls = {"fnn": mpc.Fnn, "resnet": mpc.ResNet, "polynet": mpc.PolyNet}[g["arch"]]
+    f = cls(np.array(g["W_in"]), [(np.array(w), np.array(b)) for w, b in zip(g["W_h"], g["b_h"])], np.array(g["W_out"]), activation=g["activation"])
     sys_ = mpc.ConstrainedBlackBoxControlDiscreteSystem(f, 4, 2, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_programming_type="non_linear", **kw)
     mod = C.tuning.modeler
