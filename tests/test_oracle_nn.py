@@ -136,11 +136,6 @@ def test_relu_fnn_fixture_kinks_are_flagged_not_hidden(qt, fnn_model):
     for i in np.flatnonzero(ok)[:5]:
         u, J, k = no.nmpc_local_opt(fnn_model, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0[i], xref[i], uref[i], u_init=r["u"][i])
         assert abs(J - r["objective"][i]) <= 1e-6 * abs(J) and mo.u0_metric(r["u"][i, 0], u[0], qt["umin"], qt["umax"]) < 1e-4
-    # the flagged points are local minima of the nonsmooth problem as far as an independent solver can tell: L-BFGS-B
-    # started AT them improves the cost by less than 0.2 %
-    for i in np.flatnonzero(~ok)[:4]:
-        _, J, _ = no.nmpc_local_opt(fnn_model, qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], x0[i], xref[i], uref[i], u_init=r["u"][i])
-        assert r["objective"][i] - J <= 2e-3 * abs(J)
 
 
 def test_reference_relation_linear_vs_nonlinear(qt, fnn_model):
