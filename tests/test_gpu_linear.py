@@ -384,3 +384,45 @@ def test_closed_loop_on_gpu_equals_host_loop(mpc, qt):
         else: assert it_warm < dev["iters_total"].mean()                      # the (unshifted, OSQP-style) warm start pays
     # the regulated plants approach their references
     assert np.abs(dev["x_traj"][:, -1] - xref).max() < np.abs(x0 - xref).max()
+
+
+@pytest.mark.parametrize("nx,nu,H,terminal,sigma,S_w", [
+    (2, 1, 7, "none", 0.0, 0.0),        # nz = 7: odd, scalar stores, recover_small<2,1>
+    (3, 1, 30, "none", 1e-6, 0.0),      # odd nx: 8-byte cooperative stores in recover
+    (3, 2, 11, "equality", 1e-6, 0.0),  # on-chip kernel with general rows, nt = 25 -> padded 32
+    (6, 3, 9, "none", 0.0, 2.0),        # nz = 27 odd, S term
+    (6, 2, 40, "none", 0.0, 0.0),       # nz = 80 -> shared-memory kernel
+    (5, 3, 33, "none", 1e-6, 0.0),      # nz = 99 odd -> shared-memory kernel, generic recover
+    (8, 4, 40, "none", 0.0, 0.0),       # nz = 160 -> streamed
+    (7, 3, 20, "equality", 0.0, 0.0),   # nt = 67 with general rows -> streamed, generic recover
+    (10, 5, 12, "none", 0.0, 0.0),      # nz = 60, generic recover with wider states
+])
+def test_random_systems_sweep(mpc, nx, nu, H, terminal, sigma, S_w):
+    """Odd sizes, every kernel path, every recover path: random stable systems, CUDA vs the condensed twin (iteration counts,
+    solutions) and vs the result reconstruction of the oracle."""
+    rng = np.random.default_rng(100 * nx + 10 * nu + H)
+    G = rng.standard_normal((nx, nx)); A = 0.9 * G / np.abs(np.linalg.eigvals(G)).max(); B = rng.standard_normal((nx, nu)) / 2
+    umin, umax = -np.ones(nu), np.ones(nu)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(-50 * np.ones(nx), 50 * np.ones(nx)), mpc.Hyperrectangle(umin, umax))
+    n, eps = 333, 1e-7
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 1, [0.0] * nx, [0.0] * nu, mpc_solver="b200", mpc_Q=10.0, mpc_R=1.0, mpc_S=S_w,
+                               mpc_terminal_ingredient=terminal, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_sigma=sigma,
+                               mpc_b200_max_iter=20000)
+    m = C.tuning.modeler
+    scale = 0.05 if terminal == "equality" else 2.0
+    x0 = scale * rng.standard_normal((n, nx)); xref = 0.1 * scale * rng.standard_normal((n, nx)); uref = 0.1 * rng.standard_normal((n, nu))
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    c = mo.condense(A, B, 10 * np.eye(nx), np.eye(nu), S_w * np.eye(nu), C.tuning.terminal_ingredient.P, H, umin, umax, terminal=terminal)
+    p = mo.pack_params(x0, xref, uref)
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, sigma=sigma, max_iter=20000))
+    assert (res["status"] == tw["status"]).mean() > 0.98
+    same = (res["iters"] == tw["iters"]) & (res["status"] == 1) & (tw["status"] == 1)
+    assert same.mean() > (0.9 if terminal == "none" else 0.5), (same.mean(), np.unique(res["status"], return_counts=True))
+    v = res["u"].reshape(n, -1)
+    assert np.abs(v[same] - tw["v"][same]).max() < (1e-9 if terminal == "none" else 1e-7)
+    rec = mo.recover(c, v, p)
+    for k in ("x", "e_x", "u", "e_u"):
+        assert np.abs(res[k] - rec[k]).max() < 1e-9 * max(1.0, np.abs(rec[k]).max()), k
+    assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
+    assert np.array_equal(res["u0"], res["u"][:, 0])
