@@ -25,7 +25,7 @@
 
 namespace mpcb {
 
-enum : int { NN_FNN = 0, NN_RESNET = 1, NN_POLYNET = 2 };
+enum : int { NN_FNN = 0, NN_RESNET = 1, NN_POLYNET = 2, NN_DENSENET = 3 };
 enum : int { ACT_RELU = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_SWISH = 3, ACT_IDENTITY = 4 };
 
 struct NetDev {            // device pointers, Julia column-major
@@ -34,7 +34,10 @@ struct NetDev {            // device pointers, Julia column-major
   const double* b_h;       // nh x nn
   const double* W_out;     // nx x nn
   int arch, act, nx, nu, nn, nh, nin;
-  __host__ __device__ size_t weight_count() const { return (size_t)nn * nin + (size_t)nh * nn * nn + (size_t)nh * nn + (size_t)nx * nn; }
+  // densenet: hidden layer l (1..nh) maps the concatenation of the l earlier blocks, W_l is nn x (l nn); W_out is nx x ((nh+1) nn)
+  __host__ __device__ size_t wh_count() const { return arch == NN_DENSENET ? (size_t)nn * nn * nh * (nh + 1) / 2 : (size_t)nh * nn * nn; }
+  __host__ __device__ size_t wout_count() const { return arch == NN_DENSENET ? (size_t)nx * nn * (nh + 1) : (size_t)nx * nn; }
+  __host__ __device__ size_t weight_count() const { return (size_t)nn * nin + wh_count() + (size_t)nh * nn + wout_count(); }
 };
 
 // The weights of one network staged in shared memory.
@@ -46,7 +49,7 @@ struct NetSm {
 __device__ __forceinline__ NetSm stage_network(const NetDev& N, double* dst, int tid, int nthreads) {
   NetSm S;
   S.arch = N.arch; S.act = N.act; S.nx = N.nx; S.nu = N.nu; S.nn = N.nn; S.nh = N.nh; S.nin = N.nin;
-  const int n1 = N.nn * N.nin, n2 = N.nh * N.nn * N.nn, n3 = N.nh * N.nn, n4 = N.nx * N.nn;
+  const int n1 = N.nn * N.nin, n2 = (int)N.wh_count(), n3 = N.nh * N.nn, n4 = (int)N.wout_count();
   for (int i = tid; i < n1; i += nthreads) dst[i] = N.W_in[i];
   for (int i = tid; i < n2; i += nthreads) dst[n1 + i] = N.W_h[i];
   for (int i = tid; i < n3; i += nthreads) dst[n1 + n2 + i] = N.b_h[i];
@@ -89,6 +92,80 @@ __device__ __forceinline__ void jac_layer(const double* __restrict__ W, const do
   }
 }
 
+// DenseNet (densenet/mpc_modeler_implementation_densenet.jl:128-162): y_1 = W_in [x;u];  y_j = [act(W_j y_{j-1} + b_{j-1}); y_{j-1}]
+// (the new block goes in FRONT, so y_j has j nn entries);  x+ = W_out y_{nh+1}.  Blocks are kept in creation order in
+// ycat[(nh+1) nn] (block 0 = y_1); column block bp of W_j multiplies creation block (l - 1 - bp).  JAC: Jcat[(nh+1)][nin][nn].
+template <bool JAC>
+__device__ __forceinline__ void nn_eval_dense_warp(const NetSm& N, const double* xu, double* f, double* ycat, double* Jcat, double* AB, double* sd,
+                                                   int lane) {
+  const int nn = N.nn, nin = N.nin, nx = N.nx, nh = N.nh;
+  for (int i = lane; i < nn; i += 32) {
+    double s = 0.0;
+    for (int j = 0; j < nin; j++) s = fma(N.W_in[j * nn + i], xu[j], s);
+    ycat[i] = s;
+  }
+  if (JAC)
+    for (int i = lane; i < nn * nin; i += 32) Jcat[i] = N.W_in[i];
+  __syncwarp();
+  const double* W = N.W_h;
+  for (int l = 1; l <= nh; l++) {
+    const double* b = N.b_h + (l - 1) * nn;
+    for (int i = lane; i < nn; i += 32) {
+      double s = b[i];
+      for (int bp = 0; bp < l; bp++) {
+        const double* yb_ = ycat + (l - 1 - bp) * nn;
+        const double* Wb = W + (size_t)bp * nn * nn;
+#pragma unroll 4
+        for (int j = 0; j < nn; j++) s = fma(Wb[j * nn + i], yb_[j], s);
+      }
+      double a, da;
+      act_eval(N.act, s, a, da);
+      ycat[l * nn + i] = a;
+      if (JAC) sd[i] = da;
+    }
+    __syncwarp();
+    if (JAC) {
+      double* Jw = Jcat + (size_t)l * nn * nin;
+      for (int o = lane; o < nn * nin; o += 32) {
+        const int c = o / nn, i = o - c * nn;
+        double t = 0.0;
+        for (int bp = 0; bp < l; bp++) {
+          const double* Jr = Jcat + (size_t)(l - 1 - bp) * nn * nin + c * nn;
+          const double* Wb = W + (size_t)bp * nn * nn;
+#pragma unroll 4
+          for (int j = 0; j < nn; j++) t = fma(Wb[j * nn + i], Jr[j], t);
+        }
+        Jw[o] = t * sd[i];
+      }
+      __syncwarp();
+    }
+    W += (size_t)l * nn * nn;
+  }
+  for (int i = lane; i < nx; i += 32) {
+    double s = 0.0;
+    for (int bp = 0; bp <= nh; bp++) {
+      const double* yb_ = ycat + (nh - bp) * nn;
+      const double* Wb = N.W_out + (size_t)bp * nn * nx;
+#pragma unroll 4
+      for (int j = 0; j < nn; j++) s = fma(Wb[j * nx + i], yb_[j], s);
+    }
+    f[i] = s;
+  }
+  if (JAC)
+    for (int o = lane; o < nx * nin; o += 32) {
+      const int c = o / nx, i = o - c * nx;
+      double s = 0.0;
+      for (int bp = 0; bp <= nh; bp++) {
+        const double* Jr = Jcat + (size_t)(nh - bp) * nn * nin + c * nn;
+        const double* Wb = N.W_out + (size_t)bp * nn * nx;
+#pragma unroll 4
+        for (int j = 0; j < nn; j++) s = fma(Wb[j * nx + i], Jr[j], s);
+      }
+      AB[o] = s;
+    }
+  __syncwarp();
+}
+
 // Warp-cooperative network evaluation.  xu[nin] (shared) -> f[nx] (shared).  Scratch: ya, yb, yc3 [nn] (yc3: the PolyNet
 // branch).  With JAC also AB[nin][nx] (column-major nx x nin: d f / d [x;u]) using Ja, Jb, Jc3 [nin][nn] and sd, sd2 [nn]
 // (activation derivatives).  Ends with a __syncwarp().
@@ -99,6 +176,23 @@ template <bool JAC>
 __device__ __forceinline__ void nn_eval_warp(const NetSm& N, const double* xu, double* f, double* ya, double* yb, double* Ja, double* Jb,
                                              double* AB, double* sd, int lane) {
   const int nn = N.nn, nin = N.nin, nx = N.nx;
+  if (N.arch == NN_DENSENET) {     // the caller's scratch is one block [xu | f | ya ...]: the concatenated layers live from ya on
+    double* ycat = ya;
+    double* Jcat = ycat + (size_t)(N.nh + 1) * nn;
+    double* ABd = Jcat + (JAC ? (size_t)(N.nh + 1) * nn * nin : 0);
+    double* sdd = ABd + (JAC ? nx * nin : 0);
+    nn_eval_dense_warp<JAC>(N, xu, f, ycat, Jcat, ABd, sdd, lane);
+    if (JAC) {                     // hand the Jacobian back where the caller expects it
+      for (int o0 = 0; o0 < nx * nin; o0 += 32) {          // the two regions may overlap: read a pass, then write it
+        const int o = o0 + lane;
+        const double v = o < nx * nin ? ABd[o] : 0.0;
+        __syncwarp();
+        if (o < nx * nin) AB[o] = v;
+        __syncwarp();
+      }
+    }
+    return;
+  }
   double* yc3 = sd + (JAC ? 2 * nn : 0);            // scratch layout: [sd | sd2 |] br [| Jbr]   (see nn_eval_scratch_doubles)
   double* sd2 = sd + nn;
   double* Jc3 = yc3 + nn;
@@ -204,7 +298,9 @@ struct NnBatchParams {
 };
 
 __host__ __device__ inline size_t nn_eval_scratch_doubles(const NetDev& N, bool jac) {
-  return (size_t)N.nin + N.nx + 3 * N.nn + (jac ? (size_t)3 * N.nn * N.nin + (size_t)N.nx * N.nin + 2 * N.nn : 0);
+  const size_t std_ = (size_t)N.nin + N.nx + 3 * N.nn + (jac ? (size_t)3 * N.nn * N.nin + (size_t)N.nx * N.nin + 2 * N.nn : 0);
+  const size_t dense = (size_t)N.nin + N.nx + (size_t)(N.nh + 1) * N.nn + (jac ? (size_t)(N.nh + 1) * N.nn * N.nin + 2 * (size_t)N.nx * N.nin + N.nn : 0);
+  return N.arch == NN_DENSENET ? (dense > std_ ? dense : std_) : std_;
 }
 __host__ __device__ inline size_t nn_batch_smem_bytes(const NetDev& N, bool jac) {
   return sizeof(double) * (N.weight_count() + NN_WARPS * nn_eval_scratch_doubles(N, jac));

@@ -65,8 +65,8 @@ int check_device(int device, int* sm_count) {
 
 int validate_nn(const mpcb_nn_desc* d) {
   if (!d) return api_fail(MPCB_ERR_INVALID, "null network description");
-  if (d->arch != MPCB_NN_FNN && d->arch != MPCB_NN_RESNET && d->arch != MPCB_NN_POLYNET)
-    return api_fail(MPCB_ERR_INVALID, "unknown network architecture (fnn, resnet and polynet are supported)");
+  if (d->arch < MPCB_NN_FNN || d->arch > MPCB_NN_DENSENET)
+    return api_fail(MPCB_ERR_INVALID, "unknown network architecture (fnn, resnet, polynet and densenet are supported)");
   if (d->activation < MPCB_ACT_RELU || d->activation > MPCB_ACT_IDENTITY) return api_fail(MPCB_ERR_INVALID, "unknown activation id");
   if (d->nx <= 0 || d->nu <= 0 || d->n_neurons <= 0 || d->n_hidden < 0) return api_fail(MPCB_ERR_INVALID, "bad network sizes");
   if (!d->W_in || !d->W_out || (d->n_hidden > 0 && (!d->W_hidden || !d->b_hidden))) return api_fail(MPCB_ERR_INVALID, "null weight pointer");
@@ -154,7 +154,7 @@ int mpcb_create_nn(const mpcb_nn_desc* d, int32_t device, mpcb_nn** out) {
   n->device = device; n->sm_count = sms;
   mpcb::NetDev& N = n->net;
   N.arch = d->arch; N.act = d->activation; N.nx = d->nx; N.nu = d->nu; N.nn = d->n_neurons; N.nh = d->n_hidden; N.nin = d->nx + d->nu;
-  const size_t n1 = (size_t)N.nn * N.nin, n2 = (size_t)N.nh * N.nn * N.nn, n3 = (size_t)N.nh * N.nn, n4 = (size_t)N.nx * N.nn;
+  const size_t n1 = (size_t)N.nn * N.nin, n2 = N.wh_count(), n3 = (size_t)N.nh * N.nn, n4 = N.wout_count();
   std::vector<double> w(n1 + n2 + n3 + n4);
   std::memcpy(w.data(), d->W_in, n1 * sizeof(double));
   if (n2) std::memcpy(w.data() + n1, d->W_hidden, n2 * sizeof(double));

@@ -168,7 +168,7 @@ function nn_arrays(params::Vector, arch::Symbol, activation::String)
     W_h = n_hidden == 0 ? zeros(1) : vcat((vec(Matrix{Float64}(params[i])) for i in 2:2:length(params)-1)...)
     b_h = n_hidden == 0 ? zeros(1) : vcat((Vector{Float64}(params[i+1]) for i in 2:2:length(params)-1)...)
     nx = size(W_out, 1); nu = size(W_in, 2) - nx
-    return (W_in, W_h, b_h, W_out), (Int32(arch == :resnet ? 1 : arch == :polynet ? 2 : 0), Int32(_ACTIVATION_IDS[activation]), Int32(nx), Int32(nu),
+    return (W_in, W_h, b_h, W_out), (Int32(arch == :resnet ? 1 : arch == :polynet ? 2 : arch == :densenet ? 3 : 0), Int32(_ACTIVATION_IDS[activation]), Int32(nx), Int32(nu),
                                        Int32(size(W_in, 1)), Int32(n_hidden))
 end
 

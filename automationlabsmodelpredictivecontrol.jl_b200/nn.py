@@ -31,8 +31,10 @@ class _Chain:
         self.W_h = [_f(W) for W, _ in hidden]; self.b_h = [np.ascontiguousarray(b, np.float64) for _, b in hidden]
         self.n_neurons, nin = self.W_in.shape
         self.nx = self.W_out.shape[0]; self.nu = nin - self.nx
-        if self.nu <= 0 or self.W_out.shape[1] != self.n_neurons or any(W.shape != (self.n_neurons, self.n_neurons) for W in self.W_h) or \
-                any(b.shape != (self.n_neurons,) for b in self.b_h):
+        n, nh = self.n_neurons, len(self.W_h)
+        dense = self.arch == "densenet"          # layer j sees the concatenation of all earlier blocks
+        ok_h = all(W.shape == (n, (l + 1) * n if dense else n) for l, W in enumerate(self.W_h))
+        if self.nu <= 0 or self.W_out.shape[1] != ((nh + 1) * n if dense else n) or not ok_h or any(b.shape != (n,) for b in self.b_h):
             raise ValueError("inconsistent layer shapes")
         self.device = device
         self._h = None
@@ -51,7 +53,7 @@ class _Chain:
         bh = np.concatenate(self.b_h) if nh else np.zeros(1)
         keep = [self.W_in, Wh, bh, self.W_out]
         p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-        d = _lib.NnDesc({"fnn": _lib.NN_FNN, "resnet": _lib.NN_RESNET, "polynet": _lib.NN_POLYNET}[self.arch], _lib.ACTIVATION_IDS[self.activation], self.nx, self.nu,
+        d = _lib.NnDesc({"fnn": _lib.NN_FNN, "resnet": _lib.NN_RESNET, "polynet": _lib.NN_POLYNET, "densenet": _lib.NN_DENSENET}[self.arch], _lib.ACTIVATION_IDS[self.activation], self.nx, self.nu,
                         self.n_neurons, nh, p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]))
         return d, keep
 
@@ -111,6 +113,12 @@ class ResNet(_Chain):
 class PolyNet(_Chain):
     """AutomationLabsSystems.PolyNet: br = act(W_j y + b_j); y_j = y_{j-1} + br + act(W_j br + b_j)  (polynet.jl:132-149)."""
     arch = "polynet"
+
+
+class DenseNet(_Chain):
+    """AutomationLabsSystems.DenseNet: y_j = [act(W_j y_{j-1} + b_{j-1}); y_{j-1}], W_j of size n x ((j-1) n), W_out nx x ((n_hidden+1) n)
+    (densenet.jl:128-162)."""
+    arch = "densenet"
 
 
 def linearize(nn: _Chain, x, u):

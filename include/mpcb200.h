@@ -226,6 +226,8 @@ void mpcb_free_pinned(void* p);
  * ------------------------------------------------------------------------------------------------------------------ */
 #define MPCB_NN_FNN 0
 #define MPCB_NN_RESNET 1
+#define MPCB_NN_DENSENET 3 /* y_j = [act(W_j y_{j-1} + b_{j-1}); y_{j-1}]: W_j is n_neurons x ((j-1) n_neurons), W_out nx x ((n_hidden+1) n_neurons)
+                               (densenet/mpc_modeler_implementation_densenet.jl:128-162) */
 #define MPCB_NN_POLYNET 2 /* br = act(W y + b); y+ = y + br + act(W br + b)  (polynet/mpc_modeler_implementation_polynet.jl:132-149) */
 
 #define MPCB_ACT_RELU 0
@@ -242,9 +244,9 @@ typedef struct {
   int32_t activation; /* MPCB_ACT_*  (design_mpc.jl:472-496 reads it off the first hidden layer) */
   int32_t nx, nu, n_neurons, n_hidden;
   const double* W_in;     /* n_neurons x (nx+nu) column-major */
-  const double* W_hidden; /* n_hidden matrices n_neurons x n_neurons, back to back */
+  const double* W_hidden; /* n_hidden matrices n_neurons x n_neurons (densenet: n_neurons x (j n_neurons), j = 1..n_hidden), back to back */
   const double* b_hidden; /* n_hidden vectors of n_neurons, back to back */
-  const double* W_out;    /* nx x n_neurons */
+  const double* W_out;    /* nx x n_neurons (densenet: nx x ((n_hidden+1) n_neurons)) */
 } mpcb_nn_desc;
 
 /* A network resident on `device`. */

@@ -47,7 +47,7 @@ def dact(name, h):
 @dataclasses.dataclass
 class NeuralModel:
     """`Flux.params(system.f)` as the reference parses it: params[1] = W_in, then (W_j, b_j) pairs, last = W_out."""
-    arch: str                 # "fnn" | "resnet" | "polynet"
+    arch: str                 # "fnn" | "resnet" | "polynet" | "densenet"
     activation: str
     W_in: np.ndarray          # (n_neur, nx + nu)
     W_h: list                 # n_hidden x (n_neur, n_neur)
@@ -71,6 +71,10 @@ def hidden_states(m: NeuralModel, x, u):
     ys = [xu @ m.W_in.T]; pre = []
     for W, b in zip(m.W_h, m.b_h):
         h = ys[-1] @ W.T + b
+        if m.arch == "densenet":       # densenet.jl:139-155: the new block is PREPENDED to the previous layer's vector
+            pre.append(h)
+            ys.append(np.concatenate([act(m.activation, h), ys[-1]], axis=1))
+            continue
         if m.arch == "polynet":        # polynet.jl:132-149: branch = act(W y + b); y+ = y + branch + act(W branch + b)  (same W, b)
             br = act(m.activation, h)
             h2 = br @ W.T + b
@@ -94,6 +98,9 @@ def jacobian(m: NeuralModel, x, u):
     Bn = ys[0].shape[0]
     Jm = np.broadcast_to(m.W_in, (Bn,) + m.W_in.shape).copy()          # d y_1 / d [x;u]
     for W, h in zip(m.W_h, pre):
+        if m.arch == "densenet":
+            Jm = np.concatenate([dact(m.activation, h)[:, :, None] * (W @ Jm), Jm], axis=1)
+            continue
         if m.arch == "polynet":
             Jb = dact(m.activation, h[0])[:, :, None] * (W @ Jm)
             Jm = Jm + Jb + dact(m.activation, h[1])[:, :, None] * (W @ Jb)

@@ -71,11 +71,12 @@ def main():
     import sys
     only = set(sys.argv[1:])          # optional: regenerate only the named files (the others are kept bit for bit)
     for fname, arch, actname in (("qt_resnet_model.json", "resnet", "relu"), ("qt_fnn_tanh_model.json", "fnn", "tanh"),
-                                 ("qt_resnet_swish_model.json", "resnet", "swish"), ("qt_polynet_tanh_model.json", "polynet", "tanh")):
+                                 ("qt_resnet_swish_model.json", "resnet", "swish"), ("qt_polynet_tanh_model.json", "polynet", "tanh"),
+                                 ("qt_densenet_tanh_model.json", "densenet", "tanh")):
         if only and fname not in only: continue
         torch.manual_seed(2)
         W_in = (0.3 * torch.randn(13, 6)).requires_grad_(); W_h = (0.3 * torch.randn(13, 13)).requires_grad_()
-        b_h = torch.zeros(13, requires_grad=True); W_out = (0.3 * torch.randn(4, 13)).requires_grad_()
+        b_h = torch.zeros(13, requires_grad=True); W_out = (0.3 * torch.randn(4, 26 if arch == "densenet" else 13)).requires_grad_()
         params = [W_in, W_h, b_h, W_out]
         sigma = acts[actname]
 
@@ -83,6 +84,7 @@ def main():
             y1 = Xi @ W_in.T
             a = sigma(y1 @ W_h.T + b_h)
             if arch == "polynet": return (y1 + a + sigma(a @ W_h.T + b_h)) @ W_out.T      # polynet.jl:132-149
+            if arch == "densenet": return torch.cat([a, y1], 1) @ W_out.T                  # densenet.jl:139-162: new block in front
             return ((y1 + a) if arch == "resnet" else a) @ W_out.T
 
         loss_fn = lambda: (((net() - Yt) * 100.0) ** 2).mean()          # error in centimetres

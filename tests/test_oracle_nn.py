@@ -78,6 +78,24 @@ def test_jacobian_forward_mode_vs_finite_differences(fnn_model, resnet_model, ac
             assert np.allclose((no.forward(m, x, u + d) - no.forward(m, x, u - d)) / (2 * h), B[:, :, i], atol=2e-7)
 
 
+def test_densenet_layer_equations_and_jacobian():
+    """densenet.jl:128-162 spelled out with loops (the new block is prepended; W_j is n x ((j-1) n), W_out nx x ((n_hid+1) n))."""
+    rng = np.random.default_rng(8)
+    n, nh, nx, nu = 5, 3, 3, 2
+    m = no.NeuralModel("densenet", "swish", 0.4 * rng.standard_normal((n, nx + nu)), [0.3 * rng.standard_normal((n, (l + 1) * n)) for l in range(nh)],
+                       [0.1 * rng.standard_normal(n) for _ in range(nh)], 0.3 * rng.standard_normal((nx, (nh + 1) * n)))
+    x, u = rng.standard_normal(nx), rng.standard_normal(nu)
+    y = [m.W_in @ np.concatenate([x, u])]
+    for j in range(nh):
+        a = np.array([no.act("swish", m.W_h[j][i, :] @ y[-1] + m.b_h[j][i]) for i in range(n)])
+        y.append(np.concatenate([a, y[-1]]))
+    assert np.allclose(m.W_out @ y[-1], no.forward(m, x[None], u[None])[0], rtol=0, atol=1e-14)
+    f, A, B = no.jacobian(m, x[None], u[None]); h = 1e-6
+    for i in range(nx):
+        d = np.zeros(nx); d[i] = h
+        assert np.allclose((no.forward(m, (x + d)[None], u[None]) - no.forward(m, (x - d)[None], u[None]))[0] / (2 * h), A[0, :, i], atol=1e-7)
+
+
 def test_gradient_forward_sensitivities_equal_adjoint(qt, fnn_model):
     m = dataclasses.replace(fnn_model, activation="tanh")
     H, n = 12, 16
