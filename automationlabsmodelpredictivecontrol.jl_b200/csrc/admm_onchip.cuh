@@ -37,6 +37,7 @@ struct OnchipParams {
   const double* rho;    // [NT] (padding rows: 1)
   const double* rinv;   // [NT]
   int nz, nt, np, nx, nu;
+  int nball;            // contractive terminal set: general rows nz .. nz+nball-1 form one ball (HAS_G kernels only)
   double rho_box, sigma, alpha, eps_abs, eps_rel, eps_pinf;
   int max_iter, check_every;
   // batch
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
   long long pi = -1;   // problem held by this slot (quad-uniform)
   int it_s = 0;        // its iteration count
   double qn = 0.0;     // ||q||_inf
+  double rad = 0.0;    // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this slot's ball
   bool exhausted = false;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
 
@@ -188,6 +190,13 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         }
       }
       __syncwarp();
+      if (HAS_G && P.nball > 0) {
+        double d2 = 0.0;
+        if (fresh)
+          for (int j = l4; j < P.nx; j += 4) { const double dv = sP[g * npad + j] - sP[g * npad + P.nx + j]; d2 = fma(dv, dv, d2); }
+        d2 = quad_sum(d2);
+        if (fresh) rad = sqrt(0.9 * d2);
+      }
       double zw[HAS_G ? EPL : 1];   // warm-start z of general rows needs G x0 (one C pass)
       (void)zw;
       if (fresh) {
@@ -307,6 +316,20 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
 #pragma unroll
           for (int tn = 0; tn < NTL; tn++) dmma884(t[2 * tn], t[2 * tn + 1], rr, sT[(s * NTL + tn) * 32 + lane]);
         }
+        // contractive terminal set (design_mpc.jl:333-340): the rows nz .. nz+nball-1 of a slot are projected onto ONE ball
+        // |w - b|_2 <= rad (centre b = the per-problem offset kept in q) instead of a box; the squared distance is summed over
+        // the quad that owns the slot
+        double bscale = 1.0;
+        if (P.nball > 0) {
+          double d2 = 0.0;
+#pragma unroll
+          for (int le = 0; le < EPL; le++) {
+            const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
+            if (e >= nz && e < nz + P.nball) { const double dv = fma(oma, c[le], alpha * t[le]) + r[le] - q[le]; d2 = fma(dv, dv, d2); }
+          }
+          d2 = quad_sum(d2);
+          if (d2 > rad * rad) bscale = rad / sqrt(d2);
+        }
 #pragma unroll
         for (int tn = 0; tn < NTL; tn++) {
           const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
@@ -321,7 +344,11 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
             double lo_e = jj ? lo2.y : lo2.x, hi_e = jj ? hi2.y : hi2.x;
             if (box) x[le] = fma(oma, x[le], at);
             else { lo_e += q[le]; hi_e += q[le]; }
-            const double zn = dclamp(w, lo_e, hi_e);
+            double zn = dclamp(w, lo_e, hi_e);
+            if (P.nball > 0) {
+              const int e = 8 * tn + 2 * l4 + jj;
+              if (e >= nz && e < nz + P.nball) zn = fma(w - q[le], bscale, q[le]);
+            }
             const double yn = w - zn;
             if (chk) {
               const double rho_e = jj ? rh2.y : rh2.x;
@@ -366,7 +393,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         supp += (sHi[e] + off) * dmaxf(dy, 0.0) + (sLo[e] + off) * (dy < 0.0 ? dy : 0.0);
       }
       ndy = quad_max(ndy); supp = quad_sum(supp);
-      const bool cand = (pi >= 0) && !conv && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);
+      const bool cand = (pi >= 0) && !conv && (P.nball == 0) && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);   // no certificate is evaluated for ball rows
       if (__any_sync(0xffffffffu, cand)) {
         double in[EPL], cc[EPL];
 #pragma unroll

@@ -224,8 +224,8 @@ bool dare_sda(const Mat& A, const Mat& B, const Mat& Q, const Mat& R, Mat& P, st
 int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, std::string& err) {
   if (d.nx <= 0 || d.nu <= 0 || d.horizon <= 0) { err = "nx, nu, horizon must be positive"; return MPCB_ERR_INVALID; }
   if (!d.A || !d.B || !d.Q || !d.R || !d.umin || !d.umax) { err = "A, B, Q, R, umin, umax are required"; return MPCB_ERR_INVALID; }
-  if (d.terminal_mode != MPCB_TERMINAL_NONE && d.terminal_mode != MPCB_TERMINAL_EQUALITY) {
-    err = "terminal_mode: only none / equality are supported (contractive is a QCQP, neighborhood is unimplemented in the reference)";
+  if (d.terminal_mode != MPCB_TERMINAL_NONE && d.terminal_mode != MPCB_TERMINAL_EQUALITY && d.terminal_mode != MPCB_TERMINAL_CONTRACTIVE) {
+    err = "terminal_mode: none / equality / contractive are supported (neighborhood is unimplemented in the reference)";
     return MPCB_ERR_INVALID;
   }
   if (d.state_constraint && (!d.xmin || !d.xmax)) { err = "state_constraint needs xmin/xmax"; return MPCB_ERR_INVALID; }
@@ -288,7 +288,9 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
     }
   }
   // general rows
-  const int mg = (d.terminal_mode == MPCB_TERMINAL_EQUALITY ? nx : 0) + (d.state_constraint ? nx * H : 0);
+  const bool term_rows = d.terminal_mode == MPCB_TERMINAL_EQUALITY || d.terminal_mode == MPCB_TERMINAL_CONTRACTIVE;
+  const int mg = (term_rows ? nx : 0) + (d.state_constraint ? nx * H : 0);
+  D.nball = d.terminal_mode == MPCB_TERMINAL_CONTRACTIVE ? nx : 0;
   D.mg = mg; D.nt = nz + mg;
   D.G = Mat(mg, nz); D.Lb = Mat(mg, np);
   D.lo.assign(D.nt, 0.0); D.hi.assign(D.nt, 0.0); D.is_eq.assign(D.nt, 0);
@@ -313,7 +315,8 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
       D.is_eq[nz + row] = equality ? 1 : 0;
     }
   };
-  if (d.terminal_mode == MPCB_TERMINAL_EQUALITY) add_rows(H, true);
+  if (term_rows) add_rows(H, true);      // contractive: the same rows e_H = G v - b(p); their set is a ball, not {0} (bounds unused)
+  for (int i = 0; i < D.nball; i++) { D.lo[nz + i] = -1e30; D.hi[nz + i] = 1e30; D.is_eq[nz + i] = 0; }
   if (d.state_constraint)
     for (int k = 1; k <= H; k++) add_rows(k, false);
 
@@ -328,6 +331,11 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
     double rn = 0.0;
     for (int j = 0; j < nz; j++) rn += D.G(i, j) * D.G(i, j);
     D.rho_vec[nz + i] = (D.is_eq[nz + i] ? s.rho_eq_scale * D.rho : D.rho) / std::max(rn, 1e-12);
+  }
+  if (D.nball) {      // the projection onto a ball is closed-form only for one common step size on its rows: rho / mean |G_i|^2
+    double mean = 0.0;
+    for (int i = 0; i < D.nball; i++) { double rn = 0.0; for (int j = 0; j < nz; j++) rn += D.G(i, j) * D.G(i, j); mean += rn / D.nball; }
+    for (int i = 0; i < D.nball; i++) D.rho_vec[nz + i] = D.rho / std::max(mean, 1e-12);
   }
   // K = Pc + (sigma + rho) I + G' diag(rho_g) G ;  T = [I;G] K^-1 [I,G'] ;  C = [[Pc,G'],[G,0]]
   Mat K = D.Pc;

@@ -44,6 +44,7 @@ bool dare_sda(const Mat& A, const Mat& B, const Mat& Q, const Mat& R, Mat& P, st
 // Everything the kernels need, still on the host.
 struct Design {
   int nx = 0, nu = 0, H = 0, nz = 0, mg = 0, nt = 0, np = 0;  // np = 2nx+nu parameter length [x0; xref; uref]
+  int nball = 0;   // contractive terminal set: the first nball general rows form one ball |G v - b(p)|_2 <= sqrt(0.9) |x0 - xref|_2
   Mat A, B, Q, R, S, P;
   bool use_R = true, use_S = false;
   Mat Pc;   // nz x nz   Hessian in absolute-input coordinates (includes the S term)

@@ -181,7 +181,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
   if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     OnchipParams P;
     P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
-    P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu;
+    P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu; P.nball = D.nball;
     P.rho_box = D.rho; P.sigma = h->st.sigma; P.alpha = h->st.alpha; P.eps_abs = h->st.eps_abs; P.eps_rel = h->st.eps_rel;
     P.eps_pinf = h->st.eps_prim_inf; P.max_iter = h->st.max_iter; P.check_every = h->st.check_every;
     P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
@@ -300,6 +300,7 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   const bool smem_ok = D.mg == 0 && nt8 > 64 && nt8 <= 120 && mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) <= (size_t)prop.sharedMemPerBlockOptin;
   if (kernel == MPCB_KERNEL_AUTO) kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : MPCB_KERNEL_STREAMED);
   if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
+  if (D.nball > 0 && kernel != MPCB_KERNEL_ONCHIP) { delete h; return fail(MPCB_ERR_INVALID, "the contractive terminal set is implemented in the on-chip kernel only: needs nz + mg <= 64"); }
   if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs a box-only problem with 64 < nz <= 120 that fits 227 KB"); }
   if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;

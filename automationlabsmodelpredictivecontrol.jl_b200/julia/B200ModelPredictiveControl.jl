@@ -102,14 +102,14 @@ Replaces `_model_predictive_control_modeler_implementation(::LinearProgramming, 
 """
 function B200Modeler(A, B, Q, R, S, P, umin, umax, xmin, xmax, horizon::Int;
                      state_constraint::Bool=false, terminal::String="none", settings::MpcbSettings=default_settings())
-    terminal in ("none", "equality") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\" and \"equality\" only")
+    terminal in ("none", "equality", "contractive") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\", \"equality\" and \"contractive\" only")
     nx, nu = size(B)
     mats = map(M -> Matrix{Float64}(M), (A, B, Q, R, S, P))
     vecs = map(v -> Vector{Float64}(v), (umin, umax, xmin, xmax))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve mats vecs begin
         d = MpcbLinearDesc(nx, nu, horizon, map(pointer, mats)..., map(pointer, vecs)..., state_constraint ? 1 : 0,
-                           terminal == "equality" ? 1 : 0)
+                           terminal == "equality" ? 1 : terminal == "contractive" ? 2 : 0)
         check(ccall((:mpcb_create_linear, libmpcb200), Cint, (Ref{MpcbLinearDesc}, Ref{MpcbSettings}, Ref{Ptr{Cvoid}}), d, settings, h),
               "mpcb_create_linear")
     end

@@ -22,17 +22,16 @@ class B200Modeler:
         L = _lib.lib()
         self.nx, self.nu = np.asarray(B).shape
         self.horizon = int(horizon)
-        if terminal not in ("none", "equality"):
-            # "contractive" is a quadratic constraint (design_mpc.jl:333-340) and "neighborhood" is a @warn stub
-            # (design_mpc.jl:342-345): neither is a QP the ADMM path can take.
+        if terminal not in ("none", "equality", "contractive"):
+            # "neighborhood" is a @warn stub in the reference (design_mpc.jl:342-345)
             raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported by mpc_solver='b200' "
-                                 "(only 'none' and 'equality')")
+                                 "(only 'none', 'equality' and 'contractive')")
         keep = [_colmajor(A), _colmajor(B), _colmajor(Q), _colmajor(R), _colmajor(S),
                 None if P is None else _colmajor(P), _colmajor(umin), _colmajor(umax),
                 None if xmin is None else _colmajor(xmin), None if xmax is None else _colmajor(xmax)]
         ptr = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
         d = _lib.LinearDesc(self.nx, self.nu, self.horizon, *[ptr(a) for a in keep], 1 if state_constraint else 0,
-                            _lib.TERMINAL_EQUALITY if terminal == "equality" else _lib.TERMINAL_NONE)
+                            {"none": _lib.TERMINAL_NONE, "equality": _lib.TERMINAL_EQUALITY, "contractive": _lib.TERMINAL_CONTRACTIVE}[terminal])
         self.settings = settings if settings is not None else _lib.default_settings()
         self._h = C.c_void_p()
         _lib.check(L.mpcb_create_linear(C.byref(d), C.byref(self.settings), C.byref(self._h)), "mpcb_create_linear")

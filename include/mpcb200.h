@@ -42,10 +42,12 @@ extern "C" {
 #define MPCB_STATUS_PRIMAL_INFEASIBLE -3
 #define MPCB_STATUS_UNSOLVED -10
 
-/* terminal ingredient (src/sub/design_mpc.jl:298-394: "none" | "equality"; "contractive" is a QCQP and
- * "neighborhood" is unimplemented in the reference -> rejected with MPCB_ERR_INVALID) */
+/* terminal ingredient (src/sub/design_mpc.jl:298-394).  "contractive" (e_H' e_H <= 0.9 e_0' e_0, :333-340) is a quadratic
+ * constraint OSQP cannot take; here it is a ball projection inside the ADMM (linear path, on-chip kernel: nz + nx <= 64).
+ * "neighborhood" is unimplemented in the reference (:342-345) -> rejected with MPCB_ERR_INVALID. */
 #define MPCB_TERMINAL_NONE 0
 #define MPCB_TERMINAL_EQUALITY 1
+#define MPCB_TERMINAL_CONTRACTIVE 2
 
 /* kernel selection */
 #define MPCB_KERNEL_AUTO 0

@@ -210,6 +210,7 @@ class CondensedQP:
     Gam: np.ndarray      # (H+1, nx, nz)
     Qs: np.ndarray; Ps: np.ndarray; Rs: np.ndarray; Ss: np.ndarray
     A: np.ndarray; B: np.ndarray
+    nball: int = 0       # terminal "contractive": the first nball general rows form ONE ball  |G v - b(p)|_2 <= sqrt(0.9) |x0 - xref|_2
 
     @property
     def nz(self): return self.nu * self.H
@@ -251,9 +252,13 @@ def condense(A, B, Q, R, S, P, H, umin, umax, xmin=None, xmax=None, state_constr
     Lq = np.hstack([2.0 * Fe, -2.0 * Fe, -Pc_dev @ E1])
     lb = np.tile(np.asarray(umin, float), H); ub = np.tile(np.asarray(umax, float), H)
     Gs, Lbs, lgs, ugs, eqs = [], [], [], [], []
+    nball = 0
     if terminal == "equality":      # e_H = 0  <=>  Gam_H v = Gam_H ubar - Phi_H e0
         Gs.append(Gam[H]); Lbs.append(np.hstack([-Phi[H], Phi[H], Gam[H] @ E1]))
         lgs.append(np.zeros(nx)); ugs.append(np.zeros(nx)); eqs.append(np.ones(nx, bool))
+    elif terminal == "contractive":  # e_H' e_H <= 0.9 e_0' e_0  (design_mpc.jl:333-340, P_contract = I): e_H = Gam_H v - b(p), a ball
+        Gs.append(Gam[H]); Lbs.append(np.hstack([-Phi[H], Phi[H], Gam[H] @ E1]))
+        lgs.append(np.zeros(nx)); ugs.append(np.zeros(nx)); eqs.append(np.zeros(nx, bool)); nball = nx
     if state_constraint:            # xmin <= xref + e_k <= xmax for k = 1..H (k = 0 is the fixed x0: constant)
         for k in range(1, H + 1):
             Gs.append(Gam[k]); Lbs.append(np.hstack([-Phi[k], Phi[k] - np.eye(nx), Gam[k] @ E1]))
@@ -262,7 +267,7 @@ def condense(A, B, Q, R, S, P, H, umin, umax, xmin=None, xmax=None, state_constr
         G = np.vstack(Gs); Lb = np.vstack(Lbs); lg = np.concatenate(lgs); ug = np.concatenate(ugs); eq = np.concatenate(eqs)
     else:
         G = np.zeros((0, nz)); Lb = np.zeros((0, 2 * nx + nu)); lg = np.zeros(0); ug = np.zeros(0); eq = np.zeros(0, bool)
-    return CondensedQP(nx, nu, H, Psum, Lq, lb, ub, G, Lb, lg, ug, eq, Phi, Gam, Q, P, R, S, A, B)
+    return CondensedQP(nx, nu, H, Psum, Lq, lb, ub, G, Lb, lg, ug, eq, Phi, Gam, Q, P, R, S, A, B, nball)
 
 
 def pack_params(x0, xref, uref):
@@ -326,6 +331,8 @@ def admm_matrices(c: CondensedQP, s: AdmmSettings):
     nz, mg = c.nz, c.mg
     rho = s.rho if s.rho > 0 else auto_rho(c.Pc)
     rho_g = np.where(c.eq_mask, s.rho_eq_scale * rho, rho) / np.maximum((c.G ** 2).sum(1), 1e-12)   # row-equilibrated step sizes
+    if c.nball:      # the projection onto a ball is closed-form only for one common step size on its rows
+        rho_g[:c.nball] = rho / np.maximum((c.G[:c.nball] ** 2).sum(1).mean(), 1e-12)
     K = c.Pc + (s.sigma + rho) * np.eye(nz) + c.G.T @ (rho_g[:, None] * c.G)
     Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.T)
     Ac = np.vstack([np.eye(nz), c.G])
@@ -355,6 +362,11 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
     b = p @ c.Lb.T if mg else np.zeros((Bn, 0))
     lo = np.concatenate([np.broadcast_to(c.lb, (Bn, nz)), c.lg + b], axis=1)
     hi = np.concatenate([np.broadcast_to(c.ub, (Bn, nz)), c.ug + b], axis=1)
+    nb_ = c.nball
+    if nb_:          # ball rows: centre b(p), radius sqrt(0.9) |x0 - xref|_2; no box on them
+        rad = np.sqrt(0.9) * np.linalg.norm(p[:, :c.nx] - p[:, c.nx:2 * c.nx], axis=1)
+        cen = b[:, :nb_]
+        lo[:, nz:nz + nb_] = -OSQP_INFTY; hi[:, nz:nz + nb_] = OSQP_INFTY
     Ac = np.vstack([np.eye(nz), c.G])
     if v0 is None:
         x = np.zeros((Bn, nz)); z = np.zeros((Bn, nt)); ys = np.zeros((Bn, nt))
@@ -372,6 +384,11 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
         t = r @ T                      # T symmetric: [x~; z~_g] with z~_g = G x~
         w = s.alpha * t + (1 - s.alpha) * z + ys
         zn = np.minimum(np.maximum(w, lo), hi)
+        if nb_:
+            dev = w[:, nz:nz + nb_] - cen
+            nrm = np.linalg.norm(dev, axis=1)
+            scale = np.where(nrm > rad, rad / np.maximum(nrm, 1e-300), 1.0)
+            zn[:, nz:nz + nb_] = cen + dev * scale[:, None]
         ysn = w - zn
         x = s.alpha * t[:, :nz] + (1 - s.alpha) * x
         dy = rho_vec * (ysn - ys)
@@ -389,7 +406,7 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
             supp = (hi * np.maximum(dy, 0)).sum(1) + (lo * np.minimum(dy, 0)).sum(1)
             atdy = np.abs(dy @ Ac).max(1)
             pinf = (ndy > s.eps_prim_inf) & (supp < -s.eps_prim_inf * ndy) & (atdy <= s.eps_prim_inf * ndy) & ~conv
-            if mg == 0: pinf[:] = False     # a non-empty box is always feasible
+            if mg == 0 or nb_: pinf[:] = False     # a non-empty box is always feasible; no certificate is evaluated for ball rows
             fin = active & (conv | pinf | (it >= max_iter))
             status[active & conv] = STATUS_SOLVED
             status[active & pinf] = STATUS_PRIMAL_INF

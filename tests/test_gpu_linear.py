@@ -426,3 +426,41 @@ def test_random_systems_sweep(mpc, nx, nu, H, terminal, sigma, S_w):
         assert np.abs(res[k] - rec[k]).max() < 1e-9 * max(1.0, np.abs(rec[k]).max()), k
     assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
     assert np.array_equal(res["u0"], res["u"][:, 0])
+
+
+
+def test_contractive_terminal_set(mpc, qt):
+    """mpc_terminal_ingredient = "contractive" (design_mpc.jl:333-340): e_H' e_H <= 0.9 e_0' e_0, a quadratic constraint the
+    reference needs SCIP / Ipopt for; here a ball projection inside the ADMM.  Short horizon and a lazy controller (Q = 1,
+    R = 10) make the ball active.  CUDA vs twin, and vs an independent SLSQP solve of the QCQP."""
+    from scipy.optimize import minimize
+    H, n, eps = 3, 512, 1e-8
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(qt["xmin"], qt["xmax"]), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_Q=1.0, mpc_R=10.0,
+                               mpc_terminal_ingredient="contractive", mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    m = C.tuning.modeler
+    assert m.info.mg == 4 and m.info.kernel == 1
+    rng = np.random.default_rng(3)
+    xref = rng.uniform(0.5, 0.9, (n, 4)); x0 = xref + 0.15 * rng.standard_normal((n, 4))
+    mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
+    res = mpc.calculate(C)
+    c = mo.condense(qt["A"], qt["B"], np.eye(4), 10 * np.eye(2), qt["S"], C.tuning.terminal_ingredient.P, H, qt["umin"], qt["umax"], terminal="contractive")
+    p = mo.pack_params(x0, xref, qt["u_ref"])
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000))
+    assert (res["status"] == 1).all() and (tw["status"] == 1).all()
+    assert (res["iters"] == tw["iters"]).mean() > 0.98 and np.abs(res["u"].reshape(n, -1) - tw["v"]).max() < 1e-8
+    e0 = np.linalg.norm(res["e_x"][:, 0], axis=1); eH = np.linalg.norm(res["e_x"][:, H], axis=1)
+    assert (eH <= np.sqrt(0.9) * e0 + 1e-7).all()
+    active = np.abs(eH - np.sqrt(0.9) * e0) < 1e-6
+    assert active.sum() >= n // 10                                       # the ball is really active on part of the batch
+    for i in np.flatnonzero(active)[:4]:
+        q = c.Lq @ p[i]; b = c.Lb @ p[i]; r2 = 0.9 * e0[i] ** 2
+        r = minimize(lambda v: (0.5 * v @ c.Pc @ v + q @ v, c.Pc @ v + q), res["u"][i].ravel(), jac=True, method="SLSQP", bounds=list(zip(c.lb, c.ub)),
+                     constraints=[{"type": "ineq", "fun": lambda v: r2 - np.sum((c.G @ v - b) ** 2), "jac": lambda v: -2 * (c.G @ v - b) @ c.G}],
+                     options={"maxiter": 1000, "ftol": 1e-16})
+        assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL
+        v = res["u"][i].ravel()
+        assert abs(r.fun - (0.5 * v @ c.Pc @ v + q @ v)) <= OBJ_TOL * max(1.0, abs(r.fun))
+    # too large for the on-chip kernel -> refused, not approximated
+    with pytest.raises(mpc.MpcbError):
+        make_controller(mpc, qt, 40, terminal="contractive")

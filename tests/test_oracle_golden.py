@@ -171,3 +171,29 @@ def test_twin_matches_exact_and_warm_start_helps(qt):
     assert (np.abs(J - Jex) / np.abs(Jex)).max() < 1e-6
     warm = mo.admm_condensed(c, p, s, v0=tw["v"], y0=tw["y"])
     assert warm["iters"].max() <= s.check_every and (warm["status"] == 1).all()
+
+
+def test_contractive_ball_twin_vs_slsqp(qt):
+    """Terminal "contractive" (design_mpc.jl:333-340) in the condensed twin: the ball projection inside the ADMM reproduces an
+    independent SLSQP solve of the QCQP, and the constraint is active on part of the batch."""
+    from scipy.optimize import minimize
+    H, n = 3, 96
+    Q, R = np.eye(4), 10 * np.eye(2)
+    P = mo.dare(qt["A"], qt["B"], Q, R)
+    c = mo.condense(qt["A"], qt["B"], Q, R, qt["S"], P, H, qt["umin"], qt["umax"], terminal="contractive")
+    assert c.nball == 4 and c.mg == 4
+    rng = np.random.default_rng(3)
+    xref = rng.uniform(0.5, 0.9, (n, 4)); x0 = xref + 0.15 * rng.standard_normal((n, 4))
+    p = mo.pack_params(x0, xref, qt["u_ref"])
+    tw = mo.admm_condensed(c, p, mo.AdmmSettings(eps_abs=1e-8, eps_rel=1e-8, check_every=5, max_iter=20000))
+    assert (tw["status"] == 1).all()
+    rec = mo.recover(c, tw["v"], p)
+    e0 = np.linalg.norm(rec["e_x"][:, 0], axis=1); eH = np.linalg.norm(rec["e_x"][:, H], axis=1)
+    active = np.abs(eH - np.sqrt(0.9) * e0) < 1e-6
+    assert (eH <= np.sqrt(0.9) * e0 + 1e-7).all() and active.sum() >= 8
+    for i in np.flatnonzero(active)[:3]:
+        q = c.Lq @ p[i]; b = c.Lb @ p[i]; r2 = 0.9 * e0[i] ** 2
+        r = minimize(lambda v: (0.5 * v @ c.Pc @ v + q @ v, c.Pc @ v + q), tw["v"][i], jac=True, method="SLSQP", bounds=list(zip(c.lb, c.ub)),
+                     constraints=[{"type": "ineq", "fun": lambda v: r2 - np.sum((c.G @ v - b) ** 2), "jac": lambda v: -2 * (c.G @ v - b) @ c.G}],
+                     options={"maxiter": 1000, "ftol": 1e-16})
+        assert np.abs(r.x - tw["v"][i]).max() < 1e-5
