@@ -95,8 +95,9 @@ __device__ __forceinline__ void jac_layer(const double* __restrict__ W, const do
 // DenseNet (densenet/mpc_modeler_implementation_densenet.jl:128-162): y_1 = W_in [x;u];  y_j = [act(W_j y_{j-1} + b_{j-1}); y_{j-1}]
 // (the new block goes in FRONT, so y_j has j nn entries);  x+ = W_out y_{nh+1}.  Blocks are kept in creation order in
 // ycat[(nh+1) nn] (block 0 = y_1); column block bp of W_j multiplies creation block (l - 1 - bp).  JAC: Jcat[(nh+1)][nin][nn].
+// __noinline__: kept out of the SQP kernel's register allocation (inlined it cost the common architectures spills in their hot loops)
 template <bool JAC>
-__device__ __forceinline__ void nn_eval_dense_warp(const NetSm& N, const double* xu, double* f, double* ycat, double* Jcat, double* AB, double* sd,
+__device__ __noinline__ void nn_eval_dense_warp(const NetSm& N, const double* xu, double* f, double* ycat, double* Jcat, double* AB, double* sd,
                                                    int lane) {
   const int nn = N.nn, nin = N.nin, nx = N.nx, nh = N.nh;
   for (int i = lane; i < nn; i += 32) {

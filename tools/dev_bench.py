@@ -6,13 +6,23 @@ import almpc_b200 as mpc
 from almpc_b200 import _lib
 import bench
 
-def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0):
+def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None):
+    """near > 0: x0 = x_ref + near * N(0, I) with the design reference (feasible terminal constraints); state_box: tight box + references beyond it"""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
+    if state_box: xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
+    extra = {}
+    if state_box: extra["mpc_state_constraint"] = True
+    if Qw is not None: extra["mpc_Q"] = Qw
+    if Rw is not None: extra["mpc_R"] = Rw
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_terminal_ingredient=terminal,
-                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho)
+                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho,
+                               mpc_b200_max_iter=20000, **extra)
     m = C.tuning.modeler
     x0_h, xref_h, uref_h = bench.make_batch(n, 0)
+    rng = np.random.default_rng(7)
+    if near > 0: xref_h = np.tile(x_ref, (n, 1)); x0_h = xref_h + near * rng.standard_normal((n, 4))
+    if state_box: xref_h = rng.uniform(0.70, 0.82, (n, 4)); x0_h = rng.uniform(0.62, 0.72, (n, 4))
     dev = torch.device("cuda", 0)
     x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
     status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
@@ -33,7 +43,8 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0):
     it = iters.cpu().numpy()
     fl = bench.algorithmic_flops(m.info, it, check)
     ms = min(ts)
-    print(json.dumps({"H": H, "n": n, "eps": eps, "check": check, "sigma": sigma, "terminal": terminal, "full": full, "ms": round(ms, 4),
+    print(json.dumps({"H": H, "n": n, "eps": eps, "check": check, "sigma": sigma, "terminal": terminal, "state_box": state_box, "kernel": m.info.kernel, "nt": m.info.nt,
+                      "full": full, "ms": round(ms, 4), "max_iters": int(it.max()),
                       "mean_iters": round(float(it.mean()), 2), "solves_per_s": round(n / ms * 1e3), "tflops": round(fl / ms / 1e9, 2),
                       "frac": round(fl / ms / 1e9 / bench.FP64_PEAK_TFLOPS, 3), "solved": float((status.cpu().numpy() == 1).mean()), "rho": round(m.info.rho, 4)}), flush=True)
 
@@ -83,7 +94,7 @@ def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
     """NMPC with a neural dynamics model, SQP kernel."""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     g = json.loads((ROOT / "tests" / "golden" / fixture).read_text())          # the fixture weights, read directly (no oracle import here)
-    cls = {"fnn": mpc.Fnn, "resnet": mpc.ResNet, "polynet": mpc.PolyNet}[g["arch"]]
+    cls = {"fnn": mpc.Fnn, "resnet": mpc.ResNet, "polynet": mpc.PolyNet, "densenet": mpc.DenseNet}[g["arch"]]
     f = cls(np.array(g["W_in"]), [(np.array(w), np.array(b)) for w, b in zip(g["W_h"], g["b_h"])], np.array(g["W_out"]), activation=g["activation"])
     sys_ = mpc.ConstrainedBlackBoxControlDiscreteSystem(f, 4, 2, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_programming_type="non_linear", **kw)
@@ -135,8 +146,14 @@ if __name__ == "__main__":
     elif a.set == "hsweep":
         for H in (10, 20, 30, 50, 75, 100, 150, 200):
             run(H, 16384, 1e-7, 5, 0.0, reps=2)
+    elif a.set == "rows":        # general-row variants of the QT controller (a3 / a4 rows of SURVEY 8a)
+        run(20, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.002, reps=3)
+        run(10, 65536, 1e-7, 5, 0.0, state_box=True, reps=3)
+        run(20, 16384, 1e-7, 5, 0.0, state_box=True, reps=2)
+        run(3, 65536, 1e-8, 5, 0.0, terminal="contractive", near=0.15, Qw=1.0, Rw=10.0, reps=3)
     elif a.set == "nmpc":
-        for fx in ("qt_resnet_model.json", "qt_fnn_tanh_model.json", "qt_resnet_swish_model.json", "qt_fnn_model.json"):
+        for fx in ("qt_resnet_model.json", "qt_fnn_tanh_model.json", "qt_resnet_swish_model.json", "qt_polynet_tanh_model.json", "qt_densenet_tanh_model.json",
+                   "qt_fnn_model.json"):
             run_nmpc(fx)
         run_nmpc("qt_resnet_model.json", n=65536)
     elif a.set == "nmpc1":
