@@ -464,3 +464,36 @@ def test_contractive_terminal_set(mpc, qt):
     # too large for the on-chip kernel -> refused, not approximated
     with pytest.raises(mpc.MpcbError):
         make_controller(mpc, qt, 40, terminal="contractive")
+
+
+def test_c_abi_error_behaviour(mpc, qt):
+    """Errors are return codes + mpcb_last_error (never exceptions across the boundary, never a silent fallback); per-problem
+    solver outcomes are data."""
+    import ctypes as C
+    L = mpc._lib.lib(); lib = mpc._lib
+    Cn = make_controller(mpc, qt, 20)
+    m = Cn.tuning.modeler
+    io = lib.BatchIO(); io.batch = 4
+    assert L.mpcb_solve_linear_batch(m._h, C.byref(io)) == -1 and b"x0" in L.mpcb_last_error()          # missing inputs
+    x0 = np.zeros((4, 4)); io.x0 = x0.ctypes.data; io.xref = x0.ctypes.data; io.uref = x0.ctypes.data
+    io.batch = 0
+    assert L.mpcb_solve_linear_batch(m._h, C.byref(io)) == -1 and b"batch" in L.mpcb_last_error()
+    io.batch = 4; io.warm_u = x0.ctypes.data                                                                 # warm_u without warm_y
+    assert L.mpcb_solve_linear_batch(m._h, C.byref(io)) == -1 and b"warm" in L.mpcb_last_error()
+    assert L.mpcb_solve_linear_batch(None, C.byref(io)) == -1
+    # design-time failures
+    for kw, frag in (({"mpc_terminal_ingredient": "neighborhood"}, "not supported"), ({"mpc_b200_kernel": 9}, "kernel"), ({"mpc_b200_alpha": 2.5}, "settings"),
+                     ({"mpc_b200_device": 99}, "device")):
+        with pytest.raises(mpc.MpcbError, match=frag):
+            make_controller(mpc, qt, 20, **({"terminal": kw.pop("mpc_terminal_ingredient")} if "mpc_terminal_ingredient" in kw else {}), **kw)
+    with pytest.raises(mpc.MpcbError, match="on-chip"):
+        make_controller(mpc, qt, 50, mpc_b200_kernel=1)                                                      # nz = 100 does not fit the register-resident kernel
+    sys_bad = mpc.ConstrainedLinearControlDiscreteSystem(1.5 * np.eye(2), np.zeros((2, 1)), mpc.Hyperrectangle([-1, -1], [1, 1]), mpc.Hyperrectangle([-1], [1]))
+    with pytest.raises(mpc.MpcbError):                                                                       # unstabilisable pair: the Riccati iteration must fail loudly
+        mpc.proceed_controller(sys_bad, "model_predictive_control", 5, 1, [0, 0], [0], mpc_solver="b200")
+    # max_iter is data, not an error
+    Cs = make_controller(mpc, qt, 20, mpc_b200_eps_abs=1e-12, mpc_b200_eps_rel=1e-12, mpc_b200_max_iter=10, mpc_b200_check_every=5)
+    x0b, xrefb, urefb = qt_batch(qt, 64)
+    mpc.update_initialization(Cs, x0b, references=(xrefb, urefb))
+    r = mpc.calculate(Cs)
+    assert (r["status"] == -2).all() and (r["iters"] == 10).all()
