@@ -6,7 +6,7 @@ bodies are commented out, src/main/computation_mpc.jl:58-284, so they are not pr
 from . import _lib
 from ._lib import MpcbError, default_settings
 from .computation_mpc import calculate, update_initialization
-from .design_mpc import _DEFAULT_PARAMETERS_MODEL_PREDICTIVE_CONTROL, _model_predictive_control_design, dare
+from .design_mpc import _DEFAULT_PARAMETERS_MODEL_PREDICTIVE_CONTROL, _model_predictive_control_design, dare, dare_batch
 from .main_mpc import _design_reference_mpc, proceed_controller
 from .modeler import B200Modeler
 from .nmpc import B200NonlinearModeler

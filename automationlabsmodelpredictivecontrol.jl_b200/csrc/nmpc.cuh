@@ -23,6 +23,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dare.cuh"
+
 namespace mpcb {
 
 enum : int { NN_FNN = 0, NN_RESNET = 1, NN_POLYNET = 2, NN_DENSENET = 3 };
@@ -355,6 +357,8 @@ struct NmpcParams {
   int max_iter, check_every;
   double sqp_tol, ls_c1, ls_noise;
   double rho_eq_scale;   // terminal equality rows: rho_e,i = rho_eq_scale * rho / |Gamma_H,i|^2
+  const double* Rinv;    // nu x nu (LIN kernels: G_0 = B R^-1 B' of the per-problem Riccati equation)
+  int lin_dare;          // LIN kernels: 1 = terminal weight from the per-problem DARE, 0 = the design's Pt for every problem
   const double* xmin;    // nx, state box (SB kernels only)
   const double* xmax;
   int sqp_max_iter, ls_max;
@@ -372,8 +376,9 @@ struct NmpcParams {
 __host__ __device__ inline int nmpc_ldk(int nz) { return nz | 1; }
 // per-warp shared memory (doubles)
 __host__ __device__ inline int nmpc_ldg(int nz, bool sb) { return sb ? (nz | 1) : nz; }   // odd pitch: row-per-lane dot products are conflict-free
-__host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int nz, bool sb) {
-  return (size_t)nz * nmpc_ldk(nz)            // K
+__host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int nz, bool sb, bool lin = false) {
+  return (lin ? (size_t)N.nx * N.nin + (size_t)N.nx * N.nx + dare_scratch_doubles(N.nx) : 0)      // LIN: [A B] and P of this problem, Riccati workspace
+         + (size_t)nz * nmpc_ldk(nz)            // K
          + (sb ? (size_t)(H + 1) * N.nx * nmpc_ldg(nz, true)      // all Gamma_k (state-box rows) + W Gamma scratch
                : 2 * (size_t)N.nx * nz)       // Gamma double buffer (the idle one holds W Gamma)
          + (sb ? 8 * (size_t)H * N.nx : 0)    // state-box rows: rho_g, lo, hi, z_g, ys_g, m, n, y_g
@@ -386,15 +391,19 @@ __host__ __device__ inline size_t nmpc_warp_doubles(const NetDev& N, int H, int 
 __host__ __device__ inline size_t nmpc_const_doubles(const NetDev& N, int nz) {
   return N.weight_count() + 2 * (size_t)N.nx * N.nx + (size_t)nz * nz + 2 * (size_t)nz + 2 * (size_t)N.nx;
 }
-__host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz, int warps, bool sb) {
-  return sizeof(double) * (nmpc_const_doubles(N, nz) + (size_t)warps * nmpc_warp_doubles(N, H, nz, sb));
+__host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz, int warps, bool sb, bool lin = false) {
+  return sizeof(double) * (nmpc_const_doubles(N, nz) + (size_t)warps * nmpc_warp_doubles(N, H, nz, sb, lin));
 }
 
 // ROWS = ceil(nz / 32): decision-variable rows owned by each lane (row e = lane + 32 * i)
 constexpr int NMPC_MAX_WARPS = 10;      // CTA width is chosen at design time to maximise resident warps per SM (shared-memory bound)
 // EQ: terminal equality e_x[:,end] == 0 (design_mpc.jl:330-331) as nx linearised rows Gamma_H v = Gamma_H u - e_H(u).
 // SB: state box xmin <= x[:,k] <= xmax for k = 2..H+1 (fnn.jl:146-154) as nx*H linearised inequality rows.
-template <int ROWS, bool EQ, bool SB>
+// LIN: the reference's LINEAR method on a black-box model (design_mpc.jl:319-327), re-designed per problem on the device:
+//      the network is linearised once at this problem's reference (x_ref, u_ref), the terminal weight comes from this
+//      problem's Riccati equation (dare.cuh), the prediction model is the deviation model x+ = x_ref + A (x - x_ref) +
+//      B (u - u_ref) of linear.jl:59, and the (now exact) condensed QP is solved once.  Everything else is shared.
+template <int ROWS, bool EQ, bool SB, bool LIN>
 __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const NmpcParams P) {
   extern __shared__ __align__(16) double sm[];
   const int nwarps = blockDim.x >> 5;
@@ -414,7 +423,10 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   (void)nwarps;
-  double* w = sXmax + nx + (size_t)warp * nmpc_warp_doubles(P.net, H, nz, SB);
+  double* w = sXmax + nx + (size_t)warp * nmpc_warp_doubles(P.net, H, nz, SB, LIN);
+  double* lAB = w;                       w += LIN ? nx * nin : 0;      // LIN: [A B] at this problem's reference
+  double* lP = w;                        w += LIN ? nx * nx : 0;       //      terminal weight of this problem
+  double* lws = w;                       w += LIN ? dare_scratch_doubles(nx) : 0;
   double* K = w;                         w += (size_t)nz * ldk;
   double* G0 = w;                        w += SB ? (size_t)H * nx * ldg : (size_t)nx * nz;   // SB: Gamma_1 .. Gamma_H, one block of nx rows each
   double* G1 = w;                        w += SB ? (size_t)nx * ldg : (size_t)nx * nz;       // SB: W Gamma scratch
@@ -457,6 +469,39 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
     const double* x0 = P.x0 + p * nx;
     const double* xr = P.xref + (P.xref_bc ? 0 : p) * nx;
     const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
+    const double* Wt = sPt;   // terminal weight
+    const double* ABk = AB;   // stage Jacobians [A_k B_k]
+    if (LIN) {
+      for (int i = lane; i < nx; i += 32) xu[i] = xr[i];
+      for (int i = lane; i < nu; i += 32) xu[nx + i] = ur[i];
+      __syncwarp();
+      nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
+      for (int o = lane; o < nx * nin; o += 32) lAB[o] = AB[o];
+      __syncwarp();
+      ABk = lAB;
+      if (P.lin_dare) {
+        const int dit = dare_sda_warp(nx, nu, lAB, lAB + nx * nx, sQ, P.Rinv, lP, lws, lane);
+        if (dit < 0) {           // no stabilising solution for this linearisation: reported as data, like the host design's error
+          if (lane == 0) { P.status[p] = -4; P.iters[p] = 0; if (P.inner_iters) P.inner_iters[p] = 0; }
+          continue;
+        }
+        Wt = lP;
+      }
+    }
+    // one step of the prediction model from xu = [x; u]: the network, or (LIN) the deviation model around the reference
+    auto model_step = [&]() {
+      if (LIN) {
+        for (int i = lane; i < nx; i += 32) {
+          double sacc = xr[i];
+          for (int j = 0; j < nx; j++) sacc = fma(lAB[j * nx + i], xu[j] - xr[j], sacc);
+          for (int j = 0; j < nu; j++) sacc = fma(lAB[(nx + j) * nx + i], xu[nx + j] - ur[j], sacc);
+          f[i] = sacc;
+        }
+        __syncwarp();
+      } else {
+        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
+      }
+    };
     double yd[ROWS];          // duals of the box rows (carried across SQP iterations)
     double mu = 0.0;          // l1 merit weight of the terminal rows
     const int ny = nz + ms + (EQ ? nx : 0);       // duals: [input box | state-box rows | terminal rows]
@@ -482,7 +527,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
       __syncwarp();
       for (int k = 0; k <= H; k++) {
-        const double* W = (k == H) ? sPt : sQ;
+        const double* W = (k == H) ? Wt : sQ;
         double part = 0.0;
         for (int i = lane; i < nx; i += 32) {
           double s = 0.0;
@@ -493,7 +538,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         if (k == H) break;
         for (int i = lane; i < nu; i += 32) xu[nx + i] = uu[k * nu + i];
         __syncwarp();
-        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
+        model_step();
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; }
         __syncwarp();
       }
@@ -550,22 +595,23 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         for (int i = lane; i < nu; i += 32) xu[nx + i] = su[k * nu + i];
         __syncwarp();
         NMPC_PROF(0);
-        nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
+        if (LIN) model_step();
+        else nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
         NMPC_PROF(5);
         const int ncol = (k + 1) * nu;                 // non-zero columns of Gamma_{k+1}
         // Gamma_{k+1} = A_k Gamma_k, block k = B_k            (stored [i][c], c fastest)
         for (int i = 0; i < nx; i++)
           for (int c = lane; c < ncol; c += 32) {
             double s;
-            if (c >= k * nu) s = AB[(nx + c - k * nu) * nx + i];
+            if (c >= k * nu) s = ABk[(nx + c - k * nu) * nx + i];
             else {
               s = 0.0;
 #pragma unroll 4
-              for (int j = 0; j < nx; j++) s = fma(AB[j * nx + i], Gc[j * ldg + c], s);
+              for (int j = 0; j < nx; j++) s = fma(ABk[j * nx + i], Gc[j * ldg + c], s);
             }
             Gn[i * ldg + c] = s;
           }
-        const double* W = (k + 1 == H) ? sPt : sQ;
+        const double* W = (k + 1 == H) ? Wt : sQ;
         for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; se[i] = v - xr[i]; }
         __syncwarp();
         for (int i = lane; i < nx; i += 32) {
@@ -906,6 +952,12 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       dmax = warp_max(dmax); gd = warp_sum(gd);
       step = dmax;
       __syncwarp();
+      if (LIN) {                         // the QP is the problem: its solution is the answer, its convergence the status
+        for (int e = lane; e < nz; e += 32) su[e] = sv[e];
+        __syncwarp();
+        status = qp_conv ? 1 : -2; step = rp; have_traj = false;
+        break;
+      }
       if (EQ || SB) {
         if (qp_failed) { status = -3; have_traj = false; break; }
         gd -= mu * cviol;                // directional derivative of the l1 merit (the full step zeroes the linearised rows)

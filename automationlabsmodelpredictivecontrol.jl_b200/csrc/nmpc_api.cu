@@ -32,10 +32,11 @@ struct mpcb_nmpc {
   mpcb_nn* nn = nullptr;
   mpcb_nmpc_settings st{};
   int H = 0, nz = 0, rows = 0, warps = 0;
+  int warps_lin = 0;          // CTA width of the re-linearised (LIN) kernels: a little more shared memory per warp
   bool terminal_eq = false, state_box = false;
   double rho = 0.0;
   mpcb::Mat A, B, P;
-  DevBuf<double> Q, Pt, Hc, lb, ub, xmin, xmax;
+  DevBuf<double> Q, Pt, Hc, lb, ub, xmin, xmax, Rinv;
   DevBuf<unsigned long long> counter;
   // host-entry workspaces
   DevBuf<double> x0, xref, uref, warm_u, warm_y, u, e_u, x, e_x, u0, obj, y, step, dres;
@@ -43,7 +44,7 @@ struct mpcb_nmpc {
   PinBuf<int32_t> stage_int;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   mpcb_timing timing{};
-  size_t smem_set = 0;
+  size_t smem_set = 0, smem_set_lin = 0;
 };
 
 namespace {
@@ -95,7 +96,7 @@ int jacobian_device(mpcb_nn* n, int64_t batch, const double* x, const double* u,
   return launch_nn_batch<true>(n, P, st);
 }
 
-int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
+int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st, bool lin = false) {
   mpcb_nn* n = h->nn;
   const long long Bn = io.batch;
   if (Bn <= 0) return api_fail(MPCB_ERR_INVALID, "batch must be positive");
@@ -115,14 +116,19 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st) {
   P.u = io.u; P.e_u = io.e_u; P.x = io.x; P.e_x = io.e_x; P.u0 = io.u0; P.objective = io.objective; P.y = io.y;
   P.status = d_status; P.iters = d_iters; P.inner_iters = io.inner_iters; P.step = io.prim_res; P.qp_dres = io.dual_res;
   P.counter = h->counter.p;
-  const int threads = h->warps * 32;
-  const size_t smem = mpcb::nmpc_smem_bytes(n->net, h->H, h->nz, h->warps, h->state_box);
-  const long long blocks = (Bn + h->warps - 1) / h->warps;
+  P.Rinv = h->Rinv.p; P.lin_dare = 1;
+  if (lin && h->warps_lin == 0) return api_fail(MPCB_ERR_INVALID, "problem too large for the re-linearised kernel");
+  if (lin && !h->Rinv.p) return api_fail(MPCB_ERR_NUMERIC, "re-linearised solve: the per-problem Riccati equation needs a non-singular R and nu <= 3 nx");
+  const int warps = lin ? h->warps_lin : h->warps;
+  const int threads = warps * 32;
+  const size_t smem = mpcb::nmpc_smem_bytes(n->net, h->H, h->nz, warps, h->state_box, lin);
+  const long long blocks = (Bn + warps - 1) / warps;
   const int per_sm = std::max<int>(1, (int)((226 * 1024) / smem));
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * per_sm));
   cudaError_t e;
   if (h->rows < 1 || h->rows > 4) return api_fail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
-  e = mpcb::launch_sqp(h->terminal_eq, h->state_box, h->rows, P, grid, threads, smem, &h->smem_set, st);
+  if (lin) e = mpcb::launch_lin(h->terminal_eq, h->state_box, h->rows, P, grid, threads, smem, &h->smem_set_lin, st);
+  else e = mpcb::launch_sqp(h->terminal_eq, h->state_box, h->rows, P, grid, threads, smem, &h->smem_set, st);
   if (e != cudaSuccess) return api_fail(MPCB_ERR_CUDA, std::string("nmpc_sqp_kernel launch: ") + cudaGetErrorString(e));
   h->timing.kernel_launches = 1;
   h->timing.batch = Bn;
@@ -226,6 +232,59 @@ int mpcb_nn_jacobian_batch(mpcb_nn* n, int64_t batch, const double* x, const dou
   return MPCB_OK;
 }
 
+// Batched Riccati equations (dare.cuh): A, B, P, status are DEVICE arrays, Q and R small HOST matrices.
+int mpcb_dare_batch_device(int32_t device, int64_t batch, int32_t nx, int32_t nu, const double* A, const double* B, const double* Q, const double* R, double* P,
+                           int32_t* status, void* cuda_stream) {
+  if (batch <= 0 || nx <= 0 || nu <= 0 || !A || !B || !Q || !R || !P) return api_fail(MPCB_ERR_INVALID, "mpcb_dare_batch: bad arguments");
+  if (nu > 3 * nx) return api_fail(MPCB_ERR_INVALID, "mpcb_dare_batch: nu <= 3 nx is required");
+  int sms = 0;
+  int rc = check_device(device, &sms);
+  if (rc != MPCB_OK) return rc;
+  const size_t smem = mpcb::dare_batch_smem_bytes(nx, nu);
+  if (smem > 200 * 1024) return api_fail(MPCB_ERR_INVALID, "mpcb_dare_batch: system too large for the shared-memory resident kernel");
+  mpcb::Mat Ri = mpcb::Mat::eye(nu);
+  if (!mpcb::lu_solve(mpcb::Mat::from(R, nu, nu), Ri)) return api_fail(MPCB_ERR_NUMERIC, "dare: R is singular");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  double* consts = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&consts, sizeof(double) * ((size_t)nx * nx + (size_t)nu * nu), st));
+  cudaError_t e = cudaMemcpyAsync(consts, Q, sizeof(double) * nx * nx, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(consts + (size_t)nx * nx, Ri.a.data(), sizeof(double) * nu * nu, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && smem > 48 * 1024) e = cudaFuncSetAttribute(mpcb::dare_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    mpcb::DareBatchParams D{};
+    D.nx = nx; D.nu = nu; D.batch = batch; D.A = A; D.B = B; D.Q = consts; D.Rinv = consts + (size_t)nx * nx; D.P = P; D.status = status;
+    const long long blocks = (batch + mpcb::DARE_WARPS - 1) / mpcb::DARE_WARPS;
+    const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)sms * 8));
+    mpcb::dare_batch_kernel<<<grid, mpcb::DARE_WARPS * 32, smem, st>>>(D);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(consts, st);
+  if (e != cudaSuccess) { cudaGetLastError(); return api_fail(MPCB_ERR_CUDA, std::string("mpcb_dare_batch: ") + cudaGetErrorString(e)); }
+  return MPCB_OK;
+}
+
+int mpcb_dare_batch(int32_t device, int64_t batch, int32_t nx, int32_t nu, const double* A, const double* B, const double* Q, const double* R, double* P,
+                    int32_t* status) {
+  if (batch <= 0 || nx <= 0 || nu <= 0 || !A || !B || !Q || !R || !P) return api_fail(MPCB_ERR_INVALID, "mpcb_dare_batch: bad arguments");
+  int sms = 0;
+  int rc = check_device(device, &sms);
+  if (rc != MPCB_OK) return rc;
+  const size_t nA = (size_t)batch * nx * nx, nB = (size_t)batch * nx * nu;
+  DevBuf<double> dA, dB, dP;
+  DevBuf<int32_t> dS;
+  auto done = [&](int code) { dA.release(); dB.release(); dP.release(); dS.release(); return code; };
+  if (mpcb::upload(dA, A, nA) != cudaSuccess || mpcb::upload(dB, B, nB) != cudaSuccess || dP.ensure(nA) != cudaSuccess || dS.ensure((size_t)batch) != cudaSuccess) {
+    cudaGetLastError();
+    return done(api_fail(MPCB_ERR_CUDA, "mpcb_dare_batch: device buffers"));
+  }
+  rc = mpcb_dare_batch_device(device, batch, nx, nu, dA.p, dB.p, Q, R, dP.p, dS.p, nullptr);
+  if (rc != MPCB_OK) return done(rc);
+  cudaError_t e = cudaMemcpy(P, dP.p, nA * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess && status) e = cudaMemcpy(status, dS.p, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { cudaGetLastError(); return done(api_fail(MPCB_ERR_CUDA, std::string("mpcb_dare_batch: ") + cudaGetErrorString(e))); }
+  return done(MPCB_OK);
+}
+
 void mpcb_default_nmpc_settings(mpcb_nmpc_settings* s) {
   if (!s) return;
   std::memset(s, 0, sizeof(*s));
@@ -266,6 +325,13 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
     if (resident > best) { best = resident; h->warps = w; }
   }
   if (h->warps == 0) return bail(MPCB_ERR_INVALID, "NMPC problem too large for the shared-memory resident SQP kernel");
+  best = 0;
+  for (int w = 1; w <= mpcb::NMPC_MAX_WARPS; w++) {
+    const size_t sm = mpcb::nmpc_smem_bytes(n->net, H, nz, w, h->state_box, true);
+    if (sm > 226 * 1024) break;
+    const int resident = (int)((226 * 1024) / sm) * w;
+    if (resident > best) { best = resident; h->warps_lin = w; }
+  }
 
   // linearise at the design reference ON THE GPU (the reference: proceed_system_linearization, design_mpc.jl:319-323)
   {
@@ -305,6 +371,10 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
             Hc[(size_t)b0 * nz + a0] += s2; Hc[(size_t)b1 * nz + a1] += s2; Hc[(size_t)b1 * nz + a0] -= s2; Hc[(size_t)b0 * nz + a1] -= s2;
           }
   }
+  if (nu <= 3 * nx) {          // R^-1 for the per-problem Riccati equations of the re-linearised solve (dare.cuh)
+    mpcb::Mat Ri = mpcb::Mat::eye(nu);
+    if (mpcb::lu_solve(D.R, Ri) && mpcb::upload(h->Rinv, Ri.a.data(), Ri.a.size()) != cudaSuccess) { cudaGetLastError(); return bail(MPCB_ERR_CUDA, "constant upload failed"); }
+  }
   for (int e = 0; e < nz; e++) { lb[e] = d->umin[e % nu]; ub[e] = d->umax[e % nu]; if (!(lb[e] <= ub[e])) return bail(MPCB_ERR_INVALID, "umin > umax"); }
   if (mpcb::upload(h->Q, D.Q.a.data(), D.Q.a.size()) != cudaSuccess || mpcb::upload(h->Pt, D.P.a.data(), D.P.a.size()) != cudaSuccess ||
       mpcb::upload(h->Hc, Hc.data(), Hc.size()) != cudaSuccess || mpcb::upload(h->lb, lb.data(), nz) != cudaSuccess ||
@@ -322,7 +392,7 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
 void mpcb_destroy_nmpc(mpcb_nmpc* h) {
   if (!h) return;
   if (h->nn) { cudaSetDevice(h->nn->device); if (h->nn->stream) cudaStreamSynchronize(h->nn->stream); }
-  for (DevBuf<double>* b : {&h->Q, &h->Pt, &h->Hc, &h->lb, &h->ub, &h->xmin, &h->xmax, &h->x0, &h->xref, &h->uref, &h->warm_u, &h->warm_y, &h->u, &h->e_u, &h->x, &h->e_x, &h->u0,
+  for (DevBuf<double>* b : {&h->Q, &h->Pt, &h->Hc, &h->lb, &h->ub, &h->xmin, &h->xmax, &h->Rinv, &h->x0, &h->xref, &h->uref, &h->warm_u, &h->warm_y, &h->u, &h->e_u, &h->x, &h->e_x, &h->u0,
                             &h->obj, &h->y, &h->step, &h->dres})
     b->release();
   h->status.release(); h->iters.release(); h->inner.release(); h->counter.release(); h->stage_int.release();
@@ -352,7 +422,17 @@ int mpcb_solve_nmpc_batch_device(mpcb_nmpc* h, const mpcb_batch_io* io, void* cu
   return enqueue_nmpc(h, *io, (cudaStream_t)cuda_stream);
 }
 
-int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) {
+int mpcb_solve_relinearized_batch_device(mpcb_nmpc* h, const mpcb_batch_io* io, void* cuda_stream) {
+  if (!h || !io) return api_fail(MPCB_ERR_INVALID, "null argument");
+  CUDA_TRY(cudaSetDevice(h->nn->device));
+  return enqueue_nmpc(h, *io, (cudaStream_t)cuda_stream, true);
+}
+
+static int solve_nmpc_host(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin);
+int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) { return solve_nmpc_host(h, hio, false); }
+int mpcb_solve_relinearized_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) { return solve_nmpc_host(h, hio, true); }
+
+static int solve_nmpc_host(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin) {
   if (!h || !hio) return api_fail(MPCB_ERR_INVALID, "null argument");
   const long long Bn = hio->batch;
   if (Bn <= 0) return api_fail(MPCB_ERR_INVALID, "batch must be positive");
@@ -385,7 +465,7 @@ int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) {
   }
   CUDA_TRY(h->status.ensure(B)); CUDA_TRY(h->iters.ensure(B)); CUDA_TRY(h->inner.ensure(B));
   dio.status = h->status.p; dio.iters = h->iters.p; dio.inner_iters = h->inner.p;
-  int rc = enqueue_nmpc(h, dio, st);
+  int rc = enqueue_nmpc(h, dio, st, lin);
   if (rc != MPCB_OK) return rc;
   CUDA_TRY(cudaEventRecord(h->ev[2], st));
   for (auto& o : outs)

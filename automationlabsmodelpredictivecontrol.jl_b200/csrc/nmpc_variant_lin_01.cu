@@ -1,5 +1,5 @@
 #define NMPC_EQ false
 #define NMPC_SB true
-#define NMPC_LIN false
-#define NMPC_LAUNCHER launch_sqp_01
+#define NMPC_LIN true
+#define NMPC_LAUNCHER launch_lin_01
 #include "nmpc_variant.inc"

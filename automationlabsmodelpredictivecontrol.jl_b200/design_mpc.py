@@ -42,6 +42,19 @@ def dare(A, B, Q, R):
     return np.ascontiguousarray(P)
 
 
+def dare_batch(A, B, Q, R, device=0):
+    """P_i = are(Discrete, A_i, B_i, Q, R) for many systems at once on the GPU (mpcb_dare_batch): A (n, nx, nx), B (n, nx, nu).
+    Returns (P (n, nx, nx), steps (n,)): steps > 0 doubling steps taken, -1 where the equation has no stabilising solution."""
+    A = np.asarray(A, np.float64); B = np.asarray(B, np.float64)
+    n, nx, nu = B.shape
+    Af = np.ascontiguousarray(A.transpose(0, 2, 1)); Bf = np.ascontiguousarray(B.transpose(0, 2, 1))     # column-major per system
+    Q = np.asfortranarray(Q, dtype=np.float64); R = np.asfortranarray(R, dtype=np.float64)
+    P = np.empty((n, nx, nx)); st = np.empty(n, np.int32)
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    _lib.check(_lib.lib().mpcb_dare_batch(device, n, nx, nu, p(Af), p(Bf), p(Q), p(R), p(P), st.ctypes.data_as(C.POINTER(C.c_int32))), "mpcb_dare_batch")
+    return P.transpose(0, 2, 1).copy(), st
+
+
 def _create_weights_coefficients(system, kws) -> WeightsCoefficient:
     """design_mpc.jl:235-283: scalar * identity for Q, R, S."""
     d = _DEFAULT_PARAMETERS_MODEL_PREDICTIVE_CONTROL

@@ -52,8 +52,12 @@ class B200NonlinearModeler:
         _lib.check(_lib.lib().mpcb_nmpc_get_timing(self._h, C.byref(t)), "mpcb_nmpc_get_timing")
         return {k: getattr(t, k) for k, _ in t._fields_}
 
-    def solve_batch(self, x0, xref, uref, want=("u", "e_u", "x", "e_x", "u0", "objective"), warm=None, out=None):
-        """Host-array entry (mpcb_solve_nmpc_batch).  warm = (u_init or None, y_init or None)."""
+    def solve_batch(self, x0, xref, uref, want=("u", "e_u", "x", "e_x", "u0", "objective"), warm=None, out=None, method="non_linear"):
+        """Host-array entry.  method = "non_linear": the SQP solve of the NL modeler (mpcb_solve_nmpc_batch);
+        method = "linear": the reference's linear method on the black-box model (design_mpc.jl:319-327), re-designed per
+        problem at that problem's reference on the device (mpcb_solve_relinearized_batch).
+        warm = (u_init or None, y_init or None)."""
+        if method not in ("non_linear", "linear"): raise ValueError("method must be 'non_linear' or 'linear'")
         x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, np.float64)))
         Bn = x0.shape[0]
         if x0.shape[1] != self.nx: raise ValueError("x0 must be (batch, nx)")
@@ -85,11 +89,15 @@ class B200NonlinearModeler:
                 io.warm_y = wy.ctypes.data
         for k in ("u", "e_u", "x", "e_x", "u0", "objective", "prim_res", "dual_res", "y", "status", "iters", "inner_iters"):
             if k in res: setattr(io, k, res[k].ctypes.data)
-        _lib.check(_lib.lib().mpcb_solve_nmpc_batch(self._h, C.byref(io)), "mpcb_solve_nmpc_batch")
+        if method == "linear": _lib.check(_lib.lib().mpcb_solve_relinearized_batch(self._h, C.byref(io)), "mpcb_solve_relinearized_batch")
+        else: _lib.check(_lib.lib().mpcb_solve_nmpc_batch(self._h, C.byref(io)), "mpcb_solve_nmpc_batch")
         return res
 
-    def solve_batch_device(self, io: _lib.BatchIO, stream=None):
-        _lib.check(_lib.lib().mpcb_solve_nmpc_batch_device(self._h, C.byref(io), C.c_void_p(stream or 0)), "mpcb_solve_nmpc_batch_device")
+    def solve_batch_device(self, io: _lib.BatchIO, stream=None, method="non_linear"):
+        if method == "linear":
+            _lib.check(_lib.lib().mpcb_solve_relinearized_batch_device(self._h, C.byref(io), C.c_void_p(stream or 0)), "mpcb_solve_relinearized_batch_device")
+        else:
+            _lib.check(_lib.lib().mpcb_solve_nmpc_batch_device(self._h, C.byref(io), C.c_void_p(stream or 0)), "mpcb_solve_nmpc_batch_device")
 
     def close(self):
         if getattr(self, "_h", None):

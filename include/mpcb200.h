@@ -40,6 +40,7 @@ extern "C" {
 #define MPCB_STATUS_SOLVED_INACCURATE 2 /* NMPC only: the SQP line search found no further descent (kink of a relu network) */
 #define MPCB_STATUS_MAX_ITER -2
 #define MPCB_STATUS_PRIMAL_INFEASIBLE -3
+#define MPCB_STATUS_DESIGN_FAILED -4 /* re-linearised solve: this problem's Riccati equation has no stabilising solution */
 #define MPCB_STATUS_UNSOLVED -10
 
 /* terminal ingredient (src/sub/design_mpc.jl:298-394).  "contractive" (e_H' e_H <= 0.9 e_0' e_0, :333-340) is a quadratic
@@ -166,6 +167,14 @@ void mpcb_default_settings(mpcb_settings* s);
 /* Discrete algebraic Riccati equation (replaces ControlSystems.are, design_mpc.jl:327), structure-preserving
  * doubling on the host.  All matrices column-major. */
 int mpcb_dare(int32_t nx, int32_t nu, const double* A, const double* B, const double* Q, const double* R, double* P_out);
+/* The same equation for MANY systems on the GPU, one warp per system (device-side design): A
+ * [batch][nx*nx] and B [batch][nx*nu] column-major per system, shared weights Q (nx x nx), R (nu x nu, non-singular; HOST
+ * pointers in both variants), P_out [batch][nx*nx]; status (may be NULL) = doubling steps taken (> 0) or -1 when the
+ * recurrence did not settle ((A_i, B_i) not stabilisable; P_out of that system is NaN).  nu <= 3 nx. */
+int mpcb_dare_batch(int32_t device, int64_t batch, int32_t nx, int32_t nu, const double* A, const double* B, const double* Q, const double* R,
+                    double* P_out, int32_t* status);
+int mpcb_dare_batch_device(int32_t device, int64_t batch, int32_t nx, int32_t nu, const double* dA, const double* dB, const double* Q, const double* R,
+                           double* dP_out, int32_t* dstatus, void* cuda_stream);
 
 /* Design: condense, choose rho, factor K, build the stacked operators, upload to `settings->device`.
  * Replaces modeler construction + OSQP setup (linear.jl:20-103, solver_selection.jl:92-98). */
@@ -310,6 +319,17 @@ int mpcb_nmpc_get_timing(const mpcb_nmpc* h, mpcb_timing* t);
  * _PRIMAL_INFEASIBLE (a linearised terminal constraint that the input box does not admit within the inner iteration cap). */
 int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* host_io);
 int mpcb_solve_nmpc_batch_device(mpcb_nmpc* h, const mpcb_batch_io* dev_io, void* cuda_stream);
+
+/* The reference's LINEAR method on a black-box model (design_mpc.jl:319-327: proceed_system_linearization at the
+ * reference, P = are(A, B, Q, R), then the linear modeler of linear.jl:45-93), re-designed PER PROBLEM on the device
+ * (SURVEY section 8f rank 2): every problem of the batch carries its own reference (xref_i, uref_i), so the kernel
+ * linearises the network there, solves that problem's Riccati equation for the terminal weight (always: the P of the
+ * handle belongs to the design reference only), condenses and factors that problem's QP and solves it once -- a batch of B different
+ * LTI controllers designed and evaluated in one launch.  Same handle, io meanings and constraints (input box, optional
+ * state box, terminal "none"/"equality") as mpcb_solve_nmpc_batch; x / e_x are the predictions of the linearised model,
+ * iters = 1, prim_res / dual_res = residuals of the QP, status = _SOLVED / _MAX_ITER / _DESIGN_FAILED. */
+int mpcb_solve_relinearized_batch(mpcb_nmpc* h, const mpcb_batch_io* host_io);
+int mpcb_solve_relinearized_batch_device(mpcb_nmpc* h, const mpcb_batch_io* dev_io, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -414,3 +414,39 @@ def nmpc_local_opt(m, Q, R, S, P, H, umin, umax, x0, xref, uref, u_init=None):
     r = minimize(fg, v0, jac=True, method="L-BFGS-B", bounds=list(zip(lb, ub)), options={"maxiter": 5000, "ftol": 1e-16, "gtol": 1e-12, "maxcor": 40})
     J, g = fg(r.x)
     return r.x.reshape(H, nu), J, float(kkt_residual(g, r.x, lb, ub))
+
+
+# --------------------------------------------------------------------------------------------------
+# The reference's LINEAR method on a black-box model, one design per problem
+# --------------------------------------------------------------------------------------------------
+def relinearized_linear_mpc(m: NeuralModel, Q, R, S, H, umin, umax, x0, xref, uref, P=None, xmin=None, xmax=None,
+                            state_constraint=False, terminal="none", eps=1e-10):
+    """For every problem i: linearise the network at (xref_i, uref_i) (proceed_system_linearization, design_mpc.jl:319-323),
+    P_i = are(A_i, B_i, Q, R) (design_mpc.jl:327) unless P is given, build the linear modeler's QP on that system
+    (linear.jl:45-93 via mpc_oracle.condense) and solve it: exactly (active-set KKT) when the general rows are
+    equalities or absent, with the ADMM twin at tight tolerance otherwise.  Checker for mpcb_solve_relinearized_batch.
+    Returns dict of u, x, e_x, objective, P, A, B and `solved` (False where the problem is infeasible)."""
+    x0 = np.atleast_2d(np.asarray(x0, float)); n = x0.shape[0]
+    xref = np.broadcast_to(np.atleast_2d(np.asarray(xref, float)), x0.shape)
+    uref = np.broadcast_to(np.atleast_2d(np.asarray(uref, float)), (n, m.nu))
+    _, A, B = jacobian(m, xref, uref)
+    out = {k: [] for k in ("u", "x", "e_x", "objective", "P", "solved")}
+    for i in range(n):
+        Pi = mo.dare(A[i], B[i], Q, R) if P is None else np.asarray(P, float)
+        c = mo.condense(A[i], B[i], Q, R, S, Pi, H, umin, umax, xmin, xmax, state_constraint=state_constraint, terminal=terminal)
+        p = mo.pack_params(x0[i], xref[i], uref[i])
+        v = None
+        if c.mg == 0 or c.eq_mask.all():
+            try: v, _ = mo.qp_exact(c, p[0])
+            except RuntimeError: v = None          # no KKT certificate: the equality rows are not reachable inside the input box
+        if v is None:
+            r = mo.admm_condensed(c, p, mo.AdmmSettings(eps_abs=eps, eps_rel=eps, check_every=10, max_iter=100000))
+            v = r["v"][0]; out["solved"].append(r["status"][0] == 1)
+        else:
+            out["solved"].append(True)
+        rec = mo.recover(c, v, p)
+        for k in ("u", "x", "e_x", "objective"): out[k].append(rec[k][0])
+        out["P"].append(Pi)
+    res = {k: np.array(v) for k, v in out.items()}
+    res["A"] = A; res["B"] = B
+    return res

@@ -193,3 +193,24 @@ def test_twin_terminal_equality_vs_slsqp(qt):
         f_ = minimize(lambda v: float((cons(v) ** 2).sum()), np.tile(qt["u_ref"], H), method="L-BFGS-B", bounds=list(zip(lb, ub)),
                       options={"maxiter": 2000, "ftol": 1e-20, "gtol": 1e-14})
         assert np.sqrt(f_.fun) > 1e-5
+
+
+def test_relinearized_linear_method_is_the_reference_qp_per_problem(qt):
+    """oracle.relinearized_linear_mpc (checker of mpcb_solve_relinearized_batch): per problem the linear modeler's QP on the
+    Jacobian linearisation at THAT problem's reference with P = are(A_i, B_i, Q, R) (design_mpc.jl:319-327).  Checked
+    against the reference's own sparse encoding of that QP (build_reference_qp) solved by the OSQP port."""
+    from oracle import osqp_ref as orf
+    import scipy.linalg as sla
+    m = load_nn_fixture("qt_fnn_tanh_model.json")
+    rng = np.random.default_rng(3)
+    n, H = 4, 6
+    x0 = rng.uniform(0.45, 0.95, (n, 4)); xref = rng.uniform(0.45, 0.9, (n, 4)); uref = rng.uniform(0.8, 2.2, (n, 2))
+    orc = no.relinearized_linear_mpc(m, qt["Q"], qt["R"], qt["S"], H, qt["umin"], qt["umax"], x0, xref, uref)
+    assert orc["solved"].all()
+    for i in range(n):
+        Ps = sla.solve_discrete_are(orc["A"][i], orc["B"][i], qt["Q"], qt["R"])
+        assert np.abs(orc["P"][i] - Ps).max() < 1e-8 * np.abs(Ps).max()
+        qp = mo.build_reference_qp(orc["A"][i], orc["B"][i], qt["Q"], qt["R"], qt["S"], orc["P"][i], H, xref[i], uref[i], x0[i], qt["umin"], qt["umax"])
+        sol = orf.Workspace(orf.Problem(qp.P, qp.q, qp.A, qp.l, qp.u), orf.default_settings(eps_abs=1e-9, eps_rel=1e-9, max_iter=200000)).solve(cold_start=True)
+        assert np.abs(sol["x"][qp.idx["u"]].T - orc["u"][i]).max() < 1e-5
+        assert abs(sol["obj"] - orc["objective"][i]) <= 1e-6 * abs(orc["objective"][i])
