@@ -213,7 +213,9 @@ function update_initialization!(m::B200NonlinearModeler, X0::AbstractMatrix; xre
     m.X0 = Matrix{Float64}(X0); m.xref = Matrix{Float64}(xref); m.uref = Matrix{Float64}(uref)
 end
 
-function calculate!(m::B200NonlinearModeler)
+"method = :non_linear: the SQP solve of the NL modeler; method = :linear: the linear method on the black-box model re-designed per
+problem at that problem's reference (design_mpc.jl:319-327) -- mpcb_solve_relinearized_batch."
+function calculate!(m::B200NonlinearModeler; method::Symbol = :non_linear)
     nx, nu, H = m.nx, m.nu, m.horizon
     batch = size(m.X0, 2)
     batch > 0 || error("calculate!: call update_initialization! first")
@@ -224,9 +226,22 @@ function calculate!(m::B200NonlinearModeler)
         io = MpcbBatchIO(batch, pointer(m.X0), pointer(m.xref), pointer(m.uref), size(m.xref, 2) == 1 ? 1 : 0, size(m.uref, 2) == 1 ? 1 : 0,
                          C_NULL, C_NULL, pointer(m.u), pointer(m.e_u), pointer(m.x), pointer(m.e_x), C_NULL, pointer(m.status),
                          pointer(m.iterations), pointer(m.step), C_NULL, pointer(m.objective), C_NULL, pointer(m.inner_iterations))
-        check(ccall((:mpcb_solve_nmpc_batch, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbBatchIO}), m.handle, io), "mpcb_solve_nmpc_batch")
+        if method == :linear
+            check(ccall((:mpcb_solve_relinearized_batch, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbBatchIO}), m.handle, io), "mpcb_solve_relinearized_batch")
+        else
+            check(ccall((:mpcb_solve_nmpc_batch, libmpcb200), Cint, (Ptr{Cvoid}, Ref{MpcbBatchIO}), m.handle, io), "mpcb_solve_nmpc_batch")
+        end
     end
     return m
+end
+
+"ControlSystems.are(Discrete, A_i, B_i, Q, R) (design_mpc.jl:327) for many systems on the GPU: A nx x nx x n, B nx x nu x n."
+function dare_batch(A::Array{Float64,3}, B::Array{Float64,3}, Q::Matrix{Float64}, R::Matrix{Float64}; device::Integer=0)
+    nx, nu, n = size(B)
+    P = Array{Float64}(undef, nx, nx, n); steps = Vector{Int32}(undef, n)
+    check(ccall((:mpcb_dare_batch, libmpcb200), Cint, (Int32, Int64, Int32, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int32}),
+                device, n, nx, nu, A, B, Q, R, P, steps), "mpcb_dare_batch")
+    return P, steps
 end
 
 "AutomationLabsSystems.proceed_system_linearization for a Flux chain (fnn.jl:42, design_mpc.jl:319-323) on the GPU."

@@ -24,9 +24,12 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     if near > 0: xref_h = np.tile(x_ref, (n, 1)); x0_h = xref_h + near * rng.standard_normal((n, 4))
     if state_box: xref_h = rng.uniform(0.70, 0.82, (n, 4)); x0_h = rng.uniform(0.62, 0.72, (n, 4))
     dev = torch.device("cuda", 0)
+    if method == "linear":          # per-problem references: every problem is its own linearisation, Riccati equation and QP
+        rng = np.random.default_rng(3)
+        uref_h = rng.uniform(0.8, 2.2, (n, 2))
     x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
     status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
-    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 1
+    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 0 if method == "linear" else 1
     io.status = status.data_ptr(); io.iters = iters.data_ptr()
     outs = []
     if full:
@@ -69,6 +72,9 @@ def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="eq
     rng = np.random.default_rng(3)
     x0_h = scale * rng.standard_normal((n, nx)); xref_h = np.zeros(nx); uref_h = np.zeros(nu)
     dev = torch.device("cuda", 0)
+    if method == "linear":          # per-problem references: every problem is its own linearisation, Riccati equation and QP
+        rng = np.random.default_rng(3)
+        uref_h = rng.uniform(0.8, 2.2, (n, 2))
     x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
     status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
     u0 = torch.empty((n, nu), dtype=torch.float64, device=dev)
@@ -90,7 +96,7 @@ def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="eq
                       "solves_per_s": round(n / ms * 1e3), "tflops_active_rows": round(fl / ms / 1e9, 2), "launches": m.timing()["kernel_launches"]}), flush=True)
 
 
-def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
+def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, method="non_linear", **kw):
     """NMPC with a neural dynamics model, SQP kernel."""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     g = json.loads((ROOT / "tests" / "golden" / fixture).read_text())          # the fixture weights, read directly (no oracle import here)
@@ -101,19 +107,22 @@ def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
     mod = C.tuning.modeler
     x0_h, xref_h, uref_h = bench.make_batch(n, 0)
     dev = torch.device("cuda", 0)
+    if method == "linear":          # per-problem references: every problem is its own linearisation, Riccati equation and QP
+        rng = np.random.default_rng(3)
+        uref_h = rng.uniform(0.8, 2.2, (n, 2))
     x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
     status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev); inner = torch.empty(n, dtype=torch.int32, device=dev)
     u = torch.empty((n, H, 2), dtype=torch.float64, device=dev); x = torch.empty((n, H + 1, 4), dtype=torch.float64, device=dev)
     eu = torch.empty_like(u); ex = torch.empty_like(x); obj = torch.empty(n, dtype=torch.float64, device=dev)
-    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 1
+    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 0 if method == "linear" else 1
     io.status = status.data_ptr(); io.iters = iters.data_ptr(); io.inner_iters = inner.data_ptr()
     io.u = u.data_ptr(); io.x = x.data_ptr(); io.e_u = eu.data_ptr(); io.e_x = ex.data_ptr(); io.objective = obj.data_ptr()
     st = torch.cuda.current_stream().cuda_stream
-    mod.solve_batch_device(io, st); torch.cuda.synchronize()
+    mod.solve_batch_device(io, st, method=method); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
         a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
-        a.record(); mod.solve_batch_device(io, st); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+        a.record(); mod.solve_batch_device(io, st, method=method); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
     it = iters.cpu().numpy(); inn = inner.cpu().numpy(); stt = status.cpu().numpy()
     ms = min(ts)
     L = _lib.lib()
@@ -124,7 +133,7 @@ def run_nmpc(fixture="qt_resnet_model.json", H=20, n=4096, reps=3, **kw):
         tot = sum(buf) or 1
         names = ["linearise-other", "q+inverse", "admm", "final accept", "line search/init", "nn_eval+jac", "gamma+Wgamma", "K,g accumulate"]
         print(json.dumps({"nmpc_phase_share": {nm: round(buf[i] / tot, 3) for i, nm in enumerate(names)}, "cycles_per_problem_per_launch": round(tot / n / (reps + 1))}), flush=True)
-    print(json.dumps({"cfg": "nmpc", "fixture": fixture, "H": H, "n": n, "ms": round(ms, 3), "solves_per_s": round(n / ms * 1e3), "sqp_iters_mean": round(float(it.mean()), 2),
+    print(json.dumps({"cfg": "nmpc" if method == "non_linear" else "relinearized", "fixture": fixture, "H": H, "n": n, "ms": round(ms, 3), "solves_per_s": round(n / ms * 1e3), "sqp_iters_mean": round(float(it.mean()), 2),
                       "sqp_iters_max": int(it.max()), "inner_mean": round(float(inn.mean()), 1), "solved": float((stt == 1).mean()), "stalled": float((stt == 2).mean()),
                       "maxiter": float((stt == -2).mean()), "rho": round(mod.design()["rho"], 4)}), flush=True)
 
@@ -156,6 +165,10 @@ if __name__ == "__main__":
                    "qt_fnn_model.json"):
             run_nmpc(fx)
         run_nmpc("qt_resnet_model.json", n=65536)
+    elif a.set == "relin":       # per-problem linearisation + DARE + condensed QP in one launch
+        for fx, H in (("qt_fnn_tanh_model.json", 20), ("qt_resnet_model.json", 20), ("qt_fnn_tanh_model.json", 10), ("qt_densenet_tanh_model.json", 20)):
+            run_nmpc(fx, H=H, n=65536, method="linear")
+        run_nmpc("qt_fnn_tanh_model.json", H=20, n=65536, method="linear", mpc_b200_eps_abs=1e-7)
     elif a.set == "nmpc1":
         run_nmpc("qt_fnn_tanh_model.json", reps=1)
     elif a.set == "lti1":
