@@ -357,6 +357,7 @@ struct NmpcParams {
   int max_iter, check_every;
   double sqp_tol, ls_c1, ls_noise;
   double rho_eq_scale;   // terminal equality rows: rho_e,i = rho_eq_scale * rho / |Gamma_H,i|^2
+  int term_ball;         // EQ kernels: the terminal rows form the contractive ball |e_H|_2 <= sqrt(0.9) |e_0|_2 (design_mpc.jl:333-340) instead of e_H = 0
   const double* Rinv;    // nu x nu (LIN kernels: G_0 = B R^-1 B' of the per-problem Riccati equation)
   int lin_dare;          // LIN kernels: 1 = terminal weight from the per-problem DARE, 0 = the design's Pt for every problem
   const double* xmin;    // nx, state box (SB kernels only)
@@ -397,7 +398,9 @@ __host__ __device__ inline size_t nmpc_smem_bytes(const NetDev& N, int H, int nz
 
 // ROWS = ceil(nz / 32): decision-variable rows owned by each lane (row e = lane + 32 * i)
 constexpr int NMPC_MAX_WARPS = 10;      // CTA width is chosen at design time to maximise resident warps per SM (shared-memory bound)
-// EQ: terminal equality e_x[:,end] == 0 (design_mpc.jl:330-331) as nx linearised rows Gamma_H v = Gamma_H u - e_H(u).
+// EQ: terminal equality e_x[:,end] == 0 (design_mpc.jl:330-331) as nx linearised rows Gamma_H v = Gamma_H u - e_H(u); with
+//     P.term_ball the same rows carry the contractive set e_H' e_H <= 0.9 e_0' e_0 (design_mpc.jl:333-340) linearised as
+//     |Gamma_H v - b|_2 <= rad: the ADMM projects them onto that ball (one common step size) instead of the point b.
 // SB: state box xmin <= x[:,k] <= xmax for k = 2..H+1 (fnn.jl:146-154) as nx*H linearised inequality rows.
 // LIN: the reference's LINEAR method on a black-box model (design_mpc.jl:319-327), re-designed per problem on the device:
 //      the network is linearised once at this problem's reference (x_ref, u_ref), the terminal weight comes from this
@@ -469,6 +472,12 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
     const double* x0 = P.x0 + p * nx;
     const double* xr = P.xref + (P.xref_bc ? 0 : p) * nx;
     const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
+    double rad = 0.0;         // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this problem's ball
+    if (EQ && P.term_ball) {
+      double d2 = 0.0;
+      for (int i = 0; i < nx; i++) { const double dv = x0[i] - xr[i]; d2 = fma(dv, dv, d2); }
+      rad = sqrt(0.9 * d2);
+    }
     const double* Wt = sPt;   // terminal weight
     const double* ABk = AB;   // stage Jacobians [A_k B_k]
     if (LIN) {
@@ -685,18 +694,26 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       double cviol = 0.0;                  // l1 violation of the nonlinear constraints at u: |e_H|_1 (all lanes) + state-box part (per-lane partial, reduced below)
       double cviol_sb = 0.0;
       if (EQ) {
+        double n2sum = 0.0, eh2 = 0.0;
         for (int i = 0; i < nx; i++) {     // per terminal row: |G_i|^2, G_i u  (warp reductions)
           double n2 = 0.0, gu = 0.0;
           for (int cidx = lane; cidx < nz; cidx += 32) { const double gv = GH[i * ldg + cidx]; n2 = fma(gv, gv, n2); gu = fma(gv, su[cidx], gu); }
           n2 = warp_sum(n2); gu = warp_sum(gu);
           const double eh = se[i];
           cviol += fabs(eh);
+          n2sum += n2; eh2 = fma(eh, eh, eh2);
           if (lane == 0) {
             const double re = P.rho_eq_scale * rho / fmax(n2, 1e-12);
             srhoe[i] = re; sb[i] = gu - eh; szg[i] = gu; sysg[i] = syg[i] / re;     // OSQP warm start: z = A x, y kept
           }
         }
         __syncwarp();
+        if (P.term_ball) {                 // one common step size on the ball's rows (the projection needs a uniform metric)
+          const double re = rho * (double)nx / fmax(n2sum, 1e-12);
+          if (lane == 0) for (int i = 0; i < nx; i++) { srhoe[i] = re; sysg[i] = syg[i] / re; }
+          cviol = fmax(sqrt(eh2) - rad, 0.0);
+          __syncwarp();
+        }
         for (int a = 0; a < nz; a++) {     // K += G' diag(rho_e) G
           for (int i = 0; i < nx; i++) {
             const double gai = srhoe[i] * GH[i * ldg + a];
@@ -869,15 +886,38 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
             __syncwarp();
           }
           if (EQ) {            // terminal rows: t_g = G x~ ; z_g+ = b ; ys_g+ = alpha t_g + (1 - alpha) z_g + ys_g - b
-            for (int i = 0; i < nx; i++) {
-              double part = 0.0;
+            double bscale = 0.0;             // ball: z_g+ = b + bscale (w_g - b), bscale = min(1, rad / |w_g - b|_2)
+            if (P.term_ball) {
+              double d2 = 0.0;
+              for (int i = 0; i < nx; i++) {
+                double part = 0.0;
 #pragma unroll
-              for (int r = 0; r < ROWS; r++) { const int e = lane + 32 * r; if (e < nz) part = fma(GH[i * ldg + e], t[r], part); }
+                for (int r = 0; r < ROWS; r++) { const int e = lane + 32 * r; if (e < nz) part = fma(GH[i * ldg + e], t[r], part); }
+                const double zg_old = szg[i], ysg_old = sysg[i], bi = sb[i];
+                const double tgi = warp_sum(part);
+                const double dv = fma(alpha, tgi, fma(oma, zg_old, ysg_old)) - bi;
+                d2 = fma(dv, dv, d2);
+                if (lane == 0) stg[i] = tgi;
+              }
+              bscale = d2 > rad * rad ? rad / sqrt(d2) : 1.0;
+              __syncwarp();
+            }
+            for (int i = 0; i < nx; i++) {
+              double tgi;
               const double zg_old = szg[i], ysg_old = sysg[i], bi = sb[i], re = srhoe[i];     // read before the reduction (a convergence point) ...
-              const double tgi = warp_sum(part);
-              const double ysgn = fma(alpha, tgi, fma(oma, zg_old, ysg_old)) - bi;
-              if (chk) { rp = fmax(rp, fabs(tgi - bi)); nA = fmax(nA, fmax(fabs(tgi), fabs(bi))); }
-              if (lane == 0) { szg[i] = bi; sysg[i] = ysgn; ssn[i] = re * (ysgn - tgi); stg[i] = tgi; }   // ... written after it
+              if (P.term_ball) tgi = stg[i];
+              else {
+                double part = 0.0;
+#pragma unroll
+                for (int r = 0; r < ROWS; r++) { const int e = lane + 32 * r; if (e < nz) part = fma(GH[i * ldg + e], t[r], part); }
+                tgi = warp_sum(part);
+              }
+              const double wmb = fma(alpha, tgi, fma(oma, zg_old, ysg_old)) - bi;
+              const double zgn = fma(bscale, wmb, bi);
+              const double ysgn = wmb - bscale * wmb;
+              if (chk) { rp = fmax(rp, fabs(tgi - zgn)); nA = fmax(nA, fmax(fabs(tgi), fabs(zgn))); }
+              __syncwarp();
+              if (lane == 0) { szg[i] = zgn; sysg[i] = ysgn; ssn[i] = re * (ysgn - tgi); stg[i] = tgi; }   // ... written after it
             }
             __syncwarp();
           }
@@ -931,8 +971,9 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       }
       if (EQ) {
         double ymax = 0.0;
-        for (int i = 0; i < nx; i++) { const double yv = srhoe[i] * sysg[i]; ymax = fmax(ymax, fabs(yv)); if (lane == 0) syg[i] = yv; }
-        mu = fmax(mu, 1.1 * ymax);
+        double y2 = 0.0;
+        for (int i = 0; i < nx; i++) { const double yv = srhoe[i] * sysg[i]; ymax = fmax(ymax, fabs(yv)); y2 = fma(yv, yv, y2); if (lane == 0) syg[i] = yv; }
+        mu = fmax(mu, 1.1 * (P.term_ball ? sqrt(y2) : ymax));      // exact-penalty weight: dual norm of the violation measure (l1 -> max, l2 -> l2)
         qp_failed = qp_failed || !qp_conv;          // linearised rows + input box not solvable within the inner cap
         __syncwarp();
       }
@@ -982,7 +1023,11 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         double merit = Jc;
         if (EQ || SB) {
           double cv = 0.0;
-          if (EQ) for (int i = 0; i < nx; i++) cv += fabs(traj[H * nx + i] - xr[i]);
+          if (EQ) {
+            double c1 = 0.0, c2 = 0.0;
+            for (int i = 0; i < nx; i++) { const double ev = traj[H * nx + i] - xr[i]; c1 += fabs(ev); c2 = fma(ev, ev, c2); }
+            cv += P.term_ball ? fmax(sqrt(c2) - rad, 0.0) : c1;
+          }
           if (SB) {
             double part = 0.0;
             for (int r = lane; r < ms; r += 32) { const double xk = traj[nx + r]; const int i = r % nx; part += fmax(xk - sXmax[i], 0.0) + fmax(sXmin[i] - xk, 0.0); }

@@ -33,7 +33,7 @@ struct mpcb_nmpc {
   mpcb_nmpc_settings st{};
   int H = 0, nz = 0, rows = 0, warps = 0;
   int warps_lin = 0;          // CTA width of the re-linearised (LIN) kernels: a little more shared memory per warp
-  bool terminal_eq = false, state_box = false;
+  bool terminal_eq = false, terminal_ball = false, state_box = false;   // terminal_eq: the kernels with terminal rows (equality, or the contractive ball)
   double rho = 0.0;
   mpcb::Mat A, B, P;
   DevBuf<double> Q, Pt, Hc, lb, ub, xmin, xmax, Rinv;
@@ -110,7 +110,7 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st, bool li
   P.net = n->net; P.Q = h->Q.p; P.Pt = h->Pt.p; P.Hc = h->Hc.p; P.lb = h->lb.p; P.ub = h->ub.p; P.H = h->H; P.nz = h->nz;
   const mpcb_settings& q = h->st.qp;
   P.rho = h->rho; P.sigma = q.sigma; P.alpha = q.alpha; P.eps_abs = q.eps_abs; P.eps_rel = q.eps_rel; P.max_iter = q.max_iter; P.check_every = q.check_every;
-  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.rho_eq_scale = q.rho_eq_scale; P.xmin = h->xmin.p; P.xmax = h->xmax.p; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
+  P.sqp_tol = h->st.sqp_tol; P.ls_c1 = h->st.ls_armijo; P.ls_noise = h->st.ls_noise; P.rho_eq_scale = q.rho_eq_scale; P.term_ball = h->terminal_ball ? 1 : 0; P.xmin = h->xmin.p; P.xmax = h->xmax.p; P.sqp_max_iter = h->st.sqp_max_iter; P.ls_max = h->st.ls_max_halvings;
   P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
   P.warm_u = io.warm_u; P.warm_y = io.warm_y;
   P.u = io.u; P.e_u = io.e_u; P.x = io.x; P.e_x = io.e_x; P.u0 = io.u0; P.objective = io.objective; P.y = io.y;
@@ -302,15 +302,15 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   if (q.check_every <= 0 || q.max_iter <= 0 || !(q.alpha > 0 && q.alpha < 2) || !(q.sigma >= 0) || !(q.eps_abs >= 0) || !(q.eps_rel >= 0) ||
       st.sqp_max_iter <= 0 || st.ls_max_halvings < 0 || !(st.sqp_tol >= 0) || !(st.ls_armijo > 0 && st.ls_armijo < 1) || !(st.ls_noise >= 0))
     return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: invalid settings");
-  if (d->terminal_mode != MPCB_TERMINAL_NONE && d->terminal_mode != MPCB_TERMINAL_EQUALITY)
-    return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: terminal ingredient must be 'none' or 'equality'");
+  if (d->terminal_mode != MPCB_TERMINAL_NONE && d->terminal_mode != MPCB_TERMINAL_EQUALITY && d->terminal_mode != MPCB_TERMINAL_CONTRACTIVE)
+    return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: terminal ingredient must be 'none', 'equality' or 'contractive'");
   if (d->horizon <= 0 || !d->Q || !d->R || !d->umin || !d->umax || !d->xref || !d->uref) return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: bad arguments");
   mpcb_nn* n = nullptr;
   int rc = mpcb_create_nn(d->nn, q.device, &n);
   if (rc != MPCB_OK) return rc;
   const int nx = n->net.nx, nu = n->net.nu, H = d->horizon, nz = nu * H;
   mpcb_nmpc* h = new mpcb_nmpc();
-  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32; h->terminal_eq = d->terminal_mode == MPCB_TERMINAL_EQUALITY; h->state_box = d->state_constraint != 0;
+  h->nn = n; h->st = st; h->H = H; h->nz = nz; h->rows = (nz + 31) / 32; h->terminal_eq = d->terminal_mode != MPCB_TERMINAL_NONE; h->terminal_ball = d->terminal_mode == MPCB_TERMINAL_CONTRACTIVE; h->state_box = d->state_constraint != 0;
   if (h->state_box && (!d->xmin || !d->xmax)) { mpcb_destroy_nmpc(h); return api_fail(MPCB_ERR_INVALID, "state_constraint needs xmin and xmax"); }
   auto bail = [&](int code, const std::string& msg) { mpcb_destroy_nmpc(h); return api_fail(code, msg); };
   if (h->rows > 4) return bail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");

@@ -16,8 +16,8 @@ _NMPC_SETTING_KEYS = {"mpc_b200_sqp_tol": "sqp_tol", "mpc_b200_sqp_max_iter": "s
 
 class B200NonlinearModeler:
     def __init__(self, nn, Q, R, S, P, umin, umax, xmin, xmax, horizon, xref, uref, state_constraint=False, terminal="none", kws=None):
-        if terminal not in ("none", "equality"):
-            raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported by mpc_solver='b200' (only 'none' and 'equality')")
+        if terminal not in ("none", "equality", "contractive"):
+            raise _lib.MpcbError(f"mpc_terminal_ingredient={terminal!r} is not supported by mpc_solver='b200' (only 'none', 'equality' and 'contractive')")
         kws = kws or {}
         self.nn = nn
         self.nx, self.nu, self.horizon = nn.nx, nn.nu, int(horizon)
@@ -29,7 +29,7 @@ class B200NonlinearModeler:
         self.terminal = terminal
         keep_x = [f(xmin), f(xmax)]
         d = _lib.NmpcDesc(C.pointer(nd), self.horizon, *[p(a) for a in keep],
-                          _lib.TERMINAL_EQUALITY if terminal == "equality" else _lib.TERMINAL_NONE, 1 if state_constraint else 0,
+                          {"equality": _lib.TERMINAL_EQUALITY, "contractive": _lib.TERMINAL_CONTRACTIVE}.get(terminal, _lib.TERMINAL_NONE), 1 if state_constraint else 0,
                           p(keep_x[0]), p(keep_x[1]))
         self._h = C.c_void_p()
         _lib.check(_lib.lib().mpcb_create_nmpc(C.byref(d), C.byref(self.settings), C.byref(self._h)), "mpcb_create_nmpc")
@@ -37,7 +37,7 @@ class B200NonlinearModeler:
         self.nz = self.nu * self.horizon
         self.state_constraint = bool(state_constraint)
         # duals: input box rows [+ state-box rows] [+ terminal rows]
-        self.ny = self.nz + (self.nx * self.horizon if state_constraint else 0) + (self.nx if terminal == "equality" else 0)
+        self.ny = self.nz + (self.nx * self.horizon if state_constraint else 0) + (self.nx if terminal != "none" else 0)
         self.x0 = self.xref = self.uref = None
         self.warm = None
 

@@ -234,10 +234,11 @@ def admm_box_per_problem(Kinv, q, lb, ub, s: mo.AdmmSettings, rho, x0, y0):
     return xo, yo, iters, status, pres, dres
 
 
-def admm_box_gen_per_problem(Kinv, q, lb, ub, G, lo_g, hi_g, rho_g, s: mo.AdmmSettings, rho, x0, y0, yg0):
+def admm_box_gen_per_problem(Kinv, q, lb, ub, G, lo_g, hi_g, rho_g, s: mo.AdmmSettings, rho, x0, y0, yg0, nball=0, rad=None):
     """As admm_box_per_problem plus GENERAL rows  lo_g <= G v <= hi_g  (linearised state box and / or terminal equality,
-    lo = hi), per-row step sizes rho_g; Kinv is the inverse of  Kgn + (sigma + rho) I + G' diag(rho_g) G.  Returns the box
-    and row multipliers."""
+    lo = hi), per-row step sizes rho_g; Kinv is the inverse of  Kgn + (sigma + rho) I + G' diag(rho_g) G.  With nball > 0 the LAST
+    nball rows form one ball |G v - lo_g|_2 <= rad (contractive terminal set): projected onto the ball instead of a box.
+    Returns the box and row multipliers."""
     Bn, nz = q.shape
     x = x0.copy(); z = x0.copy(); ys = y0 / rho
     zg = np.einsum("bij,bj->bi", G, x0); ysg = yg0 / rho_g
@@ -254,6 +255,11 @@ def admm_box_gen_per_problem(Kinv, q, lb, ub, G, lo_g, hi_g, rho_g, s: mo.AdmmSe
         ysn = w - zn
         wg = s.alpha * tg + (1 - s.alpha) * zg + ysg
         zgn = np.minimum(np.maximum(wg, lo_g), hi_g)
+        if nball:
+            dv = wg[:, -nball:] - lo_g[:, -nball:]
+            nd = np.sqrt((dv ** 2).sum(1))
+            sc = np.where(nd > rad, rad / np.maximum(nd, 1e-300), 1.0)
+            zgn[:, -nball:] = lo_g[:, -nball:] + sc[:, None] * dv
         ysgn = wg - zgn
         x = s.alpha * t + (1 - s.alpha) * x
         z, ys, zg, ysg = zn, ysn, zgn, ysgn
@@ -295,7 +301,9 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
     y = np.zeros((Bn, nz)) if y_init is None else np.array(y_init, float).reshape(Bn, nz)
     status = np.full(Bn, mo.STATUS_MAX_ITER, np.int32); sqp_iters = np.zeros(Bn, np.int32); inner = np.zeros(Bn, np.int64)
     step = np.zeros(Bn); qp_dres = np.zeros(Bn)
-    eq = terminal == "equality"; sb = bool(state_constraint)
+    ball = terminal == "contractive"       # e_H' e_H <= 0.9 e_0' e_0 (design_mpc.jl:333-340): the terminal rows are projected onto a ball
+    eq = terminal == "equality" or ball; sb = bool(state_constraint)
+    rad = np.sqrt(0.9) * np.sqrt(((x0 - xref) ** 2).sum(1))
     xmin_ = np.asarray(xmin, float) if sb else None; xmax_ = np.asarray(xmax, float) if sb else None
     mg = (nx * H if sb else 0) + (nx if eq else 0)
     yg = np.zeros((Bn, mg)); mu = np.zeros(Bn)
@@ -305,7 +313,8 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
         xr_ = xref[idx] if sel is None else xref[idx][sel]
         c = np.zeros(xt.shape[0])
         if sb: c += (np.maximum(xt[:, 1:] - xmax_, 0.0) + np.maximum(xmin_ - xt[:, 1:], 0.0)).sum((1, 2))
-        if eq: c += np.abs(xt[:, H] - xr_).sum(1)
+        if ball: c += np.maximum(np.sqrt(((xt[:, H] - xr_) ** 2).sum(1)) - (rad[idx] if sel is None else rad[idx][sel]), 0.0)
+        elif eq: c += np.abs(xt[:, H] - xr_).sum(1)
         return c
 
     act_ = np.ones(Bn, bool)
@@ -329,14 +338,18 @@ def nmpc_sqp(m: NeuralModel, Q, R, S, P, H, umin, umax, x0, xref, uref, rho, s: 
                 eH = xa[:, H] - xref[idx]
                 bq = np.einsum("bij,bj->bi", GT, ua) - eH
                 Gs.append(GT); los.append(bq); his.append(bq)
-                rhos.append(rho_eq_scale * rho / np.maximum((GT ** 2).sum(2), 1e-12))
+                n2 = (GT ** 2).sum(2)
+                rhos.append(np.repeat((rho * nx / np.maximum(n2.sum(1), 1e-12))[:, None], nx, 1) if ball else rho_eq_scale * rho / np.maximum(n2, 1e-12))
             Gg = np.concatenate(Gs, 1); lo_g = np.concatenate(los, 1); hi_g = np.concatenate(his, 1); rho_g = np.concatenate(rhos, 1)
             K = Pc + (s.qp.sigma + rho) * np.eye(nz) + np.einsum("bia,bi,bic->bac", Gg, rho_g, Gg)
             Kinv = np.linalg.inv(K); Kinv = 0.5 * (Kinv + Kinv.transpose(0, 2, 1))
-            v, yn, ygn, its, st_qp, _pr, dr = admm_box_gen_per_problem(Kinv, q, lb, ub, Gg, lo_g, hi_g, rho_g, s.qp, rho, ua, y[idx], yg[idx])
+            v, yn, ygn, its, st_qp, _pr, dr = admm_box_gen_per_problem(Kinv, q, lb, ub, Gg, lo_g, hi_g, rho_g, s.qp, rho, ua, y[idx], yg[idx],
+                                                                       nball=nx if ball else 0, rad=rad[idx])
             qp_failed = st_qp != mo.STATUS_SOLVED
             yg[idx] = ygn
-            mu[idx] = np.maximum(mu[idx], 1.1 * np.abs(ygn).max(1))
+            # exact-penalty weight: dual norm of the violation measure (l1 measure -> max norm; the ball's l2 distance -> l2 norm; state rows l1)
+            if ball: mu[idx] = np.maximum(mu[idx], 1.1 * np.maximum(np.sqrt((ygn[:, -nx:] ** 2).sum(1)), np.abs(ygn[:, :-nx]).max(1, initial=0.0)))
+            else: mu[idx] = np.maximum(mu[idx], 1.1 * np.abs(ygn).max(1))
             c0 = violation(xa)
         else:
             K = Pc + (s.qp.sigma + rho) * np.eye(nz)

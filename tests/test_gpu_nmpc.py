@@ -158,7 +158,7 @@ def test_sqp_warm_start_and_ragged_batches(mpc, qt, resnet_model):
     assert (warm["iters"] == 1).all() and (warm["status"] == 1).all() and np.abs(warm["u"] - full["u"]).max() < 2e-6
     assert warm["inner_iters"].mean() < 0.2 * full["inner_iters"].mean()
     # unsupported configurations are refused, not approximated
-    for kw in ({"mpc_terminal_ingredient": "contractive"}, {"mpc_terminal_ingredient": "neighborhood"}):
+    for kw in ({"mpc_terminal_ingredient": "neighborhood"},):
         with pytest.raises(mpc.MpcbError):
             mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", 20, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
                                    mpc_programming_type="non_linear", **kw)
@@ -197,6 +197,57 @@ def test_sqp_terminal_equality(mpc, qt, fixture):
         assert np.abs(cons(r.x)).max() < 1e-9
         assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL and abs(r.fun - res["objective"][i]) <= OBJ_TOL * abs(r.fun)
 
+
+
+@pytest.mark.parametrize("fixture,method", [("qt_fnn_tanh_model.json", "non_linear"), ("qt_resnet_swish_model.json", "non_linear"), ("qt_fnn_tanh_model.json", "linear")])
+def test_sqp_contractive_terminal_set(mpc, qt, fixture, method):
+    """mpc_terminal_ingredient = "contractive" on an NL model (design_mpc.jl:333-340 added to the NL modeler's problem -- the
+    reference hands this NLP to Ipopt): the SQP kernel projects the linearised terminal rows onto the ball.  Sluggish weights
+    (Q = I, R = 10 I, H = 3) make the set active.  CUDA vs twin, and vs an independent SLSQP solve of the same NLP.
+    method = "linear": the same constraint on the per-problem re-linearised controllers, against the linear path's oracle."""
+    from scipy.optimize import minimize
+    m = load_nn_fixture(fixture)
+    H, n = 3, 200
+    Q, R, S = np.eye(4), 10.0 * np.eye(2), np.zeros((2, 2))
+    C = mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="non_linear", mpc_terminal_ingredient="contractive", mpc_Q=1.0, mpc_R=10.0)
+    mod = C.tuning.modeler
+    rng = np.random.default_rng(4)
+    xref = np.tile(qt["x_ref"], (n, 1)); x0 = xref + rng.uniform(-0.15, 0.15, (n, 4)); uref = qt["u_ref"].copy()
+    e0 = ((x0 - xref) ** 2).sum(1)
+    if method == "linear":
+        res = mod.solve_batch(x0, xref, uref, want=("u", "u0", "e_x", "objective"), method="linear")
+        assert (res["status"] == 1).all()
+        _, A, B = no.jacobian(m, qt["x_ref"][None], qt["u_ref"][None]); P = mo.dare(A[0], B[0], Q, R)
+        c = mo.condense(A[0], B[0], Q, R, S, P, H, qt["umin"], qt["umax"], terminal="contractive")
+        p = mo.pack_params(x0, xref, uref)
+        tw = mo.admm_condensed(c, p, mo.AdmmSettings(eps_abs=1e-10, eps_rel=1e-10, check_every=5, max_iter=50000))
+        assert (tw["status"] == 1).all()
+        rec = mo.recover(c, tw["v"], p)
+        ratio = (res["e_x"][:, H] ** 2).sum(1) / e0
+        assert (ratio <= 0.9 + 1e-7).all() and 0.1 < (ratio > 0.9 - 1e-6).mean() < 0.9
+        assert mo.u0_metric(res["u0"], rec["u"][:, 0], qt["umin"], qt["umax"]).max() < U0_TOL
+        assert (np.abs(res["objective"] - rec["objective"]) <= OBJ_TOL * np.abs(rec["objective"])).all()
+        return
+    res = mod.solve_batch(x0, xref, uref, want=("u", "u0", "x", "e_x", "objective", "y"))
+    d = mod.design()
+    tw = no.nmpc_sqp(m, Q, R, S, d["P"], H, qt["umin"], qt["umax"], x0, xref, np.tile(uref, (n, 1)), d["rho"], terminal="contractive")
+    assert (res["status"] == tw["status"]).mean() > 0.98
+    ok = (res["status"] == 1) & (tw["status"] == 1)
+    assert ok.mean() > 0.95
+    assert np.abs(res["u"][ok] - tw["u"][ok]).max() < 5e-6 and np.abs(res["objective"][ok] - tw["objective"][ok]).max() <= 1e-8 * np.abs(tw["objective"][ok]).max()
+    ratio = (res["e_x"][:, H] ** 2).sum(1) / e0
+    assert (ratio[ok] <= 0.9 + 1e-7).all()
+    act = ok & (ratio > 0.9 - 1e-6)
+    assert 0.2 < act.mean() < 0.9                                          # the set is active on a good share, inactive on the rest
+    assert np.abs(res["y"][ok & ~act][:, 2 * H:]).max() < 1e-5             # multipliers of the terminal rows vanish where it is inactive
+    Hc = no.constant_hessian(2, H, R, S); lb, ub = np.tile(qt["umin"], H), np.tile(qt["umax"], H)
+    for i in list(np.flatnonzero(act)[:3]) + list(np.flatnonzero(ok & ~act)[:1]):
+        fg = lambda v: tuple(a[0] for a in no.grad_adjoint(m, Q, d["P"], Hc, v.reshape(1, H, 2), x0[i:i + 1], xref[i:i + 1], uref[None]))
+        cons = lambda v: 0.9 * e0[i] - ((no.rollout(m, x0[i:i + 1], v.reshape(1, H, 2))[0, H] - xref[i]) ** 2).sum()
+        r = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), np.tile(uref, H), jac=True, method="SLSQP", bounds=list(zip(lb, ub)),
+                     constraints=[{"type": "ineq", "fun": cons}], options={"maxiter": 500, "ftol": 1e-15})
+        assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL and abs(r.fun - res["objective"][i]) <= OBJ_TOL * abs(r.fun)
 
 
 @pytest.mark.parametrize("fixture,terminal", [("qt_resnet_model.json", "none"), ("qt_fnn_tanh_model.json", "none"), ("qt_resnet_model.json", "equality")])

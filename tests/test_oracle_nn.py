@@ -195,6 +195,36 @@ def test_twin_terminal_equality_vs_slsqp(qt):
         assert np.sqrt(f_.fun) > 1e-5
 
 
+def test_twin_contractive_terminal_set_vs_slsqp(qt):
+    """NL model + mpc_terminal_ingredient = "contractive" (design_mpc.jl:333-340: e_H' e_H <= 0.9 e_0' e_0 added to the NL modeler's
+    problem): the twin projects the linearised terminal rows onto the ball.  Sluggish weights (Q = I, R = 10 I, H = 3) make
+    the constraint active on a good share of the problems; checked against an independent SLSQP solve of the same NLP."""
+    from scipy.optimize import minimize
+    m = load_nn_fixture("qt_fnn_tanh_model.json")
+    H, n = 3, 48
+    Q, R, S = np.eye(4), 10.0 * np.eye(2), np.zeros((2, 2))
+    _, A, B = no.jacobian(m, qt["x_ref"][None], qt["u_ref"][None])
+    P = mo.dare(A[0], B[0], Q, R)
+    rho = mo.auto_rho(mo.condense(A[0], B[0], Q, R, S, P, H, qt["umin"], qt["umax"]).Pc)
+    rng = np.random.default_rng(4)
+    xref = np.tile(qt["x_ref"], (n, 1)); x0 = xref + rng.uniform(-0.15, 0.15, (n, 4)); uref = np.tile(qt["u_ref"], (n, 1))
+    r = no.nmpc_sqp(m, Q, R, S, P, H, qt["umin"], qt["umax"], x0, xref, uref, rho, terminal="contractive")
+    free = no.nmpc_sqp(m, Q, R, S, P, H, qt["umin"], qt["umax"], x0, xref, uref, rho)
+    e0 = ((x0 - xref) ** 2).sum(1)
+    ratio = (r["e_x"][:, H] ** 2).sum(1) / e0; ratio_free = (free["e_x"][:, H] ** 2).sum(1) / e0
+    assert (r["status"] == 1).all() and (ratio <= 0.9 + 1e-8).all()
+    viol = ratio_free > 0.9 + 1e-6
+    assert 0.2 < viol.mean() < 0.8 and np.abs(ratio[viol] - 0.9).max() < 1e-7              # active exactly where the free optimum violates it
+    assert np.abs(r["u"][~viol] - free["u"][~viol]).max() < 1e-5                             # and inactive elsewhere
+    Hc = no.constant_hessian(2, H, R, S); lb, ub = np.tile(qt["umin"], H), np.tile(qt["umax"], H)
+    for i in list(np.flatnonzero(viol)[:3]) + list(np.flatnonzero(~viol)[:1]):
+        fg = lambda v: tuple(a[0] for a in no.grad_adjoint(m, Q, P, Hc, v.reshape(1, H, 2), x0[i:i + 1], xref[i:i + 1], uref[i:i + 1]))
+        cons = lambda v: 0.9 * e0[i] - ((no.rollout(m, x0[i:i + 1], v.reshape(1, H, 2))[0, H] - xref[i]) ** 2).sum()
+        s_ = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), np.tile(qt["u_ref"], H), jac=True, method="SLSQP", bounds=list(zip(lb, ub)),
+                      constraints=[{"type": "ineq", "fun": cons}], options={"maxiter": 500, "ftol": 1e-15})
+        assert mo.u0_metric(r["u"][i, 0], s_.x[:2], qt["umin"], qt["umax"]) < 1e-4 and abs(s_.fun - r["objective"][i]) <= 1e-6 * abs(s_.fun)
+
+
 def test_relinearized_linear_method_is_the_reference_qp_per_problem(qt):
     """oracle.relinearized_linear_mpc (checker of mpcb_solve_relinearized_batch): per problem the linear modeler's QP on the
     Jacobian linearisation at THAT problem's reference with P = are(A_i, B_i, Q, R) (design_mpc.jl:319-327).  Checked
