@@ -81,7 +81,7 @@ EXPORTED_SYMBOLS = (
     "mpcb_create_nn", "mpcb_destroy_nn", "mpcb_nn_rollout_batch", "mpcb_nn_rollout_batch_device", "mpcb_nn_jacobian_batch",
     "mpcb_nn_jacobian_batch_device", "mpcb_default_nmpc_settings", "mpcb_create_nmpc", "mpcb_destroy_nmpc", "mpcb_nmpc_get_design",
     "mpcb_nmpc_get_timing", "mpcb_solve_nmpc_batch", "mpcb_solve_nmpc_batch_device", "mpcb_solve_relinearized_batch",
-    "mpcb_solve_relinearized_batch_device", "mpcb_dare_batch", "mpcb_dare_batch_device",
+    "mpcb_solve_relinearized_batch_device", "mpcb_dare_batch", "mpcb_dare_batch_device", "mpcb_closed_loop_nmpc_batch",
 )
 
 _lib = None
@@ -131,6 +131,7 @@ def lib():
         L.mpcb_solve_nmpc_batch.argtypes = [C.c_void_p, C.POINTER(BatchIO)]
         L.mpcb_solve_nmpc_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIO), C.c_void_p]
         L.mpcb_solve_relinearized_batch.argtypes = [C.c_void_p, C.POINTER(BatchIO)]
+        L.mpcb_closed_loop_nmpc_batch.argtypes = [C.c_void_p, C.POINTER(ClosedLoopIO)]
         L.mpcb_solve_relinearized_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIO), C.c_void_p]
         L.mpcb_dare_batch.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int32)]
         L.mpcb_dare_batch_device.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, _dp, _dp, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -96,6 +96,62 @@ int jacobian_device(mpcb_nn* n, int64_t batch, const double* x, const double* u,
   return launch_nn_batch<true>(n, P, st);
 }
 
+// Plant step of the GPU-resident closed loop on a neural model: one warp per plant applies u0 to the network itself
+// (x+ = f(x, u0): the plant IS the model, as in the reference's closed-loop test pattern), appends to the trajectories,
+// accumulates the counters and prepares the next solve's warm start: inputs and input-box duals shifted by one stage
+// (the last stage repeated), the duals of the state / terminal rows carried over as they are.
+struct NnPlantParams {
+  mpcb::NetDev net;
+  int H, nz, ny, t, steps;
+  long long batch;
+  const double* u;          // [batch][nz] solution of this step
+  const double* y;          // [batch][ny] duals of this step (null without warm start)
+  const int32_t *status, *inner;
+  const double* x_in;       // [batch][nx]
+  double* x_out;
+  double *warm_u, *warm_y;  // next step's warm start (null without warm start)
+  double *x_traj, *u_traj;
+  int32_t *iters_total, *unsolved;
+};
+
+__global__ void __launch_bounds__(mpcb::NN_THREADS) nn_plant_step_kernel(const NnPlantParams P) {
+  extern __shared__ __align__(16) double sm[];
+  const mpcb::NetSm N = mpcb::stage_network(P.net, sm, threadIdx.x, mpcb::NN_THREADS);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nx = N.nx, nu = N.nu, nin = N.nin, nn = N.nn, nz = P.nz;
+  double* w = sm + P.net.weight_count() + warp * mpcb::nn_eval_scratch_doubles(P.net, false);
+  double* xu = w; double* f = xu + nin; double* ya = f + nx; double* yb = ya + nn; double* sd = yb + nn;
+  for (long long p = (long long)blockIdx.x * mpcb::NN_WARPS + warp; p < P.batch; p += (long long)gridDim.x * mpcb::NN_WARPS) {
+    for (int i = lane; i < nx; i += 32) {
+      const double v = P.x_in[p * nx + i];
+      xu[i] = v;
+      if (P.t == 0 && P.x_traj) P.x_traj[(p * (P.steps + 1)) * nx + i] = v;
+    }
+    for (int i = lane; i < nu; i += 32) {
+      const double v = P.u[p * nz + i];
+      xu[nx + i] = v;
+      if (P.u_traj) P.u_traj[(p * P.steps + P.t) * nu + i] = v;
+    }
+    __syncwarp();
+    mpcb::nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
+    for (int i = lane; i < nx; i += 32) {
+      const double v = f[i];
+      P.x_out[p * nx + i] = v;
+      if (P.x_traj) P.x_traj[(p * (P.steps + 1) + P.t + 1) * nx + i] = v;
+    }
+    if (P.warm_u)
+      for (int e = lane; e < nz; e += 32) P.warm_u[p * nz + e] = P.u[p * nz + (e + nu < nz ? e + nu : e)];
+    if (P.warm_y && P.y)
+      for (int e = lane; e < P.ny; e += 32) P.warm_y[p * P.ny + e] = P.y[p * P.ny + ((e < nz && e + nu < nz) ? e + nu : e)];
+    if (lane == 0) {
+      if (P.iters_total) P.iters_total[p] = (P.t == 0 ? 0 : P.iters_total[p]) + P.inner[p];
+      if (P.unsolved) P.unsolved[p] = (P.t == 0 ? 0 : P.unsolved[p]) + (P.status[p] == 1 ? 0 : 1);
+    }
+    __syncwarp();
+  }
+}
+
 int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st, bool lin = false) {
   mpcb_nn* n = h->nn;
   const long long Bn = io.batch;
@@ -487,6 +543,76 @@ static int solve_nmpc_host(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin) {
   h->timing.recover_ms = 0.f;
   cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[2], h->ev[3]);
   cudaEventElapsedTime(&h->timing.total_ms, h->ev[0], h->ev[3]);
+  return MPCB_OK;
+}
+
+int mpcb_closed_loop_nmpc_batch(mpcb_nmpc* h, const mpcb_closed_loop_io* cio) {
+  if (!h || !cio) return api_fail(MPCB_ERR_INVALID, "null argument");
+  const long long Bn = cio->batch;
+  const int T = cio->steps;
+  if (Bn <= 0 || T <= 0) return api_fail(MPCB_ERR_INVALID, "batch and steps must be positive");
+  if (!cio->x0 || !cio->xref || !cio->uref) return api_fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  mpcb_nn* n = h->nn;
+  CUDA_TRY(cudaSetDevice(n->device));
+  cudaStream_t st = n->stream;
+  const size_t nx = n->net.nx, nu = n->net.nu, H = h->H, nz = h->nz, B = (size_t)Bn, ny = nz + (h->state_box ? nx * H : 0) + (h->terminal_eq ? nx : 0);
+  const size_t n_xref = cio->xref_broadcast ? nx : nx * B, n_uref = cio->uref_broadcast ? nu : nu * B;
+  const size_t smem = sizeof(double) * (n->net.weight_count() + mpcb::NN_WARPS * mpcb::nn_eval_scratch_doubles(n->net, false));
+  if (smem > 200 * 1024) return api_fail(MPCB_ERR_INVALID, "network too large for the shared-memory resident kernels");
+  const bool warm = cio->warm_start != 0;
+  DevBuf<double> xa, xb, ub, yb, wu, wy, xtraj, utraj;
+  DevBuf<int32_t> itot, unsol;
+  auto cleanup = [&]() { xa.release(); xb.release(); ub.release(); yb.release(); wu.release(); wy.release(); xtraj.release(); utraj.release(); itot.release(); unsol.release(); };
+#define CL_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cudaGetLastError(); cleanup(); return api_fail(MPCB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); } } while (0)
+  CL_TRY(xa.ensure(nx * B)); CL_TRY(xb.ensure(nx * B)); CL_TRY(ub.ensure(nz * B));
+  if (warm) { CL_TRY(yb.ensure(ny * B)); CL_TRY(wu.ensure(nz * B)); CL_TRY(wy.ensure(ny * B)); }
+  CL_TRY(h->xref.ensure(n_xref)); CL_TRY(h->uref.ensure(n_uref)); CL_TRY(h->status.ensure(B)); CL_TRY(h->iters.ensure(B)); CL_TRY(h->inner.ensure(B));
+  if (cio->x_traj) CL_TRY(xtraj.ensure(nx * (size_t)(T + 1) * B));
+  if (cio->u_traj) CL_TRY(utraj.ensure(nu * (size_t)T * B));
+  if (cio->iters_total) CL_TRY(itot.ensure(B));
+  if (cio->unsolved_steps) CL_TRY(unsol.ensure(B));
+  if (smem > 48 * 1024) CL_TRY(cudaFuncSetAttribute(nn_plant_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CL_TRY(cudaMemcpyAsync(xa.p, cio->x0, nx * B * sizeof(double), cudaMemcpyHostToDevice, st));
+  CL_TRY(cudaMemcpyAsync(h->xref.p, cio->xref, n_xref * sizeof(double), cudaMemcpyHostToDevice, st));
+  CL_TRY(cudaMemcpyAsync(h->uref.p, cio->uref, n_uref * sizeof(double), cudaMemcpyHostToDevice, st));
+  CL_TRY(cudaEventRecord(h->ev[0], st));
+  int launches = 0;
+  double *xc = xa.p, *xn = xb.p;
+  const long long blocks = (Bn + mpcb::NN_WARPS - 1) / mpcb::NN_WARPS;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * 8));
+  for (int t = 0; t < T; t++) {
+    mpcb_batch_io dio;
+    std::memset(&dio, 0, sizeof(dio));
+    dio.batch = Bn; dio.x0 = xc; dio.xref = h->xref.p; dio.uref = h->uref.p; dio.xref_broadcast = cio->xref_broadcast; dio.uref_broadcast = cio->uref_broadcast;
+    if (warm && t > 0) { dio.warm_u = wu.p; dio.warm_y = wy.p; }
+    dio.status = h->status.p; dio.iters = h->iters.p; dio.inner_iters = h->inner.p;
+    dio.u = ub.p; dio.y = warm ? yb.p : nullptr;
+    int rc = enqueue_nmpc(h, dio, st);
+    if (rc != MPCB_OK) { cleanup(); return rc; }
+    NnPlantParams Pp{};
+    Pp.net = n->net; Pp.H = h->H; Pp.nz = h->nz; Pp.ny = (int)ny; Pp.t = t; Pp.steps = T; Pp.batch = Bn;
+    Pp.u = ub.p; Pp.y = warm ? yb.p : nullptr; Pp.status = h->status.p; Pp.inner = h->inner.p; Pp.x_in = xc; Pp.x_out = xn;
+    Pp.warm_u = warm ? wu.p : nullptr; Pp.warm_y = warm ? wy.p : nullptr;
+    Pp.x_traj = cio->x_traj ? xtraj.p : nullptr; Pp.u_traj = cio->u_traj ? utraj.p : nullptr;
+    Pp.iters_total = cio->iters_total ? itot.p : nullptr; Pp.unsolved = cio->unsolved_steps ? unsol.p : nullptr;
+    nn_plant_step_kernel<<<grid, mpcb::NN_THREADS, smem, st>>>(Pp);
+    CL_TRY(cudaGetLastError());
+    launches += 2;
+    std::swap(xc, xn);
+  }
+  CL_TRY(cudaEventRecord(h->ev[2], st));
+  if (cio->x_traj) CL_TRY(cudaMemcpyAsync(cio->x_traj, xtraj.p, nx * (size_t)(T + 1) * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (cio->u_traj) CL_TRY(cudaMemcpyAsync(cio->u_traj, utraj.p, nu * (size_t)T * B * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (cio->iters_total) CL_TRY(cudaMemcpyAsync(cio->iters_total, itot.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (cio->unsolved_steps) CL_TRY(cudaMemcpyAsync(cio->unsolved_steps, unsol.p, B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CL_TRY(cudaEventRecord(h->ev[3], st));
+  CL_TRY(cudaStreamSynchronize(st));
+#undef CL_TRY
+  cudaEventElapsedTime(&h->timing.solve_ms, h->ev[0], h->ev[2]);
+  cudaEventElapsedTime(&h->timing.d2h_ms, h->ev[2], h->ev[3]);
+  h->timing.h2d_ms = 0.f; h->timing.recover_ms = 0.f; h->timing.total_ms = h->timing.solve_ms + h->timing.d2h_ms;
+  h->timing.batch = Bn; h->timing.kernel_launches = launches; h->timing.chunks = 1; h->timing.total_iterations = 0;
+  cleanup();
   return MPCB_OK;
 }
 

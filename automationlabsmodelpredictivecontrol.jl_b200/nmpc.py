@@ -99,6 +99,22 @@ class B200NonlinearModeler:
         else:
             _lib.check(_lib.lib().mpcb_solve_nmpc_batch_device(self._h, C.byref(io), C.c_void_p(stream or 0)), "mpcb_solve_nmpc_batch_device")
 
+    def closed_loop(self, x0, xref, uref, steps, warm_start=True):
+        """GPU-resident closed loop on the network as the plant (mpcb_closed_loop_nmpc_batch): x0 (B, nx) -> x_traj (B, steps+1, nx),
+        u_traj (B, steps, nu), iters_total (B,) inner ADMM iterations, unsolved_steps (B,)."""
+        x0 = np.ascontiguousarray(np.atleast_2d(np.asarray(x0, np.float64))); Bn = x0.shape[0]
+        xref = np.ascontiguousarray(np.asarray(xref, np.float64)); uref = np.ascontiguousarray(np.asarray(uref, np.float64))
+        xb = xref.ndim == 1 or xref.shape[0] == 1 and Bn != 1
+        ub = uref.ndim == 1 or uref.shape[0] == 1 and Bn != 1
+        if x0.shape[1] != self.nx or xref.size != (self.nx if xb else self.nx * Bn) or uref.size != (self.nu if ub else self.nu * Bn):
+            raise ValueError("closed_loop: shapes")
+        out = {"x_traj": np.empty((Bn, steps + 1, self.nx)), "u_traj": np.empty((Bn, steps, self.nu)), "iters_total": np.empty(Bn, np.int32),
+               "unsolved_steps": np.empty(Bn, np.int32)}
+        io = _lib.ClosedLoopIO(Bn, int(steps), int(bool(warm_start)), x0.ctypes.data, xref.ctypes.data, uref.ctypes.data, int(xb), int(ub),
+                               out["x_traj"].ctypes.data, out["u_traj"].ctypes.data, out["iters_total"].ctypes.data, out["unsolved_steps"].ctypes.data)
+        _lib.check(_lib.lib().mpcb_closed_loop_nmpc_batch(self._h, C.byref(io)), "mpcb_closed_loop_nmpc_batch")
+        return out
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().mpcb_destroy_nmpc(self._h); self._h = None

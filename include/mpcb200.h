@@ -287,7 +287,7 @@ typedef struct {
   const double* umax;
   const double* xref; /* nx */
   const double* uref; /* nu */
-  int32_t terminal_mode; /* MPCB_TERMINAL_NONE | MPCB_TERMINAL_EQUALITY (e_x[:,end] == 0, design_mpc.jl:330-331) */
+  int32_t terminal_mode; /* MPCB_TERMINAL_NONE | _EQUALITY (e_x[:,end] == 0, design_mpc.jl:330-331) | _CONTRACTIVE (e_H'e_H <= 0.9 e_0'e_0, :333-340) */
   int32_t state_constraint; /* != 0: kw `mpc_state_constraint` present -> xmin <= x[:,k] <= xmax for k = 2..H+1 (fnn.jl:146-154) */
   const double* xmin; /* nx, first / last vertex of system.X; read only when state_constraint != 0 */
   const double* xmax;
@@ -328,6 +328,13 @@ int mpcb_solve_nmpc_batch_device(mpcb_nmpc* h, const mpcb_batch_io* dev_io, void
  * LTI controllers designed and evaluated in one launch.  Same handle, io meanings and constraints (input box, optional
  * state box, terminal "none"/"equality") as mpcb_solve_nmpc_batch; x / e_x are the predictions of the linearised model,
  * iters = 1, prim_res / dual_res = residuals of the QP, status = _SOLVED / _MAX_ITER / _DESIGN_FAILED. */
+/* Closed-loop batched simulation of the nonlinear controller, resident on the GPU (NN plant):
+ * repeats { SQP solve from the current state; apply the first input to the network itself, x+ = f(x, u0) } `steps` times
+ * for a whole batch of plants.  Same io struct and meanings as mpcb_closed_loop_linear_batch; iters_total counts inner
+ * ADMM iterations; with warm_start != 0 each solve starts from the previous solution and input-box duals shifted by one
+ * stage (last stage repeated), the duals of state / terminal rows carried as they are. */
+int mpcb_closed_loop_nmpc_batch(mpcb_nmpc* h, const mpcb_closed_loop_io* host_io);
+
 int mpcb_solve_relinearized_batch(mpcb_nmpc* h, const mpcb_batch_io* host_io);
 int mpcb_solve_relinearized_batch_device(mpcb_nmpc* h, const mpcb_batch_io* dev_io, void* cuda_stream);
 

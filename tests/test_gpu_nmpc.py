@@ -296,3 +296,39 @@ def test_sqp_state_constraint(mpc, qt, fixture, terminal):
         r = minimize(lambda v: (float(fg(v)[0]), fg(v)[1]), res["u"][i].ravel(), jac=True, method="SLSQP", bounds=list(zip(lb, ub)), constraints=cons,
                      options={"maxiter": 500, "ftol": 1e-15})
         assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL and abs(r.fun - res["objective"][i]) <= OBJ_TOL * abs(r.fun)
+
+
+@pytest.mark.parametrize("fixture,kw", [("qt_fnn_tanh_model.json", {}), ("qt_resnet_model.json", {"mpc_state_constraint": True})])
+def test_closed_loop_on_gpu_equals_host_loop(mpc, qt, fixture, kw):
+    """SURVEY 8f-1 with the network as the plant: solve -> apply u[:,1] to system.f -> re-solve, kept on the device for a batch of
+    plants, must reproduce the same loop driven from the host through the batched solve and rollout entries (same shifted warm
+    start).  The regulated plants approach their references."""
+    m = load_nn_fixture(fixture)
+    H, n, steps = 10, 150, 8
+    C = mpc.proceed_controller(make_system(mpc, qt, m), "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200",
+                               mpc_programming_type="non_linear", **kw)
+    mod = C.tuning.modeler
+    f = mod.nn
+    rng = np.random.default_rng(2)
+    x0 = rng.uniform(0.5, 0.8, (n, 4)); xref = np.tile(qt["x_ref"], (n, 1)) + rng.uniform(-0.03, 0.03, (n, 4)); uref = qt["u_ref"].copy()
+    for warm in (True, False):
+        dev = mod.closed_loop(x0, xref, uref, steps, warm_start=warm)
+        x = x0.copy(); w = None
+        xs, us, its, bad = [x.copy()], [], np.zeros(n, np.int64), np.zeros(n, np.int64)
+        for t in range(steps):
+            r = mod.solve_batch(x, xref, uref, want=("u", "u0", "y"), warm=w)
+            its += r["inner_iters"]; bad += r["status"] != 1
+            x = f.rollout(x, r["u0"][:, None, :])[:, 1]
+            xs.append(x.copy()); us.append(r["u0"].copy())
+            if warm:
+                wu = np.concatenate([r["u"][:, 1:], r["u"][:, -1:]], 1)
+                wy = r["y"].copy(); yb = wy[:, :2 * H].reshape(n, H, 2); wy[:, :2 * H] = np.concatenate([yb[:, 1:], yb[:, -1:]], 1).reshape(n, -1)
+                w = (wu, wy)
+        xs = np.stack(xs, 1); us = np.stack(us, 1)
+        assert np.array_equal(dev["x_traj"], xs) and np.array_equal(dev["u_traj"], us)          # same kernels, same inputs: bit-identical
+        assert np.array_equal(dev["iters_total"], its) and np.array_equal(dev["unsolved_steps"], bad)
+        assert (bad == 0).mean() > 0.9
+        if warm: it_warm = its.mean()
+        else: assert it_warm < 0.95 * its.mean()                                # the shifted warm start pays
+    good = bad == 0
+    assert np.abs(dev["x_traj"][good, -1] - xref[good]).mean() < np.abs(x0 - xref)[good].mean()          # slow plant, 8 steps: the mean tracking error shrinks
