@@ -4,10 +4,11 @@ never imported from here)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import pathlib
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libmpcb200.so"
+LIB_PATH = pathlib.Path(os.environ["MPCB200_LIB"]) if os.environ.get("MPCB200_LIB") else _PKG / "libmpcb200.so"   # the override serves A/B builds of the kernels (tools/)
 
 MPCB_OK = 0
 KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED, KERNEL_ONCHIP_SMEM = 0, 1, 2, 3

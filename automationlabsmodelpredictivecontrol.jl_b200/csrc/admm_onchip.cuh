@@ -70,6 +70,36 @@ __device__ __forceinline__ double dclamp(double w, double lo, double hi) {
   const double t = w < lo ? lo : w;
   return t > hi ? hi : t;
 }
+// The FP64 pipe is the bound of these kernels (DMMA and scalar FP64 share it), the integer pipe idles: comparisons of doubles
+// run on the integer pipe instead.  dkey maps a double to a 64-bit integer with the same ordering (sign-magnitude -> two's
+// complement; -0.0 sorts just below +0.0, NaNs beyond the infinities), so a clamp is two integer compares + selects, and the
+// max of ABSOLUTE values is an unsigned integer max of the bit patterns with the sign cleared.  Values are never changed.
+__device__ __forceinline__ long long dkey(double x) {
+  const long long b = __double_as_longlong(x);
+  return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+#ifndef MPCB_INT_CLAMP
+#define MPCB_INT_CLAMP 0    // measured on B200: the integer clamp is SLOWER (0.515 vs 0.492 ms, QT H=20) -- longer dependent chains per row; kept as a knob
+#endif
+#ifndef MPCB_INT_MAX
+#define MPCB_INT_MAX 1      // 0: A/B knob, the residual maxima back on the FP64 pipe
+#endif
+__device__ __forceinline__ double iclamp_k(double w, double lo, double hi, long long klo, long long khi) {
+  if (!MPCB_INT_CLAMP) { const double t0 = w < lo ? lo : w; return t0 > hi ? hi : t0; }
+  const long long kw = dkey(w);
+  const double t = kw < klo ? lo : w;
+  return kw > khi ? hi : t;
+}
+__device__ __forceinline__ unsigned long long absbits(double x) {      // inline PTX: written in C++, the mask is recognised as fabs and comes back as a DADD
+  if (!MPCB_INT_MAX) return (unsigned long long)__double_as_longlong(fabs(x));
+  unsigned long long r;
+  asm("{ .reg .b32 lo, hi; mov.b64 {lo, hi}, %1; and.b32 hi, hi, 0x7fffffff; mov.b64 %0, {lo, hi}; }" : "=l"(r) : "d"(x));
+  return r;
+}
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) {
+  if (!MPCB_INT_MAX) return (unsigned long long)__double_as_longlong(dmaxf(__longlong_as_double((long long)a), __longlong_as_double((long long)b)));
+  return a > b ? a : b;
+}
 __device__ __forceinline__ double quad_max(double v) {
   v = dmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
   v = dmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
@@ -126,8 +156,14 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
     if (HAS_G) sC[i] = P.Cfrag[i];
   }
   for (int i = threadIdx.x; i < P.np * NT; i += ONCHIP_THREADS) sL[i] = P.Lt[i];
-  for (int i = threadIdx.x; i < NT; i += ONCHIP_THREADS) { sLo[i] = P.lo[i]; sHi[i] = P.hi[i]; sRho[i] = P.rho[i]; sRinv[i] = P.rinv[i]; }
+  for (int i = threadIdx.x; i < NT; i += ONCHIP_THREADS) {
+    sLo[i] = P.lo[i]; sHi[i] = P.hi[i];
+    if (HAS_G) { sRho[i] = P.rho[i]; sRinv[i] = P.rinv[i]; }
+    else { sRho[i] = __longlong_as_double(dkey(P.lo[i])); sRinv[i] = __longlong_as_double(dkey(P.hi[i])); }   // box-only: the slots hold the bounds' integer keys
+  }
   __syncthreads();
+  const long long* sLoK = reinterpret_cast<const long long*>(sRho);
+  const long long* sHiK = reinterpret_cast<const long long*>(sRinv);
 
   const int lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
   const double sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha;
@@ -251,6 +287,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
 
     // ------------------------------------------------------------------ check_every ADMM iterations, the last one checks
     double rp = 0.0, rd = 0.0, nA = 0.0, nD = 0.0;
+    unsigned long long urp = 0ULL, urd = 0ULL, unA = 0ULL, unD = 0ULL;     // box-only path: the same maxima as bit patterns (integer pipe)
     double xt[HAS_G ? EPL : 1], yo[HAS_G ? EPL : 1];   // x~ (general rows: z~) and y+ of the checking iteration
     (void)xt; (void)yo;
     for (int ii = 0; ii < P.check_every; ii++) {
@@ -279,18 +316,20 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         for (int tn = 0; tn < NTL; tn++) {
           const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
           const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
+          const longlong2 kl2 = *reinterpret_cast<const longlong2*>(&sLoK[8 * tn + 2 * l4]);
+          const longlong2 kh2 = *reinterpret_cast<const longlong2*>(&sHiK[8 * tn + 2 * l4]);
 #pragma unroll
           for (int jj = 0; jj < 2; jj++) {
             const int le = 2 * tn + jj;
             const double w = fma(alpha, t[le], c[le]);
-            const double zn = dclamp(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x);
+            const double zn = iclamp_k(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x, jj ? kl2.y : kl2.x, jj ? kh2.y : kh2.x);
             if (chk) {   // residuals of (x~, z+, y+): Pc x~ = r - (sigma + rho) x~
               const double pc = fma(-sig_rho, t[le], R_SMEM ? sR[le * 32] : r[le]);
               const double yb = rho_s * (w - zn);
-              rp = dmaxf(rp, fabs(t[le] - zn));
-              rd = dmaxf(rd, fabs(pc + q[le] + yb));
-              nA = dmaxf(nA, dmaxf(fabs(t[le]), fabs(zn)));
-              nD = dmaxf(nD, dmaxf(fabs(pc), fabs(yb)));
+              urp = umax64(urp, absbits(t[le] - zn));
+              urd = umax64(urd, absbits(pc + q[le] + yb));
+              unA = umax64(unA, umax64(absbits(t[le]), absbits(zn)));
+              unD = umax64(unD, umax64(absbits(pc), absbits(yb)));
               sXt[le * 32] = t[le];
               if (P.y_out != nullptr) sYo[le * 32] = yb;
             }
@@ -380,6 +419,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
           nD = dmaxf(nD, dmaxf(fabs(cc[le]), fabs(yo[le])));
         }
     }
+    if (!HAS_G) { rp = __longlong_as_double((long long)urp); rd = __longlong_as_double((long long)urd); nA = __longlong_as_double((long long)unA); nD = __longlong_as_double((long long)unD); }
     rp = quad_max(rp); rd = quad_max(rd); nA = quad_max(nA); nD = quad_max(nD);
     const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
     if (HAS_G) {  // OSQP primal infeasibility certificate on delta_y of the last iteration

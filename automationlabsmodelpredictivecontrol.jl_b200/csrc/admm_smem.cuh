@@ -20,10 +20,10 @@ namespace mpcb {
 constexpr int SMEMK_WARPS = 4;
 constexpr int SMEMK_THREADS = SMEMK_WARPS * 32;
 
-// shared memory: T fragments NT*NT, lo/hi NT each, per-warp parameter staging [8][npad], per-warp state (3 or 4) x KS x 32
+// shared memory: T fragments NT*NT, lo/hi and their integer keys (admm_onchip.cuh: dkey) NT each, per-warp parameter staging [8][npad], per-warp state (3 or 4) x KS x 32
 __host__ __device__ inline size_t smemk_bytes(int NT, int np, bool sig) {
   const int npad = (np + 1) & ~1;
-  return sizeof(double) * ((size_t)NT * NT + 2 * NT + (size_t)SMEMK_WARPS * 8 * npad + (size_t)SMEMK_WARPS * (sig ? 4 : 3) * (NT / 4) * 32);
+  return sizeof(double) * ((size_t)NT * NT + 4 * NT + (size_t)SMEMK_WARPS * 8 * npad + (size_t)SMEMK_WARPS * (sig ? 4 : 3) * (NT / 4) * 32);
 }
 
 template <int NT, bool SIG>
@@ -35,15 +35,17 @@ __global__ void __launch_bounds__(SMEMK_THREADS, 1) admm_smem_kernel(const Onchi
   double* sHi = sLo + NT;
   const int npad = (P.np + 1) & ~1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
-  double* sP = sHi + NT + warp * 8 * npad;
-  double* st = sHi + NT + SMEMK_WARPS * 8 * npad + (size_t)warp * (SIG ? 4 : 3) * KS * 32 + lane;   // this lane's column
+  long long* sLoK = reinterpret_cast<long long*>(sHi + NT);
+  long long* sHiK = sLoK + NT;
+  double* sP = sHi + 3 * NT + warp * 8 * npad;
+  double* st = sHi + 3 * NT + SMEMK_WARPS * 8 * npad + (size_t)warp * (SIG ? 4 : 3) * KS * 32 + lane;   // this lane's column
   double* sC = st;                 // c = (1 - alpha) z + y / rho
   double* sR = st + KS * 32;       // r = rho (z - y/rho) + sigma x - q : the next MMA operand
   double* sQ = st + 2 * KS * 32;
   double* sX = st + 3 * KS * 32;   // only when SIG
 
   for (int i = threadIdx.x; i < NT * NT; i += SMEMK_THREADS) sT[i] = P.Tfrag[i];
-  for (int i = threadIdx.x; i < NT; i += SMEMK_THREADS) { sLo[i] = P.lo[i]; sHi[i] = P.hi[i]; }
+  for (int i = threadIdx.x; i < NT; i += SMEMK_THREADS) { sLo[i] = P.lo[i]; sHi[i] = P.hi[i]; sLoK[i] = dkey(P.lo[i]); sHiK[i] = dkey(P.hi[i]); }
   __syncthreads();
 
   const double sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha;
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(SMEMK_THREADS, 1) admm_smem_kernel(const Onchi
     if (!__any_sync(0xffffffffu, pi >= 0)) break;
 
     // ------------------------------------------------------------------ check_every ADMM iterations, the last one checks
-    double rp = 0.0, rd = 0.0, nA = 0.0, nD = 0.0;
+    unsigned long long urp = 0ULL, urd = 0ULL, unA = 0ULL, unD = 0ULL;     // maxima of absolute values as bit patterns (integer pipe)
     double t[EPL];
     for (int ii = 0; ii < P.check_every; ii++) {
       const bool chk = (ii == P.check_every - 1);
@@ -128,19 +130,21 @@ __global__ void __launch_bounds__(SMEMK_THREADS, 1) admm_smem_kernel(const Onchi
       for (int tn = 0; tn < NTL; tn++) {
         const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
         const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
+        const longlong2 kl2 = *reinterpret_cast<const longlong2*>(&sLoK[8 * tn + 2 * l4]);
+        const longlong2 kh2 = *reinterpret_cast<const longlong2*>(&sHiK[8 * tn + 2 * l4]);
 #pragma unroll
         for (int jj = 0; jj < 2; jj++) {
           const int le = 2 * tn + jj;
           const double cv = sC[le * 32], qv = sQ[le * 32];
           const double w = fma(alpha, t[le], cv);
-          const double zn = dclamp(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x);
+          const double zn = iclamp_k(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x, jj ? kl2.y : kl2.x, jj ? kh2.y : kh2.x);
           if (chk) {   // residuals of (x~, z+, y+): Pc x~ = r - (sigma + rho) x~
             const double pc = fma(-sig_rho, t[le], sR[le * 32]);
             const double yb = rho_s * (w - zn);
-            rp = dmaxf(rp, fabs(t[le] - zn));
-            rd = dmaxf(rd, fabs(pc + qv + yb));
-            nA = dmaxf(nA, dmaxf(fabs(t[le]), fabs(zn)));
-            nD = dmaxf(nD, dmaxf(fabs(pc), fabs(yb)));
+            urp = umax64(urp, absbits(t[le] - zn));
+            urd = umax64(urd, absbits(pc + qv + yb));
+            unA = umax64(unA, umax64(absbits(t[le]), absbits(zn)));
+            unD = umax64(unD, umax64(absbits(pc), absbits(yb)));
           }
           sC[le * 32] = fma(-alpha, zn, w);
           const double d = fma(2.0, zn, -w);
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(SMEMK_THREADS, 1) admm_smem_kernel(const Onchi
     it_s += P.check_every;
 
     // ------------------------------------------------------------------ termination (OSQP criteria at x~, z+, y+)
+    double rp = __longlong_as_double((long long)urp), rd = __longlong_as_double((long long)urd), nA = __longlong_as_double((long long)unA), nD = __longlong_as_double((long long)unD);
     rp = quad_max(rp); rd = quad_max(rd); nA = quad_max(nA); nD = quad_max(nD);
     const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
     const bool fin = (pi >= 0) && (conv || it_s >= max_iter);

@@ -4,7 +4,7 @@
 set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-OUT=../libmpcb200.so
+OUT=${MPCB_OUT:-../libmpcb200.so}
 OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall ${MPCB_NVCC_EXTRA:-}"

@@ -24,12 +24,9 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     if near > 0: xref_h = np.tile(x_ref, (n, 1)); x0_h = xref_h + near * rng.standard_normal((n, 4))
     if state_box: xref_h = rng.uniform(0.70, 0.82, (n, 4)); x0_h = rng.uniform(0.62, 0.72, (n, 4))
     dev = torch.device("cuda", 0)
-    if method == "linear":          # per-problem references: every problem is its own linearisation, Riccati equation and QP
-        rng = np.random.default_rng(3)
-        uref_h = rng.uniform(0.8, 2.2, (n, 2))
     x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
     status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
-    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 0 if method == "linear" else 1
+    io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 1
     io.status = status.data_ptr(); io.iters = iters.data_ptr()
     outs = []
     if full:
@@ -72,9 +69,6 @@ def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="eq
     rng = np.random.default_rng(3)
     x0_h = scale * rng.standard_normal((n, nx)); xref_h = np.zeros(nx); uref_h = np.zeros(nu)
     dev = torch.device("cuda", 0)
-    if method == "linear":          # per-problem references: every problem is its own linearisation, Riccati equation and QP
-        rng = np.random.default_rng(3)
-        uref_h = rng.uniform(0.8, 2.2, (n, 2))
     x0 = torch.from_numpy(x0_h).to(dev); xref = torch.from_numpy(xref_h).to(dev); uref = torch.from_numpy(uref_h).to(dev)
     status = torch.empty(n, dtype=torch.int32, device=dev); iters = torch.empty(n, dtype=torch.int32, device=dev)
     u0 = torch.empty((n, nu), dtype=torch.float64, device=dev)
