@@ -78,6 +78,9 @@ __device__ __forceinline__ long long dkey(double x) {
   const long long b = __double_as_longlong(x);
   return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
 }
+#ifndef MPCB_FUSED_ED
+#define MPCB_FUSED_ED 1     // 0: A/B knob, the plain product / update loop of the box-only path
+#endif
 #ifndef MPCB_INT_CLAMP
 #define MPCB_INT_CLAMP 0    // measured on B200: the integer clamp is SLOWER (0.515 vs 0.492 ms, QT H=20) -- longer dependent chains per row; kept as a knob
 #endif
@@ -290,6 +293,80 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
     unsigned long long urp = 0ULL, urd = 0ULL, unA = 0ULL, unD = 0ULL;     // box-only path: the same maxima as bit patterns (integer pipe)
     double xt[HAS_G ? EPL : 1], yo[HAS_G ? EPL : 1];   // x~ (general rows: z~) and y+ of the checking iteration
     (void)xt; (void)yo;
+    if (!HAS_G && MPCB_FUSED_ED && !R_SMEM) {
+      // -------- box-only fast path, software-pipelined: the elementwise update of row s (which yields the A operand of k-step s of
+      // the NEXT product) is issued right before that k-step's DMMAs, so one warp keeps the tensor pipe busy through what used to
+      // be its elementwise phase instead of relying on the other warps of the scheduler.  One period of check_every iterations =
+      // [plain product] [check_every - 1 fused update+product passes] [checking update].  Same operations per row in the same
+      // order as the plain loop: results are bit-identical.  The operand r of the last product is parked in shared memory for
+      // the dual residual (its registers are reused by the second accumulator set during the fused passes).
+      double t[EPL];
+#pragma unroll
+      for (int i = 0; i < EPL; i++) t[i] = 0.0;
+#pragma unroll
+      for (int s = 0; s < KS; s++) {
+#pragma unroll
+        for (int tn = 0; tn < NTL; tn++) dmma884(t[2 * tn], t[2 * tn + 1], r[s], sT[(s * NTL + tn) * 32 + lane]);
+      }
+      if (P.check_every == 1) {
+#pragma unroll
+        for (int s = 0; s < KS; s++) sR[s * 32] = r[s];
+      }
+      for (int ii = 1; ii < P.check_every; ii++) {
+        const bool last = (ii == P.check_every - 1);
+        double t2[EPL];
+#pragma unroll
+        for (int i = 0; i < EPL; i++) t2[i] = 0.0;
+#pragma unroll
+        for (int s = 0; s < KS; s++) {
+          const int e = 8 * (s >> 1) + 2 * l4 + (s & 1);
+          const double w = fma(alpha, t[s], c[s]);
+          const double zn = dclamp(w, sLo[e], sHi[e]);
+          c[s] = fma(-alpha, zn, w);
+          const double d = fma(2.0, zn, -w);
+          double rn;
+          if (SIG) {
+            x[s] = fma(alpha, t[s], oma * x[s]);
+            rn = fma(rho_s, d, fma(sigma, x[s], -q[s]));
+          } else {
+            rn = fma(rho_s, d, -q[s]);
+          }
+          if (last) sR[s * 32] = rn;
+#pragma unroll
+          for (int tn = 0; tn < NTL; tn++) dmma884(t2[2 * tn], t2[2 * tn + 1], rn, sT[(s * NTL + tn) * 32 + lane]);
+        }
+#pragma unroll
+        for (int i = 0; i < EPL; i++) t[i] = t2[i];
+      }
+      // checking update: residuals of (x~, z+, y+) with Pc x~ = r - (sigma + rho) x~, and the operand of the next period
+#pragma unroll
+      for (int tn = 0; tn < NTL; tn++) {
+        const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
+        const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+          const int le = 2 * tn + jj;
+          const double w = fma(alpha, t[le], c[le]);
+          const double zn = dclamp(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x);
+          const double pc = fma(-sig_rho, t[le], sR[le * 32]);
+          const double yb = rho_s * (w - zn);
+          urp = umax64(urp, absbits(t[le] - zn));
+          urd = umax64(urd, absbits(pc + q[le] + yb));
+          unA = umax64(unA, umax64(absbits(t[le]), absbits(zn)));
+          unD = umax64(unD, umax64(absbits(pc), absbits(yb)));
+          sXt[le * 32] = t[le];
+          if (P.y_out != nullptr) sYo[le * 32] = yb;
+          c[le] = fma(-alpha, zn, w);
+          const double d = fma(2.0, zn, -w);
+          if (SIG) {
+            x[le] = fma(alpha, t[le], oma * x[le]);
+            r[le] = fma(rho_s, d, fma(sigma, x[le], -q[le]));
+          } else {
+            r[le] = fma(rho_s, d, -q[le]);
+          }
+        }
+      }
+    } else
     for (int ii = 0; ii < P.check_every; ii++) {
       const bool chk = (ii == P.check_every - 1);
       double t[EPL];

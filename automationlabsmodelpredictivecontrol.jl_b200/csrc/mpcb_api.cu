@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,6 +84,7 @@ cudaError_t launch_onchip_t(const OnchipParams& P, int sm_count, int* blocks_per
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, mpcb::ONCHIP_THREADS, smem);
     if (e != cudaSuccess) return e;
+    if (const char* cap = std::getenv("MPCB_CTAS_PER_SM")) { const int c = std::atoi(cap); if (c > 0) occ = std::min(occ, c); }   // experiment knob (tools/ab_onchip.sh)
     *blocks_per_sm_cache = std::max(occ, 1);
   }
   const long long warps_needed = (P.batch + 7) / 8;
@@ -440,8 +442,21 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
     for (int i = 0; i < 9; i++)
       if (out_ptrs[i]) { out_bytes += per_out[i] * (size_t)Bn * sizeof(double); if (!is_pinned_or_device(out_ptrs[i])) pinned = false; }
     if (pinned && h->info.kernel != MPCB_KERNEL_STREAMED && out_bytes >= ((size_t)32 << 20) && Bn >= 4096) {
-      const int nch = (int)std::min<size_t>(8, std::max<size_t>(2, out_bytes / ((size_t)16 << 20)));   // 16 chunks measured slower (2.81 vs 2.73 ms on the bench workload)
-      const long long Bc = (Bn + nch - 1) / nch;
+      int nch = (int)std::min<size_t>(8, std::max<size_t>(2, out_bytes / ((size_t)16 << 20)));   // 16 chunks measured slower (2.81 vs 2.73 ms on the bench workload)
+      int first_div = 1;        // first chunk = 1/first_div of the others (its solve is the only one no download overlaps).  Measured on B200:
+                                // 4..10 chunks x first_div 1..4 all land within 2.68-2.77 ms -- the 133 MB download at ~50 GB/s is the floor
+      if (const char* e = std::getenv("MPCB_NCH")) { const int v = std::atoi(e); if (v >= 2 && v <= 16) nch = v; }            // experiment knobs
+      if (const char* e = std::getenv("MPCB_FIRST_DIV")) { const int v = std::atoi(e); if (v >= 1 && v <= 16) first_div = v; }
+      // chunk c covers [cb[c], cb[c+1]): nch - 1 equal chunks of Bc problems preceded by one of Bc / first_div
+      long long cb[17];
+      {
+        const double units = (double)(nch - 1) + 1.0 / first_div;
+        const long long Bc = (long long)std::ceil((double)Bn / units);
+        long long first = std::max<long long>(1, Bc / first_div);
+        cb[0] = 0;
+        for (int c = 1; c <= nch; c++) cb[c] = std::min<long long>(Bn, first + (long long)(c - 1) * Bc);
+        cb[nch] = Bn;
+      }
       DevBuf<double>* in_dev[5] = {&h->x0, &h->xref, &h->uref, &h->warm_v, &h->warm_y};
       const size_t per_in[5] = {nx, hio->xref_broadcast ? 0 : nx, hio->uref_broadcast ? 0 : nu, nz, nt};
       const size_t n_in[5] = {nx * (size_t)Bn, n_xref, n_uref, nz * (size_t)Bn, nt * (size_t)Bn};
@@ -459,8 +474,8 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
         }
       int launches = 0;
       for (int c = 0; c < nch; c++) {
-        const long long b0 = c * Bc, bn = std::min<long long>(Bc, Bn - b0);
-        if (bn <= 0) break;
+        const long long b0 = cb[c], bn = cb[c + 1] - b0;
+        if (bn <= 0) continue;
         for (int i = 0; i < 5; i++)
           if (in_ptrs[i] && per_in[i])
             CUDA_TRY(cudaMemcpyAsync(in_dev[i]->p + b0 * per_in[i], in_ptrs[i] + b0 * per_in[i], bn * per_in[i] * sizeof(double), cudaMemcpyHostToDevice, st));

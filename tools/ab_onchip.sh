@@ -1,9 +1,10 @@
 #!/bin/bash
-# A/B of kernel build variants on one box: gpurun_in/ab/lib_*.so against the in-tree library, interleaved twice.
+# A/B of kernel build variants on one box: every gpurun_in/ab/lib_*.so against the in-tree library, interleaved twice.
 for rep in 1 2; do
-  for lib in "" gpurun_in/ab/lib_00.so gpurun_in/ab/lib_10.so gpurun_in/ab/lib_01.so; do
+  for lib in "" $(ls gpurun_in/ab/lib_*.so 2>/dev/null); do
     echo "== lib=${lib:-default} rep=$rep"
-    MPCB200_LIB=${lib:+$PWD/$lib} timeout 120 python tools/dev_bench.py --set one 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms'], d['frac'])"
-    MPCB200_LIB=${lib:+$PWD/$lib} timeout 120 python tools/dev_bench.py --set h50 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('h50', d['ms'])"
+    for set in ${AB_SETS:-one h50}; do
+      MPCB200_LIB=${lib:+$PWD/$lib} timeout 120 python tools/dev_bench.py --set $set 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$set', d['ms'], d.get('frac'), d.get('mean_iters'))"
+    done
   done
 done

@@ -6,7 +6,7 @@ import almpc_b200 as mpc
 from almpc_b200 import _lib
 import bench
 
-def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None):
+def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000):
     """near > 0: x0 = x_ref + near * N(0, I) with the design reference (feasible terminal constraints); state_box: tight box + references beyond it"""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     if state_box: xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
@@ -17,7 +17,7 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     if Rw is not None: extra["mpc_R"] = Rw
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_terminal_ingredient=terminal,
                                mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho,
-                               mpc_b200_max_iter=20000, **extra)
+                               mpc_b200_max_iter=max_iter, **extra)
     m = C.tuning.modeler
     x0_h, xref_h, uref_h = bench.make_batch(n, 0)
     rng = np.random.default_rng(7)
@@ -142,6 +142,12 @@ if __name__ == "__main__":
         run(20, 65536, 1e-7, 5, 0.0, full=True)
         run(20, 65536, 1e-3, 25, 1e-6)
         run(20, 65536, 1e-3, 5, 0.0)
+    elif a.set == "steady":      # no drain, no spread: every problem runs exactly 50 iterations and the batch is a whole number of slot loads
+        for n in (14208 * 4, 14208 * 16, 65536):
+            run(20, n, 1e-300, 5, 0.0, max_iter=50)
+        run(20, 65536 * 4, 1e-7, 5, 0.0)
+    elif a.set == "steady1":
+        run(20, 14208 * 8, 1e-300, 5, 0.0, max_iter=50, reps=3)
     elif a.set == "one":
         run(20, 65536, 1e-7, 5, 0.0)
     elif a.set == "onefull":
