@@ -79,7 +79,7 @@ __device__ __forceinline__ long long dkey(double x) {
   return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
 }
 #ifndef MPCB_FUSED_ED
-#define MPCB_FUSED_ED 1     // 0: A/B knob, the plain product / update loop of the box-only path
+#define MPCB_FUSED_ED 0     // 1: software-pipelined update+product passes (bit-identical; measured no faster: 0.659 vs 0.671 of peak on the bench batch)
 #endif
 #ifndef MPCB_INT_CLAMP
 #define MPCB_INT_CLAMP 0    // measured on B200: the integer clamp is SLOWER (0.515 vs 0.492 ms, QT H=20) -- longer dependent chains per row; kept as a knob

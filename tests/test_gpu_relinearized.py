@@ -123,3 +123,32 @@ def test_relinearized_constraints(mpc, qt):
             assert (res["x"][ok][:, 1:] <= xmax + 1e-7).all() and (res["x"][ok][:, 1:] >= xmin - 1e-7).all()
             assert (res["x"][ok][:, 1:] > xmax - 1e-6).any(axis=(1, 2)).mean() > 0.5
         if terminal == "equality": assert np.abs(res["e_x"][ok][:, H]).max() < 1e-7
+
+
+def test_relinearized_design_failure_is_reported_per_problem(mpc):
+    """A model whose linearisation has an unstable mode the input cannot reach has no stabilising Riccati solution: the host
+    design refuses it (mpcb_create_nmpc without P), and the per-problem device design reports it as data (status -4) while the
+    call itself succeeds -- mirroring how the linear path reports solver outcomes (status[] of OSQP's codes)."""
+    # identity activation: f(x, u) = [1.5 x1, 0.5 x2 + u]
+    f = mpc.Fnn(np.eye(3), [(np.eye(3), np.zeros(3))], np.array([[1.5, 0.0, 0.0], [0.0, 0.5, 1.0]]), activation="identity")
+    Q, R, S = np.eye(2), np.eye(1), np.zeros((1, 1))
+    args = (Q, R, S)
+    with pytest.raises(mpc.MpcbError, match="dare"):
+        mpc.B200NonlinearModeler(f, *args, None, [-1.0], [1.0], None, None, 5, np.zeros(2), np.zeros(1))
+    mod = mpc.B200NonlinearModeler(f, *args, 10.0 * np.eye(2), [-1.0], [1.0], None, None, 5, np.zeros(2), np.zeros(1))
+    x0 = np.random.default_rng(0).uniform(-0.1, 0.1, (37, 2))
+    res = mod.solve_batch(x0, np.zeros(2), np.zeros(1), want=("u",), method="linear")
+    assert (res["status"] == mpc._lib.STATUS_DESIGN_FAILED).all() and (res["iters"] == 0).all()
+    # the SQP solve of the same controller (terminal weight given) is unaffected
+    res = mod.solve_batch(x0, np.zeros(2), np.zeros(1), want=("u",))
+    assert set(np.unique(res["status"])) <= {1, -2}
+    # a stabilisable sibling in the same process: f = [0.9 x1 + 0.3 u, 0.5 x2 + u]
+    g = mpc.Fnn(np.eye(3), [(np.eye(3), np.zeros(3))], np.array([[0.9, 0.0, 0.3], [0.0, 0.5, 1.0]]), activation="identity")
+    mod2 = mpc.B200NonlinearModeler(g, *args, None, [-1.0], [1.0], None, None, 5, np.zeros(2), np.zeros(1))
+    r2 = mod2.solve_batch(x0, np.zeros(2), np.zeros(1), want=("u", "objective"), method="linear")
+    assert (r2["status"] == 1).all()
+    A = np.array([[0.9, 0.0], [0.0, 0.5]]); B = np.array([[0.3], [1.0]])
+    c = mo.condense(A, B, Q, R, S, mo.dare(A, B, Q, R), 5, [-1.0], [1.0])
+    for i in (0, 11):
+        v, _ = mo.qp_exact(c, mo.pack_params(x0[i], np.zeros(2), np.zeros(1))[0])
+        assert np.abs(r2["u"][i].ravel() - v).max() < 1e-7
