@@ -13,7 +13,7 @@ LIB_PATH = pathlib.Path(os.environ["MPCB200_LIB"]) if os.environ.get("MPCB200_LI
 MPCB_OK = 0
 KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED, KERNEL_ONCHIP_SMEM = 0, 1, 2, 3
 TERMINAL_NONE, TERMINAL_EQUALITY, TERMINAL_CONTRACTIVE = 0, 1, 2
-STATUS_SOLVED, STATUS_SOLVED_INACCURATE, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE, STATUS_DESIGN_FAILED = 1, 2, -2, -3, -4
+STATUS_SOLVED, STATUS_SOLVED_INACCURATE, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE, STATUS_DESIGN_FAILED = 1, 2, -2, -3, -20
 NN_FNN, NN_RESNET, NN_POLYNET, NN_DENSENET = 0, 1, 2, 3
 ACTIVATION_IDS = {"relu": 0, "tanh": 1, "sigmoid": 2, "swish": 3, "identity": 4}
 

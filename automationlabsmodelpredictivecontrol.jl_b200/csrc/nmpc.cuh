@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       if (P.lin_dare) {
         const int dit = dare_sda_warp(nx, nu, lAB, lAB + nx * nx, sQ, P.Rinv, lP, lws, lane);
         if (dit < 0) {           // no stabilising solution for this linearisation: reported as data, like the host design's error
-          if (lane == 0) { P.status[p] = -4; P.iters[p] = 0; if (P.inner_iters) P.inner_iters[p] = 0; }
+          if (lane == 0) { P.status[p] = -20; P.iters[p] = 0; if (P.inner_iters) P.inner_iters[p] = 0; }
           continue;
         }
         Wt = lP;

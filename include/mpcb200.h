@@ -40,7 +40,7 @@ extern "C" {
 #define MPCB_STATUS_SOLVED_INACCURATE 2 /* NMPC only: the SQP line search found no further descent (kink of a relu network) */
 #define MPCB_STATUS_MAX_ITER -2
 #define MPCB_STATUS_PRIMAL_INFEASIBLE -3
-#define MPCB_STATUS_DESIGN_FAILED -4 /* re-linearised solve: this problem's Riccati equation has no stabilising solution */
+#define MPCB_STATUS_DESIGN_FAILED -20 /* re-linearised solve: this problem's Riccati equation has no stabilising solution (outside OSQP's code range: -4 is its dual-infeasible) */
 #define MPCB_STATUS_UNSOLVED -10
 
 /* terminal ingredient (src/sub/design_mpc.jl:298-394).  "contractive" (e_H' e_H <= 0.9 e_0' e_0, :333-340) is a quadratic

@@ -127,7 +127,7 @@ def test_relinearized_constraints(mpc, qt):
 
 def test_relinearized_design_failure_is_reported_per_problem(mpc):
     """A model whose linearisation has an unstable mode the input cannot reach has no stabilising Riccati solution: the host
-    design refuses it (mpcb_create_nmpc without P), and the per-problem device design reports it as data (status -4) while the
+    design refuses it (mpcb_create_nmpc without P), and the per-problem device design reports it as data (status -20) while the
     call itself succeeds -- mirroring how the linear path reports solver outcomes (status[] of OSQP's codes)."""
     # identity activation: f(x, u) = [1.5 x1, 0.5 x2 + u]
     f = mpc.Fnn(np.eye(3), [(np.eye(3), np.zeros(3))], np.array([[1.5, 0.0, 0.0], [0.0, 0.5, 1.0]]), activation="identity")
