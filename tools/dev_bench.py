@@ -169,6 +169,11 @@ if __name__ == "__main__":
         for fx, H in (("qt_fnn_tanh_model.json", 20), ("qt_resnet_model.json", 20), ("qt_fnn_tanh_model.json", 10), ("qt_densenet_tanh_model.json", 20)):
             run_nmpc(fx, H=H, n=65536, method="linear")
         run_nmpc("qt_fnn_tanh_model.json", H=20, n=65536, method="linear", mpc_b200_eps_abs=1e-7)
+    elif a.set == "relinscale":
+        for n in (4096, 16384, 32768, 65536, 131072):
+            run_nmpc("qt_fnn_tanh_model.json", H=20, n=n, method="linear", reps=3)
+    elif a.set == "relin1":
+        run_nmpc("qt_fnn_tanh_model.json", H=20, n=16384, method="linear", reps=1)
     elif a.set == "nmpc1":
         run_nmpc("qt_fnn_tanh_model.json", reps=1)
     elif a.set == "lti1":
