@@ -357,6 +357,7 @@ struct NmpcParams {
   int max_iter, check_every;
   double sqp_tol, ls_c1, ls_noise;
   double rho_eq_scale;   // terminal equality rows: rho_e,i = rho_eq_scale * rho / |Gamma_H,i|^2
+  int sync_rounds;       // 1: the warps of a CTA advance in barrier-separated rounds of one SQP iteration (see the kernel's main loop)
   int term_ball;         // EQ kernels: the terminal rows form the contractive ball |e_H|_2 <= sqrt(0.9) |e_0|_2 (design_mpc.jl:333-340) instead of e_H = 0
   const double* Rinv;    // nu x nu (LIN kernels: G_0 = B R^-1 B' of the per-problem Riccati equation)
   int lin_dare;          // LIN kernels: 1 = terminal weight from the per-problem DARE, 0 = the design's Pt for every problem
@@ -464,29 +465,93 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
   const double rho = P.rho, sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha, sig_rho = P.sigma + P.rho;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
 
-  while (true) {
-    long long p = 0;
-    if (lane == 0) p = (long long)atomicAdd(P.counter, 1ULL);
-    p = __shfl_sync(0xffffffffu, p, 0);
+  // Per-problem state of this warp, kept across rounds (see the loop below).
+  long long p = -1;         // problem held by this warp (-1: none)
+  bool exhausted = false;   // the work queue has run dry
+  const double *x0 = nullptr, *xr = nullptr, *ur = nullptr;
+  double rad = 0.0;
+  const double* Wt = sPt;   // terminal weight
+  const double* ABk = AB;   // stage Jacobians [A_k B_k]
+  double yd[ROWS];          // duals of the box rows (carried across SQP iterations)
+  double mu = 0.0;          // l1 merit weight of the terminal rows
+  const int ny = nz + ms + (EQ ? nx : 0);       // duals: [input box | state-box rows | terminal rows]
+  int status = -2, sqp_it = 0, inner_total = 0;
+  double step = 0.0, qp_rd = 0.0, Jcur = 0.0;
+  bool have_traj = false;
+#pragma unroll
+  for (int i = 0; i < ROWS; i++) yd[i] = 0.0;
+  // one step of the prediction model from xu = [x; u]: the network, or (LIN) the deviation model around the reference
+  auto model_step = [&]() {
     if (LIN) {
-      // Every problem of the re-linearised solve runs the same phases (only the ADMM iteration count varies), so the warps of
-      // a CTA are kept in step, one problem per round: in step they execute the same few KB of this large kernel and share the
-      // instruction cache; left alone they drift apart over a long launch and the cache thrashes (measured on B200: 65 536
-      // problems in one launch 28.7 ms, the same problems in four launches of 16 384 4 x 5.0 ms).
-      if (!__syncthreads_or(p < P.batch)) break;
-      if (p >= P.batch) continue;
-    } else if (p >= P.batch) break;
-    const double* x0 = P.x0 + p * nx;
-    const double* xr = P.xref + (P.xref_bc ? 0 : p) * nx;
-    const double* ur = P.uref + (P.uref_bc ? 0 : p) * nu;
-    double rad = 0.0;         // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this problem's ball
+      for (int i = lane; i < nx; i += 32) {
+        double sacc = xr[i];
+        for (int j = 0; j < nx; j++) sacc = fma(lAB[j * nx + i], xu[j] - xr[j], sacc);
+        for (int j = 0; j < nu; j++) sacc = fma(lAB[(nx + j) * nx + i], xu[nx + j] - ur[j], sacc);
+        f[i] = sacc;
+      }
+      __syncwarp();
+    } else {
+      nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
+    }
+  };
+  // forward rollout of the inputs in `uu` -> traj, returns the true cost J (all lanes)
+  auto rollout_cost = [&](const double* uu) -> double {
+    double J = 0.0;
+    for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
+    __syncwarp();
+    for (int k = 0; k <= H; k++) {
+      const double* W = (k == H) ? Wt : sQ;
+      double part = 0.0;
+      for (int i = lane; i < nx; i += 32) {
+        double s = 0.0;
+        for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], xu[j] - xr[j], s);
+        part = fma(xu[i] - xr[i], s, part);
+      }
+      J += part;
+      if (k == H) break;
+      for (int i = lane; i < nu; i += 32) xu[nx + i] = uu[k * nu + i];
+      __syncwarp();
+      model_step();
+      for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; }
+      __syncwarp();
+    }
+    double part = 0.0;                 // 1/2 du' Hc du
+    for (int e = lane; e < nz; e += 32) scol[e] = uu[e] - ur[e % nu];
+    __syncwarp();
+    for (int e = lane; e < nz; e += 32) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
+      part = fma(0.5 * scol[e], s, part);
+    }
+    __syncwarp();
+    return warp_sum(J + part);
+  };
+
+  // The warps of a CTA advance in ROUNDS of one SQP iteration each, separated by a CTA barrier: a warp whose problem finished
+  // fetches the next one at the round boundary.  In step, the warps execute the same few KB of this large kernel at the same
+  // time and share the instruction cache; left alone they drift apart within a few problems and the cache thrashes (measured
+  // on the re-linearised solve: 65 536 problems 28.7 -> 19.4 ms; SQP on the ResNet surrogate 45.5 -> 34.3 ms; a second barrier after
+  // the variable-length ADMM phase changes nothing).
+  NMPC_PROF_DECL
+  while (true) {
+    if (p < 0 && !exhausted) {
+      long long pn = 0;
+      if (lane == 0) pn = (long long)atomicAdd(P.counter, 1ULL);
+      pn = __shfl_sync(0xffffffffu, pn, 0);
+      if (pn >= P.batch) exhausted = true;
+      else {
+      p = pn;
+      x0 = P.x0 + p * nx;
+      xr = P.xref + (P.xref_bc ? 0 : p) * nx;
+      ur = P.uref + (P.uref_bc ? 0 : p) * nu;
+      rad = 0.0;                // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this problem's ball
     if (EQ && P.term_ball) {
       double d2 = 0.0;
       for (int i = 0; i < nx; i++) { const double dv = x0[i] - xr[i]; d2 = fma(dv, dv, d2); }
       rad = sqrt(0.9 * d2);
     }
-    const double* Wt = sPt;   // terminal weight
-    const double* ABk = AB;   // stage Jacobians [A_k B_k]
+      Wt = sPt; ABk = AB;
     if (LIN) {
       for (int i = lane; i < nx; i += 32) xu[i] = xr[i];
       for (int i = lane; i < nu; i += 32) xu[nx + i] = ur[i];
@@ -499,28 +564,12 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
         const int dit = dare_sda_warp(nx, nu, lAB, lAB + nx * nx, sQ, P.Rinv, lP, lws, lane);
         if (dit < 0) {           // no stabilising solution for this linearisation: reported as data, like the host design's error
           if (lane == 0) { P.status[p] = -20; P.iters[p] = 0; if (P.inner_iters) P.inner_iters[p] = 0; }
-          continue;
-        }
-        Wt = lP;
+          p = -1;                // this warp sits the round out
+        } else Wt = lP;
       }
     }
-    // one step of the prediction model from xu = [x; u]: the network, or (LIN) the deviation model around the reference
-    auto model_step = [&]() {
-      if (LIN) {
-        for (int i = lane; i < nx; i += 32) {
-          double sacc = xr[i];
-          for (int j = 0; j < nx; j++) sacc = fma(lAB[j * nx + i], xu[j] - xr[j], sacc);
-          for (int j = 0; j < nu; j++) sacc = fma(lAB[(nx + j) * nx + i], xu[nx + j] - ur[j], sacc);
-          f[i] = sacc;
-        }
-        __syncwarp();
-      } else {
-        nn_eval_warp<false>(N, xu, f, ya, yb, nullptr, nullptr, nullptr, sd, lane);
-      }
-    };
-    double yd[ROWS];          // duals of the box rows (carried across SQP iterations)
-    double mu = 0.0;          // l1 merit weight of the terminal rows
-    const int ny = nz + ms + (EQ ? nx : 0);       // duals: [input box | state-box rows | terminal rows]
+      if (p >= 0) {
+      mu = 0.0;
     if (SB) { for (int r = lane; r < ms; r += 32) gy[r] = P.warm_y ? P.warm_y[p * ny + nz + r] : 0.0; }
     if (EQ) { for (int i = lane; i < nx; i += 32) syg[i] = P.warm_y ? P.warm_y[p * ny + nz + ms + i] : 0.0; }
 #pragma unroll
@@ -536,46 +585,17 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       }
     }
     __syncwarp();
-
-    // forward rollout of the inputs in `uu` -> traj, returns the true cost J (all lanes)
-    auto rollout_cost = [&](const double* uu) -> double {
-      double J = 0.0;
-      for (int i = lane; i < nx; i += 32) { const double v = x0[i]; xu[i] = v; traj[i] = v; }
-      __syncwarp();
-      for (int k = 0; k <= H; k++) {
-        const double* W = (k == H) ? Wt : sQ;
-        double part = 0.0;
-        for (int i = lane; i < nx; i += 32) {
-          double s = 0.0;
-          for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], xu[j] - xr[j], s);
-          part = fma(xu[i] - xr[i], s, part);
-        }
-        J += part;
-        if (k == H) break;
-        for (int i = lane; i < nu; i += 32) xu[nx + i] = uu[k * nu + i];
-        __syncwarp();
-        model_step();
-        for (int i = lane; i < nx; i += 32) { const double v = f[i]; xu[i] = v; traj[(k + 1) * nx + i] = v; }
-        __syncwarp();
       }
-      double part = 0.0;                 // 1/2 du' Hc du
-      for (int e = lane; e < nz; e += 32) scol[e] = uu[e] - ur[e % nu];
-      __syncwarp();
-      for (int e = lane; e < nz; e += 32) {
-        double s = 0.0;
-#pragma unroll 8
-        for (int j = 0; j < nz; j++) s = fma(sHc[j * nz + e], scol[j], s);
-        part = fma(0.5 * scol[e], s, part);
+      status = -2; sqp_it = 0; inner_total = 0; step = 0.0; qp_rd = 0.0; Jcur = 0.0; have_traj = false;
       }
-      __syncwarp();
-      return warp_sum(J + part);
-    };
-
-    NMPC_PROF_DECL
-    int status = -2, sqp_it = 0, inner_total = 0;
-    double step = 0.0, qp_rd = 0.0, Jcur = 0.0;
-    bool have_traj = false;
-    for (sqp_it = 1; sqp_it <= P.sqp_max_iter; sqp_it++) {
+    }
+    if (P.sync_rounds) {
+      if (!__syncthreads_or(p >= 0)) break;
+      if (p < 0) continue;
+    } else if (p < 0) break;        // few problems per warp: the barrier would cost more than the shared cache gives (host's choice)
+    sqp_it++;
+    bool fell = false;
+    do {
       NMPC_PROF(4);
       // ---------------------------------------------------------------- 1. linearise along the trajectory of u
       for (int a = 0; a < nz; a++)
@@ -1049,8 +1069,9 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       for (int e = lane; e < nz; e += 32) su[e] = sv[e];
       __syncwarp();
       have_traj = true;
-    }
-    if (sqp_it > P.sqp_max_iter) sqp_it = P.sqp_max_iter;
+      fell = true;
+    } while (0);
+    if (fell && sqp_it < P.sqp_max_iter) continue;       // next round: another SQP iteration of the same problem
     NMPC_PROF(3);
     if (!have_traj) Jcur = rollout_cost(su);
     // ------------------------------------------------------------------ outputs
@@ -1079,6 +1100,7 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       if (P.qp_dres) P.qp_dres[p] = qp_rd;
     }
     __syncwarp();
+    p = -1;
   }
 }
 
