@@ -181,7 +181,8 @@ int enqueue_nmpc(mpcb_nmpc* h, const mpcb_batch_io& io, cudaStream_t st, bool li
   const long long blocks = (Bn + warps - 1) / warps;
   const int per_sm = std::max<int>(1, (int)((226 * 1024) / smem));
   const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(blocks, (long long)n->sm_count * per_sm));
-  P.sync_rounds = Bn >= 6LL * (long long)grid * warps ? 1 : 0;      // measured: +33 % at 49 problems per warp, -4 % at 3
+  P.sync_rounds = Bn > (long long)grid * warps ? 1 : 0;      // off only when no warp gets a second problem.  Measured: +33 % at 49 problems per warp;
+                                                              // at 3 per warp +10..18 % for the 6-9-iteration networks, -4 % for the 2-iteration ResNet
   cudaError_t e;
   if (h->rows < 1 || h->rows > 4) return api_fail(MPCB_ERR_INVALID, "NMPC supports nu*horizon <= 128");
   if (lin) e = mpcb::launch_lin(h->terminal_eq, h->state_box, h->rows, P, grid, threads, smem, &h->smem_set_lin, st);
