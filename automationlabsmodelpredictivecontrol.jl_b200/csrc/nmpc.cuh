@@ -18,7 +18,8 @@
 //   3. ADMM in absolute inputs v (box umin <= v <= umax), warm-started at (u, y): per iteration one K^-1 mat-vec from
 //      shared memory + the fused projection / dual update / residual reductions of admm_onchip.cuh (box-only form)
 //   4. step d = v - u; accept if ||d||_inf <= tol, else Armijo backtracking on the TRUE cost (forward rollouts only)
-// Problems are handed out through a global atomic counter (SQP iteration counts vary from 2 to the cap).
+// Problems are handed out through a global atomic counter (SQP iteration counts vary from 2 to the cap); the warps of a CTA
+// advance in barrier-separated rounds of one SQP iteration so that they share the instruction cache (see the main loop).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -541,58 +542,58 @@ __global__ void __launch_bounds__(NMPC_MAX_WARPS * 32, 1) nmpc_sqp_kernel(const 
       pn = __shfl_sync(0xffffffffu, pn, 0);
       if (pn >= P.batch) exhausted = true;
       else {
-      p = pn;
-      x0 = P.x0 + p * nx;
-      xr = P.xref + (P.xref_bc ? 0 : p) * nx;
-      ur = P.uref + (P.uref_bc ? 0 : p) * nu;
-      rad = 0.0;                // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this problem's ball
-    if (EQ && P.term_ball) {
-      double d2 = 0.0;
-      for (int i = 0; i < nx; i++) { const double dv = x0[i] - xr[i]; d2 = fma(dv, dv, d2); }
-      rad = sqrt(0.9 * d2);
-    }
-      Wt = sPt; ABk = AB;
-    if (LIN) {
-      for (int i = lane; i < nx; i += 32) xu[i] = xr[i];
-      for (int i = lane; i < nu; i += 32) xu[nx + i] = ur[i];
-      __syncwarp();
-      nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
-      for (int o = lane; o < nx * nin; o += 32) lAB[o] = AB[o];
-      __syncwarp();
-      ABk = lAB;
-      if (P.lin_dare) {
-        const int dit = dare_sda_warp(nx, nu, lAB, lAB + nx * nx, sQ, P.Rinv, lP, lws, lane);
-        if (dit < 0) {           // no stabilising solution for this linearisation: reported as data, like the host design's error
-          if (lane == 0) { P.status[p] = -20; P.iters[p] = 0; if (P.inner_iters) P.inner_iters[p] = 0; }
-          p = -1;                // this warp sits the round out
-        } else Wt = lP;
-      }
-    }
-      if (p >= 0) {
-      mu = 0.0;
-    if (SB) { for (int r = lane; r < ms; r += 32) gy[r] = P.warm_y ? P.warm_y[p * ny + nz + r] : 0.0; }
-    if (EQ) { for (int i = lane; i < nx; i += 32) syg[i] = P.warm_y ? P.warm_y[p * ny + nz + ms + i] : 0.0; }
+        p = pn;
+        x0 = P.x0 + p * nx;
+        xr = P.xref + (P.xref_bc ? 0 : p) * nx;
+        ur = P.uref + (P.uref_bc ? 0 : p) * nu;
+        rad = 0.0;                // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this problem's ball
+        if (EQ && P.term_ball) {
+          double d2 = 0.0;
+          for (int i = 0; i < nx; i++) { const double dv = x0[i] - xr[i]; d2 = fma(dv, dv, d2); }
+          rad = sqrt(0.9 * d2);
+        }
+        Wt = sPt; ABk = AB;
+        if (LIN) {
+          for (int i = lane; i < nx; i += 32) xu[i] = xr[i];
+          for (int i = lane; i < nu; i += 32) xu[nx + i] = ur[i];
+          __syncwarp();
+          nn_eval_warp<true>(N, xu, f, ya, yb, Ja, Jb, AB, sd, lane);
+          for (int o = lane; o < nx * nin; o += 32) lAB[o] = AB[o];
+          __syncwarp();
+          ABk = lAB;
+          if (P.lin_dare) {
+            const int dit = dare_sda_warp(nx, nu, lAB, lAB + nx * nx, sQ, P.Rinv, lP, lws, lane);
+            if (dit < 0) {           // no stabilising solution for this linearisation: reported as data, like the host design's error
+              if (lane == 0) { P.status[p] = -20; P.iters[p] = 0; if (P.inner_iters) P.inner_iters[p] = 0; }
+              p = -1;                // this warp sits the round out
+            } else Wt = lP;
+          }
+        }
+        if (p >= 0) {
+          mu = 0.0;
+          if (SB) { for (int r = lane; r < ms; r += 32) gy[r] = P.warm_y ? P.warm_y[p * ny + nz + r] : 0.0; }
+          if (EQ) { for (int i = lane; i < nx; i += 32) syg[i] = P.warm_y ? P.warm_y[p * ny + nz + ms + i] : 0.0; }
 #pragma unroll
-    for (int i = 0; i < ROWS; i++) {
-      const int e = lane + 32 * i;
-      yd[i] = 0.0;
-      if (e < nz) {
-        double u0v;
-        if (P.warm_u) u0v = P.warm_u[p * nz + e];
-        else { const double r0 = ur[e % nu]; u0v = r0 < sLb[e] ? sLb[e] : (r0 > sUb[e] ? sUb[e] : r0); }
-        su[e] = u0v;
-        if (P.warm_y) yd[i] = P.warm_y[p * ny + e];
-      }
-    }
-    __syncwarp();
-      }
-      status = -2; sqp_it = 0; inner_total = 0; step = 0.0; qp_rd = 0.0; Jcur = 0.0; have_traj = false;
+          for (int i = 0; i < ROWS; i++) {
+            const int e = lane + 32 * i;
+            yd[i] = 0.0;
+            if (e < nz) {
+              double u0v;
+              if (P.warm_u) u0v = P.warm_u[p * nz + e];
+              else { const double r0 = ur[e % nu]; u0v = r0 < sLb[e] ? sLb[e] : (r0 > sUb[e] ? sUb[e] : r0); }
+              su[e] = u0v;
+              if (P.warm_y) yd[i] = P.warm_y[p * ny + e];
+            }
+          }
+          __syncwarp();
+        }
+        status = -2; sqp_it = 0; inner_total = 0; step = 0.0; qp_rd = 0.0; Jcur = 0.0; have_traj = false;
       }
     }
     if (P.sync_rounds) {
       if (!__syncthreads_or(p >= 0)) break;
       if (p < 0) continue;
-    } else if (p < 0) break;        // few problems per warp: the barrier would cost more than the shared cache gives (host's choice)
+    } else if (p < 0) break;        // no warp gets a second problem: nothing to keep in step (host's choice)
     sqp_it++;
     bool fell = false;
     do {
