@@ -24,7 +24,8 @@ _ip = C.POINTER(C.c_int32)
 class Settings(C.Structure):
     _fields_ = [("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("rho", C.c_double),
                 ("rho_eq_scale", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("max_iter", C.c_int32),
-                ("check_every", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("check_every", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32), ("ladder_iter", C.c_int32), ("ladder_kappa", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
 
 
 class LinearDesc(C.Structure):

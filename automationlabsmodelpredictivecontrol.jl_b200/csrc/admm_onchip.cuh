@@ -54,6 +54,11 @@ struct OnchipParams {
   int32_t* iters;
   double* pres;
   double* dres;
+  // second pass over the problems the first pass left unsolved (rho ladder, mpcb_api.cu): ticket t works on problem remap[t],
+  // the number of tickets is read from device memory, and the reported iteration count continues from the first pass
+  const int32_t* remap;                  // null: ticket = problem index
+  const unsigned long long* batch_dev;   // null: `batch` tickets
+  int iters_add;
   unsigned long long* counter;  // [0] work queue head, [1] CTAs that have drained it; both zero at launch, the last CTA to
                                 // finish re-zeroes them so that back-to-back launches need no memset in between
 };
@@ -196,6 +201,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
   double rad = 0.0;    // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this slot's ball
   bool exhausted = false;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
+  const long long batch_eff = P.batch_dev ? (long long)*P.batch_dev : P.batch;
 
   // one product  out = M in  with M in fragment order
   auto mma_pass = [&](const double* __restrict__ sM, const double (&in)[EPL], double (&out)[EPL]) {
@@ -215,10 +221,10 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
       long long np_i = -1;
       if (need && l4 == 0) np_i = (long long)atomicAdd(P.counter, 1ULL);
       np_i = __shfl_sync(0xffffffffu, np_i, lane & ~3);
-      const bool fresh = need && np_i < P.batch;
+      const bool fresh = need && np_i < batch_eff;
       if (need && !fresh) exhausted = true;
       if (fresh) {
-        pi = np_i;
+        pi = P.remap ? (long long)P.remap[np_i] : np_i;
         it_s = 0;
         for (int j = l4; j < P.np; j += 4) {
           double v;
@@ -544,7 +550,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
       }
       if (l4 == 0) {
         P.status[pi] = conv ? 1 : (pinf ? -3 : -2);
-        P.iters[pi] = it_s;
+        P.iters[pi] = it_s + P.iters_add;
         P.pres[pi] = rp;
         P.dres[pi] = rd;
       }

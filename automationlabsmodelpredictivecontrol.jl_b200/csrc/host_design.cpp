@@ -221,7 +221,7 @@ bool dare_sda(const Mat& A, const Mat& B, const Mat& Q, const Mat& R, Mat& P, st
   return false;
 }
 
-int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, std::string& err) {
+int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, std::string& err, double ineq_scale) {
   if (d.nx <= 0 || d.nu <= 0 || d.horizon <= 0) { err = "nx, nu, horizon must be positive"; return MPCB_ERR_INVALID; }
   if (!d.A || !d.B || !d.Q || !d.R || !d.umin || !d.umax) { err = "A, B, Q, R, umin, umax are required"; return MPCB_ERR_INVALID; }
   if (d.terminal_mode != MPCB_TERMINAL_NONE && d.terminal_mode != MPCB_TERMINAL_EQUALITY && d.terminal_mode != MPCB_TERMINAL_CONTRACTIVE) {
@@ -330,7 +330,7 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
   for (int i = 0; i < mg; i++) {
     double rn = 0.0;
     for (int j = 0; j < nz; j++) rn += D.G(i, j) * D.G(i, j);
-    D.rho_vec[nz + i] = (D.is_eq[nz + i] ? s.rho_eq_scale * D.rho : D.rho) / std::max(rn, 1e-12);
+    D.rho_vec[nz + i] = (D.is_eq[nz + i] ? s.rho_eq_scale * D.rho : ineq_scale * D.rho) / std::max(rn, 1e-12);
   }
   if (D.nball) {      // the projection onto a ball is closed-form only for one common step size on its rows: rho / mean |G_i|^2
     double mean = 0.0;

@@ -60,6 +60,7 @@ struct Design {
   double rho = 0, lmin = 0, lmax = 0;
 };
 
-int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& out, std::string& err);
+// ineq_scale multiplies the step size of the INEQUALITY general rows (state box): the second rung of the rho ladder (mpcb_api.cu)
+int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& out, std::string& err, double ineq_scale = 1.0);
 
 }  // namespace mpcb

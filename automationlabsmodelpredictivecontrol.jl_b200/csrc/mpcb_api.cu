@@ -46,6 +46,7 @@ int fail(int code, const std::string& msg) { return mpcb::api_fail(code, msg); }
 
 struct mpcb_handle {
   mpcb::Design D;
+  mpcb::Design D2;      // second rung of the rho ladder (only T and rho_vec are used)
   mpcb_settings st;
   mpcb_info info;
   mpcb_timing timing;
@@ -56,6 +57,9 @@ struct mpcb_handle {
   cudaEvent_t chunk_ev[16] = {};
   // per-system constants
   DevBuf<double> Tfrag, Cfrag, Lt, lo, hi, rho, rinv, A, B, Q, R, S, P;
+  DevBuf<double> Tfrag2, rho2, rinv2;       // second rung of the rho ladder (settings.ladder_iter): operator and step sizes
+  DevBuf<int32_t> remap;                    // problems the first pass left unsolved
+  bool ladder = false;
   DevBuf<unsigned long long> counter;
   mpcb::StreamConsts sc;  // streamed-kernel constants
   // batch workspaces (device)
@@ -73,6 +77,12 @@ struct mpcb_handle {
 namespace {
 
 using mpcb::OnchipParams;
+
+// rho ladder: the indices of the problems that hit the first pass's iteration cap, in any order; count[2] of the work counter block
+__global__ void collect_unsolved_kernel(const int32_t* status, long long n, int32_t* remap, unsigned long long* count) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && status[i] == MPCB_STATUS_MAX_ITER) remap[atomicAdd(count, 1ULL)] = (int32_t)i;
+}
 
 template <int NT, bool HAS_G, bool SIG, int MINB>
 cudaError_t launch_onchip_t(const OnchipParams& P, int sm_count, int* blocks_per_sm_cache, cudaStream_t st) {
@@ -138,8 +148,8 @@ int upload_design(mpcb_handle* h) {
   CUDA_TRY(upload(h->R, D.R.a.data(), D.R.a.size()));
   CUDA_TRY(upload(h->S, D.S.a.data(), D.S.a.size()));
   CUDA_TRY(upload(h->P, D.P.a.data(), D.P.a.size()));
-  CUDA_TRY(h->counter.ensure(2));
-  CUDA_TRY(cudaMemset(h->counter.p, 0, 2 * sizeof(unsigned long long)));   // once: the on-chip kernel re-arms it itself
+  CUDA_TRY(h->counter.ensure(3));
+  CUDA_TRY(cudaMemset(h->counter.p, 0, 3 * sizeof(unsigned long long)));   // once: the on-chip kernel re-arms it itself
   if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     const int NT = h->NT, nt = D.nt, np = D.np;
     std::vector<double> tf = to_fragments(D.T, nt, NT), cf = to_fragments(D.C, nt, NT);
@@ -156,6 +166,13 @@ int upload_design(mpcb_handle* h) {
     CUDA_TRY(upload(h->hi, hi.data(), NT));
     CUDA_TRY(upload(h->rho, rho.data(), NT));
     CUDA_TRY(upload(h->rinv, rinv.data(), NT));
+    if (h->ladder) {
+      std::vector<double> tf2 = to_fragments(h->D2.T, nt, NT);
+      for (int i = 0; i < nt; i++) { rho[i] = h->D2.rho_vec[i]; rinv[i] = 1.0 / h->D2.rho_vec[i]; }
+      CUDA_TRY(upload(h->Tfrag2, tf2.data(), tf2.size()));
+      CUDA_TRY(upload(h->rho2, rho.data(), NT));
+      CUDA_TRY(upload(h->rinv2, rinv.data(), NT));
+    }
   } else {
     std::string err;
     cudaError_t e = mpcb::stream_upload(D, h->sc, err);
@@ -181,11 +198,11 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
   if (!d_dres) { CUDA_TRY(h->dres.ensure(Bn)); d_dres = h->dres.p; }
   int launches = 0;
   if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
-    OnchipParams P;
+    OnchipParams P{};
     P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
     P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu; P.nball = D.nball;
     P.rho_box = D.rho; P.sigma = h->st.sigma; P.alpha = h->st.alpha; P.eps_abs = h->st.eps_abs; P.eps_rel = h->st.eps_rel;
-    P.eps_pinf = h->st.eps_prim_inf; P.max_iter = h->st.max_iter; P.check_every = h->st.check_every;
+    P.eps_pinf = h->st.eps_prim_inf; P.max_iter = h->ladder ? h->st.ladder_iter : h->st.max_iter; P.check_every = h->st.check_every;
     P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
     P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = v_buf; P.y_out = io.y;
     P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres; P.counter = h->counter.p;
@@ -193,6 +210,22 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
                                                          : mpcb::launch_smemk(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
     launches += 1;
+    if (h->ladder) {
+      // second rung: the problems that ran into the first pass's cap, from a cold start, with the stiffer state-box step sizes.
+      // No host round trip: the kernel reads the number of tickets from the counter block; with none, its CTAs exit at once.
+      CUDA_TRY(h->remap.ensure(Bn));
+      CUDA_TRY(cudaMemsetAsync(h->counter.p + 2, 0, sizeof(unsigned long long), st));
+      collect_unsolved_kernel<<<(unsigned)((Bn + 255) / 256), 256, 0, st>>>(d_status, Bn, h->remap.p, h->counter.p + 2);
+      CUDA_TRY(cudaGetLastError());
+      OnchipParams P2 = P;
+      P2.Tfrag = h->Tfrag2.p; P2.rho = h->rho2.p; P2.rinv = h->rinv2.p;
+      P2.max_iter = h->st.max_iter - h->st.ladder_iter; P2.iters_add = P.max_iter;
+      P2.warm_v = nullptr; P2.warm_y = nullptr;
+      P2.remap = h->remap.p; P2.batch_dev = h->counter.p + 2;
+      e = launch_onchip(h->NT, true, P2, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+      if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip (second rung) launch: ") + cudaGetErrorString(e));
+      launches += 2;
+    }
   } else {
     std::string err;
     mpcb::StreamBatch sb;
@@ -306,6 +339,15 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs a box-only problem with 64 < nz <= 120 that fits 227 KB"); }
   if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;
+  // rho ladder: only where it applies -- inequality general rows (state box; the ball rows are not boxes) on the on-chip kernel
+  if (st.ladder_iter > 0 && kernel == MPCB_KERNEL_ONCHIP && D.mg > D.nball && desc->state_constraint) {
+    if (st.ladder_iter >= st.max_iter) { delete h; return fail(MPCB_ERR_INVALID, "settings.ladder_iter must be below max_iter"); }
+    h->st.ladder_iter = ((st.ladder_iter + st.check_every - 1) / st.check_every) * st.check_every;
+    if (h->st.ladder_kappa <= 0) h->st.ladder_kappa = 10;
+    rc = mpcb::build_design(*desc, st, h->D2, err, (double)h->st.ladder_kappa);
+    if (rc != MPCB_OK) { delete h; return fail(rc, "second rung of the rho ladder: " + err); }
+    h->ladder = true;
+  }
   h->NT = (kernel == MPCB_KERNEL_STREAMED) ? mpcb::stream_padded(D.nt) : nt8;
   h->info.nt_pad = h->NT;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
@@ -324,7 +366,8 @@ void mpcb_destroy(mpcb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->st.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (DevBuf<double>* b : {&h->Tfrag, &h->Cfrag, &h->Lt, &h->lo, &h->hi, &h->rho, &h->rinv, &h->A, &h->B, &h->Q, &h->R, &h->S, &h->P, &h->x0,
+  h->remap.release();
+  for (DevBuf<double>* b : {&h->Tfrag, &h->Cfrag, &h->Lt, &h->lo, &h->hi, &h->rho, &h->rinv, &h->Tfrag2, &h->rho2, &h->rinv2, &h->A, &h->B, &h->Q, &h->R, &h->S, &h->P, &h->x0,
                             &h->xref, &h->uref, &h->warm_v, &h->warm_y, &h->v, &h->y, &h->pres, &h->dres, &h->u, &h->e_u, &h->x, &h->e_x,
                             &h->u0, &h->obj})
     b->release();

@@ -20,7 +20,9 @@ struct MpcbSettings
     eps_abs::Cdouble; eps_rel::Cdouble; eps_prim_inf::Cdouble; rho::Cdouble; rho_eq_scale::Cdouble
     sigma::Cdouble; alpha::Cdouble
     max_iter::Int32; check_every::Int32; device::Int32; kernel::Int32
-    reserved::NTuple{4,Int32}
+    ladder_iter::Int32          # rho ladder for state-box rows (0: off), see include/mpcb200.h
+    ladder_kappa::Int32
+    reserved::NTuple{2,Int32}
 end
 
 struct MpcbLinearDesc

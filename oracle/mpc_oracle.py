@@ -314,6 +314,7 @@ class AdmmSettings:
     eps_prim_inf: float = 1e-4
     max_iter: int = 4000
     check_every: int = 25
+    ineq_scale: float = 1.0   # multiplies the step size of the inequality general rows (second rung of the rho ladder)
 
 
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_PRIMAL_INF = 1, -2, -3
@@ -330,7 +331,7 @@ def admm_matrices(c: CondensedQP, s: AdmmSettings):
     OSQP's row equilibration of the constraint matrix amounts to for a per-row step size."""
     nz, mg = c.nz, c.mg
     rho = s.rho if s.rho > 0 else auto_rho(c.Pc)
-    rho_g = np.where(c.eq_mask, s.rho_eq_scale * rho, rho) / np.maximum((c.G ** 2).sum(1), 1e-12)   # row-equilibrated step sizes
+    rho_g = np.where(c.eq_mask, s.rho_eq_scale * rho, s.ineq_scale * rho) / np.maximum((c.G ** 2).sum(1), 1e-12)   # row-equilibrated step sizes
     if c.nball:      # the projection onto a ball is closed-form only for one common step size on its rows
         rho_g[:c.nball] = rho / np.maximum((c.G[:c.nball] ** 2).sum(1).mean(), 1e-12)
     K = c.Pc + (s.sigma + rho) * np.eye(nz) + c.G.T @ (rho_g[:, None] * c.G)
@@ -421,6 +422,23 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
 # --------------------------------------------------------------------------------------------------
 # Exact solve (ground truth): primal-dual active set + KKT certificate
 # --------------------------------------------------------------------------------------------------
+def admm_condensed_ladder(c: CondensedQP, p, s: AdmmSettings, ladder_iter, kappa=10.0):
+    """Twin of the rho ladder (settings.ladder_iter / ladder_kappa, mpcb_api.cu): a first pass capped at ladder_iter iterations;
+    the problems it leaves unsolved are re-solved from a cold start with the step size of the inequality general rows
+    multiplied by kappa, for the remaining max_iter - ladder_iter iterations; their iteration counts continue from the cap."""
+    ladder_iter = -(-ladder_iter // s.check_every) * s.check_every
+    rho = s.rho if s.rho > 0 else auto_rho(c.Pc)
+    r = admm_condensed(c, p, dataclasses.replace(s, rho=rho, max_iter=ladder_iter))
+    idx = np.flatnonzero(r["status"] == STATUS_MAX_ITER)
+    if idx.size:
+        r2 = admm_condensed(c, np.atleast_2d(p)[idx], dataclasses.replace(s, rho=rho, max_iter=s.max_iter - ladder_iter, ineq_scale=float(kappa)))
+        for k in r:
+            if isinstance(r[k], np.ndarray) and r[k].shape[:1] == r["status"].shape and k in r2: r[k][idx] = r2[k]
+        r["iters"][idx] = r2["iters"] + ladder_iter
+    r["second_rung"] = idx
+    return r
+
+
 def qp_exact(c: CondensedQP, p, v_init=None, tol=1e-9, max_pdas=60):
     """Exact optimum of ONE condensed problem (strictly convex => the KKT point is unique).  Handles box
     rows and EQUALITY general rows (terminal constraint); inequality general rows are not supported here.

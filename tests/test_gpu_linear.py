@@ -497,3 +497,41 @@ def test_c_abi_error_behaviour(mpc, qt):
     mpc.update_initialization(Cs, x0b, references=(xrefb, urefb))
     r = mpc.calculate(Cs)
     assert (r["status"] == -2).all() and (r["iters"] == 10).all()
+
+
+def test_rho_ladder_bounds_the_state_box_tail(mpc, qt):
+    """settings.ladder_iter / ladder_kappa: with active state-box rows a batch-wide fixed rho leaves a few problems per 10^4 with
+    thousands of iterations (OSQP adapts rho per problem there).  The ladder re-solves what the first pass leaves unsolved with a
+    second cached operator (state-box step sizes x kappa).  CUDA vs the twin of the same two-pass scheme: same problems on the
+    second rung, same iteration counts, same solutions; and against the single-pass solve: same optima, a bounded tail."""
+    H, n, eps = 10, 20000, 1e-7
+    xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    kw = dict(mpc_solver="b200", mpc_state_constraint=True, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    C1 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), **kw)
+    C2 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_b200_ladder_iter=300, mpc_b200_ladder_kappa=10, **kw)
+    rng = np.random.default_rng(7)
+    xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    out = []
+    for C in (C1, C2):
+        mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
+        out.append({k: v.copy() for k, v in mpc.calculate(C).items()})
+    one, two = out
+    assert (one["status"] == 1).all() and (two["status"] == 1).all()
+    second = one["iters"] > 300
+    assert 5 <= second.sum() <= n // 50                                  # a thin tail ...
+    assert one["iters"].max() > 3000 and two["iters"].max() < 0.4 * one["iters"].max()     # ... that the second rung cuts
+    assert np.array_equal(one["iters"][~second], two["iters"][~second]) and np.array_equal(one["u"][~second], two["u"][~second])
+    # the stragglers are the ill-conditioned problems (flat directions of the objective): both solves meet the same residual tolerance,
+    # the objective agrees to the parity tolerance, the inputs of the worst straggler to a few 1e-4
+    assert mo.u0_metric(one["u"][:, 0], two["u"][:, 0], qt["umin"], qt["umax"]).max() < 5e-4 and np.abs(one["u"] - two["u"]).max() < 5e-3
+    assert (np.abs(one["objective"] - two["objective"]) <= 1e-6 * np.abs(one["objective"])).all()
+    # the twin of the two-pass scheme
+    P = C2.tuning.terminal_ingredient.P
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], xmin, xmax, state_constraint=True)
+    sel = np.concatenate([np.flatnonzero(second), np.flatnonzero(~second)[:500]])
+    tw = mo.admm_condensed_ladder(c, mo.pack_params(x0[sel], xref[sel], qt["u_ref"]),
+                                  mo.AdmmSettings(rho=C2.tuning.modeler.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000), 300, 10.0)
+    assert set(tw["second_rung"]) == set(range(int(second.sum())))
+    assert (tw["status"] == 1).all() and (two["iters"][sel] == tw["iters"]).mean() > 0.97
+    assert np.abs(two["u"][sel].reshape(len(sel), -1) - tw["v"]).max() < 1e-5

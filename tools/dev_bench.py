@@ -6,7 +6,7 @@ import almpc_b200 as mpc
 from almpc_b200 import _lib
 import bench
 
-def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000):
+def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0):
     """near > 0: x0 = x_ref + near * N(0, I) with the design reference (feasible terminal constraints); state_box: tight box + references beyond it"""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     if state_box: xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
@@ -15,6 +15,7 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     if state_box: extra["mpc_state_constraint"] = True
     if Qw is not None: extra["mpc_Q"] = Qw
     if Rw is not None: extra["mpc_R"] = Rw
+    if ladder: extra["mpc_b200_ladder_iter"] = ladder
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_terminal_ingredient=terminal,
                                mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho,
                                mpc_b200_max_iter=max_iter, **extra)
@@ -44,7 +45,7 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     fl = bench.algorithmic_flops(m.info, it, check)
     ms = min(ts)
     print(json.dumps({"H": H, "n": n, "eps": eps, "check": check, "sigma": sigma, "terminal": terminal, "state_box": state_box, "kernel": m.info.kernel, "nt": m.info.nt,
-                      "full": full, "ms": round(ms, 4), "max_iters": int(it.max()),
+                      "full": full, "ladder": ladder, "ms": round(ms, 4), "max_iters": int(it.max()),
                       "mean_iters": round(float(it.mean()), 2), "solves_per_s": round(n / ms * 1e3), "tflops": round(fl / ms / 1e9, 2),
                       "frac": round(fl / ms / 1e9 / bench.FP64_PEAK_TFLOPS, 3), "solved": float((status.cpu().numpy() == 1).mean()), "rho": round(m.info.rho, 4)}), flush=True)
 
@@ -158,6 +159,7 @@ if __name__ == "__main__":
     elif a.set == "rows":        # general-row variants of the QT controller (a3 / a4 rows of SURVEY 8a)
         run(20, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.002, reps=3)
         run(10, 65536, 1e-7, 5, 0.0, state_box=True, reps=3)
+        run(10, 65536, 1e-7, 5, 0.0, state_box=True, reps=3, ladder=300)      # rho ladder: second rung for the tail
         run(20, 16384, 1e-7, 5, 0.0, state_box=True, reps=2)
         run(3, 65536, 1e-8, 5, 0.0, terminal="contractive", near=0.15, Qw=1.0, Rw=10.0, reps=3)
     elif a.set == "nmpc":
