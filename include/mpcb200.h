@@ -74,7 +74,7 @@ typedef struct {
   int32_t device;       /* CUDA device ordinal this handle lives on */
   int32_t kernel;       /* MPCB_KERNEL_* */
   int32_t ladder_iter;  /* 0 (off).  > 0: rho ladder for controllers with state-box rows on the on-chip kernel -- problems still unsolved
-                           after ladder_iter iterations are re-solved from a cold start with the step size of the state-box rows
+                           after ladder_iter iterations continue from their iterate with the step size of the state-box rows
                            multiplied by ladder_kappa (a second cached operator), for the remaining max_iter - ladder_iter iterations.
                            A batch-wide fixed rho leaves a few problems per 10^4 with thousands of iterations when many state
                            bounds are active (OSQP would adapt rho per problem); the second rung bounds that tail. */

@@ -424,14 +424,15 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
 # --------------------------------------------------------------------------------------------------
 def admm_condensed_ladder(c: CondensedQP, p, s: AdmmSettings, ladder_iter, kappa=10.0):
     """Twin of the rho ladder (settings.ladder_iter / ladder_kappa, mpcb_api.cu): a first pass capped at ladder_iter iterations;
-    the problems it leaves unsolved are re-solved from a cold start with the step size of the inequality general rows
+    the problems it leaves unsolved continue from their iterate (x, y) with the step size of the inequality general rows
     multiplied by kappa, for the remaining max_iter - ladder_iter iterations; their iteration counts continue from the cap."""
     ladder_iter = -(-ladder_iter // s.check_every) * s.check_every
     rho = s.rho if s.rho > 0 else auto_rho(c.Pc)
     r = admm_condensed(c, p, dataclasses.replace(s, rho=rho, max_iter=ladder_iter))
     idx = np.flatnonzero(r["status"] == STATUS_MAX_ITER)
     if idx.size:
-        r2 = admm_condensed(c, np.atleast_2d(p)[idx], dataclasses.replace(s, rho=rho, max_iter=s.max_iter - ladder_iter, ineq_scale=float(kappa)))
+        r2 = admm_condensed(c, np.atleast_2d(p)[idx], dataclasses.replace(s, rho=rho, max_iter=s.max_iter - ladder_iter, ineq_scale=float(kappa)),
+                            v0=r["v"][idx], y0=r["y"][idx])
         for k in r:
             if isinstance(r[k], np.ndarray) and r[k].shape[:1] == r["status"].shape and k in r2: r[k][idx] = r2[k]
         r["iters"][idx] = r2["iters"] + ladder_iter
