@@ -301,7 +301,7 @@ typedef struct {
 
 typedef struct {
   mpcb_settings qp;        /* inner ADMM; defaults: eps_abs = 1e-9, eps_rel = 0 (|q| is the cost gradient, so a relative dual
-                              tolerance would be far looser than the SQP step tolerance), check_every = 5, sigma = 0, rest as OSQP */
+                              tolerance would be far looser than the SQP step tolerance), check_every = 5, sigma = 0, max_iter = 1000 per QP, rest as OSQP */
   double sqp_tol;          /* stop when the SQP step ||d||_inf <= sqp_tol          (1e-6) */
   double ls_armijo;        /* sufficient-decrease constant                           (1e-4) */
   double ls_noise;         /* round-off floor of a cost evaluation, relative to max(1,|J|): added to the Armijo bound (1e-10) */

@@ -194,7 +194,7 @@ def linearize_trajectory(m, Q, P, Hc, u, x0, xref, uref):
 
 @dataclasses.dataclass
 class SqpSettings:
-    qp: mo.AdmmSettings = dataclasses.field(default_factory=lambda: mo.AdmmSettings(eps_abs=1e-9, eps_rel=0.0, sigma=0.0, check_every=5))
+    qp: mo.AdmmSettings = dataclasses.field(default_factory=lambda: mo.AdmmSettings(eps_abs=1e-9, eps_rel=0.0, sigma=0.0, check_every=5, max_iter=1000))
     sqp_max_iter: int = 20
     sqp_tol: float = 1e-6         # ||step||_inf
     ls_max: int = 12              # Armijo halvings

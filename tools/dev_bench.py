@@ -174,6 +174,11 @@ if __name__ == "__main__":
     elif a.set == "relinscale":
         for n in (4096, 16384, 32768, 65536, 131072):
             run_nmpc("qt_fnn_tanh_model.json", H=20, n=n, method="linear", reps=3)
+    elif a.set == "relucap":     # the reference's relu FNN fixture: how much of its time is the inner iteration cap of non-converging QPs
+        for cap in (4000, 1000, 500, 200):
+            run_nmpc("qt_fnn_model.json", mpc_b200_max_iter=cap)
+        for cap in (4000, 500, 200):
+            run_nmpc("qt_fnn_tanh_model.json", mpc_b200_max_iter=cap)
     elif a.set == "relin1":
         run_nmpc("qt_fnn_tanh_model.json", H=20, n=16384, method="linear", reps=1)
     elif a.set == "nmpc1":
