@@ -152,3 +152,33 @@ def test_relinearized_design_failure_is_reported_per_problem(mpc):
     for i in (0, 11):
         v, _ = mo.qp_exact(c, mo.pack_params(x0[i], np.zeros(2), np.zeros(1))[0])
         assert np.abs(r2["u"][i].ravel() - v).max() < 1e-7
+
+
+def test_c_abi_error_behaviour_of_the_design_entries(mpc, qt):
+    """Return codes + mpcb_last_error for the nonlinear / device-design entry points (no exceptions across the boundary)."""
+    import ctypes as C
+    L = mpc._lib.lib(); lib = mpc._lib
+    m = load_nn_fixture("qt_fnn_tanh_model.json")
+    mod = mpc.B200NonlinearModeler(to_chain(mpc, m), qt["Q"], qt["R"], qt["S"], None, qt["umin"], qt["umax"], None, None, 5, qt["x_ref"], qt["u_ref"])
+    io = lib.BatchIO(); io.batch = 3
+    for fn in (L.mpcb_solve_relinearized_batch, L.mpcb_solve_nmpc_batch):
+        assert fn(mod._h, C.byref(io)) == -1 and b"x0" in L.mpcb_last_error()                    # missing inputs
+        assert fn(None, C.byref(io)) == -1
+    x0 = np.zeros((3, 4)); io.x0 = x0.ctypes.data; io.xref = x0.ctypes.data; io.uref = x0.ctypes.data; io.batch = 0
+    assert L.mpcb_solve_relinearized_batch(mod._h, C.byref(io)) == -1 and b"batch" in L.mpcb_last_error()
+    cio = lib.ClosedLoopIO(); cio.batch = 3; cio.steps = 0; cio.x0 = x0.ctypes.data; cio.xref = x0.ctypes.data; cio.uref = x0.ctypes.data
+    assert L.mpcb_closed_loop_nmpc_batch(mod._h, C.byref(cio)) == -1 and b"steps" in L.mpcb_last_error()
+    # batched Riccati equations
+    p = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    A = np.zeros((2, 4)); B = np.zeros((2, 2)); Q = np.eye(2); R = np.eye(1); P = np.zeros((2, 4))
+    assert L.mpcb_dare_batch(0, 0, 2, 1, p(A), p(B), p(Q), p(R), p(P), None) == -1 and b"bad arguments" in L.mpcb_last_error()
+    assert L.mpcb_dare_batch(99, 2, 2, 1, p(A), p(B), p(Q), p(R), p(P), None) == -1 and b"device" in L.mpcb_last_error()
+    B7 = np.zeros((2, 14)); R7 = np.eye(7)
+    assert L.mpcb_dare_batch(0, 2, 2, 7, p(A), p(B7), p(Q), p(R7), p(P), None) == -1 and b"nu <= 3 nx" in L.mpcb_last_error()
+    # design-time refusals of the nonlinear controller
+    with pytest.raises(mpc.MpcbError, match="not supported"):
+        mpc.B200NonlinearModeler(to_chain(mpc, m), qt["Q"], qt["R"], qt["S"], None, qt["umin"], qt["umax"], None, None, 5, qt["x_ref"], qt["u_ref"], terminal="neighborhood")
+    with pytest.raises(mpc.MpcbError, match="xmin"):
+        mpc.B200NonlinearModeler(to_chain(mpc, m), qt["Q"], qt["R"], qt["S"], None, qt["umin"], qt["umax"], None, None, 5, qt["x_ref"], qt["u_ref"], state_constraint=True)
+    with pytest.raises(mpc.MpcbError, match="128"):
+        mpc.B200NonlinearModeler(to_chain(mpc, m), qt["Q"], qt["R"], qt["S"], None, qt["umin"], qt["umax"], None, None, 70, qt["x_ref"], qt["u_ref"])
