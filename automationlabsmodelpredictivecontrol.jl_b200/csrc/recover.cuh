@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
 // runs for u / e_u at NX=4, NU=2).  History (profiles/r01/recover_qt_h20_ncu_full*.txt): with per-lane 16-byte stores
 // every store instruction touched 32 different 128-byte lines, the kernel sat on lg/mio-throttle and long-scoreboard
 // stalls and reached 1.5 TB/s.
-constexpr int RECOVER_RCH = 4;
+#ifndef MPCB_RECOVER_RCH
+#define MPCB_RECOVER_RCH 2     // steps per staged chunk.  Measured on B200 (QT, 65536 problems, solve + recover): 4 -> 0.577 ms (67 KB per CTA,
+#endif                         // 3 CTAs/SM: the 512 CTAs need 1.15 waves), 3 -> 0.572, 2 -> 0.560 (39 KB, 5 CTAs/SM, one wave), 1 -> 0.581
+constexpr int RECOVER_RCH = MPCB_RECOVER_RCH;
 template <int NX, int NU>
 __host__ __device__ constexpr int recover_small_warp_doubles() {
   return 32 * (2 * (RECOVER_RCH * NX + 2) + 3 * (RECOVER_RCH * NU + 2));
