@@ -133,13 +133,13 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
 // runs for u / e_u at NX=4, NU=2).  History (profiles/r01/recover_qt_h20_ncu_full*.txt): with per-lane 16-byte stores
 // every store instruction touched 32 different 128-byte lines, the kernel sat on lg/mio-throttle and long-scoreboard
 // stalls and reached 1.5 TB/s.
-#ifndef MPCB_RECOVER_RCH
-#define MPCB_RECOVER_RCH 2     // steps per staged chunk.  Measured on B200 (QT, 65536 problems, solve + recover): 4 -> 0.577 ms (67 KB per CTA,
-#endif                         // 3 CTAs/SM: the 512 CTAs need 1.15 waves), 3 -> 0.572, 2 -> 0.560 (39 KB, 5 CTAs/SM, one wave), 1 -> 0.581
-constexpr int RECOVER_RCH = MPCB_RECOVER_RCH;
-template <int NX, int NU>
+// RCH = steps per staged chunk, two instantiations.  Measured on B200 (QT, solve + recover): 65536 problems: 4 -> 0.577 ms (67 KB per
+// CTA, 3 CTAs/SM: the 512 CTAs need 1.15 waves), 3 -> 0.572, 2 -> 0.560 (39 KB, 5 CTAs/SM, one wave), 1 -> 0.581; one problem (the
+// closed-loop latency path): 4 -> 24 us, 2 -> 28 us (more passes over the horizon).  So: 2 for batches, 4 for a handful of problems.
+constexpr int RECOVER_RCH_BATCH = 2, RECOVER_RCH_FEW = 4;
+template <int NX, int NU, int RCH>
 __host__ __device__ constexpr int recover_small_warp_doubles() {
-  return 32 * (2 * (RECOVER_RCH * NX + 2) + 3 * (RECOVER_RCH * NU + 2));
+  return 32 * (2 * (RCH * NX + 2) + 3 * (RCH * NU + 2));
 }
 
 // moves a [32 problems][n doubles] tile (pitch `pitch`) between shared memory and rows of global memory that are
@@ -162,17 +162,17 @@ __device__ __forceinline__ void warp_tile_copy(double* tile, int pitch, double* 
   }
 }
 
-template <int NX, int NU>
+template <int NX, int NU, int RCH>
 __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const RecoverParams P) {
   __shared__ double sA[NX * NX], sB[NX * NU], sQ[NX * NX], sPt[NX * NX], sR[NU * NU], sS[NU * NU];
   extern __shared__ __align__(16) double tiles[];
-  constexpr int RCH = RECOVER_RCH, PX = RCH * NX + 2, PU = RCH * NU + 2;
+  constexpr int PX = RCH * NX + 2, PU = RCH * NU + 2;
   const int tid = threadIdx.x, H = P.H, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < NX * NX; i += RECOVER_THREADS) { sA[i] = P.A[i]; sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
   for (int i = tid; i < NX * NU; i += RECOVER_THREADS) sB[i] = P.B[i];
   for (int i = tid; i < NU * NU; i += RECOVER_THREADS) { sR[i] = P.R[i]; sS[i] = P.S ? P.S[i] : 0.0; }
   __syncthreads();
-  double* tX = tiles + warp * recover_small_warp_doubles<NX, NU>();
+  double* tX = tiles + warp * recover_small_warp_doubles<NX, NU, RCH>();
   double* tEX = tX + 32 * PX;
   double* tV = tEX + 32 * PX;
   double* tU = tV + 32 * PU;
@@ -280,20 +280,26 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const Re
 // returns false when no specialisation exists (caller falls back to recover_kernel)
 inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
   const unsigned grid = (unsigned)((R.batch + RECOVER_THREADS - 1) / RECOVER_THREADS);
-#define MPCB_RS(NX_, NU_) \
-  if (R.nx == NX_ && R.nu == NU_) {                                                                                       \
-    constexpr size_t smem = sizeof(double) * (RECOVER_THREADS / 32) * recover_small_warp_doubles<NX_, NU_>();              \
-    static bool attr_set = false;                                                                                       \
-    if (smem > 48 * 1024 && !attr_set) {                                                                                \
-      cudaFuncSetAttribute(recover_small_kernel<NX_, NU_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-      attr_set = true;                                                                                                  \
-    }                                                                                                                   \
-    recover_small_kernel<NX_, NU_><<<grid, RECOVER_THREADS, smem, st>>>(R);                                             \
-    return true;                                                                                                        \
+#define MPCB_RS1(NX_, NU_, RCH_)                                                                                           \
+  {                                                                                                                        \
+    constexpr size_t smem = sizeof(double) * (RECOVER_THREADS / 32) * recover_small_warp_doubles<NX_, NU_, RCH_>();         \
+    static bool attr_set = false;                                                                                         \
+    if (smem > 48 * 1024 && !attr_set) {                                                                                  \
+      cudaFuncSetAttribute(recover_small_kernel<NX_, NU_, RCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      attr_set = true;                                                                                                    \
+    }                                                                                                                     \
+    recover_small_kernel<NX_, NU_, RCH_><<<grid, RECOVER_THREADS, smem, st>>>(R);                                         \
+    return true;                                                                                                          \
+  }
+#define MPCB_RS(NX_, NU_)                                                    \
+  if (R.nx == NX_ && R.nu == NU_) {                                          \
+    if (R.batch >= 4096) MPCB_RS1(NX_, NU_, RECOVER_RCH_BATCH)               \
+    MPCB_RS1(NX_, NU_, RECOVER_RCH_FEW)                                      \
   }
   MPCB_RS(2, 1) MPCB_RS(2, 2) MPCB_RS(3, 1) MPCB_RS(3, 2) MPCB_RS(4, 1) MPCB_RS(4, 2) MPCB_RS(4, 4) MPCB_RS(6, 2) MPCB_RS(6, 3)
   MPCB_RS(8, 2) MPCB_RS(8, 4)
 #undef MPCB_RS
+#undef MPCB_RS1
   return false;
 }
 
