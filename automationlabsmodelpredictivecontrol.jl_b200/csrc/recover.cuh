@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
 // stalls and reached 1.5 TB/s.
 // RCH = steps per staged chunk, two instantiations.  Measured on B200 (QT, solve + recover): 65536 problems: 4 -> 0.577 ms (67 KB per
 // CTA, 3 CTAs/SM: the 512 CTAs need 1.15 waves), 3 -> 0.572, 2 -> 0.560 (39 KB, 5 CTAs/SM, one wave), 1 -> 0.581; one problem (the
-// closed-loop latency path): 4 -> 24 us, 2 -> 28 us (more passes over the horizon).  So: 2 for batches, 4 for a handful of problems.
+// closed-loop latency path): 4 -> 24 us, 2 -> 28 us (more passes over the horizon); 8192-problem chunks of the pipelined host entry:
+// 2 -> 34 us.  So: 2 only when the 4-step version would not fit one wave (more than 3 CTAs x 148 SMs), 4 otherwise.
 constexpr int RECOVER_RCH_BATCH = 2, RECOVER_RCH_FEW = 4;
 template <int NX, int NU, int RCH>
 __host__ __device__ constexpr int recover_small_warp_doubles() {
@@ -293,7 +294,7 @@ inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
   }
 #define MPCB_RS(NX_, NU_)                                                    \
   if (R.nx == NX_ && R.nu == NU_) {                                          \
-    if (R.batch >= 4096) MPCB_RS1(NX_, NU_, RECOVER_RCH_BATCH)               \
+    if (grid > 444) MPCB_RS1(NX_, NU_, RECOVER_RCH_BATCH)                    \
     MPCB_RS1(NX_, NU_, RECOVER_RCH_FEW)                                      \
   }
   MPCB_RS(2, 1) MPCB_RS(2, 2) MPCB_RS(3, 1) MPCB_RS(3, 2) MPCB_RS(4, 1) MPCB_RS(4, 2) MPCB_RS(4, 4) MPCB_RS(6, 2) MPCB_RS(6, 3)
