@@ -17,17 +17,19 @@
 
 namespace mpcb {
 
-constexpr int SMEMK_WARPS = 4;
-constexpr int SMEMK_THREADS = SMEMK_WARPS * 32;
+// W warps per CTA, one CTA per SM: 8 (two warps per scheduler, so that one warp's elementwise phase hides under the other's DMMAs:
+// 0.76 vs 0.57 of the pipe in the steady-state measurement of DESIGN 5.1) wherever T and 8 state slices fit 227 KB (NT <= 96 for
+// sigma = 0), else 6, 5 or 4 (admm_smem.cu).
 
 // shared memory: T fragments NT*NT, lo/hi and their integer keys (admm_onchip.cuh: dkey) NT each, per-warp parameter staging [8][npad], per-warp state (3 or 4) x KS x 32
-__host__ __device__ inline size_t smemk_bytes(int NT, int np, bool sig) {
+__host__ __device__ inline size_t smemk_bytes(int NT, int np, bool sig, int W) {
   const int npad = (np + 1) & ~1;
-  return sizeof(double) * ((size_t)NT * NT + 4 * NT + (size_t)SMEMK_WARPS * 8 * npad + (size_t)SMEMK_WARPS * (sig ? 4 : 3) * (NT / 4) * 32);
+  return sizeof(double) * ((size_t)NT * NT + 4 * NT + (size_t)W * 8 * npad + (size_t)W * (sig ? 4 : 3) * (NT / 4) * 32);
 }
 
-template <int NT, bool SIG>
-__global__ void __launch_bounds__(SMEMK_THREADS, 1) admm_smem_kernel(const OnchipParams P) {
+template <int NT, bool SIG, int W>
+__global__ void __launch_bounds__(W * 32, 1) admm_smem_kernel(const OnchipParams P) {
+  constexpr int SMEMK_WARPS = W, SMEMK_THREADS = W * 32;
   constexpr int EPL = NT / 4, KS = NT / 4, NTL = NT / 8;
   extern __shared__ __align__(16) double smem[];
   double* sT = smem;

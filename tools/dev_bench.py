@@ -179,6 +179,9 @@ if __name__ == "__main__":
             run_nmpc("qt_fnn_model.json", mpc_b200_max_iter=cap)
         for cap in (4000, 500, 200):
             run_nmpc("qt_fnn_tanh_model.json", mpc_b200_max_iter=cap)
+    elif a.set == "smemk":       # shared-memory kernel range (64 < nt <= 120)
+        for H in (36, 40, 44, 48, 50, 60):
+            run(H, 16384, 1e-7, 5, 0.0, reps=3)
     elif a.set == "relin1":
         run_nmpc("qt_fnn_tanh_model.json", H=20, n=16384, method="linear", reps=1)
     elif a.set == "nmpc1":

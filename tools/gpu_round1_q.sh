@@ -15,4 +15,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:nmpc
 timeout 300 python tools/dev_bench.py --set nmpc > gpurun_out/nmpc_config5_q.jsonl 2>&1
 timeout 300 python tools/dev_bench.py --set relin > gpurun_out/relin_q.jsonl 2>&1
 timeout 300 python tools/dev_bench.py --set rows > gpurun_out/rows_q.jsonl 2>&1
+timeout 300 python tools/dev_bench.py --set smemk > gpurun_out/smemk_q.jsonl 2>&1
+timeout 300 python tools/dev_bench.py --set hsweep > gpurun_out/hsweep_q.jsonl 2>&1
 ls -la gpurun_out/*_q*
