@@ -126,11 +126,15 @@ constexpr bool R_SMEM = MPCB_R_SMEM != 0;
 constexpr int ONCHIP_THREADS = 128;
 constexpr int ONCHIP_WARPS = ONCHIP_THREADS / 32;
 
+// per-warp [row][lane] slices of the box-only path: x~ and y+ of the checking iteration, plus the operand r when one of the
+// experiment knobs that stage it is on
+constexpr int ONCHIP_SLICES = (MPCB_R_SMEM != 0 || MPCB_FUSED_ED != 0) ? 3 : 2;
+
 // shared memory: T, C fragments, Lt, lo, hi, rho, rinv, then per-warp parameter staging [8][npad]
 __host__ __device__ inline size_t onchip_smem_bytes(int NT, int np, bool has_g) {
   int npad = (np + 1) & ~1;
   return sizeof(double) * ((size_t)(has_g ? 2 : 1) * NT * NT + (size_t)np * NT + 4 * NT + (size_t)ONCHIP_WARPS * 8 * npad +
-                           (has_g ? 0 : (size_t)ONCHIP_WARPS * (NT / 4) * 32 * 3));
+                           (has_g ? 0 : (size_t)ONCHIP_WARPS * (NT / 4) * 32 * ONCHIP_SLICES));
 }
 
 // NT: padded operator size; HAS_G: general rows present; SIG: sigma != 0 (box-only kernels drop the x state otherwise)
@@ -155,9 +159,9 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
   // (fully unrolled, ptxas chains the DMMAs of one accumulator back to back: 26-cycle dependent latency vs a 16-cycle
   // issue interval).  Measured on B200 (QT, H=20, 65536 problems): 0.531 ms staged vs 0.493 ms with r in registers --
   // the extra LDS/STS traffic costs more than the chaining, which three warps per scheduler already hide.
-  double* sR = sRinv + NT + ONCHIP_WARPS * 8 * npad + (threadIdx.x >> 5) * KS * 32 * 3 + (threadIdx.x & 31);
-  double* sXt = sR + KS * 32;   // candidate solution x~ / y+ of the checking iteration, same [row][lane] layout
+  double* sXt = sRinv + NT + ONCHIP_WARPS * 8 * npad + (threadIdx.x >> 5) * KS * 32 * ONCHIP_SLICES + (threadIdx.x & 31);   // x~ / y+ of the checking iteration, [row][lane]
   double* sYo = sXt + KS * 32;
+  double* sR = sYo + (ONCHIP_SLICES == 3 ? KS * 32 : 0);   // only with a staging knob on (aliases y+ otherwise and is never touched)
 
   for (int i = threadIdx.x; i < NT * NT; i += ONCHIP_THREADS) {
     sT[i] = P.Tfrag[i];

@@ -183,7 +183,8 @@ if __name__ == "__main__":
         for H in (36, 40, 44, 48, 50, 60):
             run(H, 16384, 1e-7, 5, 0.0, reps=3)
     elif a.set == "h24":
-        run(24, 65536, 1e-7, 5, 0.0, reps=3)
+        for H in (24, 28, 32):
+            run(H, 65536, 1e-7, 5, 0.0, reps=3)
     elif a.set == "relin1":
         run_nmpc("qt_fnn_tanh_model.json", H=20, n=16384, method="linear", reps=1)
     elif a.set == "nmpc1":
