@@ -114,8 +114,8 @@ cudaError_t launch_onchip_gs(int NT, const OnchipParams& P, int sm_count, int* c
     case 24: return launch_onchip_t<24, HAS_G, SIG, HAS_G ? 3 : 4>(P, sm_count, cache, st);
     case 32: return launch_onchip_t<32, HAS_G, SIG, HAS_G ? 2 : 4>(P, sm_count, cache, st);
     case 40: return launch_onchip_t<40, HAS_G, SIG, HAS_G ? 2 : 3>(P, sm_count, cache, st);
-    case 48: return launch_onchip_t<48, HAS_G, SIG, (HAS_G || SIG) ? 2 : 3>(P, sm_count, cache, st);      // box-only, sigma = 0: 170 registers at 2 CTAs/SM, fits 168 (3 CTAs/SM) without spills
-    case 56: return launch_onchip_t<56, HAS_G, SIG, (HAS_G || SIG) ? 2 : 3>(P, sm_count, cache, st);
+    case 48: return launch_onchip_t<48, HAS_G, SIG, HAS_G ? 2 : 3>(P, sm_count, cache, st);      // box-only: fits 168 registers (3 CTAs/SM) without spills, sigma = 0 or not
+    case 56: return launch_onchip_t<56, HAS_G, SIG, (HAS_G || SIG) ? 2 : 3>(P, sm_count, cache, st);      // sigma > 0 would spill at 168 registers
     case 64: return launch_onchip_t<64, HAS_G, SIG, (HAS_G || SIG) ? 2 : 3>(P, sm_count, cache, st);
     default: return cudaErrorInvalidValue;
   }

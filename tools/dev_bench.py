@@ -182,6 +182,8 @@ if __name__ == "__main__":
     elif a.set == "smemk":       # shared-memory kernel range (64 < nt <= 120)
         for H in (36, 40, 44, 48, 50, 60):
             run(H, 16384, 1e-7, 5, 0.0, reps=3)
+    elif a.set == "h24sig":
+        run(24, 65536, 1e-7, 5, 1e-6, reps=3)
     elif a.set == "h24":
         for H in (24, 28, 32):
             run(H, 65536, 1e-7, 5, 0.0, reps=3)
