@@ -182,6 +182,9 @@ if __name__ == "__main__":
     elif a.set == "smemk":       # shared-memory kernel range (64 < nt <= 120)
         for H in (36, 40, 44, 48, 50, 60):
             run(H, 16384, 1e-7, 5, 0.0, reps=3)
+    elif a.set == "small":       # small batches: about one problem per slot at full occupancy
+        for H, n in ((10, 16384), (20, 16384), (30, 16384), (20, 32768), (30, 32768), (20, 8192)):
+            run(H, n, 1e-7, 5, 0.0, reps=3)
     elif a.set == "h24sig":
         run(24, 65536, 1e-7, 5, 1e-6, reps=3)
     elif a.set == "h24":
