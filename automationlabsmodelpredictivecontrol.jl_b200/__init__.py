@@ -10,7 +10,7 @@ from .design_mpc import _DEFAULT_PARAMETERS_MODEL_PREDICTIVE_CONTROL, _model_pre
 from .main_mpc import _design_reference_mpc, proceed_controller
 from .modeler import B200Modeler
 from .nmpc import B200NonlinearModeler
-from .nn import DenseNet, Fnn, PolyNet, ResNet, linearize
+from .nn import DenseNet, Fnn, Icnn, PolyNet, Rbf, ResNet, linearize
 from .solver_selection import _IMPLEMENTATION_SOLVER_LIST, resolve_solver, solver_name
 from .systems import ConstrainedBlackBoxControlDiscreteSystem, ConstrainedLinearControlDiscreteSystem, Hyperrectangle
 from .types import (IMPLEMENTATION_PROGRAMMING_LIST, LinearProgramming, MixedIntegerLinearProgramming,

@@ -11,7 +11,7 @@ _PKG = pathlib.Path(__file__).resolve().parent
 LIB_PATH = pathlib.Path(os.environ["MPCB200_LIB"]) if os.environ.get("MPCB200_LIB") else _PKG / "libmpcb200.so"   # the override serves A/B builds of the kernels (tools/)
 
 MPCB_OK = 0
-KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED, KERNEL_ONCHIP_SMEM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_ONCHIP, KERNEL_STREAMED, KERNEL_ONCHIP_SMEM, KERNEL_RICCATI = 0, 1, 2, 3, 4
 TERMINAL_NONE, TERMINAL_EQUALITY, TERMINAL_CONTRACTIVE = 0, 1, 2
 STATUS_SOLVED, STATUS_SOLVED_INACCURATE, STATUS_MAX_ITER, STATUS_PRIMAL_INFEASIBLE, STATUS_DESIGN_FAILED = 1, 2, -2, -3, -20
 NN_FNN, NN_RESNET, NN_POLYNET, NN_DENSENET = 0, 1, 2, 3

@@ -35,7 +35,7 @@ def calculate(C: ModelPredictiveControlController, warm_start: bool = False, wan
     if m.x0 is None:
         raise RuntimeError("calculate!: call update_initialization! first")
     warm = m.warm if (warm_start and m.warm is not None and m.warm[0].shape[0] == m.x0.shape[0]) else None
-    w = tuple(want) + (("y",) if warm_start else ())
+    w = tuple(want) + (tuple(k for k in ("u", "y") if k not in want) if warm_start else ())
     res = m.solve_batch(m.x0, m.xref, m.uref, want=w, warm=warm)
     if warm_start:
         m.warm = (res["u"], res["y"])

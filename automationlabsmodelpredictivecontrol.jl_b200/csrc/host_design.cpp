@@ -221,6 +221,49 @@ bool dare_sda(const Mat& A, const Mat& B, const Mat& Q, const Mat& R, Mat& P, st
   return false;
 }
 
+// K x~ = r with K = Pc + (sigma + rho) I is the optimality system of
+//     min  sum_{k=1..H} 1/2 e_k' W_k e_k + sum_{k<H} (1/2 u_k' Rh u_k - r_k' u_k),   e_0 = 0,  e_{k+1} = A e_k + B u_k,
+// W_k = 2Q (k < H), 2P (k = H), Rh = 2R + (sigma + rho) I  (Pc of build_design below: the factor 2 is the reference's missing
+// 1/2, design_mpc.jl:436-465).  Backward Riccati recursion from Pi_H = W_H:
+//     Lam_k = Rh + B' Pi_{k+1} B,  K_k = Lam_k^-1 B' Pi_{k+1} A,  Acl_k = A - B K_k,  Pi_k = W_k + A' Pi_{k+1} Acl_k   (W_0 = 0)
+// The kernel needs K_k, K_k', Lam_k^-1, Acl_k, Acl_k' per stage (layout of admm_riccati.cu: every matrix row-major, padded to
+// an even number of doubles).
+bool riccati_factors(Design& D, double sigma) {
+  D.ric_stage.clear();
+  if (D.mg != 0 || D.use_S) return false;
+  const int nx = D.nx, nu = D.nu, H = D.H;
+  auto ev = [](int n) { return (n + 1) & ~1; };
+  const int oK = 0, oKT = oK + ev(nu * nx), oLI = oKT + ev(nx * nu), oACL = oLI + ev(nu * nu), oACLT = oACL + ev(nx * nx), SZ = oACLT + ev(nx * nx);
+  D.ric_stage.assign((size_t)H * SZ, 0.0);
+  Mat Rh(nu, nu);
+  for (int j = 0; j < nu; j++)
+    for (int i = 0; i < nu; i++) Rh(i, j) = (D.use_R ? 2.0 * D.R(i, j) : 0.0) + (i == j ? sigma + D.rho : 0.0);
+  Mat Pi(nx, nx);
+  for (size_t i = 0; i < Pi.a.size(); i++) Pi.a[i] = 2.0 * D.P.a[i];
+  const Mat At = transpose(D.A), Bt = transpose(D.B);
+  for (int k = H - 1; k >= 0; k--) {
+    const Mat PB = matmul(Pi, D.B);                         // nx x nu
+    const Mat Lam = add(Rh, matmul(Bt, PB));
+    Mat Li;
+    if (!spd_inverse(Lam, Li)) { D.ric_stage.clear(); return false; }
+    const Mat K = matmul(Li, matmul(transpose(PB), D.A));   // nu x nx   (Pi symmetric: B' Pi = (Pi B)')
+    const Mat Acl = add(D.A, matmul(D.B, K), -1.0);
+    double* st = &D.ric_stage[(size_t)k * SZ];
+    for (int i = 0; i < nu; i++)
+      for (int m = 0; m < nx; m++) { st[oK + i * nx + m] = K(i, m); st[oKT + m * nu + i] = K(i, m); }
+    for (int i = 0; i < nu; i++)
+      for (int l = 0; l < nu; l++) st[oLI + i * nu + l] = Li(i, l);
+    for (int m = 0; m < nx; m++)
+      for (int n = 0; n < nx; n++) { st[oACL + m * nx + n] = Acl(m, n); st[oACLT + n * nx + m] = Acl(m, n); }
+    Mat Pn = matmul(At, matmul(Pi, Acl));
+    if (k > 0)
+      for (size_t i = 0; i < Pn.a.size(); i++) Pn.a[i] += 2.0 * D.Q.a[i];
+    for (int j = 0; j < nx; j++)
+      for (int i = 0; i <= j; i++) { const double v = 0.5 * (Pn(i, j) + Pn(j, i)); Pi(i, j) = v; Pi(j, i) = v; }
+  }
+  return true;
+}
+
 int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, std::string& err, double ineq_scale) {
   if (d.nx <= 0 || d.nu <= 0 || d.horizon <= 0) { err = "nx, nu, horizon must be positive"; return MPCB_ERR_INVALID; }
   if (!d.A || !d.B || !d.Q || !d.R || !d.umin || !d.umax) { err = "A, B, Q, R, umin, umax are required"; return MPCB_ERR_INVALID; }
@@ -294,8 +337,11 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
   D.mg = mg; D.nt = nz + mg;
   D.G = Mat(mg, nz); D.Lb = Mat(mg, np);
   D.lo.assign(D.nt, 0.0); D.hi.assign(D.nt, 0.0); D.is_eq.assign(D.nt, 0);
+  // infinite bounds are legal for a Hyperrectangle; like OSQP (OSQP_INFTY) they are held as +-1e30 so that the support term of
+  // the infeasibility certificate never forms inf * 0
+  auto fin = [](double v) { return v > 1e30 ? 1e30 : (v < -1e30 ? -1e30 : v); };
   for (int k = 0; k < H; k++)
-    for (int j = 0; j < nu; j++) { D.lo[k * nu + j] = d.umin[j]; D.hi[k * nu + j] = d.umax[j]; }
+    for (int j = 0; j < nu; j++) { D.lo[k * nu + j] = fin(d.umin[j]); D.hi[k * nu + j] = fin(d.umax[j]); }
   int row = 0;
   auto add_rows = [&](int k, bool equality) {
     // Gam_k v in [lo,hi] + b,  b = -Phi_k x0 + (Phi_k - I*[!equality]) xref + Gam_k (1 (x) uref)
@@ -310,8 +356,8 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
         for (int kk = 0; kk < H; kk++) sacc += Gam[k](i, kk * nu + j);
         D.Lb(row, 2 * nx + j) = sacc;
       }
-      D.lo[nz + row] = equality ? 0.0 : d.xmin[i];
-      D.hi[nz + row] = equality ? 0.0 : d.xmax[i];
+      D.lo[nz + row] = equality ? 0.0 : fin(d.xmin[i]);
+      D.hi[nz + row] = equality ? 0.0 : fin(d.xmax[i]);
       D.is_eq[nz + row] = equality ? 1 : 0;
     }
   };
@@ -360,6 +406,7 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
     for (int i = 0; i < nz; i++) D.C(i, j) = D.Pc(i, j);
     for (int i = 0; i < mg; i++) { D.C(nz + i, j) = D.G(i, j); D.C(j, nz + i) = D.G(i, j); }
   }
+  if (nx <= 8 && nu <= 4) riccati_factors(D, s.sigma);      // stage-wise form of the same x-update (admm_riccati.cu), where it applies
   return MPCB_OK;
 }
 

@@ -58,9 +58,16 @@ struct Design {
   Mat C;    // nt x nt   [[Pc, G'],[G, 0]]
   Mat Ac;   // nt x nz   [I;G]  (certificate pass)
   double rho = 0, lmin = 0, lmax = 0;
+  // Stage-wise (Riccati) form of the x-update K x~ = r for box-only problems without the S term (admm_riccati.cu): per stage
+  // K_k, K_k', Lambda_k^-1, Acl_k, Acl_k' in the kernel's layout (ric_stage_doubles(nx, nu) doubles per stage); empty when
+  // the form does not apply (general rows, S term).
+  std::vector<double> ric_stage;
 };
 
 // ineq_scale multiplies the step size of the INEQUALITY general rows (state box): the second rung of the rho ladder (mpcb_api.cu)
+// cached factors of the LQ problem behind K = Pc + (sigma + rho) I (box-only, no S term): fills D.ric_stage
+bool riccati_factors(Design& D, double sigma);
+
 int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& out, std::string& err, double ineq_scale = 1.0);
 
 }  // namespace mpcb

@@ -14,6 +14,7 @@
 #include "../../include/mpcb200.h"
 #include "api_common.hpp"
 #include "admm_onchip.cuh"
+#include "admm_riccati.cuh"
 #include "admm_stream.cuh"
 #include "closed_loop.cuh"
 #include "host_design.hpp"
@@ -57,6 +58,11 @@ struct mpcb_handle {
   cudaEvent_t chunk_ev[16] = {};
   // per-system constants
   DevBuf<double> Tfrag, Cfrag, Lt, lo, hi, rho, rinv, A, B, Q, R, S, P;
+  DevBuf<double> ric_stage, ric_Lq;         // stage-wise (Riccati) kernel: per-stage factors, Lq row-major
+  DevBuf<double> rW, rQ, rD, rX, rXT, rYO;  // its tile workspaces [tiles][nz][32]
+  size_t smem_optin = 0;
+  cudaEvent_t busy_ev = nullptr;            // end of the last enqueued call: the next call's stream waits on it (one call in flight per handle)
+  bool busy_recorded = false;
   DevBuf<double> Tfrag2, rho2, rinv2;       // second rung of the rho ladder (settings.ladder_iter): operator and step sizes
   DevBuf<int32_t> remap;                    // problems the first pass left unsolved
   bool ladder = false;
@@ -156,7 +162,13 @@ int upload_design(mpcb_handle* h) {
   CUDA_TRY(upload(h->P, D.P.a.data(), D.P.a.size()));
   CUDA_TRY(h->counter.ensure(3));
   CUDA_TRY(cudaMemset(h->counter.p, 0, 3 * sizeof(unsigned long long)));   // once: the on-chip kernel re-arms it itself
-  if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
+  if (h->info.kernel == MPCB_KERNEL_RICCATI) {
+    std::vector<double> lq((size_t)D.nz * D.np);
+    for (int i = 0; i < D.nz; i++)
+      for (int j = 0; j < D.np; j++) lq[(size_t)i * D.np + j] = D.Lq(i, j);
+    CUDA_TRY(upload(h->ric_stage, D.ric_stage.data(), D.ric_stage.size()));
+    CUDA_TRY(upload(h->ric_Lq, lq.data(), lq.size()));
+  } else if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     const int NT = h->NT, nt = D.nt, np = D.np;
     std::vector<double> tf = to_fragments(D.T, nt, NT), cf = to_fragments(D.C, nt, NT);
     std::vector<double> Lt((size_t)np * NT, 0.0), lo(NT, 0.0), hi(NT, 0.0), rho(NT, 1.0), rinv(NT, 1.0);
@@ -203,7 +215,32 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
   if (!d_pres) { CUDA_TRY(h->pres.ensure(Bn)); d_pres = h->pres.p; }
   if (!d_dres) { CUDA_TRY(h->dres.ensure(Bn)); d_dres = h->dres.p; }
   int launches = 0;
-  if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
+  // One call in flight per handle (work queue counter, scratch buffers and workspaces are per handle): a call enqueued on another
+  // stream while the previous one still runs is ordered behind it instead of racing with it.
+  if (h->busy_recorded) CUDA_TRY(cudaStreamWaitEvent(st, h->busy_ev, 0));
+  if (h->info.kernel == MPCB_KERNEL_RICCATI) {
+    const size_t tile_doubles = (size_t)((Bn + 31) / 32) * D.nz * 32;
+    const bool sig = h->st.sigma != 0.0;
+    CUDA_TRY(h->rW.ensure(tile_doubles)); CUDA_TRY(h->rQ.ensure(tile_doubles)); CUDA_TRY(h->rD.ensure(tile_doubles)); CUDA_TRY(h->rXT.ensure(tile_doubles));
+    if (sig) CUDA_TRY(h->rX.ensure(tile_doubles));
+    if (io.y) CUDA_TRY(h->rYO.ensure(tile_doubles));
+    mpcb::RiccatiParams P{};
+    P.stage = h->ric_stage.p; P.Lq = h->ric_Lq.p;
+    for (int m = 0; m < D.nx; m++)
+      for (int i = 0; i < D.nu; i++) { P.Bm[m * D.nu + i] = D.B(m, i); P.Bt[i * D.nx + m] = D.B(m, i); }
+    for (int i = 0; i < D.nu; i++) { P.lo[i] = D.lo[i]; P.hi[i] = D.hi[i]; }
+    P.H = D.H; P.nz = D.nz; P.np = D.np; P.ch = 0;
+    P.rho = D.rho; P.sigma = h->st.sigma; P.alpha = h->st.alpha; P.eps_abs = h->st.eps_abs; P.eps_rel = h->st.eps_rel;
+    P.max_iter = h->st.max_iter; P.check_every = h->st.check_every;
+    P.batch = Bn; P.x0 = io.x0; P.xref = io.xref; P.uref = io.uref; P.xref_bc = io.xref_broadcast; P.uref_bc = io.uref_broadcast;
+    P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = v_buf; P.y_out = io.y;
+    P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres;
+    P.W = h->rW.p; P.Qb = h->rQ.p; P.D = h->rD.p; P.X = sig ? h->rX.p : nullptr; P.XT = h->rXT.p; P.YO = io.y ? h->rYO.p : nullptr;
+    P.counter = h->counter.p;
+    cudaError_t e = mpcb::launch_riccati(D.nx, D.nu, sig, P, h->info.sm_count, h->smem_optin, st);
+    if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_riccati launch: ") + cudaGetErrorString(e));
+    launches += 1;
+  } else if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     OnchipParams P{};
     P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
     P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu; P.nball = D.nball;
@@ -266,6 +303,8 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     CUDA_TRY(cudaGetLastError());
     launches += 1;
   }
+  CUDA_TRY(cudaEventRecord(h->busy_ev, st));
+  h->busy_recorded = true;
   h->timing.kernel_launches = launches;
   h->timing.batch = Bn;
   return MPCB_OK;
@@ -342,10 +381,18 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   const int nt8 = ((D.nt + 7) / 8) * 8;
   const bool smem_ok = D.mg == 0 && nt8 > 64 && nt8 <= 120 && mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) <= (size_t)prop.sharedMemPerBlockOptin;
   if (kernel == MPCB_KERNEL_AUTO) kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : MPCB_KERNEL_STREAMED);
+  h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  if (kernel == MPCB_KERNEL_RICCATI) {
+    int wpc = 0, ch = 0; size_t sm = 0;
+    if (D.ric_stage.empty() || !mpcb::riccati_supported(D.nx, D.nu))
+      { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: box-only problems without the S term, (nx, nu) in the compiled set"); }
+    if (!mpcb::riccati_plan(D.nx, D.nu, D.H, st.sigma != 0.0, 1 << 20, prop.multiProcessorCount, h->smem_optin, &wpc, &ch, &sm))
+      { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: the stage matrices of this horizon do not fit shared memory"); }
+  }
   if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
   if (D.nball > 0 && kernel != MPCB_KERNEL_ONCHIP) { delete h; return fail(MPCB_ERR_INVALID, "the contractive terminal set is implemented in the on-chip kernel only: needs nz + mg <= 64"); }
   if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs a box-only problem with 64 < nz <= 120 that fits 227 KB"); }
-  if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
+  if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM && kernel != MPCB_KERNEL_RICCATI) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;
   // rho ladder: only where it applies -- inequality general rows (state box; the ball rows are not boxes) on the on-chip kernel
   if (st.ladder_iter > 0 && kernel == MPCB_KERNEL_ONCHIP && D.mg > D.nball && desc->state_constraint) {
@@ -356,7 +403,7 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
     if (rc != MPCB_OK) { delete h; return fail(rc, "second rung of the rho ladder: " + err); }
     h->ladder = true;
   }
-  h->NT = (kernel == MPCB_KERNEL_STREAMED) ? mpcb::stream_padded(D.nt) : nt8;
+  h->NT = (kernel == MPCB_KERNEL_STREAMED) ? mpcb::stream_padded(D.nt) : (kernel == MPCB_KERNEL_RICCATI ? D.nt : nt8);
   h->info.nt_pad = h->NT;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
   if (cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaStreamCreate failed"); }
@@ -364,6 +411,7 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
     if (cudaEventCreate(&e) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
   for (auto& e : h->chunk_ev)
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
+  if (cudaEventCreateWithFlags(&h->busy_ev, cudaEventDisableTiming) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
   rc = upload_design(h);
   if (rc != MPCB_OK) { std::string keep = g_err; mpcb_destroy(h); return fail(rc, keep); }
   *out = h;
@@ -379,6 +427,8 @@ void mpcb_destroy(mpcb_handle* h) {
                             &h->xref, &h->uref, &h->warm_v, &h->warm_y, &h->v, &h->y, &h->pres, &h->dres, &h->u, &h->e_u, &h->x, &h->e_x,
                             &h->u0, &h->obj})
     b->release();
+  for (DevBuf<double>* b : {&h->ric_stage, &h->ric_Lq, &h->rW, &h->rQ, &h->rD, &h->rX, &h->rXT, &h->rYO}) b->release();
+  if (h->busy_ev) cudaEventDestroy(h->busy_ev);
   h->status.release(); h->iters.release(); h->counter.release();
   mpcb::stream_release(h->sc, h->sw);
   h->stage_in.release(); h->stage_out.release(); h->stage_int.release(); h->small_io.release();

@@ -170,6 +170,8 @@ function nn_arrays(params::Vector, arch::Symbol, activation::String)
     W_h = n_hidden == 0 ? zeros(1) : vcat((vec(Matrix{Float64}(params[i])) for i in 2:2:length(params)-1)...)
     b_h = n_hidden == 0 ? zeros(1) : vcat((Vector{Float64}(params[i+1]) for i in 2:2:length(params)-1)...)
     nx = size(W_out, 1); nu = size(W_in, 2) - nx
+    # :icnn and :rbf take the :fnn path: the reference's modelers for them are the Fnn ones up to the type tag (icnn.jl, rbf.jl:61-186)
+    arch in (:fnn, :icnn, :rbf, :resnet, :polynet, :densenet) || error("mpc_solver=\"b200\": unsupported network family $arch")
     return (W_in, W_h, b_h, W_out), (Int32(arch == :resnet ? 1 : arch == :polynet ? 2 : arch == :densenet ? 3 : 0), Int32(_ACTIVATION_IDS[activation]), Int32(nx), Int32(nu),
                                        Int32(size(W_in, 1)), Int32(n_hidden))
 end
@@ -188,7 +190,7 @@ resnet.jl:62-188) + `_JuMP_model_definition(::NonLinearProgramming, ::ipopt_solv
 function B200NonlinearModeler(params::Vector, arch::Symbol, activation::String, Q, R, S, P, umin, umax, horizon::Int, xref, uref;
                               terminal::String="none", state_constraint::Bool=false, xmin=zeros(0), xmax=zeros(0),
                               settings::Union{Nothing,MpcbNmpcSettings}=nothing)
-    terminal in ("none", "equality") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\" and \"equality\" only")
+    terminal in ("none", "equality", "contractive") || error("mpc_solver=\"b200\" supports mpc_terminal_ingredient \"none\", \"equality\" and \"contractive\" only")
     arrs, f = nn_arrays(params, arch, activation)
     mats = map(M -> Matrix{Float64}(M), (Q, R, S, P)); vecs = map(v -> Vector{Float64}(v), (umin, umax, xref, uref))
     xb = (Vector{Float64}(xmin), Vector{Float64}(xmax))
@@ -199,7 +201,7 @@ function B200NonlinearModeler(params::Vector, arch::Symbol, activation::String, 
         nd = Ref(MpcbNnDesc(f..., map(pointer, arrs)...))
         GC.@preserve nd begin
             d = MpcbNmpcDesc(Base.unsafe_convert(Ptr{MpcbNnDesc}, nd), horizon, map(pointer, mats)..., map(pointer, vecs)...,
-                             terminal == "equality" ? 1 : 0, state_constraint ? 1 : 0,
+                             terminal == "equality" ? 1 : terminal == "contractive" ? 2 : 0, state_constraint ? 1 : 0,
                              state_constraint ? pointer(xb[1]) : C_NULL, state_constraint ? pointer(xb[2]) : C_NULL)
             check(ccall((:mpcb_create_nmpc, libmpcb200), Cint, (Ref{MpcbNmpcDesc}, Ref{MpcbNmpcSettings}, Ref{Ptr{Cvoid}}), d, st, h), "mpcb_create_nmpc")
         end

@@ -105,6 +105,16 @@ class Fnn(_Chain):
     arch = "fnn"
 
 
+class Icnn(Fnn):
+    """AutomationLabsSystems.Icnn: the reference's NL / linear modelers for it are the Fnn ones up to the type tag
+    (icnn/mpc_modeler_implementation_icnn.jl is fnn.jl with `Fnn` -> `Icnn`)."""
+
+
+class Rbf(Fnn):
+    """AutomationLabsSystems.Rbf: rbf/mpc_modeler_implementation_rbf.jl:23-58 (linear) and :61-186 (NL) are the Fnn modelers
+    (no MILP variant)."""
+
+
 class ResNet(_Chain):
     """AutomationLabsSystems.ResNet: y_j = y_{j-1} + act(W_j y_{j-1} + b_j)  (resnet.jl:131-140)."""
     arch = "resnet"

@@ -55,6 +55,9 @@ extern "C" {
 #define MPCB_KERNEL_ONCHIP 1   /* register/shared-memory resident DMMA ADMM (nz + m_g <= 64) */
 #define MPCB_KERNEL_STREAMED 2 /* per-iteration FP64 tensor GEMM over HBM/L2-resident state */
 #define MPCB_KERNEL_ONCHIP_SMEM 3 /* shared-memory resident DMMA ADMM: box-only problems, 64 < nz <= ~120 */
+#define MPCB_KERNEL_RICCATI 4     /* stage-wise ("sparse") ADMM: the x-update by a cached Riccati sweep over the horizon, O(H) per iteration;
+                                     box-only problems without the S term, small (nx, nu); the long-horizon kernel (linear.jl:48-60 is the
+                                     reference's own stage-wise formulation) */
 
 typedef struct mpcb_handle mpcb_handle;
 

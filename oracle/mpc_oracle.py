@@ -420,6 +420,45 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
 
 
 # --------------------------------------------------------------------------------------------------
+# Stage-wise (Riccati) form of the x-update: twin of csrc/admm_riccati.cu / host_design.cpp::riccati_factors
+# --------------------------------------------------------------------------------------------------
+def riccati_factors(c: CondensedQP, sigma, rho):
+    """K x~ = r with K = Pc + (sigma + rho) I (box-only, no S term) is the optimality system of the LQ problem
+        min sum_{k=1..H} 1/2 e_k' W_k e_k + sum_{k<H} (1/2 u_k' Rh u_k - r_k' u_k),  e_0 = 0,  e_{k+1} = A e_k + B u_k
+    with W_k = 2Q (k < H), 2P (k = H), Rh = 2R + (sigma + rho) I -- the reference's own stage-wise structure
+    (linear.jl:48-60) with the ADMM penalty folded into the input weight.  Returns per-stage (K_k, Lam_k^-1, Acl_k)."""
+    assert c.mg == 0 and not (c.Ss[0, 0] != 0.0 and c.Rs[0, 0] != 0.0), "stage-wise form: box-only problems without the S term"
+    A, B, H, nx, nu = c.A, c.B, c.H, c.nx, c.nu
+    Rh = (2.0 * c.Rs if c.Rs[0, 0] != 0.0 else np.zeros((nu, nu))) + (sigma + rho) * np.eye(nu)
+    Pi = 2.0 * c.Ps
+    K = np.zeros((H, nu, nx)); Li = np.zeros((H, nu, nu)); Acl = np.zeros((H, nx, nx))
+    for k in range(H - 1, -1, -1):
+        Li[k] = np.linalg.inv(Rh + B.T @ Pi @ B)
+        K[k] = Li[k] @ B.T @ Pi @ A
+        Acl[k] = A - B @ K[k]
+        Pi = (2.0 * c.Qs if k > 0 else 0.0) + A.T @ Pi @ Acl[k]
+        Pi = 0.5 * (Pi + Pi.T)
+    return K, Li, Acl
+
+
+def riccati_apply(c: CondensedQP, fac, r):
+    """x~ = K^-1 r for a batch of right-hand sides r (Bn, nz) by one backward and one forward sweep (the kernel's two sweeps)."""
+    K, Li, Acl = fac
+    H, nx, nu, B = c.H, c.nx, c.nu, c.B
+    r = np.atleast_2d(r); Bn = r.shape[0]
+    h = r.reshape(Bn, H, nu)
+    pi = np.zeros((Bn, nx)); d = np.zeros((Bn, H, nu))
+    for k in range(H - 1, -1, -1):
+        d[:, k] = (h[:, k] + pi @ B) @ Li[k].T
+        pi = pi @ Acl[k] - h[:, k] @ K[k]
+    e = np.zeros((Bn, nx)); u = np.zeros((Bn, H, nu))
+    for k in range(H):
+        u[:, k] = d[:, k] - e @ K[k].T
+        e = e @ Acl[k].T + d[:, k] @ B.T
+    return u.reshape(Bn, H * nu)
+
+
+# --------------------------------------------------------------------------------------------------
 # Exact solve (ground truth): primal-dual active set + KKT certificate
 # --------------------------------------------------------------------------------------------------
 def admm_condensed_ladder(c: CondensedQP, p, s: AdmmSettings, ladder_iter, kappa=10.0):

@@ -197,3 +197,17 @@ def test_contractive_ball_twin_vs_slsqp(qt):
                      constraints=[{"type": "ineq", "fun": lambda v: r2 - np.sum((c.G @ v - b) ** 2), "jac": lambda v: -2 * (c.G @ v - b) @ c.G}],
                      options={"maxiter": 1000, "ftol": 1e-16})
         assert np.abs(r.x - tw["v"][i]).max() < 1e-5
+
+
+@pytest.mark.parametrize("H,sigma", [(5, 0.0), (20, 1e-6), (60, 0.0)])
+def test_stagewise_riccati_x_update_equals_condensed_operator(qt, H, sigma):
+    """The stage-wise (Riccati) x-update of csrc/admm_riccati.cu is the SAME linear map as the condensed operator
+    T = (Pc + (sigma + rho) I)^-1 of the other kernels: one backward and one forward sweep reproduce T r to round-off."""
+    P = mo.dare(qt["A"], qt["B"], qt["Q"], qt["R"])
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"])
+    s = mo.AdmmSettings(sigma=sigma)
+    T, _, _, rho = mo.admm_matrices(c, s)
+    fac = mo.riccati_factors(c, sigma, rho)
+    r = np.random.default_rng(H).standard_normal((64, c.nz))
+    t = mo.riccati_apply(c, fac, r)
+    assert np.abs(t - r @ T).max() <= 1e-12 * np.abs(t).max()

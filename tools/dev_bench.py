@@ -6,7 +6,7 @@ import almpc_b200 as mpc
 from almpc_b200 import _lib
 import bench
 
-def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0):
+def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0, kernel=0):
     """near > 0: x0 = x_ref + near * N(0, I) with the design reference (feasible terminal constraints); state_box: tight box + references beyond it"""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     if state_box: xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
@@ -18,7 +18,7 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     if ladder: extra["mpc_b200_ladder_iter"] = ladder
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_terminal_ingredient=terminal,
                                mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho,
-                               mpc_b200_max_iter=max_iter, **extra)
+                               mpc_b200_max_iter=max_iter, mpc_b200_kernel=kernel, **extra)
     m = C.tuning.modeler
     x0_h, xref_h, uref_h = bench.make_batch(n, 0)
     rng = np.random.default_rng(7)
@@ -44,7 +44,13 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     it = iters.cpu().numpy()
     fl = bench.algorithmic_flops(m.info, it, check)
     ms = min(ts)
-    print(json.dumps({"H": H, "n": n, "eps": eps, "check": check, "sigma": sigma, "terminal": terminal, "state_box": state_box, "kernel": m.info.kernel, "nt": m.info.nt,
+    extra_out = {}
+    if m.info.kernel == 4:      # stage-wise kernel: its own arithmetic (68 multiply-adds per stage and iteration for nx=4, nu=2) and its state traffic
+        nx, nu = m.info.nx, m.info.nu
+        sfl = float(it.astype(float).sum()) * H * 2 * (2 * nx * nx + 4 * nx * nu + nu * nu)
+        sby = float(it.astype(float).sum()) * (6 if sigma == 0 else 9) * m.info.nz * 8
+        extra_out = {"stage_tflops": round(sfl / ms / 1e9, 2), "state_GBps": round(sby / ms / 1e6, 1)}
+    print(json.dumps({**extra_out, "H": H, "n": n, "eps": eps, "check": check, "sigma": sigma, "terminal": terminal, "state_box": state_box, "kernel": m.info.kernel, "nt": m.info.nt,
                       "full": full, "ladder": ladder, "ms": round(ms, 4), "max_iters": int(it.max()),
                       "mean_iters": round(float(it.mean()), 2), "solves_per_s": round(n / ms * 1e3), "tflops": round(fl / ms / 1e9, 2),
                       "frac": round(fl / ms / 1e9 / bench.FP64_PEAK_TFLOPS, 3), "solved": float((status.cpu().numpy() == 1).mean()), "rho": round(m.info.rho, 4)}), flush=True)
@@ -156,6 +162,14 @@ if __name__ == "__main__":
     elif a.set == "hsweep":
         for H in (10, 20, 30, 50, 75, 100, 150, 200):
             run(H, 16384, 1e-7, 5, 0.0, reps=2)
+    elif a.set == "ricsweep":    # config 4 with the stage-wise kernel next to the condensed ones: the crossover study
+        for H in (10, 20, 30, 50, 75, 100, 150, 200):
+            run(H, 16384, 1e-7, 5, 0.0, reps=3, kernel=4)
+            run(H, 16384, 1e-7, 5, 0.0, reps=3, kernel=0)
+        for H in (20, 50):
+            run(H, 65536, 1e-7, 5, 0.0, reps=3, kernel=4)
+    elif a.set == "ric1":
+        run(50, 16384, 1e-7, 5, 0.0, reps=2, kernel=4)
     elif a.set == "rows":        # general-row variants of the QT controller (a3 / a4 rows of SURVEY 8a)
         run(20, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.002, reps=3)
         run(10, 65536, 1e-7, 5, 0.0, state_box=True, reps=3)
