@@ -8,36 +8,62 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 namespace mpcb {
+
+namespace {
+// Columns [0, n) of a product split over host threads when the product is large enough to pay for them (the design of a
+// controller with hundreds of decision variables is O(nz^3): condensing, K^-1, the stacked operator).  Every column is computed
+// by exactly one thread with the same operation order as the serial loop: results do not depend on the thread count.
+template <class F>
+void parallel_columns(int n, double work_per_column, F&& body) {
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = std::min<unsigned>(nt == 0 ? 1 : nt, 16);
+  if (work_per_column * n < 4e6 || nt < 2 || n < 2) { body(0, n); return; }
+  nt = std::min<unsigned>(nt, (unsigned)n);
+  std::vector<std::thread> th;
+  const int chunk = (n + (int)nt - 1) / (int)nt;
+  for (unsigned t = 1; t < nt; t++) {
+    const int j0 = (int)t * chunk, j1 = std::min(n, j0 + chunk);
+    if (j0 < j1) th.emplace_back([&body, j0, j1]() { body(j0, j1); });
+  }
+  body(0, std::min(n, chunk));
+  for (auto& x : th) x.join();
+}
+}  // namespace
 
 Mat matmul(const Mat& A, const Mat& B) {
   Mat C(A.r, B.c);
   const int m = A.r, k = A.c, n = B.c;
-  for (int j = 0; j < n; j++) {
-    double* cj = &C.a[(size_t)j * m];
-    for (int l = 0; l < k; l++) {
-      const double b = B(l, j);
-      if (b == 0.0) continue;
-      const double* al = &A.a[(size_t)l * m];
-      for (int i = 0; i < m; i++) cj[i] += al[i] * b;
+  parallel_columns(n, (double)m * k, [&](int j0, int j1) {
+    for (int j = j0; j < j1; j++) {
+      double* cj = &C.a[(size_t)j * m];
+      for (int l = 0; l < k; l++) {
+        const double b = B(l, j);
+        if (b == 0.0) continue;
+        const double* al = &A.a[(size_t)l * m];
+        for (int i = 0; i < m; i++) cj[i] += al[i] * b;
+      }
     }
-  }
+  });
   return C;
 }
 
 Mat matmul_tn(const Mat& A, const Mat& B) {  // A' * B, A is k x m, B is k x n
   Mat C(A.c, B.c);
   const int m = A.c, k = A.r, n = B.c;
-  for (int j = 0; j < n; j++) {
-    const double* bj = &B.a[(size_t)j * k];
-    for (int i = 0; i < m; i++) {
-      const double* ai = &A.a[(size_t)i * k];
-      double s = 0.0;
-      for (int l = 0; l < k; l++) s += ai[l] * bj[l];
-      C(i, j) = s;
+  parallel_columns(n, (double)m * k, [&](int j0, int j1) {
+    for (int j = j0; j < j1; j++) {
+      const double* bj = &B.a[(size_t)j * k];
+      for (int i = 0; i < m; i++) {
+        const double* ai = &A.a[(size_t)i * k];
+        double s = 0.0;
+        for (int l = 0; l < k; l++) s += ai[l] * bj[l];
+        C(i, j) = s;
+      }
     }
-  }
+  });
   return C;
 }
 
@@ -83,14 +109,19 @@ bool spd_inverse(const Mat& A, Mat& Ainv) {
   if (!cholesky_lower(L)) return false;
   // Linv = L^-1 (lower), column by column
   Mat Li(n, n);
-  for (int j = 0; j < n; j++) {
-    Li(j, j) = 1.0 / L(j, j);
-    for (int i = j + 1; i < n; i++) {
-      double s = 0.0;
-      for (int k = j; k < i; k++) s += L(i, k) * Li(k, j);
-      Li(i, j) = -s / L(i, i);
+  const Mat Lt = transpose(L);      // row i of L contiguous
+  parallel_columns(n, (double)n * n / 6.0, [&](int j0, int j1) {
+    for (int j = j0; j < j1; j++) {
+      Li(j, j) = 1.0 / L(j, j);
+      double* lj = &Li.a[(size_t)j * n];
+      for (int i = j + 1; i < n; i++) {
+        const double* li = &Lt.a[(size_t)i * n];
+        double s = 0.0;
+        for (int k = j; k < i; k++) s += li[k] * lj[k];
+        lj[i] = -s / li[i];
+      }
     }
-  }
+  });
   Ainv = matmul_tn(Li, Li);  // L^-T L^-1
   for (int j = 0; j < n; j++)
     for (int i = 0; i < j; i++) {
@@ -132,6 +163,9 @@ bool lu_solve(Mat A, Mat& B) {
 
 bool sym_extreme_eigs(const Mat& A, double& lmin, double& lmax) {
   const int n = A.r;
+  // rho = sqrt(lmin lmax) is a step-size heuristic: large matrices stop at 1e-10 relative change (each sweep is O(n^2))
+  const double tol = n <= 256 ? 1e-15 : 1e-9;
+  const int max_sweeps = n <= 256 ? 3000 : 400;
   std::vector<double> v(n), w(n);
   auto normalize = [&](std::vector<double>& x) {
     double s = 0;
@@ -144,7 +178,7 @@ bool sym_extreme_eigs(const Mat& A, double& lmin, double& lmax) {
   for (int i = 0; i < n; i++) v[i] = 1.0 + 0.37 * std::sin(1.0 + 1.7 * i);
   normalize(v);
   double lam = 0;
-  for (int it = 0; it < 3000; it++) {
+  for (int it = 0; it < max_sweeps; it++) {
     for (int i = 0; i < n; i++) w[i] = 0;
     for (int j = 0; j < n; j++) {
       const double vj = v[j];
@@ -155,7 +189,7 @@ bool sym_extreme_eigs(const Mat& A, double& lmin, double& lmax) {
     for (int i = 0; i < n; i++) nl += w[i] * v[i];
     normalize(w);
     v.swap(w);
-    if (it > 5 && std::fabs(nl - lam) <= 1e-15 * std::fabs(nl)) { lam = nl; break; }
+    if (it > 5 && std::fabs(nl - lam) <= tol * std::fabs(nl)) { lam = nl; break; }
     lam = nl;
   }
   lmax = lam;
@@ -165,7 +199,7 @@ bool sym_extreme_eigs(const Mat& A, double& lmin, double& lmax) {
   for (int i = 0; i < n; i++) v[i] = 1.0 + 0.41 * std::cos(0.3 + 2.3 * i);
   normalize(v);
   double mu = 0;
-  for (int it = 0; it < 3000; it++) {
+  for (int it = 0; it < max_sweeps; it++) {
     w = v;
     for (int i = 0; i < n; i++) {  // L y = v
       double s = w[i];
@@ -181,7 +215,7 @@ bool sym_extreme_eigs(const Mat& A, double& lmin, double& lmax) {
     for (int i = 0; i < n; i++) nm += w[i] * v[i];  // Rayleigh quotient of A^-1
     normalize(w);
     v.swap(w);
-    if (it > 5 && std::fabs(nm - mu) <= 1e-15 * std::fabs(nm)) { mu = nm; break; }
+    if (it > 5 && std::fabs(nm - mu) <= tol * std::fabs(nm)) { mu = nm; break; }
     mu = nm;
   }
   lmin = 1.0 / mu;
@@ -293,12 +327,40 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
       for (int i = 0; i < nx; i++) Gam[k + 1](i, k * nu + j) += D.B(i, j);
   }
   // Hessian / gradient map in deviation inputs: J = eps' M eps + 2 (Fe e0)' eps + const, Pc_dev = 2M
+  // M = sum_k Gam_k' W_k Gam_k and Fe = sum_k Gam_k' W_k Phi_k as ONE product each over the stacked rows (k, r): column c of Gam_k is
+  // zero unless k > c / nu (an input acts on later states only), so the dot product of columns i and j starts at stage max(i, j) / nu + 1,
+  // and M is symmetric: a sixth of the flops of the plain products, split over host threads by column.
   Mat M(nz, nz), Fe(nz, nx);
-  for (int k = 0; k <= H; k++) {
-    const Mat& W = (k == H) ? D.P : D.Q;
-    Mat WG = matmul(W, Gam[k]);                 // nx x nz
-    M = add(M, matmul_tn(Gam[k], WG));
-    Fe = add(Fe, matmul_tn(WG, Phi[k]));        // Gam' W Phi  (W symmetric)
+  {
+    const int rows = nx * (H + 1);
+    Mat Gall(rows, nz), WGall(rows, nz), Phall(rows, nx);
+    for (int k = 0; k <= H; k++) {
+      const Mat& W = (k == H) ? D.P : D.Q;
+      const Mat WG = matmul(W, Gam[k]);                 // nx x nz
+      for (int c = 0; c < nz; c++)
+        for (int r = 0; r < nx; r++) { Gall(k * nx + r, c) = Gam[k](r, c); WGall(k * nx + r, c) = WG(r, c); }
+      for (int c = 0; c < nx; c++)
+        for (int r = 0; r < nx; r++) Phall(k * nx + r, c) = Phi[k](r, c);
+    }
+    parallel_columns(nz, (double)rows * nz / 6.0, [&](int j0, int j1) {
+      for (int j = j0; j < j1; j++) {
+        const double* wj = &WGall.a[(size_t)j * rows];
+        for (int i = 0; i <= j; i++) {
+          const double* gi = &Gall.a[(size_t)i * rows];
+          double acc = 0.0;
+          for (int l = (j / nu + 1) * nx; l < rows; l++) acc += gi[l] * wj[l];
+          M(i, j) = acc;
+        }
+        for (int c = 0; c < nx; c++) {
+          const double* ph = &Phall.a[(size_t)c * rows];
+          double acc = 0.0;
+          for (int l = (j / nu + 1) * nx; l < rows; l++) acc += wj[l] * ph[l];
+          Fe(j, c) = acc;
+        }
+      }
+    });
+    for (int j = 0; j < nz; j++)
+      for (int i = 0; i < j; i++) M(j, i) = M(i, j);
   }
   if (D.use_R)
     for (int k = 0; k < H; k++)

@@ -380,14 +380,18 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   int kernel = st.kernel;
   const int nt8 = ((D.nt + 7) / 8) * 8;
   const bool smem_ok = D.mg == 0 && nt8 > 64 && nt8 <= 120 && mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) <= (size_t)prop.sharedMemPerBlockOptin;
-  if (kernel == MPCB_KERNEL_AUTO) kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : MPCB_KERNEL_STREAMED);
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
+  const bool ric_form = !D.ric_stage.empty() && mpcb::riccati_supported(D.nx, D.nu);
+  bool ric_fits = false;
+  if (ric_form) { int wpc = 0, ch = 0; size_t sm = 0; ric_fits = mpcb::riccati_plan(D.nx, D.nu, D.H, st.sigma != 0.0, 1 << 20, prop.multiProcessorCount, h->smem_optin, &wpc, &ch, &sm); }
+  // Kernel choice (measured crossover, profiles/r02/ricsweep_config4_*.jsonl, quadruple tank, 16 384 problems): the register- and shared-memory
+  // resident DMMA kernels win while the condensed operator fits on chip (nt <= 120: H = 50 1.17 ms vs 2.70 ms stage-wise); beyond that the
+  // stage-wise kernel replaces the streamed GEMM wherever its form applies (H = 75: 4.4 vs 6.7 ms, H = 200: 14.9 vs 33.9 ms).
+  if (kernel == MPCB_KERNEL_AUTO)
+    kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : ((ric_form && ric_fits) ? MPCB_KERNEL_RICCATI : MPCB_KERNEL_STREAMED));
   if (kernel == MPCB_KERNEL_RICCATI) {
-    int wpc = 0, ch = 0; size_t sm = 0;
-    if (D.ric_stage.empty() || !mpcb::riccati_supported(D.nx, D.nu))
-      { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: box-only problems without the S term, (nx, nu) in the compiled set"); }
-    if (!mpcb::riccati_plan(D.nx, D.nu, D.H, st.sigma != 0.0, 1 << 20, prop.multiProcessorCount, h->smem_optin, &wpc, &ch, &sm))
-      { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: the stage matrices of this horizon do not fit shared memory"); }
+    if (!ric_form) { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: box-only problems without the S term, (nx, nu) in the compiled set"); }
+    if (!ric_fits) { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: the stage matrices of this horizon do not fit shared memory"); }
   }
   if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
   if (D.nball > 0 && kernel != MPCB_KERNEL_ONCHIP) { delete h; return fail(MPCB_ERR_INVALID, "the contractive terminal set is implemented in the on-chip kernel only: needs nz + mg <= 64"); }

@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from conftest import qt_batch
+from conftest import assert_matches_twin, exact_sample, qt_batch
 from oracle import mpc_oracle as mo
 
 pytestmark = pytest.mark.gpu
@@ -61,26 +61,24 @@ def test_batch_matches_twin_and_exact(mpc, qt, H, eps, check, sigma):
     c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P)
     p = mo.pack_params(x0, xref, uref)
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=check, sigma=sigma))
-    # same algorithm, same iteration counts (summation order differs -> allow a vanishing fraction of off-by-one-check)
-    same = res["iters"] == tw["iters"]
-    assert same.mean() > 0.995, same.mean()
+    # same algorithm, same iteration counts (summation order differs -> allow a vanishing fraction of off-by-one-check); EVERY problem
+    # is compared: to round-off where the counts agree, to the solver accuracy where a borderline check flipped
     assert (res["status"] == 1).all()
-    v = res["u"].reshape(n, -1)
-    assert np.abs(v[same] - tw["v"][same]).max() < 1e-9
+    v, same = assert_matches_twin(res, tw, tight=1e-9, loose=max(1e-6, 30 * eps), min_same=0.995, check=check)
     assert np.abs(res["prim_res"][same] - tw["prim_res"][same]).max() < 1e-9
     rec = mo.recover(c, v, p)
     for k in ("x", "e_x", "u", "e_u"):
         assert np.abs(res[k] - rec[k]).max() < 1e-11, k
     assert np.abs(res["objective"] - rec["objective"]).max() <= 1e-11 * np.abs(rec["objective"]).max()
     assert np.array_equal(res["u0"], res["u"][:, 0, :])
-    if eps <= 1e-6:   # against the exact optimum
-        ne = 256
-        ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in range(ne)])
-        assert mo.u0_metric(res["u0"][:ne], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
+    if eps <= 1e-6:   # against the exact optimum, on a random sample of the batch
+        idx = exact_sample(n, frac=0.1, at_least=128, seed=H)
+        ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in idx])
+        assert mo.u0_metric(res["u0"][idx], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
         if eps <= 1e-7:   # the parity settings: eps_abs = eps_rel = 1e-7
             assert res["prim_res"].max() < RES_TOL and res["dual_res"].max() < RES_TOL
-            Jex = mo.recover(c, ex, p[:ne])["objective"]
-            assert (np.abs(res["objective"][:ne] - Jex) / np.maximum(np.abs(Jex), 1e-9)).max() < OBJ_TOL
+            Jex = mo.recover(c, ex, p[idx])["objective"]
+            assert (np.abs(res["objective"][idx] - Jex) / np.maximum(np.abs(Jex), 1e-9)).max() < OBJ_TOL
 
 
 def test_terminal_equality_matches_twin_and_exact(mpc, qt):
@@ -97,15 +95,11 @@ def test_terminal_equality_matches_twin_and_exact(mpc, qt):
     c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P, terminal="equality")
     p = mo.pack_params(x0, xref, qt["u_ref"])
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=10, max_iter=20000))
-    same = res["iters"] == tw["iters"]
-    assert same.mean() > 0.99
-    assert np.array_equal(res["status"][same], tw["status"][same])
-    v = res["u"].reshape(n, -1)
-    assert np.abs(v[same] - tw["v"][same]).max() < 1e-8
+    v, same = assert_matches_twin(res, tw, tight=1e-8, loose=1e-5, min_same=0.99, status_frac=0.995, check=10)
     ok = res["status"] == 1
     assert ok.mean() > 0.5
     assert np.abs(res["e_x"][ok][:, -1, :]).max() < 1e-5       # terminal deviation driven to zero
-    idx = np.flatnonzero(ok)[:64]
+    idx = np.random.default_rng(0).choice(np.flatnonzero(ok), 64, replace=False)
     ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in idx])
     assert mo.u0_metric(res["u0"][idx], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
 
@@ -176,10 +170,12 @@ def test_empty_and_ragged_batches(mpc, qt):
 # ------------------------------------------------------------------------------------------------------------------
 # streamed kernel (nt > 64, or forced with mpc_b200_kernel = 2)
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("H,force,sigma,expect", [(20, 2, 0.0, 2), (20, 2, 1e-6, 2), (50, 2, 0.0, 2), (35, 2, 1e-6, 2), (70, 0, 0.0, 2),
+@pytest.mark.parametrize("H,force,sigma,expect", [(20, 2, 0.0, 2), (20, 2, 1e-6, 2), (50, 2, 0.0, 2), (35, 2, 1e-6, 2), (70, 2, 0.0, 2),
+                                                   # beyond the on-chip range the stage-wise (Riccati) kernel is the automatic choice for box-only problems
+                                                   (70, 0, 0.0, 4), (60, 0, 1e-6, 4),
                                                    # shared-memory resident kernel (box-only, 64 < nz <= 120 and the state fits 227 KB):
-                                                   # picked automatically; nz = 120 with sigma > 0 (4 state arrays) does not fit -> streamed
-                                                   (50, 0, 0.0, 3), (35, 0, 1e-6, 3), (33, 3, 0.0, 3), (60, 0, 0.0, 3), (60, 0, 1e-6, 2), (47, 0, 1e-6, 3)])
+                                                   # picked automatically; nz = 120 with sigma > 0 (4 state arrays) does not fit -> stage-wise / streamed
+                                                   (50, 0, 0.0, 3), (35, 0, 1e-6, 3), (33, 3, 0.0, 3), (60, 0, 0.0, 3), (60, 2, 1e-6, 2), (47, 0, 1e-6, 3)])
 def test_streamed_matches_twin_and_exact(mpc, qt, H, force, sigma, expect):
     n, eps, check = 700, 1e-7, 5          # 700: not a multiple of the 128-row GEMM tile
     C = make_controller(mpc, qt, H, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma,
@@ -192,12 +188,11 @@ def test_streamed_matches_twin_and_exact(mpc, qt, H, force, sigma, expect):
     c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P)
     p = mo.pack_params(x0, xref, uref)
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=check, sigma=sigma))
-    same = res["iters"] == tw["iters"]
-    assert same.mean() > 0.99 and (res["status"] == 1).all()
-    v = res["u"].reshape(n, -1)
-    assert np.abs(v[same] - tw["v"][same]).max() < 1e-9
-    ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in range(64)])
-    assert mo.u0_metric(res["u0"][:64], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
+    assert (res["status"] == 1).all()
+    v, same = assert_matches_twin(res, tw, tight=1e-9, loose=1e-6, min_same=0.99, check=check)
+    idx = exact_sample(n, at_least=64, seed=H)
+    ex = np.array([mo.qp_exact(c, p[i], v_init=tw["v"][i])[0] for i in idx])
+    assert mo.u0_metric(res["u0"][idx], ex[:, :2], qt["umin"], qt["umax"]).max() < U0_TOL
     rec = mo.recover(c, v, p)
     assert np.abs(res["x"] - rec["x"]).max() < 1e-10 and np.abs(res["objective"] - rec["objective"]).max() <= 1e-10 * np.abs(rec["objective"]).max()
 
@@ -243,11 +238,9 @@ def test_streamed_terminal_equality(mpc, qt):
     c = oracle_condensed(qt, H, C.tuning.terminal_ingredient.P, terminal="equality")
     p = mo.pack_params(x0, xref, qt["u_ref"])
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=10, max_iter=6000))
-    assert (res["status"] == tw["status"]).mean() > 0.98
-    same = (res["iters"] == tw["iters"]) & (res["status"] == 1)
-    assert same.mean() > 0.5
-    assert np.abs(res["u"].reshape(n, -1)[same] - tw["v"][same]).max() < 1e-7
-    assert np.abs(res["e_x"][same][:, -1, :]).max() < 1e-5
+    v, same = assert_matches_twin(res, tw, tight=1e-7, loose=1e-4, min_same=0.5, status_frac=0.98, check=10)
+    ok = res["status"] == 1
+    assert np.abs(res["e_x"][ok][:, -1, :]).max() < 1e-5
     assert set(np.unique(res["status"])) <= {1, -2, -3}
 
 
@@ -268,10 +261,8 @@ def test_random_lti_generic_recover(mpc):
     c = mo.condense(A, B, 10 * np.eye(nx), np.eye(nu), np.zeros((nu, nu)), C.tuning.terminal_ingredient.P, H, -np.ones(nu), np.ones(nu))
     p = mo.pack_params(x0, xref, uref)
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5))
-    same = res["iters"] == tw["iters"]
-    assert same.mean() > 0.99 and (res["status"] == 1).all()
-    v = res["u"].reshape(n, -1)
-    assert np.abs(v[same] - tw["v"][same]).max() < 1e-9
+    assert (res["status"] == 1).all()
+    v, same = assert_matches_twin(res, tw, tight=1e-9, loose=1e-6, min_same=0.99)
     rec = mo.recover(c, v, p)
     for k in ("x", "e_x", "u", "e_u"):
         assert np.abs(res[k] - rec[k]).max() < 1e-10, k
@@ -416,11 +407,8 @@ def test_random_systems_sweep(mpc, nx, nu, H, terminal, sigma, S_w):
     c = mo.condense(A, B, 10 * np.eye(nx), np.eye(nu), S_w * np.eye(nu), C.tuning.terminal_ingredient.P, H, umin, umax, terminal=terminal)
     p = mo.pack_params(x0, xref, uref)
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, sigma=sigma, max_iter=20000))
-    assert (res["status"] == tw["status"]).mean() > 0.98
-    same = (res["iters"] == tw["iters"]) & (res["status"] == 1) & (tw["status"] == 1)
-    assert same.mean() > (0.9 if terminal == "none" else 0.5), (same.mean(), np.unique(res["status"], return_counts=True))
-    v = res["u"].reshape(n, -1)
-    assert np.abs(v[same] - tw["v"][same]).max() < (1e-9 if terminal == "none" else 1e-7)
+    v, same = assert_matches_twin(res, tw, tight=1e-9 if terminal == "none" else 1e-7, loose=1e-6 if terminal == "none" else 1e-4,
+                                  min_same=0.9 if terminal == "none" else 0.5, status_frac=0.98)
     rec = mo.recover(c, v, p)
     for k in ("x", "e_x", "u", "e_u"):
         assert np.abs(res[k] - rec[k]).max() < 1e-9 * max(1.0, np.abs(rec[k]).max()), k

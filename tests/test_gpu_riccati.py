@@ -5,7 +5,7 @@ against the condensed CUDA kernels."""
 import numpy as np
 import pytest
 
-from conftest import qt_batch
+from conftest import assert_matches_twin, qt_batch
 from oracle import mpc_oracle as mo
 from test_gpu_linear import OBJ_TOL, RES_TOL, U0_TOL, make_controller, oracle_condensed
 
@@ -13,16 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def check_against_twin(res, tw, n, tight=1e-9, loose=1e-6):
-    """Every problem is compared with the twin: those with the same iteration count to round-off, the rest (a borderline check
-    that flipped on a 1e-16 difference) at the accuracy both solves guarantee."""
-    same = res["iters"] == tw["iters"]
-    v = res["u"].reshape(n, -1)
-    assert same.mean() > 0.99, same.mean()
-    assert np.array_equal(res["status"], tw["status"])
-    assert np.abs(v[same] - tw["v"][same]).max() < tight
-    assert np.abs(v - tw["v"]).max() < loose
-    assert np.abs(res["iters"] - tw["iters"]).max() <= 2 * 5
-    return v
+    return assert_matches_twin(res, tw, tight=tight, loose=loose, min_same=0.99)[0]
 
 
 @pytest.mark.parametrize("H,sigma,n", [(20, 0.0, 1500), (20, 1e-6, 700), (50, 0.0, 1500), (75, 0.0, 333), (100, 1e-6, 300), (7, 0.0, 65), (33, 0.0, 1)])

@@ -170,6 +170,10 @@ if __name__ == "__main__":
             run(H, 65536, 1e-7, 5, 0.0, reps=3, kernel=4)
     elif a.set == "ric1":
         run(50, 16384, 1e-7, 5, 0.0, reps=2, kernel=4)
+    elif a.set == "ric200":
+        run(200, 16384, 1e-7, 5, 0.0, reps=1, kernel=4)
+    elif a.set == "ric20big":
+        run(20, 65536, 1e-7, 5, 0.0, reps=1, kernel=4)
     elif a.set == "rows":        # general-row variants of the QT controller (a3 / a4 rows of SURVEY 8a)
         run(20, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.002, reps=3)
         run(10, 65536, 1e-7, 5, 0.0, state_box=True, reps=3)
