@@ -91,10 +91,32 @@ class ClockSampler:
 
 
 def algorithmic_flops(info, iters, check_every):
-    """per solve  it*(2 nt^2) [T r]  +  (it/check)*(2 nt^2) [termination pass]  +  2 nt np [q = Lq p]."""
+    """SURVEY 8(d) / DESIGN.md section 5: per solve  it*(2 nt^2) [T r]  +  (it/check)*(2 nt^2) [termination pass]  +  2 nt np [q = Lq p]."""
     nt, npar = info.nt, 2 * info.nx + info.nu
     it = iters.astype(np.float64)
     return float((it * 2 * nt * nt + (it / check_every) * 2 * nt * nt + 2 * nt * npar).sum())
+
+
+def executed_flops(info, iters, check_every):
+    """What the condensed kernels actually execute: box-only problems get the dual residual in closed form (no termination pass);
+    problems with general rows run one pass with C = [[Pc, G'], [G, 0]] per check."""
+    nt, npar = info.nt, 2 * info.nx + info.nu
+    it = iters.astype(np.float64)
+    chk = (it / check_every) * 2 * nt * nt if info.mg > 0 else 0.0
+    return float((it * 2 * nt * nt + chk + 2 * nt * npar).sum())
+
+
+def kernel_name(info, sigma):
+    """The dominant kernel of a controller, as ncu names it."""
+    k = info.kernel
+    if k == 1:
+        has_g = info.mg > 0
+        sig = has_g or sigma != 0.0
+        minb = {8: 4, 16: 4, 24: 3 if has_g else 4, 32: 2 if has_g else 4, 40: 2 if has_g else 3, 48: 2 if has_g else 3}.get(info.nt_pad, 2 if (has_g or sig) else 3)
+        return f"admm_onchip_kernel<{info.nt_pad},{str(has_g).lower()},{str(sig).lower()},{minb}>"
+    if k == 3: return f"admm_smem_kernel<{info.nt_pad},{str(sigma != 0.0).lower()},*>"
+    if k == 4: return f"admm_riccati_kernel<{info.nx},{info.nu},{str(sigma != 0.0).lower()}>"
+    return "stream_iter_kernel"
 
 
 def run_ours(args):
@@ -171,6 +193,7 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     it_np = iters.cpu().numpy(); st_np = status.cpu().numpy()
+    launches_full_step = int(m.timing()["kernel_launches"])     # kernels of libmpcb200 the last full step launched (counted by the library)
     # dominant kernel alone (solve kernel, no recover): time it live with events for the roofline
     io_solve = _lib.BatchIO()
     for f, _t in io._fields_: setattr(io_solve, f, getattr(io, f))
@@ -184,8 +207,9 @@ def run_ours(args):
     kms = [a.elapsed_time(b) for a, b in kev]
     k_ms = sum(kms) / len(kms)
     flops = algorithmic_flops(info, it_np, CHECK)
-    achieved = flops / (k_ms * 1e-3) / 1e12
-    achieved_exec = float((it_np.astype(np.float64) * 2 * info.nt * info.nt + 2 * info.nt * (2 * info.nx + info.nu)).sum()) / (k_ms * 1e-3) / 1e12
+    achieved_alg = flops / (k_ms * 1e-3) / 1e12
+    flops_exec = executed_flops(info, it_np, CHECK)
+    achieved = flops_exec / (k_ms * 1e-3) / 1e12
 
     # ---------------- end-to-end leg: host-array C ABI with pinned host buffers, every rank on its own shard concurrently ----------------
     pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory()
@@ -216,6 +240,9 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             cpu = cpu_baseline(sample=args.cpu_sample)
             lat["cpu_p50_us"] = cpu.pop("latency_p50_us")
+        extra = None
+        if world == 1 and not args.no_extra:
+            extra = other_configs(mpc, dev, cpu=not args.no_cpu)
         line = {
             "metric": "MPC QP solves/sec", "value": world * n * args.steps / (ms_total * 1e-3), "unit": "solves/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -227,25 +254,197 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "what": "mpcb_solve_linear_batch on page-locked host arrays, every rank on its shard concurrently, max over ranks",
                     "phases_ms": {k: round(v, 4) for k, v in tim.items() if k.endswith("_ms")}},
-            "gpu_launches": int(2 * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "admm_onchip_kernel<40,false,false,3>", "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
-                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+            "gpu_launches": int(launches_full_step * args.steps),
+            "roofline": {"bound": "tensor", "kernel": kernel_name(info, SIGMA), "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
+                         "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (n == BATCH and info.kernel == 1 and info.nt_pad == 40) else None,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, ncu --set full capture "
                                            "profiles/r01/onchip_qt_h20_ncu_full.txt (4.26 MB read, 0 written: outputs stay in L2 until recover reads them)",
                          "peak_source": "FP64 DMMA peak measured by profiles/micro/fp64_peak.cu on this pool (MEASURED_PEAKS.json has no FP64 number)",
-                         "kernel_ms": k_ms, "algorithmic_flops_per_launch": flops, "mean_iters": float(it_np.mean()),
-                         "frac_executed_only": achieved_exec / FP64_PEAK_TFLOPS,
-                         "note": "achieved counts SURVEY 8(d)'s algorithmic work incl. one termination pass per check; box-only problems get their "
-                                 "dual residual in closed form and do not execute that pass: frac_executed_only counts it*2*nt^2 + 2*nt*np only"},
+                         "kernel_ms": k_ms, "executed_flops_per_launch": flops_exec, "algorithmic_flops_per_launch_8d": flops, "mean_iters": float(it_np.mean()),
+                         "frac_algorithmic_8d": achieved_alg / FP64_PEAK_TFLOPS,
+                         "note": "achieved / frac count the flops the kernel EXECUTES (it*2*nt^2 + 2*nt*np per solve); SURVEY 8(d)'s algorithmic count adds one "
+                                 "termination pass per check that box-only problems do not run (closed-form dual residual): frac_algorithmic_8d"},
             "solver": {"mean_iters": float(it_np.mean()), "max_iters": int(it_np.max()), "solved_frac": float((st_np == 1).mean())},
             "latency": lat, "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if extra is not None:
+            line["configs"] = extra
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[2], [3], [4] as driver-run records next to the configs[1] headline (N = 1): each at the PARITY settings its
+# GPU tests prove (tests/test_gpu_at_size.py), device-timed with CUDA events, with its own roofline entry.
+# ----------------------------------------------------------------------------------------------------------------------------
+def _time_device(solve, reps, flush):
+    import torch
+    for _ in range(2): solve()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); solve(); b.record(); torch.cuda.synchronize(); ts.append(a.elapsed_time(b))
+    return float(np.mean(ts))
+
+
+def _device_io(_lib, dev, n, nx, nu, H, x0_h, xref_h, uref_h, full=True):
+    import torch
+    f64 = dict(dtype=torch.float64, device=dev)
+    t = {"x0": torch.from_numpy(np.ascontiguousarray(x0_h)).to(dev), "xref": torch.from_numpy(np.ascontiguousarray(xref_h)).to(dev),
+         "uref": torch.from_numpy(np.ascontiguousarray(uref_h)).to(dev), "status": torch.empty(n, dtype=torch.int32, device=dev),
+         "iters": torch.empty(n, dtype=torch.int32, device=dev), "u0": torch.empty((n, nu), **f64), "objective": torch.empty(n, **f64),
+         "prim_res": torch.empty(n, **f64), "dual_res": torch.empty(n, **f64)}
+    if full:
+        t.update({"u": torch.empty((n, H, nu), **f64), "e_u": torch.empty((n, H, nu), **f64), "x": torch.empty((n, H + 1, nx), **f64), "e_x": torch.empty((n, H + 1, nx), **f64)})
+    io = _lib.BatchIO(); io.batch = n
+    io.xref_broadcast = int(xref_h.ndim == 1); io.uref_broadcast = int(uref_h.ndim == 1)
+    for k, v in t.items(): setattr(io, k, v.data_ptr())
+    return io, t
+
+
+def other_configs(mpc, dev, cpu=True):
+    import torch
+    from almpc_b200 import _lib
+    out = []
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    stream = lambda: torch.cuda.current_stream().cuda_stream
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
+
+    # ---- configs[3]: horizon sweep, quadruple tank, batch 16 384, automatic kernel choice (on-chip -> shared-memory -> stage-wise)
+    sweep = []
+    n = 16384
+    x0_h, xref_h, uref_h = make_batch(n, seed=0)
+    for Hh in (10, 20, 30, 50, 75, 100, 150, 200):
+        sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
+        Cn = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_solver="b200",
+                                    mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA)
+        m = Cn.tuning.modeler; info = m.info
+        io, t = _device_io(_lib, dev, n, 4, 2, Hh, x0_h, xref_h, uref_h)
+        ms = _time_device(lambda: m.solve_batch_device(io, stream()), 3, flush)
+        io_s = _lib.BatchIO()
+        for f, _t in io._fields_: setattr(io_s, f, getattr(io, f))
+        for f in ("u", "e_u", "x", "e_x", "u0", "objective"): setattr(io_s, f, None)
+        k_ms = _time_device(lambda: m.solve_batch_device(io_s, stream()), 3, flush)
+        it = t["iters"].cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
+        rec = {"H": Hh, "nz": info.nz, "kernel_id": info.kernel, "kernel": kernel_name(info, SIGMA), "ms": ms, "solves_per_s": n / ms * 1e3, "kernel_ms": k_ms,
+               "mean_iters": float(it.mean()), "max_iters": int(it.max()), "solved_frac": float((st == 1).mean())}
+        if info.kernel == 4:      # stage-wise kernel: bound by streaming its per-problem state (6 row passes of nz doubles per iteration)
+            by = float(it.sum()) * 6 * info.nz * 8; fl = float(it.sum()) * Hh * 2 * (2 * 16 + 4 * 8 + 4)
+            rec["roofline"] = {"bound": "hbm", "achieved": by / (k_ms * 1e-3) / 1e9, "peak": _hbm_peak(), "unit": "GB/s", "frac": by / (k_ms * 1e-3) / 1e9 / _hbm_peak(),
+                               "fp64_tflops": fl / (k_ms * 1e-3) / 1e12, "fp64_frac": fl / (k_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                               "note": "algorithmic state bytes = iterations x 6 passes x nz x 8 B (w read twice + written, q read, d written + read); stage flops = iterations x H x 2 x 68"}
+        else:
+            fl = executed_flops(info, it, CHECK)
+            rec["roofline"] = {"bound": "tensor", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (k_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
+        sweep.append(rec)
+        m.close()
+    out.append({"config": "configs[3]: quadruple-tank tracking MPC, horizon sweep H = 10..200, batch 16384 (rng(0) inputs of configs[1]), cold start",
+                "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "sigma": SIGMA, "outputs": "u,e_u,x,e_x,u0,objective,status,iters,residuals (device resident)",
+                "crossover": "condensed DMMA kernels up to nz = 120 (H = 60), stage-wise (Riccati) kernel beyond; see profiles/r02/ricsweep_config4_*.jsonl for both kernels at every H",
+                "sweep": sweep})
+
+    # ---- configs[2]: random stable LTI nx = 64, nu = 16, H = 50, terminal LQR cost + terminal equality, batch 8 192
+    rng = np.random.default_rng(1); nx, nu, Hh, n = 64, 16, 50, 8192
+    G = rng.standard_normal((nx, nx)); A3 = 0.95 * G / np.abs(np.linalg.eigvals(G)).max(); B3 = rng.standard_normal((nx, nu)) / 8
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A3, B3, mpc.Hyperrectangle(-1e3 * np.ones(nx), 1e3 * np.ones(nx)), mpc.Hyperrectangle(-np.ones(nu), np.ones(nu)))
+    t0 = time.perf_counter()
+    Cn = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 1, [0.0] * nx, [0.0] * nu, mpc_solver="b200", mpc_terminal_ingredient="equality",
+                                mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=10, mpc_b200_sigma=0.0, mpc_b200_max_iter=4000)
+    design_s = time.perf_counter() - t0
+    m = Cn.tuning.modeler; info = m.info
+    x0_h = np.random.default_rng(3).standard_normal((n, nx)); xr = np.zeros(nx); ur = np.zeros(nu)
+    io, t = _device_io(_lib, dev, n, nx, nu, Hh, x0_h, xr, ur)
+    ms = _time_device(lambda: m.solve_batch_device(io, stream()), 3, flush)
+    launches = int(m.timing()["kernel_launches"])
+    it = t["iters"].cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
+    fl = executed_flops(info, it, 10)
+    rec = {"config": "configs[2]: random stable LTI (rng(1)) nx=64 nu=16 H=50, input box [-1,1]^16, terminal LQR cost + terminal equality, batch 8192, x0 = N(0,I) (rng(3)), cold start",
+           "eps_abs": EPS, "eps_rel": EPS, "check_every": 10, "sigma": 0.0, "nz": info.nz, "mg": info.mg, "nt_pad": info.nt_pad, "kernel_id": info.kernel, "kernel": kernel_name(info, 0.0),
+           "design_s": design_s, "ms": ms, "solves_per_s": n / ms * 1e3, "gpu_launches": launches, "mean_iters": float(it.mean()), "max_iters": int(it.max()),
+           "solved_frac": float((st == 1).mean()), "infeasible": int((st == -3).sum()), "iteration_cap": int((st == -2).sum()),
+           "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                        "note": "whole solve (all launches incl. checks, compaction, recovery); flops = iterations x 2 nt^2 + one pass per check with [[Pc,G'],[G,0]], nt = 864 (unpadded), "
+                                "counted per problem up to ITS termination"}}
+    if cpu:
+        rec["cpu_baseline"] = _cpu_lti(A3, B3, nx, nu, Hh, Cn.tuning.terminal_ingredient.P, x0_h)
+    out.append(rec)
+    m.close()
+
+    # ---- configs[4]: NMPC, ResNet surrogate of the quadruple tank, H = 20, batch 4 096 (SQP kernel in place of Ipopt)
+    g = json.loads((ROOT / "tests" / "golden" / "qt_resnet_model.json").read_text())
+    f = mpc.ResNet(np.array(g["W_in"]), [(np.array(w), np.array(b)) for w, b in zip(g["W_h"], g["b_h"])], np.array(g["W_out"]), activation=g["activation"])
+    sys_ = mpc.ConstrainedBlackBoxControlDiscreteSystem(f, 4, 2, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
+    Cn = mpc.proceed_controller(sys_, "model_predictive_control", 20, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_programming_type="non_linear")
+    mod = Cn.tuning.modeler
+    n = 4096
+    x0_h, xref_h, uref_h = make_batch(n, seed=0)
+    io, t = _device_io(_lib, dev, n, 4, 2, 20, x0_h, xref_h, uref_h)
+    inner = torch.empty(n, dtype=torch.int32, device=dev); io.inner_iters = inner.data_ptr()
+    ms = _time_device(lambda: mod.solve_batch_device(io, stream()), 3, flush)
+    it = t["iters"].cpu().numpy().astype(np.float64); inn = inner.cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
+    nz = 40
+    fl = float((inn * 2 * nz * nz + it * (2 * nz * nz * 4 * 21 + 2 * nz ** 3 / 3 + 20 * 2 * (13 * 6 + 13 * 13 + 4 * 13) * (1 + 6))).sum())
+    rec = {"config": "configs[4]: NMPC with the ResNet surrogate (6 -> 13 -> [13x13 residual relu] -> 4, tests/golden/qt_resnet_model.json), H=20, batch 4096, inputs of configs[1], cold start",
+           "sqp_tol": 1e-6, "inner_eps_abs": 1e-9, "kernel": "nmpc_sqp_kernel", "ms": ms, "solves_per_s": n / ms * 1e3, "sqp_iters_mean": float(it.mean()), "sqp_iters_max": int(it.max()),
+           "inner_admm_iters_mean": float(inn.mean()), "solved_frac": float((st == 1).mean()),
+           "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
+                        "note": "useful flops = inner ADMM iterations x 2 nz^2 + SQP iterations x (K = Hc + 2 sum Gamma' W Gamma: 2 nz^2 nx (H+1); Cholesky-equivalent of the inverse nz^3 2/3; "
+                                "network + forward-mode Jacobian per stage); the kernel is latency/issue bound, not FP64 bound (DESIGN.md section 5.4)"}}
+    if cpu:
+        rec["cpu_baseline"] = _cpu_nmpc(g, x0_h, xref_h, uref_h)
+    out.append(rec)
+    mod.close()
+    return out
+
+
+def _hbm_peak():
+    try:
+        return float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except Exception:
+        return 6650.0      # B200_PROFILING.md fallback
+
+
+def _cpu_lti(A3, B3, nx, nu, Hh, P, x0_h, sample=None):
+    """The reference's path for configs[2] restated: OSQP port on the reference's sparse encoding (12 192 variables), library defaults, one
+    workspace per thread, bounded sample."""
+    from oracle import mpc_oracle as mo, osqp_ref as orf
+    ncores = os.cpu_count() or 1
+    sample = sample or max(ncores, 16)
+    qp = mo.build_reference_qp(A3, B3, 100 * np.eye(nx), 0.1 * np.eye(nu), np.zeros((nu, nu)), P, Hh, np.zeros(nx), np.zeros(nu), x0_h[0], -np.ones(nu), np.ones(nu),
+                               terminal="equality")
+    prob = orf.Problem(qp.P, qp.q, qp.A, qp.l, qp.u)
+    rows = np.concatenate([qp.x0_rows, qp.xref_rows, qp.uref_rows])
+    sel = np.concatenate([qp.idx["u"].T.ravel(), qp.idx["x"].T.ravel()])
+    vals = np.hstack([x0_h[:sample], np.zeros((sample, nx * (Hh + 1) + nu * Hh))])
+    stg = orf.default_settings()
+    orf.solve_batch(prob, stg, rows, vals[:ncores], sel, nthreads=ncores)
+    t0 = time.perf_counter()
+    r = orf.solve_batch(prob, stg, rows, vals, sel, cold_start=True, nthreads=ncores)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "solves/s", "cores": ncores, "kind": "port",
+            "sample": f"{sample} problems, OSQP 0.6 defaults (eps 1e-3) on the reference's sparse model (n=12192), cold start; mean iters {float(r['iters'].mean()):.0f}; "
+                      f"solved {float((r['status'] == 1).mean()):.2f}"}
+
+
+def _cpu_nmpc(g, x0_h, xref_h, uref_h, sample=24):
+    """Ipopt stand-in for configs[4]: the oracle's independent L-BFGS-B solve of the same NLP, one problem at a time on one core (no Ipopt / JuMP here)."""
+    from oracle import mpc_oracle as mo, nn_oracle as no
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
+    mdl = no.NeuralModel(g["arch"], g["activation"], np.array(g["W_in"]), [np.array(w) for w in g["W_h"]], [np.array(b) for b in g["b_h"]], np.array(g["W_out"]))
+    Q = 100.0 * np.eye(4); R = 0.1 * np.eye(2); S = np.zeros((2, 2))
+    _, Aj, Bj = no.jacobian(mdl, x_ref[None], u_ref[None]); P = mo.dare(Aj[0], Bj[0], Q, R)
+    t0 = time.perf_counter()
+    for i in range(sample):
+        no.nmpc_local_opt(mdl, Q, R, S, P, 20, umin, umax, x0_h[i], xref_h[i], uref_h)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "solves/s", "cores": 1, "kind": "port", "sample": f"{sample} problems, scipy L-BFGS-B on the single-shooting NLP (Ipopt stand-in), one core"}
 
 
 def closed_loop_latency(mpc, Cn, steps=200):
@@ -372,6 +571,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--ref-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[0],[2],[3],[4] records (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
