@@ -25,7 +25,7 @@ class Settings(C.Structure):
     _fields_ = [("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("rho", C.c_double),
                 ("rho_eq_scale", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("max_iter", C.c_int32),
                 ("check_every", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32), ("ladder_iter", C.c_int32), ("ladder_kappa", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("n_devices", C.c_int32), ("device_ids", C.c_int32 * 8), ("reserved", C.c_int32 * 1)]
 
 
 class LinearDesc(C.Structure):
@@ -153,6 +153,11 @@ def default_nmpc_settings(**kw) -> NmpcSettings:
     lib().mpcb_default_nmpc_settings(C.byref(s))
     for k, v in kw.items():
         if hasattr(s, k) and k != "qp": setattr(s, k, v)
+        elif k == "devices":
+            ids = [int(d) for d in v]
+            if not 1 <= len(ids) <= 8: raise ValueError("devices: 1..8 device ordinals")
+            s.qp.n_devices = len(ids); s.qp.device = ids[0]
+            for i, d in enumerate(ids): s.qp.device_ids[i] = d
         elif hasattr(s.qp, k): setattr(s.qp, k, v)
         else: raise TypeError(f"unknown NMPC setting {k!r}")
     return s
@@ -162,6 +167,12 @@ def default_settings(**kw) -> Settings:
     s = Settings()
     lib().mpcb_default_settings(C.byref(s))
     for k, v in kw.items():
+        if k == "devices":          # devices=[0, 1, ...]: one handle driving several GPUs from this process
+            ids = [int(d) for d in v]
+            if not 1 <= len(ids) <= 8: raise ValueError("devices: 1..8 device ordinals")
+            s.n_devices = len(ids); s.device = ids[0]
+            for i, d in enumerate(ids): s.device_ids[i] = d
+            continue
         if not hasattr(s, k):
             raise TypeError(f"unknown solver setting {k!r}")
         setattr(s, k, v)

@@ -18,6 +18,7 @@
 #include "admm_stream.cuh"
 #include "closed_loop.cuh"
 #include "host_design.hpp"
+#include "multi_device.hpp"
 #include "recover.cuh"
 
 namespace mpcb {
@@ -63,6 +64,9 @@ struct mpcb_handle {
   size_t smem_optin = 0;
   cudaEvent_t busy_ev = nullptr;            // end of the last enqueued call: the next call's stream waits on it (one call in flight per handle)
   bool busy_recorded = false;
+  // multi-device handle (settings.n_devices > 1): this handle is the shard owner of device_ids[0]; `peers` own the other devices
+  std::vector<mpcb_handle*> peers;
+  cudaEvent_t fan_ev = nullptr, done_ev = nullptr;   // device entry: inputs ready on the caller's stream / this peer's shard is back in the caller's arrays
   DevBuf<double> Tfrag2, rho2, rinv2;       // second rung of the rho ladder (settings.ladder_iter): operator and step sizes
   DevBuf<int32_t> remap;                    // problems the first pass left unsolved
   bool ladder = false;
@@ -310,6 +314,78 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
   return MPCB_OK;
 }
 
+mpcb::ShardDims dims_of(const mpcb_handle* h) {
+  const mpcb::Design& D = h->D;
+  return mpcb::ShardDims{(size_t)D.nx, (size_t)D.nu, (size_t)D.H, (size_t)D.nz, (size_t)D.nt};
+}
+
+// Device entry of a multi-device handle: the caller's buffers live on device_ids[0].  Shard r > 0 travels to its device as peer copies
+// (NVLink) on that device's stream, is solved there, and its results are peer-copied straight back into the caller's arrays; the caller's
+// stream waits on every peer's completion event.  Everything is enqueued: the call stays asynchronous with respect to the host (for the
+// on-chip / stage-wise kernels).
+int enqueue_device_multi(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st) {
+  const int ndev = 1 + (int)h->peers.size();
+  const mpcb::ShardDims d = dims_of(h);
+  const long long Bn = io.batch;
+  const int root = h->st.device;
+  CUDA_TRY(cudaEventRecord(h->fan_ev, st));
+  int launches = 0;
+  for (int r = 1; r < ndev; r++) {
+    mpcb_handle* p = h->peers[(size_t)r - 1];
+    long long lo, hi;
+    mpcb::shard_range(Bn, r, ndev, &lo, &hi);
+    const long long n = hi - lo;
+    if (n <= 0) continue;
+    const int dev = p->st.device;
+    CUDA_TRY(cudaSetDevice(dev));
+    cudaStream_t ps = p->stream;
+    CUDA_TRY(cudaStreamWaitEvent(ps, h->fan_ev, 0));
+    const mpcb_batch_io sio = mpcb::shard_io(io, lo, n, d);      // this shard's slices of the caller's (root-device) arrays
+    mpcb_batch_io pio = sio;                                       // the same shard in this peer's own buffers
+    struct In { const double* src; DevBuf<double>* dst; size_t cnt; const double** slot; };
+    In ins[5] = {{sio.x0, &p->x0, d.nx * (size_t)n, &pio.x0}, {sio.xref, &p->xref, io.xref_broadcast ? d.nx : d.nx * (size_t)n, &pio.xref},
+                 {sio.uref, &p->uref, io.uref_broadcast ? d.nu : d.nu * (size_t)n, &pio.uref}, {sio.warm_u, &p->warm_v, d.nz * (size_t)n, &pio.warm_u},
+                 {sio.warm_y, &p->warm_y, d.ny * (size_t)n, &pio.warm_y}};
+    for (auto& in : ins) {
+      if (!in.src) continue;
+      CUDA_TRY(in.dst->ensure(in.cnt));
+      CUDA_TRY(cudaMemcpyPeerAsync(in.dst->p, dev, in.src, root, in.cnt * sizeof(double), ps));
+      *in.slot = in.dst->p;
+    }
+    struct Out { double* dst; DevBuf<double>* buf; size_t cnt; double** slot; };
+    Out outs[9] = {{sio.u, &p->u, d.nz * (size_t)n, &pio.u}, {sio.e_u, &p->e_u, d.nz * (size_t)n, &pio.e_u}, {sio.x, &p->x, d.nx * (d.H + 1) * (size_t)n, &pio.x},
+                   {sio.e_x, &p->e_x, d.nx * (d.H + 1) * (size_t)n, &pio.e_x}, {sio.u0, &p->u0, d.nu * (size_t)n, &pio.u0}, {sio.prim_res, &p->pres, (size_t)n, &pio.prim_res},
+                   {sio.dual_res, &p->dres, (size_t)n, &pio.dual_res}, {sio.objective, &p->obj, (size_t)n, &pio.objective}, {sio.y, &p->y, d.ny * (size_t)n, &pio.y}};
+    for (auto& o : outs) {
+      if (!o.dst) continue;
+      CUDA_TRY(o.buf->ensure(o.cnt));
+      *o.slot = o.buf->p;
+    }
+    CUDA_TRY(p->status.ensure((size_t)n)); CUDA_TRY(p->iters.ensure((size_t)n));
+    pio.status = p->status.p; pio.iters = p->iters.p;
+    int rc = enqueue_device(p, pio, ps, nullptr);
+    if (rc != MPCB_OK) return rc;
+    launches += p->timing.kernel_launches;
+    for (auto& o : outs)
+      if (o.dst) CUDA_TRY(cudaMemcpyPeerAsync(o.dst, root, o.buf->p, dev, o.cnt * sizeof(double), ps));
+    if (sio.status) CUDA_TRY(cudaMemcpyPeerAsync(sio.status, root, p->status.p, dev, (size_t)n * sizeof(int32_t), ps));
+    if (sio.iters) CUDA_TRY(cudaMemcpyPeerAsync(sio.iters, root, p->iters.p, dev, (size_t)n * sizeof(int32_t), ps));
+    CUDA_TRY(cudaEventRecord(p->done_ev, ps));
+  }
+  CUDA_TRY(cudaSetDevice(root));
+  long long lo0, hi0;
+  mpcb::shard_range(Bn, 0, ndev, &lo0, &hi0);
+  int rc = enqueue_device(h, mpcb::shard_io(io, lo0, hi0 - lo0, d), st, nullptr);
+  if (rc != MPCB_OK) return rc;
+  launches += h->timing.kernel_launches;
+  for (mpcb_handle* p : h->peers) CUDA_TRY(cudaStreamWaitEvent(st, p->done_ev, 0));
+  h->timing.kernel_launches = launches;
+  h->timing.batch = Bn;
+  return MPCB_OK;
+}
+
+int solve_linear_host(mpcb_handle* h, const mpcb_batch_io* hio);
+
 }  // namespace
 
 extern "C" {
@@ -360,6 +436,9 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
     cudaGetLastError();
     return fail(MPCB_ERR_NO_DEVICE, "no CUDA device visible: libmpcb200 has no CPU fallback");
   }
+  std::vector<int> dev_ids;
+  { int rcd = mpcb::parse_devices(st, ndev, dev_ids); if (rcd != MPCB_OK) return rcd; }
+  if (!dev_ids.empty()) st.device = dev_ids[0];
   if (st.device < 0 || st.device >= ndev) return fail(MPCB_ERR_INVALID, "settings.device out of range");
   CUDA_TRY(cudaSetDevice(st.device));
   cudaDeviceProp prop;
@@ -418,13 +497,36 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   if (cudaEventCreateWithFlags(&h->busy_ev, cudaEventDisableTiming) != cudaSuccess) { mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed"); }
   rc = upload_design(h);
   if (rc != MPCB_OK) { std::string keep = g_err; mpcb_destroy(h); return fail(rc, keep); }
+  if (cudaEventCreateWithFlags(&h->fan_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->done_ev, cudaEventDisableTiming) != cudaSuccess) {
+    mpcb_destroy(h); return fail(MPCB_ERR_CUDA, "cudaEventCreate failed");
+  }
+  // multi-device handle: the same design replicated on the other devices (each peer is an ordinary single-device handle with the same
+  // kernel choice), peer access switched on both ways so that the device entry's shard copies go over NVLink directly
+  for (size_t i = 1; i < dev_ids.size(); i++) {
+    mpcb_settings ps = st;
+    ps.n_devices = 0; ps.device = dev_ids[i]; ps.kernel = h->info.kernel;
+    mpcb_handle* peer = nullptr;
+    rc = mpcb_create_linear(desc, &ps, &peer);
+    if (rc != MPCB_OK) { std::string keep = g_err; mpcb_destroy(h); return fail(rc, "device " + std::to_string(dev_ids[i]) + ": " + keep); }
+    h->peers.push_back(peer);
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dev_ids[i], st.device) == cudaSuccess && can) { cudaSetDevice(dev_ids[i]); cudaDeviceEnablePeerAccess(st.device, 0); }
+    if (cudaDeviceCanAccessPeer(&can, st.device, dev_ids[i]) == cudaSuccess && can) { cudaSetDevice(st.device); cudaDeviceEnablePeerAccess(dev_ids[i], 0); }
+    cudaGetLastError();      // "already enabled" is not an error here
+  }
+  cudaSetDevice(st.device);
+  h->st.n_devices = (int32_t)dev_ids.size();
   *out = h;
   return MPCB_OK;
 }
 
 void mpcb_destroy(mpcb_handle* h) {
   if (!h) return;
+  for (mpcb_handle* p : h->peers) mpcb_destroy(p);
+  h->peers.clear();
   cudaSetDevice(h->st.device);
+  if (h->fan_ev) cudaEventDestroy(h->fan_ev);
+  if (h->done_ev) cudaEventDestroy(h->done_ev);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->remap.release();
   for (DevBuf<double>* b : {&h->Tfrag, &h->Cfrag, &h->Lt, &h->lo, &h->hi, &h->rho, &h->rinv, &h->Tfrag2, &h->rho2, &h->rinv2, &h->A, &h->B, &h->Q, &h->R, &h->S, &h->P, &h->x0,
@@ -469,11 +571,45 @@ int mpcb_get_design(const mpcb_handle* h, double* Pc, double* Lq, double* G, dou
 int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* io, void* cuda_stream) {
   if (!h || !io) return fail(MPCB_ERR_INVALID, "null argument");
   CUDA_TRY(cudaSetDevice(h->st.device));
+  if (!h->peers.empty() && io->batch >= mpcb::MULTI_MIN_PER_DEVICE * (long long)(1 + h->peers.size())) {
+    if (!io->x0 || !io->xref || !io->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+    return enqueue_device_multi(h, *io, (cudaStream_t)cuda_stream);
+  }
   return enqueue_device(h, *io, (cudaStream_t)cuda_stream, nullptr);
 }
 
 int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
   if (!h || !hio) return fail(MPCB_ERR_INVALID, "null argument");
+  const int ndev = 1 + (int)h->peers.size();
+  if (ndev == 1 || hio->batch < mpcb::MULTI_MIN_PER_DEVICE * ndev) return solve_linear_host(h, hio);
+  if (!hio->x0 || !hio->xref || !hio->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  if ((hio->warm_u == nullptr) != (hio->warm_y == nullptr)) return fail(MPCB_ERR_INVALID, "warm_u and warm_y must be given together");
+  // one host thread per device, each running the ordinary single-device entry on its contiguous shard of the caller's arrays
+  const mpcb::ShardDims d = dims_of(h);
+  int rc = mpcb::run_sharded(ndev, [&](int r) {
+    long long lo, hi;
+    mpcb::shard_range(hio->batch, r, ndev, &lo, &hi);
+    if (hi <= lo) return (int)MPCB_OK;
+    const mpcb_batch_io sio = mpcb::shard_io(*hio, lo, hi - lo, d);
+    return solve_linear_host(r == 0 ? h : h->peers[(size_t)r - 1], &sio);
+  });
+  if (rc != MPCB_OK) return rc;
+  mpcb_timing t = h->timing;          // shard 0's; the whole job: slowest shard, summed counts
+  for (mpcb_handle* p : h->peers) {
+    t.total_ms = std::max(t.total_ms, p->timing.total_ms); t.h2d_ms = std::max(t.h2d_ms, p->timing.h2d_ms); t.solve_ms = std::max(t.solve_ms, p->timing.solve_ms);
+    t.recover_ms = std::max(t.recover_ms, p->timing.recover_ms); t.d2h_ms = std::max(t.d2h_ms, p->timing.d2h_ms);
+    t.total_iterations += p->timing.total_iterations; t.kernel_launches += p->timing.kernel_launches;
+  }
+  t.batch = hio->batch;
+  h->timing = t;
+  CUDA_TRY(cudaSetDevice(h->st.device));
+  return MPCB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int solve_linear_host(mpcb_handle* h, const mpcb_batch_io* hio) {
   const mpcb::Design& D = h->D;
   const long long Bn = hio->batch;
   if (Bn <= 0) return fail(MPCB_ERR_INVALID, "batch must be positive");
@@ -702,8 +838,34 @@ int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* hio) {
   return MPCB_OK;
 }
 
+int closed_loop_linear_single(mpcb_handle* h, const mpcb_closed_loop_io* cio);
+}  // namespace
+
+extern "C" {
+
 int mpcb_closed_loop_linear_batch(mpcb_handle* h, const mpcb_closed_loop_io* cio) {
   if (!h || !cio) return fail(MPCB_ERR_INVALID, "null argument");
+  const int ndev = 1 + (int)h->peers.size();
+  if (ndev == 1 || cio->batch < mpcb::MULTI_MIN_PER_DEVICE * ndev) return closed_loop_linear_single(h, cio);
+  if (!cio->x0 || !cio->xref || !cio->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  int rc = mpcb::run_sharded(ndev, [&](int r) {
+    long long lo, hi;
+    mpcb::shard_range(cio->batch, r, ndev, &lo, &hi);
+    if (hi <= lo) return (int)MPCB_OK;
+    const mpcb_closed_loop_io sio = mpcb::shard_closed_loop_io(*cio, lo, hi - lo, (size_t)h->D.nx, (size_t)h->D.nu);
+    return closed_loop_linear_single(r == 0 ? h : h->peers[(size_t)r - 1], &sio);
+  });
+  if (rc != MPCB_OK) return rc;
+  for (mpcb_handle* p : h->peers) { h->timing.total_ms = std::max(h->timing.total_ms, p->timing.total_ms); h->timing.kernel_launches += p->timing.kernel_launches; }
+  h->timing.batch = cio->batch;
+  CUDA_TRY(cudaSetDevice(h->st.device));
+  return MPCB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int closed_loop_linear_single(mpcb_handle* h, const mpcb_closed_loop_io* cio) {
   const mpcb::Design& D = h->D;
   const long long Bn = cio->batch;
   const int T = cio->steps;
@@ -768,4 +930,4 @@ int mpcb_closed_loop_linear_batch(mpcb_handle* h, const mpcb_closed_loop_io* cio
   return MPCB_OK;
 }
 
-}  // extern "C"
+}  // namespace

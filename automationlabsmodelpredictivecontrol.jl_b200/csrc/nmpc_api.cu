@@ -13,6 +13,7 @@
 #include "host_design.hpp"
 #include "nmpc.cuh"
 #include "nmpc_launch.hpp"
+#include "multi_device.hpp"
 
 using mpcb::api_fail;
 using mpcb::DevBuf;
@@ -45,6 +46,7 @@ struct mpcb_nmpc {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   mpcb_timing timing{};
   size_t smem_set = 0, smem_set_lin = 0;
+  std::vector<mpcb_nmpc*> peers;   // multi-device handle (settings.qp.n_devices > 1): the controllers on the other devices
 };
 
 namespace {
@@ -365,6 +367,14 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   if (d->terminal_mode != MPCB_TERMINAL_NONE && d->terminal_mode != MPCB_TERMINAL_EQUALITY && d->terminal_mode != MPCB_TERMINAL_CONTRACTIVE)
     return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: terminal ingredient must be 'none', 'equality' or 'contractive'");
   if (d->horizon <= 0 || !d->Q || !d->R || !d->umin || !d->umax || !d->xref || !d->uref) return api_fail(MPCB_ERR_INVALID, "mpcb_create_nmpc: bad arguments");
+  std::vector<int> dev_ids;
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+    int rcd = mpcb::parse_devices(q, ndev, dev_ids);
+    if (rcd != MPCB_OK) return rcd;
+    if (!dev_ids.empty()) st.qp.device = dev_ids[0];
+  }
   mpcb_nn* n = nullptr;
   int rc = mpcb_create_nn(d->nn, q.device, &n);
   if (rc != MPCB_OK) return rc;
@@ -445,12 +455,23 @@ int mpcb_create_nmpc(const mpcb_nmpc_desc* d, const mpcb_nmpc_settings* settings
   }
   for (auto& e : h->ev)
     if (cudaEventCreate(&e) != cudaSuccess) return bail(MPCB_ERR_CUDA, "cudaEventCreate failed");
+  for (size_t i = 1; i < dev_ids.size(); i++) {      // the same controller on the other devices of a multi-device handle
+    mpcb_nmpc_settings ps = st;
+    ps.qp.n_devices = 0; ps.qp.device = dev_ids[i];
+    mpcb_nmpc* peer = nullptr;
+    rc = mpcb_create_nmpc(d, &ps, &peer);
+    if (rc != MPCB_OK) { const std::string keep = mpcb_last_error(); return bail(rc, "device " + std::to_string(dev_ids[i]) + ": " + keep); }
+    h->peers.push_back(peer);
+  }
+  cudaSetDevice(st.qp.device);
   *out = h;
   return MPCB_OK;
 }
 
 void mpcb_destroy_nmpc(mpcb_nmpc* h) {
   if (!h) return;
+  for (mpcb_nmpc* p : h->peers) mpcb_destroy_nmpc(p);
+  h->peers.clear();
   if (h->nn) { cudaSetDevice(h->nn->device); if (h->nn->stream) cudaStreamSynchronize(h->nn->stream); }
   for (DevBuf<double>* b : {&h->Q, &h->Pt, &h->Hc, &h->lb, &h->ub, &h->xmin, &h->xmax, &h->Rinv, &h->x0, &h->xref, &h->uref, &h->warm_u, &h->warm_y, &h->u, &h->e_u, &h->x, &h->e_x, &h->u0,
                             &h->obj, &h->y, &h->step, &h->dres})
@@ -478,19 +499,44 @@ int mpcb_nmpc_get_timing(const mpcb_nmpc* h, mpcb_timing* t) {
 
 int mpcb_solve_nmpc_batch_device(mpcb_nmpc* h, const mpcb_batch_io* io, void* cuda_stream) {
   if (!h || !io) return api_fail(MPCB_ERR_INVALID, "null argument");
+  if (!h->peers.empty()) return api_fail(MPCB_ERR_INVALID, "multi-device NMPC handles shard through the host entries (mpcb_solve_nmpc_batch); the device entry needs a single-device handle");
   CUDA_TRY(cudaSetDevice(h->nn->device));
   return enqueue_nmpc(h, *io, (cudaStream_t)cuda_stream);
 }
 
 int mpcb_solve_relinearized_batch_device(mpcb_nmpc* h, const mpcb_batch_io* io, void* cuda_stream) {
   if (!h || !io) return api_fail(MPCB_ERR_INVALID, "null argument");
+  if (!h->peers.empty()) return api_fail(MPCB_ERR_INVALID, "multi-device NMPC handles shard through the host entries (mpcb_solve_relinearized_batch); the device entry needs a single-device handle");
   CUDA_TRY(cudaSetDevice(h->nn->device));
   return enqueue_nmpc(h, *io, (cudaStream_t)cuda_stream, true);
 }
 
 static int solve_nmpc_host(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin);
-int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) { return solve_nmpc_host(h, hio, false); }
-int mpcb_solve_relinearized_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) { return solve_nmpc_host(h, hio, true); }
+static int solve_nmpc_host_sharded(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin) {
+  if (!h || !hio) return api_fail(MPCB_ERR_INVALID, "null argument");
+  const int ndev = 1 + (int)h->peers.size();
+  if (ndev == 1 || hio->batch < mpcb::MULTI_MIN_PER_DEVICE * ndev) return solve_nmpc_host(h, hio, lin);
+  if (!hio->x0 || !hio->xref || !hio->uref) return api_fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  const size_t nx = h->nn->net.nx, nu = h->nn->net.nu, H = h->H, nz = h->nz;
+  const mpcb::ShardDims d{nx, nu, H, nz, nz + (h->state_box ? nx * H : 0) + (h->terminal_eq ? nx : 0)};
+  int rc = mpcb::run_sharded(ndev, [&](int r) {
+    long long lo, hi;
+    mpcb::shard_range(hio->batch, r, ndev, &lo, &hi);
+    if (hi <= lo) return (int)MPCB_OK;
+    const mpcb_batch_io sio = mpcb::shard_io(*hio, lo, hi - lo, d);
+    return solve_nmpc_host(r == 0 ? h : h->peers[(size_t)r - 1], &sio, lin);
+  });
+  if (rc != MPCB_OK) return rc;
+  for (mpcb_nmpc* p : h->peers) {
+    h->timing.total_ms = std::max(h->timing.total_ms, p->timing.total_ms); h->timing.solve_ms = std::max(h->timing.solve_ms, p->timing.solve_ms);
+    h->timing.total_iterations += p->timing.total_iterations; h->timing.kernel_launches += p->timing.kernel_launches;
+  }
+  h->timing.batch = hio->batch;
+  CUDA_TRY(cudaSetDevice(h->nn->device));
+  return MPCB_OK;
+}
+int mpcb_solve_nmpc_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) { return solve_nmpc_host_sharded(h, hio, false); }
+int mpcb_solve_relinearized_batch(mpcb_nmpc* h, const mpcb_batch_io* hio) { return solve_nmpc_host_sharded(h, hio, true); }
 
 static int solve_nmpc_host(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin) {
   if (!h || !hio) return api_fail(MPCB_ERR_INVALID, "null argument");
@@ -550,8 +596,25 @@ static int solve_nmpc_host(mpcb_nmpc* h, const mpcb_batch_io* hio, bool lin) {
   return MPCB_OK;
 }
 
+static int closed_loop_nmpc_single(mpcb_nmpc* h, const mpcb_closed_loop_io* cio);
 int mpcb_closed_loop_nmpc_batch(mpcb_nmpc* h, const mpcb_closed_loop_io* cio) {
   if (!h || !cio) return api_fail(MPCB_ERR_INVALID, "null argument");
+  const int ndev = 1 + (int)h->peers.size();
+  if (ndev == 1 || cio->batch < mpcb::MULTI_MIN_PER_DEVICE * ndev) return closed_loop_nmpc_single(h, cio);
+  if (!cio->x0 || !cio->xref || !cio->uref) return api_fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
+  int rc = mpcb::run_sharded(ndev, [&](int r) {
+    long long lo, hi;
+    mpcb::shard_range(cio->batch, r, ndev, &lo, &hi);
+    if (hi <= lo) return (int)MPCB_OK;
+    const mpcb_closed_loop_io sio = mpcb::shard_closed_loop_io(*cio, lo, hi - lo, (size_t)h->nn->net.nx, (size_t)h->nn->net.nu);
+    return closed_loop_nmpc_single(r == 0 ? h : h->peers[(size_t)r - 1], &sio);
+  });
+  if (rc != MPCB_OK) return rc;
+  CUDA_TRY(cudaSetDevice(h->nn->device));
+  return MPCB_OK;
+}
+
+static int closed_loop_nmpc_single(mpcb_nmpc* h, const mpcb_closed_loop_io* cio) {
   const long long Bn = cio->batch;
   const int T = cio->steps;
   if (Bn <= 0 || T <= 0) return api_fail(MPCB_ERR_INVALID, "batch and steps must be positive");

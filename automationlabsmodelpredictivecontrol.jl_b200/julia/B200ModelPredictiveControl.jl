@@ -22,7 +22,9 @@ struct MpcbSettings
     max_iter::Int32; check_every::Int32; device::Int32; kernel::Int32
     ladder_iter::Int32          # rho ladder for state-box rows (0: off), see include/mpcb200.h
     ladder_kappa::Int32
-    reserved::NTuple{2,Int32}
+    n_devices::Int32            # 2..8: one handle drives device_ids[1:n_devices] from this process (batch sharded, see include/mpcb200.h)
+    device_ids::NTuple{8,Int32}
+    reserved::NTuple{1,Int32}
 end
 
 struct MpcbLinearDesc
@@ -77,7 +79,14 @@ function default_settings(; kw...)
     ccall((:mpcb_default_settings, libmpcb200), Cvoid, (Ref{MpcbSettings},), s)
     d = Dict{Symbol,Any}(n => getfield(s[], n) for n in fieldnames(MpcbSettings))
     for (k, v) in kw
-        d[k] = v
+        if k == :devices          # devices = [0, 1, ...]: one handle, several GPUs (kw `mpc_b200_devices`)
+            ids = collect(Int32, v)
+            1 <= length(ids) <= 8 || error("devices: 1..8 device ordinals")
+            d[:n_devices] = Int32(length(ids)); d[:device] = ids[1]
+            d[:device_ids] = ntuple(i -> i <= length(ids) ? ids[i] : Int32(0), 8)
+        else
+            d[k] = v
+        end
     end
     return MpcbSettings((convert(fieldtype(MpcbSettings, n), d[n]) for n in fieldnames(MpcbSettings))...)
 end

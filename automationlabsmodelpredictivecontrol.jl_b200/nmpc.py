@@ -11,7 +11,7 @@ from . import _lib
 _NMPC_SETTING_KEYS = {"mpc_b200_sqp_tol": "sqp_tol", "mpc_b200_sqp_max_iter": "sqp_max_iter", "mpc_b200_ls_armijo": "ls_armijo", "mpc_b200_ls_noise": "ls_noise",
                       "mpc_b200_ls_max_halvings": "ls_max_halvings", "mpc_b200_eps_abs": "eps_abs", "mpc_b200_eps_rel": "eps_rel",
                       "mpc_b200_rho": "rho", "mpc_b200_max_iter": "max_iter", "mpc_b200_check_every": "check_every", "mpc_b200_device": "device",
-                      "mpc_b200_alpha": "alpha", "mpc_b200_sigma": "sigma"}
+                      "mpc_b200_alpha": "alpha", "mpc_b200_sigma": "sigma", "mpc_b200_devices": "devices"}
 
 
 class B200NonlinearModeler:

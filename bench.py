@@ -130,8 +130,10 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        gloo = dist.new_group(backend="gloo")          # host-side barrier for the phases in which only rank 0 drives the GPUs
 
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
@@ -232,6 +234,69 @@ def run_ours(args):
     if world > 1: dist.all_reduce(e2e_max, op=dist.ReduceOp.MAX)
     e2e_val = world * n * args.steps / float(e2e_max.item())          # whole job: all ranks' problems over the slowest rank's time
     assert np.array_equal(out["iters"], it_np)
+
+    # ---------------- the same end-to-end call returning only what a closed loop applies (u0 + convergence stats, 48 B per problem) ----------------
+    out0 = {k: out[k] for k in ("u0", "objective", "prim_res", "dual_res", "status", "iters")}
+    for _ in range(3): m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, want=("u0", "objective"), out=dict(out0))
+    e2e0_sum = 0.0
+    for _ in range(args.steps):
+        flush.zero_(); barrier()
+        t0 = time.perf_counter()
+        m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, want=("u0", "objective"), out=dict(out0))
+        e2e0_sum += time.perf_counter() - t0
+    e2e0_max = torch.tensor([e2e0_sum], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(e2e0_max, op=dist.ReduceOp.MAX)
+    e2e_u0_val = world * n * args.steps / float(e2e0_max.item())
+
+    # ---------------- pure device->host copy of one step's results (same bytes, same page-locked arrays, every rank at once): the PCIe ceiling of e2e ----------------
+    d2h_src = torch.empty(d2h // 8, dtype=torch.float64, device=dev); d2h_dst = torch.empty(d2h // 8, dtype=torch.float64).pin_memory()
+    for _ in range(2): d2h_dst.copy_(d2h_src, non_blocking=True); torch.cuda.synchronize()
+    cp_sum = 0.0
+    for _ in range(5):
+        barrier()
+        t0 = time.perf_counter(); d2h_dst.copy_(d2h_src, non_blocking=True); torch.cuda.synchronize(); cp_sum += time.perf_counter() - t0
+    cp_max = torch.tensor([cp_sum / 5], dtype=torch.float64, device=dev)
+    if world > 1: dist.all_reduce(cp_max, op=dist.ReduceOp.MAX)
+    d2h_copy = {"bytes_per_rank": int(d2h), "ms_max_over_ranks": float(cp_max.item()) * 1e3, "GBps_per_rank": d2h / float(cp_max.item()) / 1e9,
+                "GBps_aggregate": world * d2h / float(cp_max.item()) / 1e9,
+                "e2e_ceiling_solves_per_s": world * n / float(cp_max.item()),
+                "what": "torch copy_ of one step's result bytes device -> page-locked host, all ranks concurrently after a barrier, mean of 5, max over ranks"}
+    del d2h_src, d2h_dst
+
+    # ---------------- strong scaling: configs[1]'s fixed 65 536 problems split over the ranks (device-timed, with the gather) ----------------
+    strong = None
+    if world > 1:
+        ns = BATCH // world
+        io_s = _lib.BatchIO()
+        for f, _t in io._fields_: setattr(io_s, f, getattr(io, f))
+        io_s.batch = ns
+        pay_s = payload[:6 * ns]        # (the first ns rows of each block are what this shard writes; the gather below moves the same 48 B per problem)
+        gathered_s = [torch.empty_like(pay_s) for _ in range(world)] if rank == 0 else None
+
+        def step_s():
+            m.solve_batch_device(io_s, torch.cuda.current_stream().cuda_stream)
+            dist.gather(pay_s, gathered_s, dst=0)
+        for _ in range(3): step_s()
+        barrier()
+        se = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for k in range(args.steps):
+            flush.zero_(); se[k][0].record(); step_s(); se[k][1].record()
+        barrier()
+        ms_s = torch.tensor([sum(a.elapsed_time(b) for a, b in se)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms_s, op=dist.ReduceOp.MAX)
+        strong = {"total_batch": ns * world, "batch_per_gpu": ns, "ms_per_step": float(ms_s.item()) / args.steps, "value": ns * world * args.steps / (float(ms_s.item()) * 1e-3),
+                  "unit": "solves/s", "what": "fixed total batch split over the ranks (strong scaling), device-timed, max over ranks"}
+
+    # ---------------- ONE process driving all N GPUs through one multi-device handle (mpcb_settings.n_devices): rank 0 alone, the others wait on the host ----------------
+    single = None
+    if world > 1:
+        dist.barrier(group=gloo)
+        if rank == 0:
+            try:
+                single = single_process_multi_device(mpc, _lib, world, n, args.steps, flush)
+            except Exception as e:      # the contract line must survive a failure of this extra leg
+                single = {"error": repr(e)[:300]}
+        dist.barrier(group=gloo)
     line = None
     if rank == 0:
         # ---------------- config 1: closed-loop single-solve latency (B = 1, warm start), p50 ----------------
@@ -253,7 +318,10 @@ def run_ours(args):
                        "outputs": "u,e_u,x,e_x,u0,objective,status,iters,residuals"},
             "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "what": "mpcb_solve_linear_batch on page-locked host arrays, every rank on its shard concurrently, max over ranks",
-                    "phases_ms": {k: round(v, 4) for k, v in tim.items() if k.endswith("_ms")}},
+                    "phases_ms": {k: round(v, 4) for k, v in tim.items() if k.endswith("_ms")},
+                    "u0_only": {"value": e2e_u0_val, "unit": "solves/s", "d2h_bytes_per_step": int(sum(v.nbytes for v in out0.values())) * world,
+                                "what": "same call returning u0 + objective + residuals + status + iters only (what a closed loop consumes)"},
+                    "d2h_copy_ceiling": d2h_copy},
             "gpu_launches": int(launches_full_step * args.steps),
             "roofline": {"bound": "tensor", "kernel": kernel_name(info, SIGMA), "achieved": achieved, "peak": FP64_PEAK_TFLOPS,
                          "unit": "TFLOP/s", "frac": achieved / FP64_PEAK_TFLOPS,
@@ -272,10 +340,73 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if extra is not None:
             line["configs"] = extra
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if single is not None:
+            line["single_process_multi_device"] = single
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def single_process_multi_device(mpc, _lib, ndev, n_per_dev, steps, flush):
+    """a single host process (the Julia host of the north_star) drives all GPUs through ONE handle.  Device entry:
+    buffers on device 0, shards fanned out and gathered back over NVLink peer copies inside the call.  Host entry: page-locked host
+    arrays in, results out, one host thread + stream pair per device."""
+    import torch
+    A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = qt_model()
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
+    Cn = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS,
+                                mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA, mpc_b200_devices=list(range(ndev)))
+    m = Cn.tuning.modeler
+    n = ndev * n_per_dev
+    x0_h = np.concatenate([make_batch(n_per_dev, seed=r)[0] for r in range(ndev)]); xref_h = np.concatenate([make_batch(n_per_dev, seed=r)[1] for r in range(ndev)])
+    uref_h = make_batch(1, 0)[2]
+    dev = torch.device("cuda", 0)
+    io, t = _device_io(_lib, dev, n, 4, 2, H, x0_h, xref_h, uref_h)
+    step = lambda: m.solve_batch_device(io, torch.cuda.current_stream().cuda_stream)
+    for _ in range(3): step()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        flush.zero_(); ev[k][0].record(); step(); ev[k][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+    u0_only = _lib.BatchIO()
+    for f, _t in io._fields_: setattr(u0_only, f, getattr(io, f))
+    for f in ("u", "e_u", "x", "e_x"): setattr(u0_only, f, None)
+    step0 = lambda: m.solve_batch_device(u0_only, torch.cuda.current_stream().cuda_stream)
+    for _ in range(3): step0()
+    torch.cuda.synchronize()
+    for k in range(steps):
+        flush.zero_(); ev[k][0].record(); step0(); ev[k][1].record()
+    torch.cuda.synchronize()
+    ms0 = sum(a.elapsed_time(b) for a, b in ev) / steps
+    st = t["status"].cpu().numpy()
+    # host entry
+    pin = lambda shape, dt=torch.float64: torch.empty(shape, dtype=dt).pin_memory()
+    hx0 = pin((n, 4)); hxr = pin((n, 4)); hx0.copy_(torch.from_numpy(x0_h)); hxr.copy_(torch.from_numpy(xref_h))
+    out = {"u": pin((n, H, 2)).numpy(), "e_u": pin((n, H, 2)).numpy(), "x": pin((n, H + 1, 4)).numpy(), "e_x": pin((n, H + 1, 4)).numpy(),
+           "u0": pin((n, 2)).numpy(), "objective": pin((n,)).numpy(), "prim_res": pin((n,)).numpy(), "dual_res": pin((n,)).numpy(),
+           "status": pin((n,), torch.int32).numpy(), "iters": pin((n,), torch.int32).numpy()}
+    for _ in range(3): m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, out=out)
+    t0 = time.perf_counter()
+    for _ in range(steps): m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, out=out)
+    e2e = n * steps / (time.perf_counter() - t0)
+    out0 = {k: out[k] for k in ("u0", "objective", "prim_res", "dual_res", "status", "iters")}
+    for _ in range(3): m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, want=("u0", "objective"), out=dict(out0))
+    t0 = time.perf_counter()
+    for _ in range(steps): m.solve_batch(hx0.numpy(), hxr.numpy(), uref_h, want=("u0", "objective"), out=dict(out0))
+    e2e0 = n * steps / (time.perf_counter() - t0)
+    res = {"devices": ndev, "batch": n, "device_entry": {"ms_per_step": ms, "value": n / ms * 1e3, "unit": "solves/s",
+                                                          "what": "mpcb_solve_linear_batch_device on ONE multi-device handle: buffers on device 0, full outputs (2 KB/problem) gathered back "
+                                                                  "over NVLink peer copies inside the call; CUDA events on device 0's stream"},
+           "device_entry_u0_only": {"ms_per_step": ms0, "value": n / ms0 * 1e3, "unit": "solves/s", "what": "same, gathering u0 + stats only (48 B/problem)"},
+           "host_entry_e2e": {"value": e2e, "unit": "solves/s", "what": "mpcb_solve_linear_batch on page-locked host arrays, one host thread + stream pair per device, full outputs"},
+           "host_entry_e2e_u0_only": {"value": e2e0, "unit": "solves/s"}, "solved_frac": float((st == 1).mean())}
+    m.close()
+    return res
 
 
 # ----------------------------------------------------------------------------------------------------------------------------

@@ -82,7 +82,15 @@ typedef struct {
                            A batch-wide fixed rho leaves a few problems per 10^4 with thousands of iterations when many state
                            bounds are active (OSQP would adapt rho per problem); the second rung bounds that tail. */
   int32_t ladder_kappa; /* 10 when ladder_iter > 0 and this is <= 0 */
-  int32_t reserved[2];
+  int32_t n_devices;    /* <= 1: the handle lives on `device`.  2..8: ONE handle drives device_ids[0..n_devices-1] from one process:
+                           the per-system constants are replicated on every device at create; a batch is cut into n_devices contiguous shards
+                           (sizes differ by at most one problem) that are solved concurrently with no exchange during the solve.  Host entry
+                           (mpcb_solve_linear_batch, mpcb_closed_loop_linear_batch, and the NMPC host entries): one host thread and one stream pair
+                           per device, results land directly in the caller's arrays.  Device entry: buffers live on device_ids[0]; the shards of the other
+                           devices travel over NVLink as peer copies ordered by events (inputs out, results back into the caller's arrays), still
+                           asynchronous with respect to the host. */
+  int32_t device_ids[8];
+  int32_t reserved[1];
 } mpcb_settings;
 
 /* Linear (or linearised) MPC description = the data `_model_predictive_control_design` assembles for a
@@ -198,8 +206,11 @@ int mpcb_get_design(const mpcb_handle* h, double* Pc, double* Lq, double* G, dou
 
 /* The hot path: replaces update_initialization! + calculate! (computation_mpc.jl:17-55) for `batch` problems. */
 int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* host_io);
-/* Same with device-resident buffers on the handle's device; `cuda_stream` is a cudaStream_t (NULL = default
- * stream).  Asynchronous: returns after enqueueing. */
+/* Same with device-resident buffers on the handle's device (device_ids[0] of a multi-device handle); `cuda_stream` is a cudaStream_t
+ * (NULL = default stream).  Asynchronous: returns after enqueueing -- EXCEPT for controllers on MPCB_KERNEL_STREAMED, whose check
+ * periods are driven from the host (one stream synchronisation per check; not capturable into a CUDA graph).
+ * One call in flight per handle: the handle owns the work-queue counters and scratch buffers, so a call enqueued while the
+ * previous one still runs -- on any stream -- is ordered behind it by an event (it never races, it may serialise). */
 int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* dev_io, void* cuda_stream);
 
 /* Closed-loop batched simulation, resident on the GPU: repeats { solve from the current state (warm-started from the

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol(mpc):
 def test_struct_layouts_match_header(mpc):
     """ctypes mirrors must have the C layout (sizes computed by hand from include/mpcb200.h)."""
     L = mpc._lib
-    assert ctypes.sizeof(L.Settings) == 7 * 8 + 8 * 4
+    assert ctypes.sizeof(L.Settings) == 7 * 8 + 16 * 4
     assert ctypes.sizeof(L.LinearDesc) == 3 * 4 + 4 + 10 * 8 + 2 * 4
     assert ctypes.sizeof(L.Info) == 10 * 4 + 3 * 8
     assert ctypes.sizeof(L.BatchIO) == 8 + 3 * 8 + 2 * 4 + 14 * 8
