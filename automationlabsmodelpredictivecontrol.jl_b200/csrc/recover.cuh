@@ -281,13 +281,16 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const Re
 // returns false when no specialisation exists (caller falls back to recover_kernel)
 inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
   const unsigned grid = (unsigned)((R.batch + RECOVER_THREADS - 1) / RECOVER_THREADS);
+  int dev_slot = 0;
+  cudaGetDevice(&dev_slot);
+  dev_slot &= 63;
 #define MPCB_RS1(NX_, NU_, RCH_)                                                                                           \
   {                                                                                                                        \
     constexpr size_t smem = sizeof(double) * (RECOVER_THREADS / 32) * recover_small_warp_doubles<NX_, NU_, RCH_>();         \
-    static bool attr_set = false;                                                                                         \
-    if (smem > 48 * 1024 && !attr_set) {                                                                                  \
+    static bool attr_set[64] = {};      /* function attributes are per DEVICE (a multi-device handle launches on several) */  \
+    if (smem > 48 * 1024 && !attr_set[dev_slot]) {                                                                        \
       cudaFuncSetAttribute(recover_small_kernel<NX_, NU_, RCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-      attr_set = true;                                                                                                    \
+      attr_set[dev_slot] = true;                                                                                          \
     }                                                                                                                     \
     recover_small_kernel<NX_, NU_, RCH_><<<grid, RECOVER_THREADS, smem, st>>>(R);                                         \
     return true;                                                                                                          \
