@@ -32,7 +32,7 @@ namespace mpcb {
 
 namespace {
 
-constexpr int NBUF = 3;
+constexpr int NBUF = 2;      // double buffering: one chunk (>= 4 stages x ~500 cycles of sweep) covers the L2 / HBM latency of the next; the third buffer of the first version only cost chunk length
 constexpr int WARP_HDR = 16;   // doubles reserved per warp in front of its buffers (mbarriers), keeps the buffers 128-byte aligned
 
 constexpr int ev2(int n) { return (n + 1) & ~1; }

@@ -170,6 +170,8 @@ if __name__ == "__main__":
             run(H, 65536, 1e-7, 5, 0.0, reps=3, kernel=4)
     elif a.set == "ric1":
         run(50, 16384, 1e-7, 5, 0.0, reps=2, kernel=4)
+    elif a.set == "ric100":
+        run(100, 16384, 1e-7, 5, 0.0, reps=1, kernel=4)
     elif a.set == "ric200":
         run(200, 16384, 1e-7, 5, 0.0, reps=1, kernel=4)
     elif a.set == "ric20big":
