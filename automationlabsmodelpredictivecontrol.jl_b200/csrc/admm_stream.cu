@@ -297,6 +297,9 @@ struct InitParams {
   long long rows;
   double *Cst, *QB, *X, *R, *qn;
   int* idx; int* done; unsigned long long* red;
+  // warm start (OSQP: x = v0, z = A x = [v0; G v0], y = y0), both null for a cold start
+  const double *warm_v, *warm_y, *C, *rho;     // C: [NTp][NTp] check operator (rows >= nz hold G), rho: [NTp]
+  double alpha, sigma;
 };
 __global__ void stream_init_kernel(const InitParams P) {
   extern __shared__ double sp[];   // p vector of this problem
@@ -314,9 +317,21 @@ __global__ void stream_init_kernel(const InitParams P) {
     double acc = 0.0;
     for (int j = 0; j < P.np; j++) acc = fma(P.Lt[(size_t)j * P.NTp + n], sp[j], acc);
     const size_t off = (size_t)b * P.NTp + n;
-    P.QB[off] = acc; P.Cst[off] = 0.0; P.X[off] = 0.0;
-    P.R[off] = (n < P.nz) ? -acc : 0.0;
+    P.QB[off] = acc;
     if (n < P.nz) m = dmaxf(m, fabs(acc));
+    if (P.warm_v == nullptr || n >= P.nt) {
+      P.Cst[off] = 0.0; P.X[off] = 0.0;
+      P.R[off] = (n < P.nz) ? -acc : 0.0;
+    } else {
+      const double* v0 = P.warm_v + (size_t)b * P.nz;
+      double z;
+      if (n < P.nz) z = v0[n];
+      else { z = 0.0; for (int j = 0; j < P.nz; j++) z = fma(P.C[(size_t)n * P.NTp + j], v0[j], z); }     // general row: G v0
+      const double rho_n = P.rho[n], ys = P.warm_y[(size_t)b * P.nt + n] / rho_n;
+      P.Cst[off] = fma(1.0 - P.alpha, z, ys);
+      P.X[off] = (n < P.nz) ? z : 0.0;
+      P.R[off] = rho_n * (z - ys) + ((n < P.nz) ? fma(P.sigma, z, -acc) : 0.0);
+    }
   }
   // block max of |q|
   __shared__ double red[32];
@@ -513,7 +528,6 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
                          cudaStream_t stream, int* launches, std::string& err) {
   (void)sm_count;
   const int NTp = sc.NTp, nz = D.nz, nt = D.nt, mg = D.mg;
-  if (B.warm_v != nullptr) { err = "warm start is not supported by the streamed kernel yet"; return cudaErrorNotSupported; }
   if (B.batch > 0x7fffffffLL / 4) { err = "batch too large"; return cudaErrorInvalidValue; }
   cudaError_t e = ensure_work(sw, B.batch, NTp, st.check_every);
   if (e != cudaSuccess) { err = "workspace allocation"; return e; }
@@ -529,6 +543,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
     P.Lt = sc.Lt; P.x0 = B.x0; P.xref = B.xref; P.uref = B.uref; P.xref_bc = B.xref_bc; P.uref_bc = B.uref_bc; P.nx = D.nx; P.nu = D.nu;
     P.np = D.np; P.NTp = NTp; P.nz = nz; P.nt = nt; P.rows = rows; P.Cst = Cst; P.QB = QB; P.X = X; P.R = Rin; P.qn = qn; P.idx = idx; P.done = done;
     P.red = red;
+    P.warm_v = B.warm_v; P.warm_y = B.warm_y; P.C = sc.C; P.rho = sc.rho; P.alpha = st.alpha; P.sigma = st.sigma;
     stream_init_kernel<<<rows, 128, D.np * sizeof(double), stream>>>(P); nl++;
   }
   const int max_iter = ((st.max_iter + st.check_every - 1) / st.check_every) * st.check_every;

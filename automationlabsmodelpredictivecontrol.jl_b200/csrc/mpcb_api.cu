@@ -871,7 +871,6 @@ int closed_loop_linear_single(mpcb_handle* h, const mpcb_closed_loop_io* cio) {
   const int T = cio->steps;
   if (Bn <= 0 || T <= 0) return fail(MPCB_ERR_INVALID, "batch and steps must be positive");
   if (!cio->x0 || !cio->xref || !cio->uref) return fail(MPCB_ERR_INVALID, "x0, xref, uref are required");
-  if (cio->warm_start && h->info.kernel == MPCB_KERNEL_STREAMED) return fail(MPCB_ERR_INVALID, "warm-started closed loop needs an on-chip kernel (the streamed kernel has no warm start yet)");
   CUDA_TRY(cudaSetDevice(h->st.device));
   cudaStream_t st = h->stream;
   const size_t nx = D.nx, nu = D.nu, nz = D.nz, nt = D.nt, B = (size_t)Bn;

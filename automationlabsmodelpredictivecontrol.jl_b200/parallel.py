@@ -1,10 +1,9 @@
-"""Multi-GPU plumbing: the batch shards trivially (every (x0, reference) pair is an independent QP sharing read-only
-per-system constants), so there is NO data-path collective during the solve; one process per
-GPU solves its contiguous shard and a single gather of solutions + convergence statistics ends the step
-(NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+"""Multi-GPU plumbing of the one-process-per-GPU mode: the batch shards trivially (every (x0, reference) pair is an independent QP
+sharing read-only per-system constants), so there is NO data-path collective during the solve; every rank
+solves its contiguous shard and a single gather of solutions + convergence statistics ends the step (NCCL over NVLink on the GPU
+box, gloo in the CPU tests).  bench.py and tests/test_distributed_gloo.py both go through these functions.  (The other mode --
+one process driving several GPUs through one multi-device handle -- lives in the C ABI, csrc/multi_device.hpp.)"""
 from __future__ import annotations
-
-import numpy as np
 
 
 def shard_range(batch: int, rank: int, world: int) -> tuple[int, int]:
@@ -16,34 +15,22 @@ def shard_range(batch: int, rank: int, world: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
-def pack_payload(u0, iters, status, prim_res, dual_res, objective):
-    """One float64 row per problem: [u0..., iters, status, prim_res, dual_res, objective] -- a single contiguous buffer
-    so the final gather is one collective."""
+def payload_doubles(n: int, nu: int) -> int:
+    """Float64 slots of the flat per-shard gather payload: u0 (n x nu) | objective n | prim_res n | dual_res n | status n, iters n as int32."""
+    return (nu + 4) * n
+
+
+def payload_views(payload, n: int, nu: int):
+    """Views into the flat float64 payload that the kernels write DIRECTLY (the io pointers of the device entry point at them), so the
+    final gather needs no packing pass: 8 nu + 32 bytes per problem."""
     import torch
-    cols = [u0, iters.to(torch.float64).unsqueeze(1), status.to(torch.float64).unsqueeze(1), prim_res.unsqueeze(1),
-            dual_res.unsqueeze(1), objective.unsqueeze(1)]
-    return torch.cat(cols, dim=1).contiguous()
+    u0 = payload[: nu * n].view(n, nu)
+    obj = payload[nu * n:(nu + 1) * n]; pres = payload[(nu + 1) * n:(nu + 2) * n]; dres = payload[(nu + 2) * n:(nu + 3) * n]
+    ints = payload[(nu + 3) * n:(nu + 4) * n].view(torch.int32)
+    return {"u0": u0, "objective": obj, "prim_res": pres, "dual_res": dres, "status": ints[:n], "iters": ints[n:]}
 
 
-def unpack_payload(payload, nu: int):
-    import torch
-    return {"u0": payload[:, :nu], "iters": payload[:, nu].to(torch.int32), "status": payload[:, nu + 1].to(torch.int32),
-            "prim_res": payload[:, nu + 2], "dual_res": payload[:, nu + 3], "objective": payload[:, nu + 4]}
-
-
-def gather_to_rank0(payload, batch: int, group=None):
-    """Gather per-rank payload shards (possibly of unequal length) on rank 0, in problem order.  Returns the full
-    (batch, ncol) tensor on rank 0 and None elsewhere."""
-    import torch
+def gather_payloads(payload, gathered, dst: int = 0, group=None):
+    """The one collective of the path: every rank's payload to rank `dst` (`gathered`: list of world tensors there, None elsewhere)."""
     import torch.distributed as dist
-    world = dist.get_world_size(group); rank = dist.get_rank(group)
-    sizes = [shard_range(batch, r, world) for r in range(world)]
-    nmax = max(hi - lo for lo, hi in sizes)
-    ncol = payload.shape[1]
-    buf = torch.zeros((nmax, ncol), dtype=payload.dtype, device=payload.device)
-    buf[: payload.shape[0]] = payload
-    outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-    dist.gather(buf, outs, dst=0, group=group)
-    if rank != 0:
-        return None
-    return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(outs, sizes)], dim=0)
+    dist.gather(payload, gathered, dst=dst, group=group)

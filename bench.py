@@ -150,9 +150,10 @@ def run_ours(args):
     u = torch.empty((n, H, 2), **f64); e_u = torch.empty_like(u); x = torch.empty((n, H + 1, 4), **f64); e_x = torch.empty_like(x)
     # what the final gather carries lives in ONE flat buffer the kernels write directly (no packing pass):
     # [u0 n x 2 | objective n | prim_res n | dual_res n | status n (i32) iters n (i32)] = 6 n doubles
-    payload = torch.empty(6 * n, **f64)
-    u0 = payload[:2 * n].view(n, 2); obj = payload[2 * n:3 * n]; pres = payload[3 * n:4 * n]; dres = payload[4 * n:5 * n]
-    ints = payload[5 * n:].view(torch.int32); status = ints[:n]; iters = ints[n:]
+    from almpc_b200 import parallel
+    payload = torch.empty(parallel.payload_doubles(n, 2), **f64)
+    pv = parallel.payload_views(payload, n, 2)
+    u0, obj, pres, dres, status, iters = pv["u0"], pv["objective"], pv["prim_res"], pv["dual_res"], pv["status"], pv["iters"]
     io = _lib.BatchIO()
     io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.xref_broadcast = 0; io.uref_broadcast = 1
     io.u = u.data_ptr(); io.e_u = e_u.data_ptr(); io.x = x.data_ptr(); io.e_x = e_x.data_ptr(); io.u0 = u0.data_ptr()
@@ -167,7 +168,7 @@ def run_ours(args):
         stream = torch.cuda.current_stream().cuda_stream
         m.solve_batch_device(io, stream)
         if world > 1:
-            dist.gather(payload, gathered, dst=0)
+            parallel.gather_payloads(payload, gathered, dst=0)
 
     def barrier():
         if world > 1: dist.barrier()
@@ -266,7 +267,7 @@ def run_ours(args):
     # ---------------- strong scaling: configs[1]'s fixed 65 536 problems split over the ranks (device-timed, with the gather) ----------------
     strong = None
     if world > 1:
-        ns = BATCH // world
+        ns = min(hi - lo for lo, hi in (parallel.shard_range(BATCH, r, world) for r in range(world)))
         io_s = _lib.BatchIO()
         for f, _t in io._fields_: setattr(io_s, f, getattr(io, f))
         io_s.batch = ns
@@ -275,7 +276,7 @@ def run_ours(args):
 
         def step_s():
             m.solve_batch_device(io_s, torch.cuda.current_stream().cuda_stream)
-            dist.gather(pay_s, gathered_s, dst=0)
+            parallel.gather_payloads(pay_s, gathered_s, dst=0)
         for _ in range(3): step_s()
         barrier()
         se = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

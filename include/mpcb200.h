@@ -219,7 +219,7 @@ int mpcb_solve_linear_batch_device(mpcb_handle* h, const mpcb_batch_io* dev_io, 
  * times without leaving the device -- the update_initialization! / calculate! loop a user of the reference writes
  * (computation_mpc.jl:17-55; pattern of test/computation_mpc_test.jl:94-103) for a whole batch of plants.
  * HOST pointers.  x0 nx x batch; x_traj nx x (steps+1) x batch (column 1 = x0); u_traj nu x steps x batch; any output
- * may be NULL.  Only for controllers on the on-chip kernel when warm_start != 0. */
+ * may be NULL. */
 typedef struct {
   int64_t batch;
   int32_t steps;

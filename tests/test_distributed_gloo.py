@@ -1,6 +1,6 @@
-"""World-size-2 gloo test of the N > 1 host logic: shard ranges, payload packing, ordered gather on rank 0.
-The per-shard "solve" is stood in by the oracle twin (there is no GPU here); on the GPU box bench.py runs the same
-plumbing over NCCL with libmpcb200 doing the solves."""
+"""World-size-2 gloo test of the N > 1 host logic of the one-process-per-GPU mode: shard ranges, the flat gather payload the
+kernels write directly, the gather on rank 0 (`almpc_b200.parallel`, the same functions bench.py calls over NCCL).  The per-shard
+"solve" is stood in by the oracle twin (there is no GPU here)."""
 import os
 import socket
 
@@ -30,7 +30,7 @@ def _worker(rank, world, port, qtd, n, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import almpc_b200  # noqa: F401
-    from almpc_b200.parallel import gather_to_rank0, pack_payload, shard_range, unpack_payload
+    from almpc_b200.parallel import gather_payloads, payload_doubles, payload_views, shard_range
     from oracle import mpc_oracle as mo
     lo, hi = shard_range(n, rank, world)
     x0, xref, uref = qtd["x0"][lo:hi], qtd["xref"][lo:hi], qtd["uref"]
@@ -39,14 +39,22 @@ def _worker(rank, world, port, qtd, n, ret):
     p = mo.pack_params(x0, xref, uref)
     tw = mo.admm_condensed(c, p, mo.AdmmSettings(eps_abs=1e-5, eps_rel=1e-5, check_every=5))
     J = mo.recover(c, tw["v"], p)["objective"]
-    t = torch.from_numpy
-    payload = pack_payload(t(tw["v"][:, :2].copy()), t(tw["iters"]), t(tw["status"]), t(tw["prim_res"]), t(tw["dual_res"]), t(J))
-    full = gather_to_rank0(payload, n)
+    # every rank's payload has the size of the LARGEST shard (equal-size gather); a rank fills the first hi - lo rows of each block
+    nmax = max(b - a for a, b in (shard_range(n, r, world) for r in range(world)))
+    payload = torch.zeros(payload_doubles(nmax, 2), dtype=torch.float64)
+    pv = payload_views(payload, nmax, 2)
+    m = hi - lo
+    pv["u0"][:m] = torch.from_numpy(tw["v"][:, :2].copy()); pv["objective"][:m] = torch.from_numpy(J)
+    pv["prim_res"][:m] = torch.from_numpy(tw["prim_res"]); pv["dual_res"][:m] = torch.from_numpy(tw["dual_res"])
+    pv["status"][:m] = torch.from_numpy(tw["status"]); pv["iters"][:m] = torch.from_numpy(tw["iters"])
+    gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+    gather_payloads(payload, gathered, dst=0)
     if rank == 0:
-        out = unpack_payload(full, 2)
-        ret.put({k: v.numpy() for k, v in out.items()})
-    else:
-        assert full is None
+        out = {}
+        for r in range(world):
+            a, b = shard_range(n, r, world)
+            for k, v in payload_views(gathered[r], nmax, 2).items(): out.setdefault(k, []).append(v[: b - a].numpy().copy())
+        ret.put({k: np.concatenate(v) for k, v in out.items()})
     dist.barrier()
     dist.destroy_process_group()
 

@@ -523,3 +523,36 @@ def test_rho_ladder_bounds_the_state_box_tail(mpc, qt):
     assert set(tw["second_rung"]) == set(range(int(second.sum())))
     assert (tw["status"] == 1).all() and (two["iters"][sel] == tw["iters"]).mean() > 0.97
     assert np.abs(two["u"][sel].reshape(len(sel), -1) - tw["v"]).max() < 1e-5
+
+
+def test_streamed_warm_start(mpc, qt):
+    """OSQP's warm start (x, y of the previous solve) on the streamed kernel: same second-solve iteration counts and solutions as the
+    on-chip kernel (box-only, H = 20) and, with terminal-equality rows (z_g = G x of the warm point), as the on-chip general-row
+    kernel (H = 10); the GPU-resident closed loop runs warm-started on a streamed controller."""
+    n = 600
+    x0, xref, uref = qt_batch(qt, n, seed=23)
+    kw = dict(mpc_b200_eps_abs=1e-7, mpc_b200_eps_rel=1e-7, mpc_b200_check_every=5, mpc_b200_sigma=1e-6)
+    res = {}
+    for kern in (1, 2):
+        m = make_controller(mpc, qt, 20, mpc_b200_kernel=kern, **kw).tuning.modeler
+        r = m.solve_batch(x0, xref, uref, want=("u", "y"))
+        x1 = xref + (x0 - xref) @ qt["A"].T + (r["u"][:, 0] - uref) @ qt["B"].T          # the plants one step later
+        res[kern] = m.solve_batch(x1, xref, uref, want=("u", "y"), warm=(r["u"], r["y"]))
+        cold = m.solve_batch(x1, xref, uref, want=("u",))
+        assert res[kern]["iters"].mean() < cold["iters"].mean()
+    a, b = res[1], res[2]
+    same = a["iters"] == b["iters"]
+    assert same.mean() > 0.99 and (b["status"] == 1).all() and np.abs(a["u"][same] - b["u"][same]).max() < 1e-9 and np.abs(a["u"] - b["u"]).max() < 1e-6
+    xr = np.tile(qt["x_ref"], (n, 1)); x0e = xr + 0.002 * np.random.default_rng(3).standard_normal((n, 4))
+    out = []
+    for kern in (1, 2):
+        m = make_controller(mpc, qt, 10, terminal="equality", mpc_b200_kernel=kern, mpc_b200_max_iter=20000, **kw).tuning.modeler
+        r = m.solve_batch(x0e, xr, qt["u_ref"], want=("u", "y"))
+        out.append(m.solve_batch(x0e * 0.999 + 0.001 * xr, xr, qt["u_ref"], want=("u",), warm=(r["u"], r["y"])))
+    ok = (out[0]["status"] == 1) & (out[1]["status"] == 1)
+    assert ok.mean() > 0.5 and (out[0]["status"] == out[1]["status"]).mean() > 0.98
+    same = ok & (out[0]["iters"] == out[1]["iters"])
+    assert same.mean() > 0.45 and np.abs(out[0]["u"][same] - out[1]["u"][same]).max() < 1e-7
+    m = make_controller(mpc, qt, 70, mpc_b200_kernel=2, **kw).tuning.modeler
+    dev = m.closed_loop(x0[:64], xref[:64], uref, 3, warm_start=True)
+    assert (dev["unsolved_steps"] == 0).all()
