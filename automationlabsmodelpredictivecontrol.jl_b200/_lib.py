@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = (
     "mpcb_create_nn", "mpcb_destroy_nn", "mpcb_nn_rollout_batch", "mpcb_nn_rollout_batch_device", "mpcb_nn_jacobian_batch",
     "mpcb_nn_jacobian_batch_device", "mpcb_default_nmpc_settings", "mpcb_create_nmpc", "mpcb_destroy_nmpc", "mpcb_nmpc_get_design",
     "mpcb_nmpc_get_timing", "mpcb_solve_nmpc_batch", "mpcb_solve_nmpc_batch_device", "mpcb_solve_relinearized_batch",
-    "mpcb_solve_relinearized_batch_device", "mpcb_dare_batch", "mpcb_dare_batch_device", "mpcb_closed_loop_nmpc_batch",
+    "mpcb_solve_relinearized_batch_device", "mpcb_dare_batch", "mpcb_dare_batch_device", "mpcb_closed_loop_nmpc_batch", "mpcb_tune_rho",
 )
 
 _lib = None
@@ -112,6 +112,7 @@ def lib():
         L.mpcb_solve_linear_batch_device.argtypes = [C.c_void_p, C.POINTER(BatchIO), C.c_void_p]
         L.mpcb_closed_loop_linear_batch.argtypes = [C.c_void_p, C.POINTER(ClosedLoopIO)]
         L.mpcb_dare.argtypes = [C.c_int32, C.c_int32, _dp, _dp, _dp, _dp, _dp]
+        L.mpcb_tune_rho.argtypes = [C.POINTER(LinearDesc), C.POINTER(Settings), C.POINTER(BatchIO), C.c_int32, C.c_double, C.POINTER(C.c_double), _dp, _dp]
         L.mpcb_alloc_pinned.argtypes = [C.c_size_t]
         L.mpcb_alloc_pinned.restype = C.c_void_p
         L.mpcb_free_pinned.argtypes = [C.c_void_p]

@@ -520,6 +520,47 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   return MPCB_OK;
 }
 
+int mpcb_tune_rho(const mpcb_linear_desc* desc, const mpcb_settings* settings, const mpcb_batch_io* sample, int32_t n_candidates, double factor,
+                  double* best_rho, double* cand_rho, double* cand_mean_iters) {
+  if (!desc || !sample || !best_rho) return fail(MPCB_ERR_INVALID, "mpcb_tune_rho: null argument");
+  if (n_candidates < 1 || n_candidates > 16 || !(factor > 1.0)) return fail(MPCB_ERR_INVALID, "mpcb_tune_rho: 1..16 candidates, factor > 1");
+  if (sample->batch <= 0 || !sample->x0 || !sample->xref || !sample->uref) return fail(MPCB_ERR_INVALID, "mpcb_tune_rho: the sample needs x0, xref, uref");
+  mpcb_settings st;
+  if (settings) st = *settings; else mpcb_default_settings(&st);
+  st.n_devices = 0; st.ladder_iter = 0;
+  const long long n = sample->batch;
+  std::vector<int32_t> status((size_t)n), iters((size_t)n);
+  double rho0 = st.rho;
+  double best = 0.0, best_score = 1e300;
+  for (int c = -1; c < n_candidates; c++) {
+    // c = -1: the automatic value (only to learn rho0); candidates j = c - (n-1)/2
+    if (c == -1 && rho0 > 0.0) continue;
+    mpcb_settings sc = st;
+    sc.rho = (c == -1) ? 0.0 : rho0 * std::pow(factor, (double)(c - (n_candidates - 1) / 2));
+    mpcb_handle* h = nullptr;
+    int rc = mpcb_create_linear(desc, &sc, &h);
+    if (rc != MPCB_OK) return rc;
+    if (c == -1) { rho0 = h->info.rho; mpcb_destroy(h); continue; }
+    mpcb_batch_io io;
+    std::memset(&io, 0, sizeof(io));
+    io.batch = n; io.x0 = sample->x0; io.xref = sample->xref; io.uref = sample->uref;
+    io.xref_broadcast = sample->xref_broadcast; io.uref_broadcast = sample->uref_broadcast;
+    io.status = status.data(); io.iters = iters.data();
+    rc = mpcb_solve_linear_batch(h, &io);
+    const int cap = ((h->st.max_iter + h->st.check_every - 1) / h->st.check_every) * h->st.check_every;
+    mpcb_destroy(h);
+    if (rc != MPCB_OK) return rc;
+    double score = 0.0;
+    for (long long i = 0; i < n; i++) score += (status[(size_t)i] == MPCB_STATUS_SOLVED || status[(size_t)i] == MPCB_STATUS_PRIMAL_INFEASIBLE) ? (double)iters[(size_t)i] : 2.0 * cap;
+    score /= (double)n;
+    if (cand_rho) cand_rho[c] = sc.rho;
+    if (cand_mean_iters) cand_mean_iters[c] = score;
+    if (score < best_score) { best_score = score; best = sc.rho; }
+  }
+  *best_rho = best;
+  return MPCB_OK;
+}
+
 void mpcb_destroy(mpcb_handle* h) {
   if (!h) return;
   for (mpcb_handle* p : h->peers) mpcb_destroy(p);

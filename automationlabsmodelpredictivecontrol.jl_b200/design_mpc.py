@@ -110,7 +110,7 @@ def _model_predictive_control_design(system, horizon: int, sample_time: int, ref
     settings = _settings_from_kws(kws)
     if isinstance(method, LinearProgramming):
         modeler = B200Modeler(A, B, weights.Q, weights.R, weights.S, P, umin, umax, xmin, xmax, horizon,
-                              state_constraint=state_constraint, terminal=terminal, settings=settings)
+                              state_constraint=state_constraint, terminal=terminal, settings=settings, rho_tune=kws.get("mpc_b200_rho_tune"))
     elif isinstance(method, NonLinearProgramming):
         from .nmpc import B200NonlinearModeler
         modeler = B200NonlinearModeler(nn, weights.Q, weights.R, weights.S, P, umin, umax, xmin, xmax, horizon,

@@ -91,6 +91,23 @@ function default_settings(; kw...)
     return MpcbSettings((convert(fieldtype(MpcbSettings, n), d[n]) for n in fieldnames(MpcbSettings))...)
 end
 
+"""
+    tune_rho(desc::MpcbLinearDesc, settings::MpcbSettings, X0, xref, uref; candidates = 7, factor = 2.0) -> rho
+
+Step size for this controller chosen on a SAMPLE of the workload (`mpcb_tune_rho`): the batch-wide counterpart of OSQP's per-problem adaptive
+rho (the KKT factor is cached once for the whole batch).  Pass the result as `default_settings(rho = ...)`.
+"""
+function tune_rho(desc::MpcbLinearDesc, settings::MpcbSettings, X0::Matrix{Float64}, xref::Matrix{Float64}, uref::Matrix{Float64}; candidates::Integer = 7, factor::Float64 = 2.0)
+    best = Ref{Cdouble}(0.0)
+    GC.@preserve X0 xref uref begin
+        io = MpcbBatchIO(size(X0, 2), pointer(X0), pointer(xref), pointer(uref), size(xref, 2) == 1 ? 1 : 0, size(uref, 2) == 1 ? 1 : 0,
+                         C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
+        check(ccall((:mpcb_tune_rho, libmpcb200), Cint, (Ref{MpcbLinearDesc}, Ref{MpcbSettings}, Ref{MpcbBatchIO}, Int32, Cdouble, Ref{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                    desc, settings, io, Int32(candidates), factor, best, C_NULL, C_NULL), "mpcb_tune_rho")
+    end
+    return best[]
+end
+
 # ---- what `tuning.modeler` holds for mpc_solver = "b200" (types.jl:115 leaves the field untyped) ------------------
 mutable struct B200Modeler
     handle::Ptr{Cvoid}

@@ -18,7 +18,7 @@ def _colmajor(a, shape=None):
 
 class B200Modeler:
     def __init__(self, A, B, Q, R, S, P, umin, umax, xmin, xmax, horizon, state_constraint=False, terminal="none",
-                 settings: _lib.Settings | None = None):
+                 settings: _lib.Settings | None = None, rho_tune=None):
         L = _lib.lib()
         self.nx, self.nu = np.asarray(B).shape
         self.horizon = int(horizon)
@@ -33,6 +33,20 @@ class B200Modeler:
         d = _lib.LinearDesc(self.nx, self.nu, self.horizon, *[ptr(a) for a in keep], 1 if state_constraint else 0,
                             {"none": _lib.TERMINAL_NONE, "equality": _lib.TERMINAL_EQUALITY, "contractive": _lib.TERMINAL_CONTRACTIVE}[terminal])
         self.settings = settings if settings is not None else _lib.default_settings()
+        self.rho_tuning = None
+        if rho_tune is not None:
+            # kw `mpc_b200_rho_tune = (x0_sample, xref, uref)`: pick the step size on a sample of the workload (mpcb_tune_rho) -- the batch-wide
+            # counterpart of OSQP's per-problem adaptive rho; a design-time step
+            x0s = np.ascontiguousarray(np.atleast_2d(np.asarray(rho_tune[0], np.float64)))
+            xrs = np.ascontiguousarray(np.asarray(rho_tune[1], np.float64)); urs = np.ascontiguousarray(np.asarray(rho_tune[2], np.float64))
+            io = _lib.BatchIO(); io.batch = x0s.shape[0]; io.x0 = x0s.ctypes.data; io.xref = xrs.ctypes.data; io.uref = urs.ctypes.data
+            io.xref_broadcast = int(xrs.ndim == 1); io.uref_broadcast = int(urs.ndim == 1)
+            ncand = int(rho_tune[3]) if len(rho_tune) > 3 else 7
+            best = C.c_double(); cr = np.zeros(ncand); ci = np.zeros(ncand)
+            _lib.check(L.mpcb_tune_rho(C.byref(d), C.byref(self.settings), C.byref(io), ncand, 2.0, C.byref(best), cr.ctypes.data_as(C.POINTER(C.c_double)),
+                                       ci.ctypes.data_as(C.POINTER(C.c_double))), "mpcb_tune_rho")
+            self.settings.rho = best.value
+            self.rho_tuning = {"rho": best.value, "candidates": cr.tolist(), "mean_iters": ci.tolist()}
         self._h = C.c_void_p()
         _lib.check(L.mpcb_create_linear(C.byref(d), C.byref(self.settings), C.byref(self._h)), "mpcb_create_linear")
         self.info = _lib.Info()

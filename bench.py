@@ -475,31 +475,55 @@ def other_configs(mpc, dev, cpu=True):
         else:
             fl = executed_flops(info, it, CHECK)
             rec["roofline"] = {"bound": "tensor", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (k_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
-        sweep.append(rec)
         m.close()
+        # the other kernel family at the same H: the crossover is a driver-run number, not only a profiles/ file
+        other = 4 if info.kernel != 4 else 2
+        try:
+            Co = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_b200_eps_abs=EPS,
+                                        mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA, mpc_b200_kernel=other)
+            mo_ = Co.tuning.modeler
+            ko_ms = _time_device(lambda: mo_.solve_batch_device(io_s, stream()), 2, flush)
+            rec["other_family"] = {"kernel_id": other, "kernel": kernel_name(mo_.info, SIGMA), "kernel_ms": ko_ms,
+                                   "what": "stage-wise (Riccati) kernel forced" if other == 4 else "condensed streamed DMMA GEMM kernel forced"}
+            mo_.close()
+        except Exception as e:
+            rec["other_family"] = {"error": repr(e)[:200]}
+        sweep.append(rec)
     out.append({"config": "configs[3]: quadruple-tank tracking MPC, horizon sweep H = 10..200, batch 16384 (rng(0) inputs of configs[1]), cold start",
                 "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "sigma": SIGMA, "outputs": "u,e_u,x,e_x,u0,objective,status,iters,residuals (device resident)",
-                "crossover": "condensed DMMA kernels up to nz = 120 (H = 60), stage-wise (Riccati) kernel beyond; see profiles/r02/ricsweep_config4_*.jsonl for both kernels at every H",
+                "crossover": "condensed DMMA kernels (on chip) up to nz = 120 (H = 60), stage-wise (Riccati) kernel beyond; every H also carries the OTHER kernel family's time "
+                             "(other_family): the curves cross between H = 50 and H = 75",
                 "sweep": sweep})
 
     # ---- configs[2]: random stable LTI nx = 64, nu = 16, H = 50, terminal LQR cost + terminal equality, batch 8 192
     rng = np.random.default_rng(1); nx, nu, Hh, n = 64, 16, 50, 8192
     G = rng.standard_normal((nx, nx)); A3 = 0.95 * G / np.abs(np.linalg.eigvals(G)).max(); B3 = rng.standard_normal((nx, nu)) / 8
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A3, B3, mpc.Hyperrectangle(-1e3 * np.ones(nx), 1e3 * np.ones(nx)), mpc.Hyperrectangle(-np.ones(nu), np.ones(nu)))
-    t0 = time.perf_counter()
-    Cn = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 1, [0.0] * nx, [0.0] * nu, mpc_solver="b200", mpc_terminal_ingredient="equality",
-                                mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=10, mpc_b200_sigma=0.0, mpc_b200_max_iter=4000)
-    design_s = time.perf_counter() - t0
-    m = Cn.tuning.modeler; info = m.info
     x0_h = np.random.default_rng(3).standard_normal((n, nx)); xr = np.zeros(nx); ur = np.zeros(nu)
+    kw3 = dict(mpc_solver="b200", mpc_terminal_ingredient="equality", mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=10, mpc_b200_sigma=0.0,
+               mpc_b200_max_iter=4000)
+    t0 = time.perf_counter()
+    Ca = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 1, [0.0] * nx, [0.0] * nu, **kw3)        # automatic step size sqrt(lmin lmax)
+    design_s = time.perf_counter() - t0
     io, t = _device_io(_lib, dev, n, nx, nu, Hh, x0_h, xr, ur)
+    ma = Ca.tuning.modeler
+    ms_auto = _time_device(lambda: ma.solve_batch_device(io, stream()), 2, flush)
+    it_auto = float(t["iters"].cpu().numpy().mean()); rho_auto = ma.info.rho
+    ma.close()
+    t0 = time.perf_counter()
+    Cn = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 1, [0.0] * nx, [0.0] * nu, mpc_b200_rho_tune=(x0_h[:512], xr, ur), **kw3)   # tuned on a 512-problem sample
+    tune_s = time.perf_counter() - t0
+    m = Cn.tuning.modeler; info = m.info
     ms = _time_device(lambda: m.solve_batch_device(io, stream()), 3, flush)
     launches = int(m.timing()["kernel_launches"])
     it = t["iters"].cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
     fl = executed_flops(info, it, 10)
     rec = {"config": "configs[2]: random stable LTI (rng(1)) nx=64 nu=16 H=50, input box [-1,1]^16, terminal LQR cost + terminal equality, batch 8192, x0 = N(0,I) (rng(3)), cold start",
            "eps_abs": EPS, "eps_rel": EPS, "check_every": 10, "sigma": 0.0, "nz": info.nz, "mg": info.mg, "nt_pad": info.nt_pad, "kernel_id": info.kernel, "kernel": kernel_name(info, 0.0),
-           "design_s": design_s, "ms": ms, "solves_per_s": n / ms * 1e3, "gpu_launches": launches, "mean_iters": float(it.mean()), "max_iters": int(it.max()),
+           "design_s": design_s, "ms": ms, "solves_per_s": n / ms * 1e3, "gpu_launches": launches,
+           "step_size": {"rho": info.rho, "how": "mpcb_tune_rho on a 512-problem sample of the batch, 7 candidates rho_auto * 2^j (design time, outside the timed region: "
+                                               "the batch-wide counterpart of OSQP's per-problem adaptive rho)", "tune_s": tune_s, "candidates": m.rho_tuning,
+                         "automatic_rho": rho_auto, "ms_with_automatic_rho": ms_auto, "mean_iters_with_automatic_rho": it_auto}, "mean_iters": float(it.mean()), "max_iters": int(it.max()),
            "solved_frac": float((st == 1).mean()), "infeasible": int((st == -3).sum()), "iteration_cap": int((st == -2).sum()),
            "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
                         "note": "whole solve (all launches incl. checks, compaction, recovery); flops = iterations x 2 nt^2 + one pass per check with [[Pc,G'],[G,0]], nt = 864 (unpadded), "

@@ -193,6 +193,17 @@ int mpcb_dare_batch(int32_t device, int64_t batch, int32_t nx, int32_t nu, const
 int mpcb_dare_batch_device(int32_t device, int64_t batch, int32_t nx, int32_t nu, const double* dA, const double* dB, const double* Q, const double* R,
                            double* dP_out, int32_t* dstatus, void* cuda_stream);
 
+/* Step-size selection on a sample of the workload.  OSQP adapts rho per problem and refactors (its default, which the reference gets:
+ * solver_selection.jl:94-95 sets no attribute); here the KKT factor is cached once for the whole batch, so rho is chosen per CONTROLLER --
+ * by default from the spectrum of the condensed Hessian (sqrt(lambda_min lambda_max)), which is right when many bounds are active and can be
+ * several times too large when few are.  This call designs the controller for n_candidates step sizes rho0 * factor^j (j centred on 0,
+ * rho0 = settings->rho if > 0, else the automatic value), solves the caller's SAMPLE batch (host pointers; only x0 / xref / uref are read)
+ * with each on settings->device, and returns the candidate with the fewest mean iterations (unsolved problems count as 2 max_iter).  The
+ * caller then passes *best_rho as settings->rho to mpcb_create_linear.  A design-time step, like OSQP's setup; solutions do not depend on it
+ * beyond the termination tolerance.  cand_rho / cand_mean_iters (n_candidates each) may be NULL. */
+int mpcb_tune_rho(const mpcb_linear_desc* desc, const mpcb_settings* settings, const mpcb_batch_io* host_sample, int32_t n_candidates, double factor,
+                  double* best_rho, double* cand_rho, double* cand_mean_iters);
+
 /* Design: condense, choose rho, factor K, build the stacked operators, upload to `settings->device`.
  * Replaces modeler construction + OSQP setup (linear.jl:20-103, solver_selection.jl:92-98). */
 int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settings, mpcb_handle** out);

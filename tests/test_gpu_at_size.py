@@ -79,6 +79,34 @@ def test_config3_lti64_terminal_equality_at_size(mpc):
         assert abs(r["obj"] - res["objective"][i]) <= 1e-5 * max(1.0, abs(r["obj"]))
 
 
+def test_config3_lti64_tuned_step_size(mpc):
+    """mpcb_tune_rho (kw `mpc_b200_rho_tune`): the step size picked on a 512-problem sample of the workload -- the batch-wide counterpart of
+    OSQP's per-problem adaptive rho.  The automatic value sqrt(lambda_min lambda_max) suits batches with many active bounds; for this
+    workload (few active bounds) a smaller one needs a third of the iterations.  Same optima: u0 and objective against the automatic-rho
+    solve and the twin run at the tuned value."""
+    A, B = lti64()
+    nx, nu, H, n, eps, check = 64, 16, 50, 8192, 1e-7, 10
+    umin, umax = -np.ones(nu), np.ones(nu)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(-1e3 * np.ones(nx), 1e3 * np.ones(nx)), mpc.Hyperrectangle(umin, umax))
+    x0 = np.random.default_rng(3).standard_normal((n, nx)); xref = np.zeros(nx); uref = np.zeros(nu)
+    kw = dict(mpc_solver="b200", mpc_terminal_ingredient="equality", mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=0.0)
+    Ca = mpc.proceed_controller(sys_, "model_predictive_control", H, 1, [0.0] * nx, [0.0] * nu, **kw)
+    Ct = mpc.proceed_controller(sys_, "model_predictive_control", H, 1, [0.0] * nx, [0.0] * nu, mpc_b200_rho_tune=(x0[:512], xref, uref), **kw)
+    ma, mt = Ca.tuning.modeler, Ct.tuning.modeler
+    tun = mt.rho_tuning
+    print("rho tuning:", [(round(r, 1), round(i, 1)) for r, i in zip(tun["candidates"], tun["mean_iters"])], "-> rho", round(tun["rho"], 1), "automatic", round(ma.info.rho, 1))
+    assert abs(mt.info.rho - tun["rho"]) < 1e-9 * tun["rho"] and min(tun["mean_iters"]) == tun["mean_iters"][tun["candidates"].index(tun["rho"])]
+    ra = ma.solve_batch(x0, xref, uref, want=("u", "u0", "objective")); rt = mt.solve_batch(x0, xref, uref, want=("u", "u0", "objective"))
+    assert (ra["status"] == 1).all() and (rt["status"] == 1).all()
+    assert rt["iters"].mean() < 0.6 * ra["iters"].mean()
+    assert mo.u0_metric(rt["u0"], ra["u0"], umin, umax).max() < U0_TOL
+    assert (np.abs(rt["objective"] - ra["objective"]) <= OBJ_TOL * np.abs(ra["objective"])).all()
+    c = mo.condense(A, B, 100 * np.eye(nx), 0.1 * np.eye(nu), np.zeros((nu, nu)), Ct.tuning.terminal_ingredient.P, H, umin, umax, terminal="equality")
+    sel = np.sort(np.random.default_rng(0).choice(n, 1024, replace=False))
+    tw = mo.admm_condensed(c, mo.pack_params(x0[sel], xref, uref), mo.AdmmSettings(rho=mt.info.rho, eps_abs=eps, eps_rel=eps, check_every=check, sigma=0.0))
+    assert_matches_twin({k: rt[k][sel] for k in ("u", "status", "iters")}, tw, tight=1e-7, loose=1e-4, min_same=0.9, check=check)
+
+
 @pytest.mark.parametrize("H", [100, 150, 200])
 def test_config4_long_horizons_at_size(mpc, qt, H):
     """configs[3], long end of the horizon sweep at its batch of 16 384: the stage-wise kernel (automatic choice) against the twin
