@@ -455,18 +455,26 @@ def other_configs(mpc, dev, cpu=True):
     x0_h, xref_h, uref_h = make_batch(n, seed=0)
     for Hh in (10, 20, 30, 50, 75, 100, 150, 200):
         sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(umin, umax))
-        Cn = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_solver="b200",
-                                    mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA)
-        m = Cn.tuning.modeler; info = m.info
+        kw4 = dict(mpc_solver="b200", mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA)
         io, t = _device_io(_lib, dev, n, 4, 2, Hh, x0_h, xref_h, uref_h)
-        ms = _time_device(lambda: m.solve_batch_device(io, stream()), 3, flush)
         io_s = _lib.BatchIO()
         for f, _t in io._fields_: setattr(io_s, f, getattr(io, f))
         for f in ("u", "e_u", "x", "e_x", "u0", "objective"): setattr(io_s, f, None)
+        # automatic step size sqrt(lmin lmax) first (what a caller gets without tuning), then the step size tuned on a 4096-problem sample
+        Ca = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), **kw4)
+        ma = Ca.tuning.modeler
+        k_ms_auto = _time_device(lambda: ma.solve_batch_device(io_s, stream()), 2, flush)
+        it_auto = float(t["iters"].cpu().numpy().mean()); rho_auto = ma.info.rho
+        ma.close()
+        Cn = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_b200_rho_tune=(x0_h[:4096], xref_h[:4096], uref_h, 7), **kw4)
+        m = Cn.tuning.modeler; info = m.info
+        ms = _time_device(lambda: m.solve_batch_device(io, stream()), 3, flush)
         k_ms = _time_device(lambda: m.solve_batch_device(io_s, stream()), 3, flush)
         it = t["iters"].cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
         rec = {"H": Hh, "nz": info.nz, "kernel_id": info.kernel, "kernel": kernel_name(info, SIGMA), "ms": ms, "solves_per_s": n / ms * 1e3, "kernel_ms": k_ms,
-               "mean_iters": float(it.mean()), "max_iters": int(it.max()), "solved_frac": float((st == 1).mean())}
+               "mean_iters": float(it.mean()), "max_iters": int(it.max()), "solved_frac": float((st == 1).mean()),
+               "step_size": {"rho": info.rho, "how": "mpcb_tune_rho, 4096-problem sample, 7 candidates rho_auto * 2^j (design time)", "automatic_rho": rho_auto,
+                             "kernel_ms_with_automatic_rho": k_ms_auto, "mean_iters_with_automatic_rho": it_auto}}
         if info.kernel == 4:      # stage-wise kernel: bound by streaming its per-problem state (6 row passes of nz doubles per iteration)
             by = float(it.sum()) * 6 * info.nz * 8; fl = float(it.sum()) * Hh * 2 * (2 * 16 + 4 * 8 + 4)
             rec["roofline"] = {"bound": "hbm", "achieved": by / (k_ms * 1e-3) / 1e9, "peak": _hbm_peak(), "unit": "GB/s", "frac": by / (k_ms * 1e-3) / 1e9 / _hbm_peak(),
@@ -475,12 +483,12 @@ def other_configs(mpc, dev, cpu=True):
         else:
             fl = executed_flops(info, it, CHECK)
             rec["roofline"] = {"bound": "tensor", "achieved": fl / (k_ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (k_ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
+        rho_t = info.rho
         m.close()
-        # the other kernel family at the same H: the crossover is a driver-run number, not only a profiles/ file
+        # the other kernel family at the same H and step size: the crossover is a driver-run number, not only a profiles/ file
         other = 4 if info.kernel != 4 else 2
         try:
-            Co = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_b200_eps_abs=EPS,
-                                        mpc_b200_eps_rel=EPS, mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA, mpc_b200_kernel=other)
+            Co = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_b200_kernel=other, mpc_b200_rho=rho_t, **kw4)
             mo_ = Co.tuning.modeler
             ko_ms = _time_device(lambda: mo_.solve_batch_device(io_s, stream()), 2, flush)
             rec["other_family"] = {"kernel_id": other, "kernel": kernel_name(mo_.info, SIGMA), "kernel_ms": ko_ms,

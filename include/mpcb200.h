@@ -198,7 +198,9 @@ int mpcb_dare_batch_device(int32_t device, int64_t batch, int32_t nx, int32_t nu
  * by default from the spectrum of the condensed Hessian (sqrt(lambda_min lambda_max)), which is right when many bounds are active and can be
  * several times too large when few are.  This call designs the controller for n_candidates step sizes rho0 * factor^j (j centred on 0,
  * rho0 = settings->rho if > 0, else the automatic value), solves the caller's SAMPLE batch (host pointers; only x0 / xref / uref are read)
- * with each on settings->device, and returns the candidate with the fewest mean iterations (unsolved problems count as 2 max_iter).  The
+ * with each on settings->device, and returns the candidate whose solve of the sample takes the least GPU time (CUDA events; cand_mean_iters then holds
+ * milliseconds).  Samples of less than ~100 KB are not timed: they are scored by the mean over consecutive groups of 32 problems of the group's MAXIMUM
+ * iteration count (what a tile / slot group of the kernels waits for).  Take the sample from the workload itself, a few thousand problems.  The
  * caller then passes *best_rho as settings->rho to mpcb_create_linear.  A design-time step, like OSQP's setup; solutions do not depend on it
  * beyond the termination tolerance.  cand_rho / cand_mean_iters (n_candidates each) may be NULL. */
 int mpcb_tune_rho(const mpcb_linear_desc* desc, const mpcb_settings* settings, const mpcb_batch_io* host_sample, int32_t n_candidates, double factor,

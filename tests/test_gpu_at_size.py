@@ -95,7 +95,7 @@ def test_config3_lti64_tuned_step_size(mpc):
     ma, mt = Ca.tuning.modeler, Ct.tuning.modeler
     tun = mt.rho_tuning
     print("rho tuning:", [(round(r, 1), round(i, 1)) for r, i in zip(tun["candidates"], tun["mean_iters"])], "-> rho", round(tun["rho"], 1), "automatic", round(ma.info.rho, 1))
-    assert abs(mt.info.rho - tun["rho"]) < 1e-9 * tun["rho"] and min(tun["mean_iters"]) == tun["mean_iters"][tun["candidates"].index(tun["rho"])]
+    assert abs(mt.info.rho - tun["rho"]) < 1e-9 * tun["rho"] and min(tun["mean_iters"]) == tun["mean_iters"][tun["candidates"].index(tun["rho"])]      # ("mean_iters": the group-max cost)
     ra = ma.solve_batch(x0, xref, uref, want=("u", "u0", "objective")); rt = mt.solve_batch(x0, xref, uref, want=("u", "u0", "objective"))
     assert (ra["status"] == 1).all() and (rt["status"] == 1).all()
     assert rt["iters"].mean() < 0.6 * ra["iters"].mean()
