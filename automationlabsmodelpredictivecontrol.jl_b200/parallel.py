@@ -30,7 +30,8 @@ def payload_views(payload, n: int, nu: int):
     return {"u0": u0, "objective": obj, "prim_res": pres, "dual_res": dres, "status": ints[:n], "iters": ints[n:]}
 
 
-def gather_payloads(payload, gathered, dst: int = 0, group=None):
-    """The one collective of the path: every rank's payload to rank `dst` (`gathered`: list of world tensors there, None elsewhere)."""
+def gather_payloads(payload, gathered, dst: int = 0, group=None, async_op: bool = False):
+    """The one collective of the path: every rank's payload to rank `dst` (`gathered`: list of world tensors there, None elsewhere).
+    async_op: returns the work handle -- bench.py double-buffers the payload so that step k's gather overlaps step k+1's solve."""
     import torch.distributed as dist
-    dist.gather(payload, gathered, dst=dst, group=group)
+    return dist.gather(payload, gathered, dst=dst, group=group, async_op=async_op)

@@ -159,16 +159,34 @@ def run_ours(args):
     io.u = u.data_ptr(); io.e_u = e_u.data_ptr(); io.x = x.data_ptr(); io.e_x = e_x.data_ptr(); io.u0 = u0.data_ptr()
     io.objective = obj.data_ptr(); io.prim_res = pres.data_ptr(); io.dual_res = dres.data_ptr(); io.status = status.data_ptr(); io.iters = iters.data_ptr()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
-    gathered = None
+    # The one collective of the path: the gather of u0 + convergence stats on rank 0 (NCCL over NVLink).  It is double-buffered and
+    # asynchronous: step k's gather runs on NCCL's stream while step k+1 solves into the other payload buffer, and step k+1's timed
+    # interval ends only after the launching stream has waited for gather k -- so an interval is max(solve, what is left of the previous
+    # gather), and the last gather is waited for inside the timed region too.
+    payloads = [payload]; ios = [io]; gathered = [None, None]; works = [None, None]
     if world > 1:
-        # the one collective of the path: final gather of u0 + convergence stats on rank 0 (NCCL over NVLink)
-        gathered = [torch.empty_like(payload) for _ in range(world)] if rank == 0 else None
+        payload_b = torch.empty_like(payload)
+        pvb = parallel.payload_views(payload_b, n, 2)
+        io_b = _lib.BatchIO()
+        for f, _t in io._fields_: setattr(io_b, f, getattr(io, f))
+        io_b.u0 = pvb["u0"].data_ptr(); io_b.objective = pvb["objective"].data_ptr(); io_b.prim_res = pvb["prim_res"].data_ptr()
+        io_b.dual_res = pvb["dual_res"].data_ptr(); io_b.status = pvb["status"].data_ptr(); io_b.iters = pvb["iters"].data_ptr()
+        payloads.append(payload_b); ios.append(io_b)
+        gathered = [[torch.empty_like(payload) for _ in range(world)] if rank == 0 else None for _ in range(2)]
+    step_no = [0]
 
     def step():
         stream = torch.cuda.current_stream().cuda_stream
-        m.solve_batch_device(io, stream)
+        b = step_no[0] & 1 if world > 1 else 0
+        m.solve_batch_device(ios[b], stream)
         if world > 1:
-            parallel.gather_payloads(payload, gathered, dst=0)
+            if works[b ^ 1] is not None: works[b ^ 1].wait()          # the launching stream waits for the previous step's gather
+            works[b] = parallel.gather_payloads(payloads[b], gathered[b], dst=0, async_op=True)
+        step_no[0] += 1
+
+    def drain():
+        for w in works:
+            if w is not None: w.wait()
 
     def barrier():
         if world > 1: dist.barrier()
@@ -176,26 +194,33 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     t_wall = time.perf_counter()
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     for k in range(args.steps):
         flush.zero_()                                   # L2 flush between timed iterations (outside the per-step events)
         evs[k][0].record()
         step()
         evs[k][1].record()
+    tail[0].record(); drain(); tail[1].record()         # what is left of the last gather
     barrier()
     t_wall = time.perf_counter() - t_wall
     ms_steps = [a.elapsed_time(b) for a, b in evs]
-    ms_total = torch.tensor([sum(ms_steps)], dtype=torch.float64, device=dev)
+    ms_total = torch.tensor([sum(ms_steps) + tail[0].elapsed_time(tail[1])], dtype=torch.float64, device=dev)
     if world > 1: dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
     ms_total = float(ms_total.item())
     clocks = sampler.stop() if sampler else None
 
-    it_np = iters.cpu().numpy(); st_np = status.cpu().numpy()
+    if world > 1:         # results of the last step live in the buffer it wrote
+        pvl = parallel.payload_views(payloads[(step_no[0] - 1) & 1], n, 2)
+        it_np = pvl["iters"].cpu().numpy(); st_np = pvl["status"].cpu().numpy()
+    else:
+        it_np = iters.cpu().numpy(); st_np = status.cpu().numpy()
     launches_full_step = int(m.timing()["kernel_launches"])     # kernels of libmpcb200 the last full step launched (counted by the library)
     # dominant kernel alone (solve kernel, no recover): time it live with events for the roofline
     io_solve = _lib.BatchIO()
@@ -315,7 +340,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "configs[1]: quadruple-tank linear tracking MPC nx=4 nu=2 H=20, batch 65536 random x0/x_ref per GPU, cold start",
                        "batch_per_gpu": n, "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "sigma": SIGMA, "alpha": 1.6, "rho": info.rho, "kernel": "onchip-dmma",
-                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"batch-shard x{world}, one NCCL gather of u0+objective+residuals+status+iters (48 B/problem)" if world > 1 else "single GPU",
+                       "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"batch-shard x{world}, one NCCL gather of u0+objective+residuals+status+iters (48 B/problem) per step, double-buffered: it overlaps the next step's solve" if world > 1 else "single GPU",
                        "outputs": "u,e_u,x,e_x,u0,objective,status,iters,residuals"},
             "e2e": {"value": e2e_val, "unit": "solves/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "what": "mpcb_solve_linear_batch on page-locked host arrays, every rank on its shard concurrently, max over ranks",
