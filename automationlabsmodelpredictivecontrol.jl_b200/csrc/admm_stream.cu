@@ -66,8 +66,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// kt0: first k-tile of the product (operands known to be zero in columns < kt0 * BK are skipped -- the certificate pass G' dy_g only has
+// the mg general columns)
 __device__ __forceinline__ void gemm_tile(const double* __restrict__ In, const double* __restrict__ M, int rows, int NTp, int bm0, int bn0,
-                                          double (&acc)[4][4][2], double* smem) {
+                                          double (&acc)[4][4][2], double* smem, int kt0 = 0) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, l4 = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
   const int KT = NTp / BK;
@@ -95,11 +97,11 @@ __device__ __forceinline__ void gemm_tile(const double* __restrict__ In, const d
     for (int q = 0; q < PASSES; q++) cp_async16(st + dst[q], src[q] + kt * BK);
   };
 #pragma unroll
-  for (int kt = 0; kt < STAGES - 1; kt++) {
-    if (kt < KT) issue(kt);
+  for (int s = 0; s < STAGES - 1; s++) {
+    if (kt0 + s < KT) issue(kt0 + s);
     cp_async_commit();
   }
-  for (int kt = 0; kt < KT; kt++) {
+  for (int kt = kt0; kt < KT; kt++) {
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     if (kt + STAGES - 1 < KT) issue(kt + STAGES - 1);
@@ -251,12 +253,13 @@ struct CheckParams {
   unsigned long long* red;
   double* Out;        // optional: raw product (used for A' dy of the certificate), may be null
   int rows, NTp, nz, mode;   // mode 0: dual residual reductions ; 1: store product only
+  int kt0;                   // first k-tile (mode 1: the operand is zero on the box columns)
 };
 __global__ void __launch_bounds__(THREADS, 2) stream_check_kernel(const CheckParams P) {
   extern __shared__ __align__(16) double smem[];
   const int bn0 = blockIdx.x * BN, bm0 = blockIdx.y * BM;
   double acc[4][4][2];
-  gemm_tile(P.In, P.C, P.rows, P.NTp, bm0, bn0, acc, smem);
+  gemm_tile(P.In, P.C, P.rows, P.NTp, bm0, bn0, acc, smem, P.kt0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;
 #pragma unroll
@@ -570,9 +573,12 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
       CertParams cp;   // reuse the kernel below for dy as well (needs YP of the previous iteration; check_every >= 2)
       cp.YO = sw.YO; cp.YP = sw.YP; cp.QB = QB; cp.lo = sc.lo; cp.hi = sc.hi; cp.DY = sw.DY; cp.cert = sw.cert; cp.rows = rows; cp.NTp = NTp; cp.nz = nz; cp.nt = nt;
       if (st.check_every >= 2) { stream_cert_kernel<<<rows, 128, 0, stream>>>(cp); nl++; }
-      dim3 grid(NTp / BN, (rows + BM - 1) / BM);
+      // both check products are needed on the box columns only (G' dy_g and Pc x~ + G' y_g have nz rows); the certificate operand DY is zero on the
+      // box columns, so its product starts at the first k-tile that holds a general column
+      dim3 grid((nz + BN - 1) / BN, (rows + BM - 1) / BM);
       if (st.check_every >= 2) {   // G' dy_g into Rout (scratch: it is fully rewritten by the next iteration)
         CheckParams c2; c2.In = sw.DY; c2.C = sc.C; c2.QB = QB; c2.YO = sw.YO; c2.red = red; c2.Out = Rout; c2.rows = rows; c2.NTp = NTp; c2.nz = nz; c2.mode = 1;
+        c2.kt0 = nz / BK;
         stream_check_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(c2); nl++;
         stream_cert2_kernel<<<rows, 128, 0, stream>>>(Rout, sw.YO, sw.YP, sw.cert, NTp, nz); nl++;
       }
@@ -582,7 +588,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
       if (e != cudaSuccess) { err = "memcpy2d"; return e; }
       e = cudaMemcpy2DAsync(sw.DY + nz, NTp * sizeof(double), sw.YO + nz, NTp * sizeof(double), (NTp - nz) * sizeof(double), rows, cudaMemcpyDeviceToDevice, stream);
       if (e != cudaSuccess) { err = "memcpy2d"; return e; }
-      CheckParams c1; c1.In = sw.DY; c1.C = sc.C; c1.QB = QB; c1.YO = sw.YO; c1.red = red; c1.Out = nullptr; c1.rows = rows; c1.NTp = NTp; c1.nz = nz; c1.mode = 0;
+      CheckParams c1; c1.In = sw.DY; c1.C = sc.C; c1.QB = QB; c1.YO = sw.YO; c1.red = red; c1.Out = nullptr; c1.rows = rows; c1.NTp = NTp; c1.nz = nz; c1.mode = 0; c1.kt0 = 0;
       stream_check_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(c1); nl++;
     }
     e = cudaMemsetAsync(sw.count, 0, 2 * sizeof(int), stream);

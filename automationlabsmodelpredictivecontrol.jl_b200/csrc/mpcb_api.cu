@@ -81,7 +81,7 @@ struct mpcb_handle {
   PinBuf<int32_t> stage_int;
   PinBuf<double> small_io;     // small batches: inputs and outputs live in one page-locked block the kernels access directly
   int onchip_blocks_per_sm = 0;
-  size_t recover_smem_set = 0;
+  size_t recover_smem_set = 0, recover_wide_smem_set = 0;
 };
 
 namespace {
@@ -293,7 +293,26 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     R.nx = D.nx; R.nu = D.nu; R.H = D.H; R.use_R = D.use_R; R.use_S = D.use_S; R.batch = Bn;
     R.x0 = io.x0; R.xref = io.xref; R.uref = io.uref; R.xref_bc = io.xref_broadcast; R.uref_bc = io.uref_broadcast;
     R.v = v_buf; R.u = io.u; R.e_u = io.e_u; R.x = io.x; R.e_x = io.e_x; R.u0 = io.u0; R.objective = io.objective;
-    if (!mpcb::launch_recover_small(R, st)) {
+    if (mpcb::launch_recover_small(R, st)) {
+    } else if (mpcb::recover_wide_applies(D.nx, D.nu)) {
+      bool qdiag = true;
+      for (int j = 0; j < D.nx && qdiag; j++)
+        for (int i = 0; i < D.nx; i++) if (i != j && D.Q(i, j) != 0.0) { qdiag = false; break; }
+      const void* kern = mpcb::recover_wide_variant(D.nx, qdiag);
+      const size_t smem = mpcb::recover_wide_smem_bytes(D.nx, D.nu);
+      if (smem > 48 * 1024 && smem > h->recover_wide_smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->recover_wide_smem_set = smem;
+      }
+      const int tp = ((D.nx + 31) / 32) * 32, gpc = mpcb::RECOVER_WIDE_THREADS / tp;
+      int per_sm = 1;
+      CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, mpcb::RECOVER_WIDE_THREADS, smem));
+      const long long need = (Bn + gpc - 1) / gpc;
+      const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(need, (long long)h->info.sm_count * std::max(per_sm, 1)));
+      mpcb::RecoverParams Rc = R;
+      void* args[] = {(void*)&Rc};
+      CUDA_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(mpcb::RECOVER_WIDE_THREADS), args, smem, st));
+    } else {
       const int rt = mpcb::recover_threads_for(D.nx, D.nu);
       if (rt == 0) return fail(MPCB_ERR_INVALID, "result recovery: system too wide for the generic kernel (nx, nu)");
       const size_t smem = mpcb::recover_smem_bytes(D.nx, D.nu, rt);

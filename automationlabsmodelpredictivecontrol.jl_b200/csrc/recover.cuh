@@ -126,6 +126,129 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_kernel(const RecoverP
   if (P.objective) P.objective[p] = J;
 }
 
+// Wide systems (nx >= 16; config 3 is nx = 64, nu = 16): the one-thread-per-problem kernel above walks 51 x (64 x 80) multiply-adds
+// serially per problem with 64 threads per CTA -- 6.9 ms for 8 192 problems, a fifth of the whole config-3 solve (launch list,
+// profiles/r02/launches_lti64_tuned_summary.txt).  Here a GROUP of TP = ceil32(nx) threads owns a problem: thread i keeps row i of the
+// recursion (e_{k+1}[i] = A[i,:] e_k + B[i,:] du_k) and of the cost (e_k[i] (W e_k)[i]); A, B, Q, P sit in shared memory column-major,
+// so consecutive threads read consecutive addresses and every global store is a coalesced run of nx (nu) doubles.  Persistent CTAs of
+// 256 threads loop over problems, so the matrices are staged once per CTA.
+constexpr int RECOVER_WIDE_THREADS = 256;
+__host__ __device__ inline size_t recover_wide_smem_bytes(int nx, int nu) {
+  const int tp = ((nx + 31) / 32) * 32, gpc = RECOVER_WIDE_THREADS / tp;
+  return sizeof(double) * ((size_t)3 * nx * nx + (size_t)nx * nu + 2 * (size_t)nu * nu + (size_t)gpc * (2 * tp + 3 * nu + 8));
+}
+inline bool recover_wide_applies(int nx, int nu) { return nx >= 16 && nx <= 256 && nu <= nx && recover_wide_smem_bytes(nx, nu) <= 200 * 1024; }
+
+// NXB > 0: row i of A lives in NXB registers of thread i (nx <= NXB) -- one broadcast shared-memory read of e[j] per multiply-add instead of
+// two reads: the first version (both operands from shared memory, and the full W e product for the cost) was shared-memory bound at 3 ms
+// for config 3.  QDIAG: Q is diagonal (the reference only ever builds Q = mpc_Q * I, design_mpc.jl:264-283): the stage cost needs no product.
+template <int NXB, bool QDIAG>
+__global__ void __launch_bounds__(RECOVER_WIDE_THREADS) recover_wide_kernel(const RecoverParams P) {
+  extern __shared__ __align__(16) double sm[];
+  const int nx = P.nx, nu = P.nu, H = P.H, tid = threadIdx.x;
+  const int tp = ((nx + 31) / 32) * 32, gpc = RECOVER_WIDE_THREADS / tp;       // threads per problem, problems per CTA
+  double* sA = sm; double* sQ = sA + nx * nx; double* sPt = sQ + nx * nx; double* sB = sPt + nx * nx; double* sR = sB + nx * nu; double* sS = sR + nu * nu;
+  double* grp = sS + nu * nu + (size_t)(tid / tp) * (2 * tp + 3 * nu + 8);
+  double* se = grp; double* sn = se + tp; double* su = sn + tp; double* sp = su + nu; double* sv = sp + nu; double* sred = sv + nu;   // sred: 8 warp partials
+  for (int i = tid; i < nx * nx; i += RECOVER_WIDE_THREADS) { sA[i] = P.A[i]; sQ[i] = P.Q[i]; sPt[i] = P.Pt[i]; }
+  for (int i = tid; i < nx * nu; i += RECOVER_WIDE_THREADS) sB[i] = P.B[i];
+  for (int i = tid; i < nu * nu; i += RECOVER_WIDE_THREADS) { sR[i] = P.R[i]; sS[i] = P.S ? P.S[i] : 0.0; }
+  __syncthreads();
+  const int g = tid / tp, i = tid % tp;
+  const bool row = i < nx, urow = i < nu, live = g < gpc;
+  double areg[NXB > 0 ? NXB : 1];
+  double qii = 0.0;
+  if (NXB > 0) {
+#pragma unroll
+    for (int j = 0; j < NXB; j++) areg[j] = (row && j < nx) ? sA[j * nx + i] : 0.0;
+  }
+  if (QDIAG && row) qii = sQ[i * nx + i];
+  const long long stride = (long long)gridDim.x * gpc;
+  const long long rounds = (P.batch + stride - 1) / stride;
+  for (long long r = 0; r < rounds; r++) {
+    const long long p = r * stride + (long long)blockIdx.x * gpc + g;
+    const bool act = live && p < P.batch;
+    const long long pc = act ? p : 0;
+    const double* xr = P.xref + (P.xref_bc ? 0 : pc) * nx;
+    const double* ur = P.uref + (P.uref_bc ? 0 : pc) * nu;
+    const double* v = P.v + pc * (long long)nu * H;
+    double xri = 0.0, uri = 0.0;
+    if (live) { if (row) { xri = xr[i]; se[i] = P.x0[pc * nx + i] - xri; } else { se[i] = 0.0; sn[i] = 0.0; } }      // rows nx .. tp-1 stay zero (register-blocked products run to NXB)
+    if (live && urow) uri = ur[i];
+    __syncthreads();
+    double J = 0.0;
+    for (int k = 0; k <= H; k++) {
+      const double* W = (k == H) ? sPt : sQ;
+      if (live && row) {
+        const double ei = se[i];
+        if (act) {
+          if (P.e_x) P.e_x[(p * (H + 1) + k) * nx + i] = ei;
+          if (P.x) P.x[(p * (H + 1) + k) * nx + i] = ei + xri;
+        }
+        if (QDIAG && k < H) J = fma(qii * ei, ei, J);
+        else {
+          double s = 0.0;
+          for (int j = 0; j < nx; j++) s = fma(W[j * nx + i], se[j], s);
+          J = fma(ei, s, J);
+        }
+      }
+      if (k == H) break;
+      if (live && urow) {
+        const double ui = v[k * nu + i], eu = ui - uri;
+        su[i] = eu; sv[i] = ui;
+        if (act) {
+          if (P.u) P.u[(p * H + k) * nu + i] = ui;
+          if (P.e_u) P.e_u[(p * H + k) * nu + i] = eu;
+          if (k == 0 && P.u0) P.u0[p * nu + i] = ui;
+        }
+      }
+      __syncthreads();
+      if (live && urow && P.use_R) {
+        double s = 0.0;
+        for (int j = 0; j < nu; j++) s = fma(sR[j * nu + i], su[j], s);
+        J = fma(su[i], s, J);
+        if (P.use_S && k > 0) {      // delta_u_{k-1} = u_{k-1} - u_k  (design_mpc.jl:429-432)
+          double t = 0.0;
+          for (int j = 0; j < nu; j++) t = fma(sS[j * nu + i], sp[j] - sv[j], t);
+          J = fma(sp[i] - sv[i], t, J);
+        }
+      }
+      if (live && row) {
+        double s = 0.0, s1 = 0.0;
+        if (NXB > 0) {
+#pragma unroll
+          for (int j = 0; j < NXB; j += 2) { s = fma(areg[j], se[j], s); s1 = fma(areg[j + 1], se[j + 1], s1); }      // (se is padded with zeros up to NXB)
+          s += s1;
+        } else {
+          for (int j = 0; j < nx; j++) s = fma(sA[j * nx + i], se[j], s);
+        }
+        for (int j = 0; j < nu; j++) s = fma(sB[j * nx + i], su[j], s);
+        sn[i] = s;
+      }
+      __syncthreads();
+      if (live && urow) sp[i] = sv[i];
+      if (live && row) se[i] = sn[i];
+      __syncthreads();
+    }
+    // J: sum over the group's threads (warp shuffles, then the group's warps through shared memory)
+    for (int o = 16; o; o >>= 1) J += __shfl_xor_sync(0xffffffffu, J, o);
+    if (live && (i & 31) == 0) sred[i >> 5] = J;
+    __syncthreads();
+    if (act && i == 0 && P.objective) {
+      double t = 0.0;
+      for (int w = 0; w < tp / 32; w++) t += sred[w];
+      P.objective[p] = t;
+    }
+    __syncthreads();
+  }
+}
+
+inline const void* recover_wide_variant(int nx, bool qdiag) {
+  if (nx <= 32) return qdiag ? (const void*)recover_wide_kernel<32, true> : (const void*)recover_wide_kernel<32, false>;
+  if (nx <= 64) return qdiag ? (const void*)recover_wide_kernel<64, true> : (const void*)recover_wide_kernel<64, false>;
+  return qdiag ? (const void*)recover_wide_kernel<0, true> : (const void*)recover_wide_kernel<0, false>;
+}
+
 // Specialisation for small systems (the quadruple tank is NX=4, NU=2): one lane per problem rolls the deviation dynamics
 // in registers; everything that touches HBM goes through a per-warp shared-memory tile so that the global accesses are
 // WARP-COOPERATIVE: a chunk of RCH steps of 32 problems is staged (inputs in, results out) and moved with 16-byte

@@ -387,6 +387,8 @@ def test_closed_loop_on_gpu_equals_host_loop(mpc, qt):
     (8, 4, 40, "none", 0.0, 0.0),       # nz = 160 -> streamed
     (7, 3, 20, "equality", 0.0, 0.0),   # nt = 67 with general rows -> streamed, generic recover
     (10, 5, 12, "none", 0.0, 0.0),      # nz = 60, generic recover with wider states
+    (20, 3, 8, "none", 0.0, 1.5),       # nx >= 16: the cooperative wide recover kernel (one thread group per problem), with the S term
+    (33, 2, 10, "none", 1e-6, 0.0),     # nx = 33: thread groups of 64 with 31 idle lanes
 ])
 def test_random_systems_sweep(mpc, nx, nu, H, terminal, sigma, S_w):
     """Odd sizes, every kernel path, every recover path: random stable systems, CUDA vs the condensed twin (iteration counts,

@@ -62,7 +62,7 @@ def lti64(seed=1, nx=64, nu=16):
     return A, B
 
 
-def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="equality", reps=2, rho=0.0, max_iter=4000):
+def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="equality", reps=2, rho=0.0, max_iter=4000, full=False):
     import time
     A, B = lti64()
     nx, nu = B.shape
@@ -81,6 +81,10 @@ def run_lti(H=50, n=8192, eps=1e-5, check=10, sigma=0.0, scale=0.3, terminal="eq
     u0 = torch.empty((n, nu), dtype=torch.float64, device=dev)
     io = _lib.BatchIO(); io.batch = n; io.x0 = x0.data_ptr(); io.xref = xref.data_ptr(); io.uref = uref.data_ptr(); io.uref_broadcast = 1; io.xref_broadcast = 1
     io.status = status.data_ptr(); io.iters = iters.data_ptr(); io.u0 = u0.data_ptr()
+    if full:
+        uu = torch.empty((n, H, nu), dtype=torch.float64, device=dev); eu = torch.empty_like(uu)
+        xx = torch.empty((n, H + 1, nx), dtype=torch.float64, device=dev); ex = torch.empty_like(xx); ob = torch.empty(n, dtype=torch.float64, device=dev)
+        io.u = uu.data_ptr(); io.e_u = eu.data_ptr(); io.x = xx.data_ptr(); io.e_x = ex.data_ptr(); io.objective = ob.data_ptr()
     st = torch.cuda.current_stream().cuda_stream
     m.solve_batch_device(io, st); torch.cuda.synchronize()
     ts = []
@@ -214,6 +218,8 @@ if __name__ == "__main__":
         run_nmpc("qt_fnn_tanh_model.json", H=20, n=16384, method="linear", reps=1)
     elif a.set == "nmpc1":
         run_nmpc("qt_fnn_tanh_model.json", reps=1)
+    elif a.set == "lti_tuned":   # config 3 as bench.py runs it: eps 1e-7, the tuned step size, full outputs
+        run_lti(scale=1.0, eps=1e-7, rho=296.0242231923552, reps=2, full=True)
     elif a.set == "lti1":
         run_lti(scale=1.0, reps=1)
     elif a.set == "h50":
