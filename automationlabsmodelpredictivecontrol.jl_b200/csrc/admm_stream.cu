@@ -303,15 +303,17 @@ struct InitParams {
   // warm start (OSQP: x = v0, z = A x = [v0; G v0], y = y0), both null for a cold start
   const double *warm_v, *warm_y, *C, *rho;     // C: [NTp][NTp] check operator (rows >= nz hold G), rho: [NTp]
   double alpha, sigma;
+  const int32_t* remap;                        // row -> problem of the caller's batch (null: identity)
 };
 __global__ void stream_init_kernel(const InitParams P) {
   extern __shared__ double sp[];   // p vector of this problem
   const long long b = blockIdx.x;
+  const long long o = P.remap ? (long long)P.remap[b] : b;      // problem of the caller's batch behind this row
   for (int j = threadIdx.x; j < P.np; j += blockDim.x) {
     double v;
-    if (j < P.nx) v = P.x0[b * P.nx + j];
-    else if (j < 2 * P.nx) v = P.xref[(P.xref_bc ? 0 : b) * P.nx + (j - P.nx)];
-    else v = P.uref[(P.uref_bc ? 0 : b) * P.nu + (j - 2 * P.nx)];
+    if (j < P.nx) v = P.x0[o * P.nx + j];
+    else if (j < 2 * P.nx) v = P.xref[(P.xref_bc ? 0 : o) * P.nx + (j - P.nx)];
+    else v = P.uref[(P.uref_bc ? 0 : o) * P.nu + (j - 2 * P.nx)];
     sp[j] = v;
   }
   __syncthreads();
@@ -326,11 +328,11 @@ __global__ void stream_init_kernel(const InitParams P) {
       P.Cst[off] = 0.0; P.X[off] = 0.0;
       P.R[off] = (n < P.nz) ? -acc : 0.0;
     } else {
-      const double* v0 = P.warm_v + (size_t)b * P.nz;
+      const double* v0 = P.warm_v + (size_t)o * P.nz;
       double z;
       if (n < P.nz) z = v0[n];
       else { z = 0.0; for (int j = 0; j < P.nz; j++) z = fma(P.C[(size_t)n * P.NTp + j], v0[j], z); }     // general row: G v0
-      const double rho_n = P.rho[n], ys = P.warm_y[(size_t)b * P.nt + n] / rho_n;
+      const double rho_n = P.rho[n], ys = P.warm_y[(size_t)o * P.nt + n] / rho_n;
       P.Cst[off] = fma(1.0 - P.alpha, z, ys);
       P.X[off] = (n < P.nz) ? z : 0.0;
       P.R[off] = rho_n * (z - ys) + ((n < P.nz) ? fma(P.sigma, z, -acc) : 0.0);
@@ -344,7 +346,7 @@ __global__ void stream_init_kernel(const InitParams P) {
   if (threadIdx.x == 0) {
     double mm = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); w++) mm = dmaxf(mm, red[w]);
-    P.qn[b] = mm; P.idx[b] = (int)b; P.done[b] = 0;
+    P.qn[b] = mm; P.idx[b] = (int)o; P.done[b] = 0;
     for (int k = 0; k < 4; k++) P.red[b * 4 + k] = 0ULL;
   }
 }
@@ -404,7 +406,7 @@ struct DecideParams {
   unsigned long long* red; const double* qn; const double* cert;   // cert may be null (mg == 0)
   int* idx; int* done; int* newly;
   int32_t* status; int32_t* iters; double* pres; double* dres;
-  int rows, it, max_iter;
+  int rows, it, max_iter, iters_add;
   double eps_abs, eps_rel, eps_pinf;
   int* count;   // [0] += rows still active
 };
@@ -426,7 +428,7 @@ __global__ void stream_decide_kernel(const DecideParams P) {
   if (conv || pinf || P.it >= P.max_iter) {
     const int o = P.idx[b];
     P.status[o] = conv ? 1 : (pinf ? -3 : -2);
-    P.iters[o] = P.it; P.pres[o] = rp; P.dres[o] = rd;
+    P.iters[o] = P.it + P.iters_add; P.pres[o] = rp; P.dres[o] = rd;
     P.done[b] = 1; P.newly[b] = 1;
   } else {
     atomicAdd(P.count, 1);
@@ -546,7 +548,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
     P.Lt = sc.Lt; P.x0 = B.x0; P.xref = B.xref; P.uref = B.uref; P.xref_bc = B.xref_bc; P.uref_bc = B.uref_bc; P.nx = D.nx; P.nu = D.nu;
     P.np = D.np; P.NTp = NTp; P.nz = nz; P.nt = nt; P.rows = rows; P.Cst = Cst; P.QB = QB; P.X = X; P.R = Rin; P.qn = qn; P.idx = idx; P.done = done;
     P.red = red;
-    P.warm_v = B.warm_v; P.warm_y = B.warm_y; P.C = sc.C; P.rho = sc.rho; P.alpha = st.alpha; P.sigma = st.sigma;
+    P.warm_v = B.warm_v; P.warm_y = B.warm_y; P.C = sc.C; P.rho = sc.rho; P.alpha = st.alpha; P.sigma = st.sigma; P.remap = B.remap;
     stream_init_kernel<<<rows, 128, D.np * sizeof(double), stream>>>(P); nl++;
   }
   const int max_iter = ((st.max_iter + st.check_every - 1) / st.check_every) * st.check_every;
@@ -595,7 +597,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
     if (e != cudaSuccess) { err = "memset"; return e; }
     DecideParams dp;
     dp.red = red; dp.qn = qn; dp.cert = (mg > 0 && st.check_every >= 2) ? sw.cert : nullptr; dp.idx = idx; dp.done = done; dp.newly = sw.newly;
-    dp.status = B.status; dp.iters = B.iters; dp.pres = B.pres; dp.dres = B.dres; dp.rows = rows; dp.it = it; dp.max_iter = max_iter;
+    dp.status = B.status; dp.iters = B.iters; dp.pres = B.pres; dp.dres = B.dres; dp.rows = rows; dp.it = it; dp.max_iter = max_iter; dp.iters_add = B.iters_add;
     dp.eps_abs = st.eps_abs; dp.eps_rel = st.eps_rel; dp.eps_pinf = st.eps_prim_inf; dp.count = sw.count;
     stream_decide_kernel<<<(rows + 127) / 128, 128, 0, stream>>>(dp); nl++;
     stream_output_kernel<<<rows, 128, 0, stream>>>(sw.newly, idx, sw.XT, sw.YO, B.v_out, B.y_out, NTp, nz, nt); nl++;

@@ -46,6 +46,10 @@ struct StreamBatch {
   double *v_out, *y_out;
   int32_t *status, *iters;
   double *pres, *dres;
+  // second rung of the rho ladder (mpcb_api.cu): row b of this solve is problem remap[b] of the caller's batch (null: b itself), and the
+  // reported iteration counts continue from iters_add
+  const int32_t* remap = nullptr;
+  int iters_add = 0;
 };
 
 int stream_padded(int nt);

@@ -72,6 +72,8 @@ struct mpcb_handle {
   bool ladder = false;
   DevBuf<unsigned long long> counter;
   mpcb::StreamConsts sc;  // streamed-kernel constants
+  mpcb::StreamConsts sc2; // ... of the second rung of the rho ladder
+  PinBuf<unsigned long long> ladder_count;
   // batch workspaces (device)
   DevBuf<double> x0, xref, uref, warm_v, warm_y, v, y, pres, dres, u, e_u, x, e_x, u0, obj;
   DevBuf<int32_t> status, iters;
@@ -199,6 +201,10 @@ int upload_design(mpcb_handle* h) {
     std::string err;
     cudaError_t e = mpcb::stream_upload(D, h->sc, err);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, "stream_upload: " + err + cudaGetErrorString(e));
+    if (h->ladder) {
+      e = mpcb::stream_upload(h->D2, h->sc2, err);
+      if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, "stream_upload (second rung): " + err + cudaGetErrorString(e));
+    }
   }
   return MPCB_OK;
 }
@@ -282,9 +288,37 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     sb.warm_v = io.warm_u; sb.warm_y = io.warm_y; sb.v_out = v_buf; sb.y_out = io.y;
     sb.status = d_status; sb.iters = d_iters; sb.pres = d_pres; sb.dres = d_dres;
     int nl = 0;
-    cudaError_t e = mpcb::stream_solve(h->D, h->st, h->sc, h->sw, sb, h->info.sm_count, st, &nl, err);
+    mpcb_settings st1 = h->st;
+    if (h->ladder) {        // first rung: capped; its (x, y) are the second rung's warm start
+      st1.max_iter = h->st.ladder_iter;
+      if (!sb.y_out) { CUDA_TRY(h->y.ensure((size_t)Bn * D.nt)); sb.y_out = h->y.p; }
+    }
+    cudaError_t e = mpcb::stream_solve(h->D, st1, h->sc, h->sw, sb, h->info.sm_count, st, &nl, err);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, "admm_stream: " + err + " " + cudaGetErrorString(e));
     launches += nl;
+    if (h->ladder) {
+      // second rung (as on the on-chip kernel): the problems that ran into the cap continue from their iterate with the stiffer state-box
+      // step sizes of the second cached operator.  The streamed path is host-driven anyway, so the count is simply read back.
+      CUDA_TRY(h->remap.ensure(Bn)); CUDA_TRY(h->ladder_count.ensure(1));
+      CUDA_TRY(cudaMemsetAsync(h->counter.p + 2, 0, sizeof(unsigned long long), st));
+      collect_unsolved_kernel<<<(unsigned)((Bn + 255) / 256), 256, 0, st>>>(d_status, Bn, h->remap.p, h->counter.p + 2);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaMemcpyAsync(h->ladder_count.p, h->counter.p + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      launches += 1;
+      const long long n2 = (long long)h->ladder_count.p[0];
+      if (n2 > 0) {
+        mpcb::StreamBatch s2 = sb;
+        s2.batch = n2; s2.remap = h->remap.p; s2.iters_add = h->st.ladder_iter;
+        s2.warm_v = v_buf; s2.warm_y = sb.y_out;           // in place: a row reads its problem's warm start in the init kernel, before anything is written back
+        mpcb_settings st2 = h->st;
+        st2.max_iter = h->st.max_iter - h->st.ladder_iter;
+        int nl2 = 0;
+        e = mpcb::stream_solve(h->D2, st2, h->sc2, h->sw, s2, h->info.sm_count, st, &nl2, err);
+        if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, "admm_stream (second rung): " + err + " " + cudaGetErrorString(e));
+        launches += nl2;
+      }
+    }
   }
   if (ev_mid) CUDA_TRY(cudaEventRecord(ev_mid, st));
   if (io.u || io.e_u || io.x || io.e_x || io.u0 || io.objective) {
@@ -497,7 +531,7 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM && kernel != MPCB_KERNEL_RICCATI) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;
   // rho ladder: only where it applies -- inequality general rows (state box; the ball rows are not boxes) on the on-chip kernel
-  if (st.ladder_iter > 0 && kernel == MPCB_KERNEL_ONCHIP && D.mg > D.nball && desc->state_constraint) {
+  if (st.ladder_iter > 0 && (kernel == MPCB_KERNEL_ONCHIP || kernel == MPCB_KERNEL_STREAMED) && D.mg > D.nball && desc->state_constraint) {
     if (st.ladder_iter >= st.max_iter) { delete h; return fail(MPCB_ERR_INVALID, "settings.ladder_iter must be below max_iter"); }
     h->st.ladder_iter = ((st.ladder_iter + st.check_every - 1) / st.check_every) * st.check_every;
     if (h->st.ladder_kappa <= 0) h->st.ladder_kappa = 10;
@@ -614,6 +648,8 @@ void mpcb_destroy(mpcb_handle* h) {
   if (h->busy_ev) cudaEventDestroy(h->busy_ev);
   h->status.release(); h->iters.release(); h->counter.release();
   mpcb::stream_release(h->sc, h->sw);
+  { mpcb::StreamWork none; mpcb::stream_release(h->sc2, none); }
+  h->ladder_count.release();
   h->stage_in.release(); h->stage_out.release(); h->stage_int.release(); h->small_io.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);

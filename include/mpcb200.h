@@ -76,7 +76,7 @@ typedef struct {
   int32_t check_every;  /* 25 */
   int32_t device;       /* CUDA device ordinal this handle lives on */
   int32_t kernel;       /* MPCB_KERNEL_* */
-  int32_t ladder_iter;  /* 0 (off).  > 0: rho ladder for controllers with state-box rows on the on-chip kernel -- problems still unsolved
+  int32_t ladder_iter;  /* 0 (off).  > 0: rho ladder for controllers with state-box rows (on-chip and streamed kernels) -- problems still unsolved
                            after ladder_iter iterations continue from their iterate with the step size of the state-box rows
                            multiplied by ladder_kappa (a second cached operator), for the remaining max_iter - ladder_iter iterations.
                            A batch-wide fixed rho leaves a few problems per 10^4 with thousands of iterations when many state

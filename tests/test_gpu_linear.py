@@ -558,3 +558,42 @@ def test_streamed_warm_start(mpc, qt):
     m = make_controller(mpc, qt, 70, mpc_b200_kernel=2, **kw).tuning.modeler
     dev = m.closed_loop(x0[:64], xref[:64], uref, 3, warm_start=True)
     assert (dev["unsolved_steps"] == 0).all()
+
+
+def test_rho_ladder_on_the_streamed_kernel(mpc, qt):
+    """The same two-rung scheme on the streamed kernel (H = 20 with the state box: nt = 120 general-row problem): first rung capped at 300
+    iterations, the unsolved tail re-solved -- through an index map, warm-started in place at the first rung's (x, y) -- with the second cached
+    operator.  Against the twin of the two-pass scheme, and against the single-pass solve (same optima, a fraction of the time and tail)."""
+    import time
+    H, n, eps = 20, 6000, 1e-7
+    xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    kw = dict(mpc_solver="b200", mpc_state_constraint=True, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    C1 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), **kw)
+    C2 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_b200_ladder_iter=300, mpc_b200_ladder_kappa=10, **kw)
+    assert C1.tuning.modeler.info.kernel == 2 and C2.tuning.modeler.info.kernel == 2 and C2.tuning.modeler.info.nt == 120
+    rng = np.random.default_rng(7)
+    xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    out, ms = [], []
+    for C in (C1, C2):
+        mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
+        t0 = time.perf_counter()
+        out.append({k: v.copy() for k, v in mpc.calculate(C).items()})
+        ms.append((time.perf_counter() - t0) * 1e3)
+    one, two = out
+    print(f"streamed state-box H=20, {n} problems: single pass {ms[0]:.1f} ms (max {one['iters'].max()} iterations), ladder {ms[1]:.1f} ms (max {two['iters'].max()})")
+    assert (one["status"] == 1).all() and (two["status"] == 1).all()
+    second = one["iters"] > 300
+    assert 3 <= second.sum() <= n // 20
+    assert two["iters"].max() <= one["iters"].max()
+    assert np.array_equal(one["iters"][~second], two["iters"][~second]) and np.array_equal(one["u"][~second], two["u"][~second])
+    assert mo.u0_metric(one["u"][:, 0], two["u"][:, 0], qt["umin"], qt["umax"]).max() < 5e-4
+    assert (np.abs(one["objective"] - two["objective"]) <= 1e-6 * np.abs(one["objective"])).all()
+    P = C2.tuning.terminal_ingredient.P
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"], xmin, xmax, state_constraint=True)
+    sel = np.concatenate([np.flatnonzero(second), np.flatnonzero(~second)[:300]])
+    tw = mo.admm_condensed_ladder(c, mo.pack_params(x0[sel], xref[sel], qt["u_ref"]),
+                                  mo.AdmmSettings(rho=C2.tuning.modeler.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000), 300, 10.0)
+    assert set(tw["second_rung"]) == set(range(int(second.sum())))
+    assert (tw["status"] == 1).all() and (two["iters"][sel] == tw["iters"]).mean() > 0.95
+    assert np.abs(two["u"][sel].reshape(len(sel), -1) - tw["v"]).max() < 1e-5
