@@ -107,3 +107,22 @@ def test_riccati_refuses_what_it_cannot_do(mpc, qt):
         make_controller(mpc, qt, 20, terminal="equality", mpc_b200_kernel=4)          # general rows
     with pytest.raises(mpc.MpcbError, match="Riccati"):
         make_controller(mpc, qt, 20, mpc_S=1.0, mpc_b200_kernel=4)                    # S term couples the stages' inputs
+
+
+def test_tune_rho_small_sample_and_explicit_rho(mpc, qt):
+    """mpcb_tune_rho on a sample too small for the timed path (scored by the group-maximum iteration count instead), with an explicit starting
+    value: the candidates are centred on it, the winner is one of them, and the controller built with it solves the batch to the same optima
+    as the automatic step size."""
+    H, n = 100, 2000
+    x0, xref, uref = qt_batch(qt, n, seed=44)
+    kw = dict(mpc_b200_eps_abs=1e-7, mpc_b200_eps_rel=1e-7, mpc_b200_check_every=5, mpc_b200_sigma=0.0)
+    Ca = make_controller(mpc, qt, H, **kw)
+    Ct = make_controller(mpc, qt, H, mpc_b200_rho=2.0, mpc_b200_rho_tune=(x0[:96], xref[:96], uref, 5), **kw)
+    t = Ct.tuning.modeler.rho_tuning
+    assert len(t["candidates"]) == 5 and abs(t["candidates"][2] - 2.0) < 1e-12 and t["rho"] in t["candidates"]
+    assert all(s > 1.0 for s in t["mean_iters"])                      # iteration-count scores (a timed score would be a fraction of a millisecond)
+    assert abs(Ct.tuning.modeler.info.rho - t["rho"]) < 1e-12
+    ra = Ca.tuning.modeler.solve_batch(x0, xref, uref, want=("u0", "objective")); rt = Ct.tuning.modeler.solve_batch(x0, xref, uref, want=("u0", "objective"))
+    assert (ra["status"] == 1).all() and (rt["status"] == 1).all()
+    assert mo.u0_metric(rt["u0"], ra["u0"], qt["umin"], qt["umax"]).max() < U0_TOL
+    assert (np.abs(rt["objective"] - ra["objective"]) <= OBJ_TOL * np.abs(ra["objective"])).all()
