@@ -25,7 +25,7 @@ class Settings(C.Structure):
     _fields_ = [("eps_abs", C.c_double), ("eps_rel", C.c_double), ("eps_prim_inf", C.c_double), ("rho", C.c_double),
                 ("rho_eq_scale", C.c_double), ("sigma", C.c_double), ("alpha", C.c_double), ("max_iter", C.c_int32),
                 ("check_every", C.c_int32), ("device", C.c_int32), ("kernel", C.c_int32), ("ladder_iter", C.c_int32), ("ladder_kappa", C.c_int32),
-                ("n_devices", C.c_int32), ("device_ids", C.c_int32 * 8), ("reserved", C.c_int32 * 1)]
+                ("n_devices", C.c_int32), ("device_ids", C.c_int32 * 8), ("cold_init", C.c_int32)]
 
 
 class LinearDesc(C.Structure):

@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mpcb200.h"
+
 namespace mpcb {
 
 struct OnchipParams {
@@ -46,6 +48,7 @@ struct OnchipParams {
   const double* xref;   // [batch or 1][nx]
   const double* uref;   // [batch or 1][nu]
   int xref_bc, uref_bc;
+  const double* Lv;     // [np][NT]  transposed cold-start map (rows < nz: v_unc = Lv p; zero beyond) or null (settings.cold_init = 0)
   const double* warm_v; // [batch][nz] or null
   const double* warm_y; // [batch][nt] or null
   double* v_out;        // [batch][nz]  absolute inputs
@@ -264,19 +267,38 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         double m = 0.0;
 #pragma unroll
         for (int le = 0; le < EPL; le++) {
+          q[le] = acc[le];               // box rows: q ; general rows: bound offset b(p)
+          if ((boxbits >> le) & 1u) m = dmaxf(m, fabs(acc[le]));
+          acc[le] = 0.0;
+        }
+        const bool cold_pt = P.Lv != nullptr && P.warm_v == nullptr;     // settings.cold_init: start at the clipped unconstrained optimum Lv p
+        if (cold_pt) {
+          for (int j = 0; j < P.np; j++) {
+            const double pj = sP[g * npad + j];
+#pragma unroll
+            for (int t = 0; t < NTL; t++) {
+              const double2 l2 = __ldg(reinterpret_cast<const double2*>(&P.Lv[j * NT + 8 * t + 2 * l4]));
+              acc[2 * t] = fma(l2.x, pj, acc[2 * t]);
+              acc[2 * t + 1] = fma(l2.y, pj, acc[2 * t + 1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int le = 0; le < EPL; le++) {
           const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
           const bool box = (boxbits >> le) & 1u;
-          q[le] = acc[le];               // box rows: q ; general rows: bound offset b(p)
-          if (box) m = dmaxf(m, fabs(acc[le]));
           double v0 = 0.0, ys0 = 0.0;    // OSQP warm start: x = v0, z = A x, y = y0
           if (P.warm_v != nullptr) {
             if (box && e < nz) v0 = P.warm_v[pi * nz + e];
             if (e < P.nt) ys0 = P.warm_y[pi * P.nt + e] * (HAS_G ? sRinv[e] : rinv_s);
+          } else if (cold_pt && box && e < nz) {
+            v0 = dclamp(acc[le], sLo[e], sHi[e]);
+            ys0 = -MPCB_INIT_KAPPA * (v0 - acc[le]);      // y / rho with y = -kappa rho (x - v_unc)
           }
           if (KEEP_X) x[le] = box ? v0 : 0.0;
           if (!HAS_G) {
             c[le] = fma(oma, v0, ys0);
-            const double r0 = fma(rho_s, v0 - ys0, fma(sigma, v0, -acc[le]));
+            const double r0 = fma(rho_s, v0 - ys0, fma(sigma, v0, -q[le]));
             if (R_SMEM) sR[le * 32] = r0; else r[le] = r0;
           } else {
             c[le] = v0;    // z
@@ -286,7 +308,7 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         qn = m;
       }
       qn = quad_max(qn);
-      if (HAS_G && P.warm_v != nullptr) {
+      if (HAS_G && (P.warm_v != nullptr || P.Lv != nullptr)) {
         double in[EPL], out[EPL];
 #pragma unroll
         for (int le = 0; le < EPL; le++) in[le] = (fresh && ((boxbits >> le) & 1u)) ? c[le] : 0.0;

@@ -139,6 +139,14 @@ __global__ void __launch_bounds__(256) admm_riccati_kernel(const __grid_constant
           const double v0 = P.warm_v[p * nz + j], y0 = P.warm_y[p * nz + j];
           Wt[j * 32 + lane] = v0 + y0 / rho;
           if (SIG) Xt[j * 32 + lane] = v0;
+        } else if (P.Lv != nullptr) {
+          // settings.cold_init: x = clip(v_unc), y / rho = -kappa (x - v_unc) with v_unc = Lv p the unconstrained optimum
+          double vu = 0.0;
+#pragma unroll
+          for (int i = 0; i < NP; i++) vu = fma(__ldg(P.Lv + (size_t)j * NP + i), pv[i], vu);
+          const double v0 = dclamp(vu, P.lo[j % NU], P.hi[j % NU]);
+          Wt[j * 32 + lane] = v0 - MPCB_INIT_KAPPA * (v0 - vu);
+          if (SIG) Xt[j * 32 + lane] = v0;
         }
       }
     }
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(256) admm_riccati_kernel(const __grid_constant
     __syncwarp();
 
     bool done = !valid;
-    bool cold_first = (P.warm_v == nullptr);   // first iteration of a cold start: z = y = x = 0, nothing to read but q
+    bool cold_first = (P.warm_v == nullptr && P.Lv == nullptr);   // first iteration of a cold start: z = y = x = 0, nothing to read but q
     int it = 0;
 
     // one chunk of one array set: lane 0 arms the barrier and issues the bulk copies

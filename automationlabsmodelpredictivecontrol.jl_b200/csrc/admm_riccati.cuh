@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/mpcb200.h"
+
 namespace mpcb {
 
 constexpr int RIC_MAX_NX = 8, RIC_MAX_NU = 4;
@@ -13,6 +15,7 @@ struct RiccatiParams {
   // per-system constants
   const double* stage;   // [H][ric_stage_doubles(nx, nu)]: K, K', Lambda^-1, Acl, Acl' of every stage (host_design.cpp)
   const double* Lq;      // [nz][np] row-major: q(p) = Lq p
+  const double* Lv;      // [nz][np] row-major cold-start map v_unc(p) = Lv p, or null (settings.cold_init = 0)
   double Bm[RIC_MAX_NX * RIC_MAX_NU];   // B  row-major [nx][nu]   (kernel parameters live in the constant bank: these are
   double Bt[RIC_MAX_NU * RIC_MAX_NX];   // B' row-major [nu][nx]    direct operands of the DFMAs, no load instruction)
   double lo[RIC_MAX_NU], hi[RIC_MAX_NU];

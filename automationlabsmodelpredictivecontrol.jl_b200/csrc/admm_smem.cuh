@@ -92,6 +92,15 @@ __global__ void __launch_bounds__(W * 32, 1) admm_smem_kernel(const OnchipParams
             const double2 l2 = *reinterpret_cast<const double2*>(&P.Lt[j * NT + 8 * t + 2 * l4]);
             a0 = fma(l2.x, pj, a0); a1 = fma(l2.y, pj, a1);
           }
+          double u0 = 0.0, u1 = 0.0;       // settings.cold_init: v_unc = Lv p, the unconstrained optimum
+          const bool cold_pt = P.Lv != nullptr && P.warm_v == nullptr;
+          if (cold_pt) {
+            for (int j = 0; j < P.np; j++) {
+              const double pj = sP[g * npad + j];
+              const double2 l2 = __ldg(reinterpret_cast<const double2*>(&P.Lv[j * NT + 8 * t + 2 * l4]));
+              u0 = fma(l2.x, pj, u0); u1 = fma(l2.y, pj, u1);
+            }
+          }
 #pragma unroll
           for (int jj = 0; jj < 2; jj++) {
             const int le = 2 * t + jj, e = 8 * t + 2 * l4 + jj;
@@ -101,6 +110,10 @@ __global__ void __launch_bounds__(W * 32, 1) admm_smem_kernel(const OnchipParams
             if (P.warm_v != nullptr) {
               if (e < nz) v0 = P.warm_v[pi * nz + e];
               if (e < P.nt) ys0 = P.warm_y[pi * P.nt + e] * rinv_s;
+            } else if (cold_pt && e < nz) {
+              const double vu = jj ? u1 : u0;
+              v0 = dclamp(vu, sLo[e], sHi[e]);
+              ys0 = -MPCB_INIT_KAPPA * (v0 - vu);
             }
             sQ[le * 32] = qv;
             sC[le * 32] = fma(oma, v0, ys0);

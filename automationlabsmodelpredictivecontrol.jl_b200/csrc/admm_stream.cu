@@ -304,9 +304,14 @@ struct InitParams {
   const double *warm_v, *warm_y, *C, *rho;     // C: [NTp][NTp] check operator (rows >= nz hold G), rho: [NTp]
   double alpha, sigma;
   const int32_t* remap;                        // row -> problem of the caller's batch (null: identity)
+  // settings.cold_init: a cold start begins at x = clip(Lv p), y_box = -kappa rho (x - Lv p), z_g = G x, y_g = 0 (Lv null: zeros)
+  const double *Lv, *lo, *hi;                  // Lv: [np][NTp]
 };
 __global__ void stream_init_kernel(const InitParams P) {
-  extern __shared__ double sp[];   // p vector of this problem
+  extern __shared__ double sp[];   // p vector of this problem (+ with cold_init: x [nz], y_box / rho [nz])
+  const bool cold_pt = P.Lv != nullptr && P.warm_v == nullptr;
+  double* sv = sp + P.np;
+  double* sy = sv + P.nz;
   const long long b = blockIdx.x;
   const long long o = P.remap ? (long long)P.remap[b] : b;      // problem of the caller's batch behind this row
   for (int j = threadIdx.x; j < P.np; j += blockDim.x) {
@@ -317,6 +322,15 @@ __global__ void stream_init_kernel(const InitParams P) {
     sp[j] = v;
   }
   __syncthreads();
+  if (cold_pt) {
+    for (int n = threadIdx.x; n < P.nz; n += blockDim.x) {
+      double vu = 0.0;
+      for (int j = 0; j < P.np; j++) vu = fma(P.Lv[(size_t)j * P.NTp + n], sp[j], vu);
+      const double v0 = fmin(fmax(vu, P.lo[n]), P.hi[n]);
+      sv[n] = v0; sy[n] = -MPCB_INIT_KAPPA * (v0 - vu);
+    }
+    __syncthreads();
+  }
   double m = 0.0;
   for (int n = threadIdx.x; n < P.NTp; n += blockDim.x) {
     double acc = 0.0;
@@ -324,15 +338,15 @@ __global__ void stream_init_kernel(const InitParams P) {
     const size_t off = (size_t)b * P.NTp + n;
     P.QB[off] = acc;
     if (n < P.nz) m = dmaxf(m, fabs(acc));
-    if (P.warm_v == nullptr || n >= P.nt) {
+    if ((P.warm_v == nullptr && !cold_pt) || n >= P.nt) {
       P.Cst[off] = 0.0; P.X[off] = 0.0;
       P.R[off] = (n < P.nz) ? -acc : 0.0;
     } else {
-      const double* v0 = P.warm_v + (size_t)o * P.nz;
+      const double* v0 = cold_pt ? sv : P.warm_v + (size_t)o * P.nz;
       double z;
       if (n < P.nz) z = v0[n];
       else { z = 0.0; for (int j = 0; j < P.nz; j++) z = fma(P.C[(size_t)n * P.NTp + j], v0[j], z); }     // general row: G v0
-      const double rho_n = P.rho[n], ys = P.warm_y[(size_t)o * P.nt + n] / rho_n;
+      const double rho_n = P.rho[n], ys = cold_pt ? (n < P.nz ? sy[n] : 0.0) : P.warm_y[(size_t)o * P.nt + n] / rho_n;
       P.Cst[off] = fma(1.0 - P.alpha, z, ys);
       P.X[off] = (n < P.nz) ? z : 0.0;
       P.R[off] = rho_n * (z - ys) + ((n < P.nz) ? fma(P.sigma, z, -acc) : 0.0);
@@ -479,17 +493,19 @@ int stream_padded(int nt) { return ((nt + BN - 1) / BN) * BN; }
 cudaError_t stream_upload(const Design& D, StreamConsts& sc, std::string& err) {
   const int NTp = stream_padded(D.nt), nt = D.nt, np = D.np;
   sc.NTp = NTp;
-  std::vector<double> T((size_t)NTp * NTp, 0.0), C((size_t)NTp * NTp, 0.0), Lt((size_t)np * NTp, 0.0), lo(NTp, 0.0), hi(NTp, 0.0), rho(NTp, 1.0),
+  std::vector<double> T((size_t)NTp * NTp, 0.0), C((size_t)NTp * NTp, 0.0), Lt((size_t)np * NTp, 0.0), Lv(D.Lv.a.empty() ? 0 : (size_t)np * NTp, 0.0), lo(NTp, 0.0), hi(NTp, 0.0), rho(NTp, 1.0),
       rinv(NTp, 1.0);
   for (int j = 0; j < nt; j++)
     for (int i = 0; i < nt; i++) { T[(size_t)i * NTp + j] = D.T(i, j); C[(size_t)i * NTp + j] = D.C(i, j); }
   for (int j = 0; j < np; j++) {
     for (int i = 0; i < D.nz; i++) Lt[(size_t)j * NTp + i] = D.Lq(i, j);
     for (int i = 0; i < D.mg; i++) Lt[(size_t)j * NTp + D.nz + i] = D.Lb(i, j);
+    if (!Lv.empty()) for (int i = 0; i < D.nz; i++) Lv[(size_t)j * NTp + i] = D.Lv(i, j);
   }
   for (int i = 0; i < nt; i++) { lo[i] = D.lo[i]; hi[i] = D.hi[i]; rho[i] = D.rho_vec[i]; rinv[i] = 1.0 / D.rho_vec[i]; }
-  struct { double** p; const std::vector<double>* v; } ups[] = {{&sc.T, &T}, {&sc.C, &C}, {&sc.Lt, &Lt}, {&sc.lo, &lo}, {&sc.hi, &hi}, {&sc.rho, &rho}, {&sc.rinv, &rinv}};
+  struct { double** p; const std::vector<double>* v; } ups[] = {{&sc.T, &T}, {&sc.C, &C}, {&sc.Lt, &Lt}, {&sc.Lv, &Lv}, {&sc.lo, &lo}, {&sc.hi, &hi}, {&sc.rho, &rho}, {&sc.rinv, &rinv}};
   for (auto& u : ups) {
+    if (u.v->empty()) { *u.p = nullptr; continue; }
     cudaError_t e = dev_alloc(u.p, u.v->size());
     if (e != cudaSuccess) { err = "alloc constants"; return e; }
     e = cudaMemcpy(*u.p, u.v->data(), u.v->size() * sizeof(double), cudaMemcpyHostToDevice);
@@ -549,7 +565,8 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
     P.np = D.np; P.NTp = NTp; P.nz = nz; P.nt = nt; P.rows = rows; P.Cst = Cst; P.QB = QB; P.X = X; P.R = Rin; P.qn = qn; P.idx = idx; P.done = done;
     P.red = red;
     P.warm_v = B.warm_v; P.warm_y = B.warm_y; P.C = sc.C; P.rho = sc.rho; P.alpha = st.alpha; P.sigma = st.sigma; P.remap = B.remap;
-    stream_init_kernel<<<rows, 128, D.np * sizeof(double), stream>>>(P); nl++;
+    P.Lv = (st.cold_init && sc.Lv) ? sc.Lv : nullptr; P.lo = sc.lo; P.hi = sc.hi;
+    stream_init_kernel<<<rows, 128, (D.np + 2 * (size_t)nz) * sizeof(double), stream>>>(P); nl++;
   }
   const int max_iter = ((st.max_iter + st.check_every - 1) / st.check_every) * st.check_every;
   const bool sig = st.sigma != 0.0;
@@ -625,7 +642,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
 }
 
 void stream_release(StreamConsts& sc, StreamWork& sw) {
-  double** cs[] = {&sc.T, &sc.C, &sc.Lt, &sc.lo, &sc.hi, &sc.rho, &sc.rinv};
+  double** cs[] = {&sc.T, &sc.C, &sc.Lt, &sc.Lv, &sc.lo, &sc.hi, &sc.rho, &sc.rinv};
   for (auto p : cs) { if (*p) cudaFree(*p); *p = nullptr; }
   double** ws[] = {&sw.X, &sw.Q, &sw.Z, &sw.YS, &sw.R0, &sw.R1, &sw.DY, &sw.X2, &sw.Q2, &sw.Z2, &sw.XT, &sw.YO, &sw.YP, &sw.qn, &sw.qn2, &sw.cert};
   for (auto p : ws) { if (*p) cudaFree(*p); *p = nullptr; }

@@ -14,6 +14,7 @@ struct StreamConsts {
   double* T = nullptr;     // [NTp][NTp] row-major (symmetric), zero padded
   double* C = nullptr;     // [NTp][NTp]
   double* Lt = nullptr;    // [np][NTp]
+  double* Lv = nullptr;    // [np][NTp] cold-start map (settings.cold_init) or null
   double* lo = nullptr;    // [NTp]
   double* hi = nullptr;
   double* rho = nullptr;

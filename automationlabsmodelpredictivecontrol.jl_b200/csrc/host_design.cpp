@@ -469,6 +469,14 @@ int build_design(const mpcb_linear_desc& d, const mpcb_settings& s, Design& D, s
     for (int i = 0; i < mg; i++) { D.C(nz + i, j) = D.G(i, j); D.C(j, nz + i) = D.G(i, j); }
   }
   if (nx <= 8 && nu <= 4) riccati_factors(D, s.sigma);      // stage-wise form of the same x-update (admm_riccati.cu), where it applies
+  // cold-start map (settings.cold_init): v_unc(p) = Lv p = -Pc^-1 Lq p, the unconstrained optimum
+  D.Lv = Mat(0, 0);
+  if (s.cold_init) {
+    Mat Pinv;
+    if (!spd_inverse(D.Pc, Pinv)) { err = "condensed Hessian is not positive definite"; return MPCB_ERR_NUMERIC; }
+    D.Lv = matmul(Pinv, D.Lq);
+    for (double& v : D.Lv.a) v = -v;
+  }
   return MPCB_OK;
 }
 

@@ -49,6 +49,7 @@ struct Design {
   bool use_R = true, use_S = false;
   Mat Pc;   // nz x nz   Hessian in absolute-input coordinates (includes the S term)
   Mat Lq;   // nz x np   q(p) = Lq p
+  Mat Lv;   // nz x np   unconstrained optimum v_unc(p) = Lv p = -Pc^-1 Lq p (settings.cold_init; empty otherwise)
   Mat G;    // mg x nz   general rows
   Mat Lb;   // mg x np   bound offset b(p) = Lb p
   std::vector<double> lo, hi;        // nt: constant part of the bounds ([umin..|lg..], [umax..|ug..])

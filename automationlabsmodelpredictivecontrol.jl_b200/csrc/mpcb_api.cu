@@ -58,7 +58,7 @@ struct mpcb_handle {
   cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t chunk_ev[16] = {};
   // per-system constants
-  DevBuf<double> Tfrag, Cfrag, Lt, lo, hi, rho, rinv, A, B, Q, R, S, P;
+  DevBuf<double> Tfrag, Cfrag, Lt, Lv, lo, hi, rho, rinv, A, B, Q, R, S, P;
   DevBuf<double> ric_stage, ric_Lq;         // stage-wise (Riccati) kernel: per-stage factors, Lq row-major
   DevBuf<double> rW, rQ, rD, rX, rXT, rYO;  // its tile workspaces [tiles][nz][32]
   size_t smem_optin = 0;
@@ -174,6 +174,11 @@ int upload_design(mpcb_handle* h) {
       for (int j = 0; j < D.np; j++) lq[(size_t)i * D.np + j] = D.Lq(i, j);
     CUDA_TRY(upload(h->ric_stage, D.ric_stage.data(), D.ric_stage.size()));
     CUDA_TRY(upload(h->ric_Lq, lq.data(), lq.size()));
+    if (!D.Lv.a.empty()) {
+      for (int i = 0; i < D.nz; i++)
+        for (int j = 0; j < D.np; j++) lq[(size_t)i * D.np + j] = D.Lv(i, j);
+      CUDA_TRY(upload(h->Lv, lq.data(), lq.size()));
+    }
   } else if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     const int NT = h->NT, nt = D.nt, np = D.np;
     std::vector<double> tf = to_fragments(D.T, nt, NT), cf = to_fragments(D.C, nt, NT);
@@ -186,6 +191,12 @@ int upload_design(mpcb_handle* h) {
     CUDA_TRY(upload(h->Tfrag, tf.data(), tf.size()));
     CUDA_TRY(upload(h->Cfrag, cf.data(), cf.size()));
     CUDA_TRY(upload(h->Lt, Lt.data(), Lt.size()));
+    if (!D.Lv.a.empty()) {      // cold-start map in the same [np][NT] layout (general rows stay zero)
+      std::fill(Lt.begin(), Lt.end(), 0.0);
+      for (int j = 0; j < np; j++)
+        for (int i = 0; i < D.nz; i++) Lt[(size_t)j * NT + i] = D.Lv(i, j);
+      CUDA_TRY(upload(h->Lv, Lt.data(), Lt.size()));
+    }
     CUDA_TRY(upload(h->lo, lo.data(), NT));
     CUDA_TRY(upload(h->hi, hi.data(), NT));
     CUDA_TRY(upload(h->rho, rho.data(), NT));
@@ -235,7 +246,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     if (sig) CUDA_TRY(h->rX.ensure(tile_doubles));
     if (io.y) CUDA_TRY(h->rYO.ensure(tile_doubles));
     mpcb::RiccatiParams P{};
-    P.stage = h->ric_stage.p; P.Lq = h->ric_Lq.p;
+    P.stage = h->ric_stage.p; P.Lq = h->ric_Lq.p; P.Lv = h->st.cold_init ? h->Lv.p : nullptr;
     for (int m = 0; m < D.nx; m++)
       for (int i = 0; i < D.nu; i++) { P.Bm[m * D.nu + i] = D.B(m, i); P.Bt[i * D.nx + m] = D.B(m, i); }
     for (int i = 0; i < D.nu; i++) { P.lo[i] = D.lo[i]; P.hi[i] = D.hi[i]; }
@@ -252,7 +263,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     launches += 1;
   } else if (h->info.kernel == MPCB_KERNEL_ONCHIP || h->info.kernel == MPCB_KERNEL_ONCHIP_SMEM) {
     OnchipParams P{};
-    P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
+    P.Tfrag = h->Tfrag.p; P.Cfrag = h->Cfrag.p; P.Lt = h->Lt.p; P.Lv = h->st.cold_init ? h->Lv.p : nullptr; P.lo = h->lo.p; P.hi = h->hi.p; P.rho = h->rho.p; P.rinv = h->rinv.p;
     P.nz = D.nz; P.nt = D.nt; P.np = D.np; P.nx = D.nx; P.nu = D.nu; P.nball = D.nball;
     P.rho_box = D.rho; P.sigma = h->st.sigma; P.alpha = h->st.alpha; P.eps_abs = h->st.eps_abs; P.eps_rel = h->st.eps_rel;
     P.eps_pinf = h->st.eps_prim_inf; P.max_iter = h->ladder ? h->st.ladder_iter : h->st.max_iter; P.check_every = h->st.check_every;
@@ -457,7 +468,7 @@ void mpcb_default_settings(mpcb_settings* s) {
   if (!s) return;
   std::memset(s, 0, sizeof(*s));
   s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->rho = 0.0; s->rho_eq_scale = 1e3;
-  s->sigma = 1e-6; s->alpha = 1.6; s->max_iter = 4000; s->check_every = 25; s->device = 0; s->kernel = MPCB_KERNEL_AUTO;
+  s->sigma = 1e-6; s->alpha = 1.6; s->max_iter = 4000; s->check_every = 25; s->device = 0; s->kernel = MPCB_KERNEL_AUTO; s->cold_init = 0;
 }
 
 void* mpcb_alloc_pinned(size_t bytes) {
@@ -640,7 +651,7 @@ void mpcb_destroy(mpcb_handle* h) {
   if (h->done_ev) cudaEventDestroy(h->done_ev);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->remap.release();
-  for (DevBuf<double>* b : {&h->Tfrag, &h->Cfrag, &h->Lt, &h->lo, &h->hi, &h->rho, &h->rinv, &h->Tfrag2, &h->rho2, &h->rinv2, &h->A, &h->B, &h->Q, &h->R, &h->S, &h->P, &h->x0,
+  for (DevBuf<double>* b : {&h->Tfrag, &h->Cfrag, &h->Lt, &h->Lv, &h->lo, &h->hi, &h->rho, &h->rinv, &h->Tfrag2, &h->rho2, &h->rinv2, &h->A, &h->B, &h->Q, &h->R, &h->S, &h->P, &h->x0,
                             &h->xref, &h->uref, &h->warm_v, &h->warm_y, &h->v, &h->y, &h->pres, &h->dres, &h->u, &h->e_u, &h->x, &h->e_x,
                             &h->u0, &h->obj})
     b->release();

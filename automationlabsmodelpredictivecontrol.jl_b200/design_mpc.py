@@ -25,7 +25,8 @@ _DEFAULT_PARAMETERS_MODEL_PREDICTIVE_CONTROL = dict(mpc_solver="auto", mpc_termi
 _B200_SETTING_KEYS = {"mpc_b200_eps_abs": "eps_abs", "mpc_b200_eps_rel": "eps_rel", "mpc_b200_rho": "rho", "mpc_b200_max_iter": "max_iter",
                       "mpc_b200_check_every": "check_every", "mpc_b200_device": "device", "mpc_b200_kernel": "kernel",
                       "mpc_b200_alpha": "alpha", "mpc_b200_sigma": "sigma", "mpc_b200_eps_prim_inf": "eps_prim_inf",
-                      "mpc_b200_ladder_iter": "ladder_iter", "mpc_b200_ladder_kappa": "ladder_kappa", "mpc_b200_devices": "devices"}
+                      "mpc_b200_ladder_iter": "ladder_iter", "mpc_b200_ladder_kappa": "ladder_kappa", "mpc_b200_devices": "devices",
+                      "mpc_b200_cold_init": "cold_init"}
 
 
 def _settings_from_kws(kws) -> _lib.Settings:

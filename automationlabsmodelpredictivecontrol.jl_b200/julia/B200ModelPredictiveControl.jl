@@ -24,7 +24,7 @@ struct MpcbSettings
     ladder_kappa::Int32
     n_devices::Int32            # 2..8: one handle drives device_ids[1:n_devices] from this process (batch sharded, see include/mpcb200.h)
     device_ids::NTuple{8,Int32}
-    reserved::NTuple{1,Int32}
+    cold_init::Int32            # 0 (default): OSQP cold start; 1: cold starts begin at the clipped unconstrained optimum (include/mpcb200.h)
 end
 
 struct MpcbLinearDesc

@@ -90,8 +90,15 @@ typedef struct {
                            devices travel over NVLink as peer copies ordered by events (inputs out, results back into the caller's arrays), still
                            asynchronous with respect to the host. */
   int32_t device_ids[8];
-  int32_t reserved[1];
+  int32_t cold_init;    /* 0 (default): OSQP's cold start x = z = y = 0.  1: a cold start (no warm_u / warm_y) begins at the clipped unconstrained optimum
+                           x = clip(-Pc^-1 q(p), umin, umax), z = [x; G x], with the dual guess y = -MPCB_INIT_KAPPA rho (x - v_unc) on the input-box rows
+                           (zero where the box is inactive, the sign of the multiplier where it clips) and y = 0 on the general rows -- v_unc(p) is one
+                           more per-system linear map of the parameters, like q(p).  Same iteration, fixed point and termination test.  Measured
+                           (profiles/r02/cold_init_twin.txt, coldinit_ab_v1.jsonl): 8-20 % fewer iterations on AVERAGE, but the problems with many
+                           active bounds -- the ones a batch waits for -- gain nothing: -3 % time on the on-chip kernel (H = 20, 65 536 problems),
+                           +2..9 % on the shared-memory and stage-wise kernels, whose time follows the maximum over a tile.  Hence opt-in. */
 } mpcb_settings;
+#define MPCB_INIT_KAPPA 2.0
 
 /* Linear (or linearised) MPC description = the data `_model_predictive_control_design` assembles for a
  * ConstrainedLinearControlDiscreteSystem (src/sub/design_mpc.jl:54-129):

@@ -315,6 +315,8 @@ class AdmmSettings:
     max_iter: int = 4000
     check_every: int = 25
     ineq_scale: float = 1.0   # multiplies the step size of the inequality general rows (second rung of the rho ladder)
+    cold_init: int = 0        # cold start: 0 = OSQP's zeros (default), 1 = the clipped unconstrained optimum with a dual guess (cold_start_point)
+    init_kappa: float = 2.0
 
 
 STATUS_SOLVED, STATUS_MAX_ITER, STATUS_PRIMAL_INF = 1, -2, -3
@@ -343,6 +345,21 @@ def admm_matrices(c: CondensedQP, s: AdmmSettings):
     return T, C, rho_vec, rho
 
 
+def cold_start_point(c: CondensedQP, p, rho, kappa):
+    """Cold-start iterate of settings.cold_init = 1 (csrc: the refill / init code of every ADMM kernel; the map Lv = -Pc^-1 Lq is a
+    per-system constant from host_design.cpp).  x = clip(v_unc, lb, ub) with v_unc = Lv p the unconstrained optimum; dual guess on the
+    box rows y = -kappa rho (x - v_unc): zero where the box is inactive, the sign of the true multiplier where it clips (the exact
+    value would be -(Pc (x - v_unc)), a full operator pass; kappa rho is a one-number stand-in for Pc); general rows start at
+    z = G x, y = 0 like an OSQP warm start.  It is a starting point only: the iteration, its fixed point and the termination test are
+    unchanged."""
+    p = np.atleast_2d(p)
+    Lv = -np.linalg.solve(c.Pc, c.Lq)
+    vunc = p @ Lv.T
+    x = np.minimum(np.maximum(vunc, c.lb), c.ub)
+    y = np.concatenate([-kappa * rho * (x - vunc), np.zeros((p.shape[0], c.mg))], axis=1)
+    return x, y
+
+
 def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
     """Batched over problems (rows of p).  Mirrors OSQP's iteration (update_xz_tilde / update_x / update_z /
     update_y, osqp 0.6 `osqp_solve`) on the reduced KKT system with a cached operator.
@@ -369,6 +386,8 @@ def admm_condensed(c: CondensedQP, p, s: AdmmSettings, v0=None, y0=None):
         cen = b[:, :nb_]
         lo[:, nz:nz + nb_] = -OSQP_INFTY; hi[:, nz:nz + nb_] = OSQP_INFTY
     Ac = np.vstack([np.eye(nz), c.G])
+    if v0 is None and s.cold_init:
+        v0, y0 = cold_start_point(c, p, rho, s.init_kappa)
     if v0 is None:
         x = np.zeros((Bn, nz)); z = np.zeros((Bn, nt)); ys = np.zeros((Bn, nt))
     else:                                   # OSQP warm start: x = x0, z = A x0, y = y0

@@ -597,3 +597,39 @@ def test_rho_ladder_on_the_streamed_kernel(mpc, qt):
     assert set(tw["second_rung"]) == set(range(int(second.sum())))
     assert (tw["status"] == 1).all() and (two["iters"][sel] == tw["iters"]).mean() > 0.95
     assert np.abs(two["u"][sel].reshape(len(sel), -1) - tw["v"]).max() < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,kernel,terminal,state_box,sigma", [(20, 1, "none", False, 0.0), (20, 1, "none", False, 1e-6), (10, 1, "equality", False, 1e-6),
+                                                                 (10, 1, "none", True, 1e-6), (50, 3, "none", False, 0.0), (20, 2, "none", False, 0.0),
+                                                                 (10, 2, "equality", False, 1e-6), (10, 2, "none", True, 1e-6), (20, 4, "none", False, 0.0),
+                                                                 (100, 4, "none", False, 1e-6)])
+def test_cold_init_parity_on_every_kernel(mpc, qt, H, kernel, terminal, state_box, sigma):
+    """settings.cold_init = 1 (kw `mpc_b200_cold_init`): the cold-start point x = clip(Lv p), y_box = -kappa rho (x - Lv p), z_g = G x of every ADMM
+    kernel (register-resident with and without general rows, shared-memory, streamed, stage-wise) against the twin's `cold_start_point`: same
+    statuses and iteration counts, solutions to round-off; fewer iterations on average than OSQP's zeros, same optima."""
+    n, eps = 700, 1e-7
+    xmin, xmax = (np.full(4, 0.55), np.full(4, 0.75)) if state_box else (qt["xmin"], qt["xmax"])
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    kw = dict(mpc_solver="b200", mpc_terminal_ingredient=terminal, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_sigma=sigma,
+              mpc_b200_kernel=kernel, mpc_b200_max_iter=20000)
+    if state_box: kw["mpc_state_constraint"] = True
+    C1 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_b200_cold_init=1, **kw)
+    C0 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), **kw)
+    assert C1.tuning.modeler.info.kernel == kernel
+    rng = np.random.default_rng(31)
+    if state_box: xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    elif terminal == "equality": xref = np.tile(qt["x_ref"], (n, 1)); x0 = xref + rng.uniform(-0.004, 0.004, (n, 4))
+    else: x0, xref, _ = qt_batch(qt, n, seed=31)
+    uref = qt["u_ref"]
+    r1 = C1.tuning.modeler.solve_batch(x0, xref, uref, want=("u", "y", "objective"))
+    r0 = C0.tuning.modeler.solve_batch(x0, xref, uref, want=("u", "objective"))
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], C1.tuning.terminal_ingredient.P, H, qt["umin"], qt["umax"], xmin, xmax,
+                    state_constraint=state_box, terminal=terminal)
+    tw = mo.admm_condensed(c, mo.pack_params(x0, xref, uref), mo.AdmmSettings(rho=C1.tuning.modeler.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, sigma=sigma,
+                                                                               max_iter=20000, cold_init=1))
+    assert_matches_twin(r1, tw, tight=1e-8, loose=2e-5 if state_box else 1e-6, min_same=0.97, check=5)
+    both = (r1["status"] == 1) & (r0["status"] == 1)
+    assert both.mean() > 0.99
+    assert r1["iters"][both].mean() < r0["iters"][both].mean()
+    assert (np.abs(r1["objective"][both] - r0["objective"][both]) <= 1e-6 * np.maximum(1e-3, np.abs(r0["objective"][both]))).all()

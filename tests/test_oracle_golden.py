@@ -173,6 +173,37 @@ def test_twin_matches_exact_and_warm_start_helps(qt):
     assert warm["iters"].max() <= s.check_every and (warm["status"] == 1).all()
 
 
+def test_cold_start_point_saves_iterations_and_keeps_the_solution(qt):
+    """settings.cold_init = 1 (opt-in): a cold start at the clipped unconstrained optimum with the one-number dual guess needs fewer iterations
+    than OSQP's zeros and ends at the same optimum (both within the parity tolerance of the exact solve); where no bound is active it IS
+    the optimum and the first check terminates."""
+    import dataclasses
+    H, n = 20, 256
+    P = mo.dare(qt["A"], qt["B"], qt["Q"], qt["R"])
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, qt["umin"], qt["umax"])
+    rng = np.random.default_rng(4)
+    x0 = rng.uniform(qt["xmin"], qt["xmax"], (n, 4)); xref = rng.uniform(0.4, 1.0, (n, 4))
+    p = mo.pack_params(x0, xref, qt["u_ref"])
+    s0 = mo.AdmmSettings(eps_abs=1e-7, eps_rel=1e-7, check_every=5, sigma=0.0)
+    assert s0.cold_init == 0                          # opt-in: the default stays OSQP's cold start
+    s1 = dataclasses.replace(s0, cold_init=1)
+    r1, r0 = mo.admm_condensed(c, p, s1), mo.admm_condensed(c, p, s0)
+    assert (r1["status"] == 1).all() and (r0["status"] == 1).all()
+    assert r1["iters"].mean() < 0.95 * r0["iters"].mean() and r1["iters"].max() <= r0["iters"].max()
+    ex = np.array([mo.qp_exact(c, p[i], v_init=r1["v"][i])[0] for i in range(64)])
+    for r in (r0, r1): assert mo.u0_metric(r["v"][:64, :2], ex[:, :2], qt["umin"], qt["umax"]).max() < 1e-4
+    assert np.abs(r1["v"] - r0["v"]).max() < 5e-5
+    # the starting point itself: inside the box the dual guess is zero, on the box it has the multiplier's sign
+    x, y = mo.cold_start_point(c, p, r1["rho"], s1.init_kappa)
+    vunc = -np.linalg.solve(c.Pc, (p @ c.Lq.T).T).T
+    assert np.abs(x - np.clip(vunc, c.lb, c.ub)).max() < 1e-9 and (y[(x > c.lb) & (x < c.ub)] == 0).all()
+    assert (y[x >= c.ub] >= 0).all() and (y[x <= c.lb] <= 0).all()      # OSQP's sign: positive on an active upper bound
+    # no active bound: one check
+    wide = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], P, H, -1e3 * np.ones(2), 1e3 * np.ones(2))
+    rw = mo.admm_condensed(wide, p, s1)
+    assert (rw["iters"] == s1.check_every).all() and np.abs(rw["v"] - vunc).max() < 1e-9
+
+
 def test_contractive_ball_twin_vs_slsqp(qt):
     """Terminal "contractive" (design_mpc.jl:333-340) in the condensed twin: the ball projection inside the ADMM reproduces an
     independent SLSQP solve of the QCQP, and the constraint is active on part of the batch."""

@@ -6,7 +6,7 @@ import almpc_b200 as mpc
 from almpc_b200 import _lib
 import bench
 
-def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0, kernel=0):
+def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0, kernel=0, cold_init=1):
     """near > 0: x0 = x_ref + near * N(0, I) with the design reference (feasible terminal constraints); state_box: tight box + references beyond it"""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     if state_box: xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
@@ -16,6 +16,7 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
     if Qw is not None: extra["mpc_Q"] = Qw
     if Rw is not None: extra["mpc_R"] = Rw
     if ladder: extra["mpc_b200_ladder_iter"] = ladder
+    extra["mpc_b200_cold_init"] = cold_init
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_terminal_ingredient=terminal,
                                mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=check, mpc_b200_sigma=sigma, mpc_b200_rho=rho,
                                mpc_b200_max_iter=max_iter, mpc_b200_kernel=kernel, **extra)
@@ -51,7 +52,7 @@ def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, n
         sby = float(it.astype(float).sum()) * (6 if sigma == 0 else 9) * m.info.nz * 8
         extra_out = {"stage_tflops": round(sfl / ms / 1e9, 2), "state_GBps": round(sby / ms / 1e6, 1)}
     print(json.dumps({**extra_out, "H": H, "n": n, "eps": eps, "check": check, "sigma": sigma, "terminal": terminal, "state_box": state_box, "kernel": m.info.kernel, "nt": m.info.nt,
-                      "full": full, "ladder": ladder, "ms": round(ms, 4), "max_iters": int(it.max()),
+                      "full": full, "ladder": ladder, "cold_init": cold_init, "ms": round(ms, 4), "max_iters": int(it.max()),
                       "mean_iters": round(float(it.mean()), 2), "solves_per_s": round(n / ms * 1e3), "tflops": round(fl / ms / 1e9, 2),
                       "frac": round(fl / ms / 1e9 / bench.FP64_PEAK_TFLOPS, 3), "solved": float((status.cpu().numpy() == 1).mean()), "rho": round(m.info.rho, 4)}), flush=True)
 
@@ -157,6 +158,14 @@ if __name__ == "__main__":
         for n in (14208 * 4, 14208 * 16, 65536):
             run(20, n, 1e-300, 5, 0.0, max_iter=50)
         run(20, 65536 * 4, 1e-7, 5, 0.0)
+    elif a.set == "coldinit":    # A/B of settings.cold_init: steady state (every problem exactly 50 iterations: isolates the refill cost), the headline batch, the sweep
+        for ci in (0, 1):
+            run(20, 14208 * 16, 1e-300, 5, 0.0, max_iter=50, cold_init=ci)
+            run(20, 65536, 1e-7, 5, 0.0, cold_init=ci)
+            run(20, 65536, 1e-7, 5, 0.0, full=True, cold_init=ci)
+        for H in (10, 30, 50, 100, 200):
+            for ci in (0, 1): run(H, 16384, 1e-7, 5, 0.0, reps=3, cold_init=ci)
+        for ci in (0, 1): run(10, 65536, 1e-7, 5, 0.0, reps=3, state_box=True, cold_init=ci, ladder=300)
     elif a.set == "steady1":
         run(20, 14208 * 8, 1e-300, 5, 0.0, max_iter=50, reps=3)
     elif a.set == "one":
