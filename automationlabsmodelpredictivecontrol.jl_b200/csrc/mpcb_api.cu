@@ -25,6 +25,8 @@ namespace mpcb {
 // admm_smem.cu (own translation unit: 14 kernel instantiations compile in parallel with this file)
 size_t smemk_bytes_host(int NT, int np, bool sig);
 cudaError_t launch_smemk(int NT, const OnchipParams& P, int sm_count, int* attr_set, cudaStream_t st);
+size_t smemg_bytes_host(int NT, int np, bool sig);
+cudaError_t launch_smemg(int NT, const OnchipParams& P, int sm_count, cudaStream_t st);      // general rows, 64 < nt <= 120 (admm_smemg.cuh)
 }  // namespace mpcb
 
 namespace {
@@ -271,8 +273,12 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     P.warm_v = io.warm_u; P.warm_y = io.warm_y; P.v_out = v_buf; P.y_out = io.y;
     if (h->ladder && !P.y_out) { CUDA_TRY(h->y.ensure((size_t)Bn * D.nt)); P.y_out = h->y.p; }     // the second rung starts from the first pass's iterate
     P.status = d_status; P.iters = d_iters; P.pres = d_pres; P.dres = d_dres; P.counter = h->counter.p;
-    cudaError_t e = h->info.kernel == MPCB_KERNEL_ONCHIP ? launch_onchip(h->NT, D.mg > 0, P, h->info.sm_count, &h->onchip_blocks_per_sm, st)
-                                                         : mpcb::launch_smemk(h->NT, P, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+    auto launch_slots = [&](const OnchipParams& Q) {      // register-resident (nt <= 64) or shared-memory resident (box-only / general rows)
+      if (h->info.kernel == MPCB_KERNEL_ONCHIP) return launch_onchip(h->NT, D.mg > 0, Q, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+      if (D.mg > 0) return mpcb::launch_smemg(h->NT, Q, h->info.sm_count, st);
+      return mpcb::launch_smemk(h->NT, Q, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+    };
+    cudaError_t e = launch_slots(P);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
     launches += 1;
     if (h->ladder) {
@@ -288,7 +294,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
       P2.max_iter = h->st.max_iter - h->st.ladder_iter; P2.iters_add = P.max_iter;
       P2.warm_v = P.v_out; P2.warm_y = P.y_out;
       P2.remap = h->remap.p; P2.batch_dev = h->counter.p + 2;
-      e = launch_onchip(h->NT, true, P2, h->info.sm_count, &h->onchip_blocks_per_sm, st);
+      e = launch_slots(P2);
       if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip (second rung) launch: ") + cudaGetErrorString(e));
       launches += 2;
     }
@@ -522,7 +528,8 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   h->info.device = st.device; h->info.sm_count = prop.multiProcessorCount;
   int kernel = st.kernel;
   const int nt8 = ((D.nt + 7) / 8) * 8;
-  const bool smem_ok = D.mg == 0 && nt8 > 64 && nt8 <= 120 && mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) <= (size_t)prop.sharedMemPerBlockOptin;
+  const bool smem_ok = nt8 > 64 && nt8 <= 120 &&
+                       (D.mg == 0 ? mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) : mpcb::smemg_bytes_host(nt8, D.np, st.sigma != 0.0)) <= (size_t)prop.sharedMemPerBlockOptin;
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   const bool ric_form = !D.ric_stage.empty() && mpcb::riccati_supported(D.nx, D.nu);
   bool ric_fits = false;
@@ -537,12 +544,12 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
     if (!ric_fits) { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: the stage matrices of this horizon do not fit shared memory"); }
   }
   if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
-  if (D.nball > 0 && kernel != MPCB_KERNEL_ONCHIP) { delete h; return fail(MPCB_ERR_INVALID, "the contractive terminal set is implemented in the on-chip kernel only: needs nz + mg <= 64"); }
-  if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs a box-only problem with 64 < nz <= 120 that fits 227 KB"); }
+  if (D.nball > 0 && kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_ONCHIP_SMEM) { delete h; return fail(MPCB_ERR_INVALID, "the contractive terminal set is implemented in the on-chip kernels only: needs nz + mg <= 120"); }
+  if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs 64 < nz + mg <= 120 and an operator that fits 227 KB"); }
   if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM && kernel != MPCB_KERNEL_RICCATI) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;
   // rho ladder: only where it applies -- inequality general rows (state box; the ball rows are not boxes) on the on-chip kernel
-  if (st.ladder_iter > 0 && (kernel == MPCB_KERNEL_ONCHIP || kernel == MPCB_KERNEL_STREAMED) && D.mg > D.nball && desc->state_constraint) {
+  if (st.ladder_iter > 0 && (kernel == MPCB_KERNEL_ONCHIP || kernel == MPCB_KERNEL_ONCHIP_SMEM || kernel == MPCB_KERNEL_STREAMED) && D.mg > D.nball && desc->state_constraint) {
     if (st.ladder_iter >= st.max_iter) { delete h; return fail(MPCB_ERR_INVALID, "settings.ladder_iter must be below max_iter"); }
     h->st.ladder_iter = ((st.ladder_iter + st.check_every - 1) / st.check_every) * st.check_every;
     if (h->st.ladder_kappa <= 0) h->st.ladder_kappa = 10;

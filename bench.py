@@ -114,7 +114,7 @@ def kernel_name(info, sigma):
         sig = has_g or sigma != 0.0
         minb = {8: 4, 16: 4, 24: 3 if has_g else 4, 32: 2 if has_g else 4, 40: 2 if has_g else 3, 48: 2 if has_g else 3}.get(info.nt_pad, 2 if (has_g or sig) else 3)
         return f"admm_onchip_kernel<{info.nt_pad},{str(has_g).lower()},{str(sig).lower()},{minb}>"
-    if k == 3: return f"admm_smem_kernel<{info.nt_pad},{str(sigma != 0.0).lower()},*>"
+    if k == 3: return f"admm_smem{'g' if info.mg > 0 else ''}_kernel<{info.nt_pad},{str(sigma != 0.0).lower()},*>"
     if k == 4: return f"admm_riccati_kernel<{info.nx},{info.nu},{str(sigma != 0.0).lower()}>"
     return "stream_iter_kernel"
 

@@ -224,12 +224,15 @@ def test_streamed_equals_onchip(mpc, qt):
     assert np.abs(res[0]["y"][same] - res[1]["y"][same]).max() < 1e-8
 
 
-def test_streamed_terminal_equality(mpc, qt):
+@pytest.mark.parametrize("kernel", [2, 0])
+def test_streamed_terminal_equality(mpc, qt, kernel):
+    """Terminal-equality rows at nt = 84: the streamed kernel (forced) and, chosen automatically since round 2, the shared-memory resident
+    general-row kernel (admm_smemg.cuh) -- both against the twin."""
     H, n, eps = 40, 300, 1e-7
     C = make_controller(mpc, qt, H, terminal="equality", mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=10, mpc_b200_max_iter=6000,
-                        mpc_b200_rho=10.0)
+                        mpc_b200_rho=10.0, mpc_b200_kernel=kernel)
     m = C.tuning.modeler
-    assert m.info.kernel == 2 and m.info.mg == 4 and m.info.nt == 84
+    assert m.info.kernel == (2 if kernel == 2 else 3) and m.info.mg == 4 and m.info.nt == 84
     rng = np.random.default_rng(5)
     xref = np.tile(qt["x_ref"], (n, 1))
     x0 = xref + 0.05 * rng.standard_normal((n, 4))
@@ -312,7 +315,7 @@ def test_pipelined_host_entry_equals_plain(mpc, qt):
 @pytest.mark.parametrize("H", [10, 20])
 def test_state_constraint_rows(mpc, qt, H):
     """kw `mpc_state_constraint` (linear.jl:62-70): state-box rows on x[:,2..H+1] become general inequality rows
-    (H = 10: nt = 60, on-chip kernel with general rows; H = 20: nt = 120, streamed kernel).  The box is tightened to
+    (H = 10: nt = 60, on-chip kernel with general rows; H = 20: nt = 120, shared-memory resident general-row kernel).  The box is tightened to
     [0.55, 0.75] and the references sit partly beyond it, so the optimal trajectories press against the state bounds.
     CUDA vs the condensed twin, and vs the OSQP port run on the reference's own sparse formulation (independent encoding
     and solver) at tight tolerance."""
@@ -323,7 +326,7 @@ def test_state_constraint_rows(mpc, qt, H):
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_state_constraint=True,
                                mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
     m = C.tuning.modeler
-    assert m.info.mg == 4 * H and m.info.kernel == (1 if H == 10 else 2)
+    assert m.info.mg == 4 * H and m.info.kernel == (1 if H == 10 else 3)      # nt = 60: register-resident; nt = 120: shared-memory resident general-row kernel
     rng = np.random.default_rng(5)
     xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
     mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
@@ -451,9 +454,37 @@ def test_contractive_terminal_set(mpc, qt):
         assert mo.u0_metric(res["u0"][i], r.x[:2], qt["umin"], qt["umax"]) < U0_TOL
         v = res["u"][i].ravel()
         assert abs(r.fun - (0.5 * v @ c.Pc @ v + q @ v)) <= OBJ_TOL * max(1.0, abs(r.fun))
-    # too large for the on-chip kernel -> refused, not approximated
+    # too large for the on-chip kernels (nt > 120) -> refused, not approximated
     with pytest.raises(mpc.MpcbError):
-        make_controller(mpc, qt, 40, terminal="contractive")
+        make_controller(mpc, qt, 60, terminal="contractive")
+
+
+def test_contractive_terminal_set_shared_memory_kernel(mpc):
+    """The ball projection on the shared-memory resident general-row kernel (H = 40: nt = 84), against the twin.  A slow plant (poles at
+    0.998 .. 0.9995: A^40 alone does not contract by sqrt(0.9)) with an expensive input makes the ball active on most of the batch."""
+    H, n, eps = 40, 256, 1e-8
+    rng = np.random.default_rng(12)
+    A = np.diag([0.999, 0.9985, 0.9995, 0.998]); A[0, 1] = 0.001; A[2, 3] = -0.0005
+    B = 0.01 * rng.standard_normal((4, 2))
+    umin, umax = -np.ones(2), np.ones(2)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(-10 * np.ones(4), 10 * np.ones(4)), mpc.Hyperrectangle(umin, umax))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, [0.0] * 4, [0.0] * 2, mpc_solver="b200", mpc_Q=1.0, mpc_R=1000.0,
+                               mpc_terminal_ingredient="contractive", mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    m = C.tuning.modeler
+    assert m.info.mg == 4 and m.info.nt == 84 and m.info.kernel == 3
+    x0 = 0.5 * rng.standard_normal((n, 4)); xref = np.zeros((n, 4)); uref = np.zeros(2)
+    mpc.update_initialization(C, x0, references=(xref, uref))
+    res = mpc.calculate(C)
+    c = mo.condense(A, B, np.eye(4), 1000 * np.eye(2), np.zeros((2, 2)), C.tuning.terminal_ingredient.P, H, umin, umax, terminal="contractive")
+    tw = mo.admm_condensed(c, mo.pack_params(x0, xref, uref), mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000))
+    assert (res["status"] == tw["status"]).mean() > 0.98 and (res["status"] == 1).mean() > 0.9
+    ok = (res["status"] == 1) & (tw["status"] == 1)
+    assert (res["iters"][ok] == tw["iters"][ok]).mean() > 0.95 and np.abs(res["u"].reshape(n, -1)[ok] - tw["v"][ok]).max() < 1e-6
+    e0 = np.linalg.norm(res["e_x"][:, 0], axis=1); eH = np.linalg.norm(res["e_x"][:, H], axis=1)
+    assert (eH[ok] <= np.sqrt(0.9) * e0[ok] + 1e-6).all()
+    active = np.abs(eH - np.sqrt(0.9) * e0) < 1e-6
+    print(f"contractive H=40 on the shared-memory kernel: ball active on {int(active.sum())} of {n}, solved {int(ok.sum())}, mean iterations {res['iters'].mean():.0f}")
+    assert active.sum() >= n // 10
 
 
 def test_c_abi_error_behaviour(mpc, qt):
@@ -560,18 +591,22 @@ def test_streamed_warm_start(mpc, qt):
     assert (dev["unsolved_steps"] == 0).all()
 
 
-def test_rho_ladder_on_the_streamed_kernel(mpc, qt):
-    """The same two-rung scheme on the streamed kernel (H = 20 with the state box: nt = 120 general-row problem): first rung capped at 300
+@pytest.mark.parametrize("kernel", [2, 3])
+def test_rho_ladder_on_the_streamed_kernel(mpc, qt, kernel):
+    """(kernel 3: the same workload and assertions on the shared-memory resident general-row kernel, which takes it by default since round 2 and
+    never synchronises with the host.)
+    The same two-rung scheme on the streamed kernel (H = 20 with the state box: nt = 120 general-row problem): first rung capped at 300
     iterations, the unsolved tail re-solved -- through an index map, warm-started in place at the first rung's (x, y) -- with the second cached
     operator.  Against the twin of the two-pass scheme, and against the single-pass solve (same optima, a fraction of the time and tail)."""
     import time
     H, n, eps = 20, 6000, 1e-7
     xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
-    kw = dict(mpc_solver="b200", mpc_state_constraint=True, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    kw = dict(mpc_solver="b200", mpc_state_constraint=True, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000,
+              mpc_b200_kernel=kernel)
     C1 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), **kw)
     C2 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_b200_ladder_iter=300, mpc_b200_ladder_kappa=10, **kw)
-    assert C1.tuning.modeler.info.kernel == 2 and C2.tuning.modeler.info.kernel == 2 and C2.tuning.modeler.info.nt == 120
+    assert C1.tuning.modeler.info.kernel == kernel and C2.tuning.modeler.info.kernel == kernel and C2.tuning.modeler.info.nt == 120
     rng = np.random.default_rng(7)
     xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
     out, ms = [], []
@@ -581,7 +616,7 @@ def test_rho_ladder_on_the_streamed_kernel(mpc, qt):
         out.append({k: v.copy() for k, v in mpc.calculate(C).items()})
         ms.append((time.perf_counter() - t0) * 1e3)
     one, two = out
-    print(f"streamed state-box H=20, {n} problems: single pass {ms[0]:.1f} ms (max {one['iters'].max()} iterations), ladder {ms[1]:.1f} ms (max {two['iters'].max()})")
+    print(f"kernel {kernel} state-box H=20, {n} problems: single pass {ms[0]:.1f} ms (max {one['iters'].max()} iterations), ladder {ms[1]:.1f} ms (max {two['iters'].max()})")
     assert (one["status"] == 1).all() and (two["status"] == 1).all()
     second = one["iters"] > 300
     assert 3 <= second.sum() <= n // 20
@@ -603,7 +638,7 @@ def test_rho_ladder_on_the_streamed_kernel(mpc, qt):
 @pytest.mark.parametrize("H,kernel,terminal,state_box,sigma", [(20, 1, "none", False, 0.0), (20, 1, "none", False, 1e-6), (10, 1, "equality", False, 1e-6),
                                                                  (10, 1, "none", True, 1e-6), (50, 3, "none", False, 0.0), (20, 2, "none", False, 0.0),
                                                                  (10, 2, "equality", False, 1e-6), (10, 2, "none", True, 1e-6), (20, 4, "none", False, 0.0),
-                                                                 (100, 4, "none", False, 1e-6)])
+                                                                 (100, 4, "none", False, 1e-6), (40, 3, "equality", False, 1e-6), (20, 3, "none", True, 0.0)])
 def test_cold_init_parity_on_every_kernel(mpc, qt, H, kernel, terminal, state_box, sigma):
     """settings.cold_init = 1 (kw `mpc_b200_cold_init`): the cold-start point x = clip(Lv p), y_box = -kappa rho (x - Lv p), z_g = G x of every ADMM
     kernel (register-resident with and without general rows, shared-memory, streamed, stage-wise) against the twin's `cold_start_point`: same

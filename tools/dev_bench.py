@@ -166,6 +166,14 @@ if __name__ == "__main__":
         for H in (10, 30, 50, 100, 200):
             for ci in (0, 1): run(H, 16384, 1e-7, 5, 0.0, reps=3, cold_init=ci)
         for ci in (0, 1): run(10, 65536, 1e-7, 5, 0.0, reps=3, state_box=True, cold_init=ci, ladder=300)
+    elif a.set == "sbox20":      # state box at H = 20 (nt = 120): shared-memory resident general-row kernel (auto) vs the streamed kernel, with and without the rho ladder
+        for n in (6000, 16384):
+            for kern in (0, 2):
+                for lad in (0, 300):
+                    if kern == 2 and n > 6000 and lad: continue
+                    run(20, n, 1e-7, 5, 0.0, state_box=True, kernel=kern, ladder=lad, reps=2)
+        run(40, 16384, 1e-7, 10, 0.0, terminal="equality", near=0.02, kernel=0, reps=3)
+        run(40, 16384, 1e-7, 10, 0.0, terminal="equality", near=0.02, kernel=2, reps=3)
     elif a.set == "steady1":
         run(20, 14208 * 8, 1e-300, 5, 0.0, max_iter=50, reps=3)
     elif a.set == "one":
