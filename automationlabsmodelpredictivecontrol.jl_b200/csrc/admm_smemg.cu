@@ -43,7 +43,7 @@ cudaError_t launch_smemg(int NT, const OnchipParams& P, int sm_count, cudaStream
   const bool sig = P.sigma != 0.0;
   switch (NT) {
 #define MPCB_SG(N_) case N_: return sig ? launch_smemg_t<N_, true>(P, sm_count, st) : launch_smemg_t<N_, false>(P, sm_count, st);
-    MPCB_SG(72) MPCB_SG(80) MPCB_SG(88) MPCB_SG(96) MPCB_SG(104) MPCB_SG(112) MPCB_SG(120)
+    MPCB_SG(32) MPCB_SG(40) MPCB_SG(48) MPCB_SG(56) MPCB_SG(64) MPCB_SG(72) MPCB_SG(80) MPCB_SG(88) MPCB_SG(96) MPCB_SG(104) MPCB_SG(112) MPCB_SG(120)
 #undef MPCB_SG
     default: return cudaErrorInvalidValue;
   }

@@ -528,7 +528,13 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   h->info.device = st.device; h->info.sm_count = prop.multiProcessorCount;
   int kernel = st.kernel;
   const int nt8 = ((D.nt + 7) / 8) * 8;
-  const bool smem_ok = nt8 > 64 && nt8 <= 120 &&
+  // The general-row variant of the shared-memory kernel also takes nt8 = 48 .. 64 by default: the register-resident general-row kernels run at 255
+  // registers with spills there.  Measured (profiles/r02/smemg_ab_*.jsonl, 65 536 problems, terminal equality): nt8 = 40 0.752 vs 0.749 ms (a tie, and
+  // the register kernel has the shorter single-problem latency: it keeps nt8 <= 40), 48: 1.25 -> 1.06, 56: 2.18 -> 1.54, 64: 3.31 -> 2.07 ms; state box
+  // H = 10 (nt = 60) with the ladder 14.4 -> 11.8 ms.  kernel = 3 reaches it from nt8 = 32.
+  const bool gen_rows = D.mg > 0;
+  const int smem_lo = gen_rows ? (st.kernel == MPCB_KERNEL_ONCHIP_SMEM ? 32 : 48) : 72;
+  const bool smem_ok = nt8 >= smem_lo && nt8 <= 120 &&
                        (D.mg == 0 ? mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) : mpcb::smemg_bytes_host(nt8, D.np, st.sigma != 0.0)) <= (size_t)prop.sharedMemPerBlockOptin;
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;
   const bool ric_form = !D.ric_stage.empty() && mpcb::riccati_supported(D.nx, D.nu);
@@ -537,15 +543,17 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   // Kernel choice (measured crossover, profiles/r02/ricsweep_config4_*.jsonl, quadruple tank, 16 384 problems): the register- and shared-memory
   // resident DMMA kernels win while the condensed operator fits on chip (nt <= 120: H = 50 1.17 ms vs 2.70 ms stage-wise); beyond that the
   // stage-wise kernel replaces the streamed GEMM wherever its form applies (H = 75: 4.4 vs 6.7 ms, H = 200: 14.9 vs 33.9 ms).
-  if (kernel == MPCB_KERNEL_AUTO)
-    kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : ((ric_form && ric_fits) ? MPCB_KERNEL_RICCATI : MPCB_KERNEL_STREAMED));
+  if (kernel == MPCB_KERNEL_AUTO) {
+    if (gen_rows && smem_ok) kernel = MPCB_KERNEL_ONCHIP_SMEM;
+    else kernel = (D.nt <= 64) ? MPCB_KERNEL_ONCHIP : (smem_ok ? MPCB_KERNEL_ONCHIP_SMEM : ((ric_form && ric_fits) ? MPCB_KERNEL_RICCATI : MPCB_KERNEL_STREAMED));
+  }
   if (kernel == MPCB_KERNEL_RICCATI) {
     if (!ric_form) { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: box-only problems without the S term, (nx, nu) in the compiled set"); }
     if (!ric_fits) { delete h; return fail(MPCB_ERR_INVALID, "stage-wise (Riccati) kernel: the stage matrices of this horizon do not fit shared memory"); }
   }
   if (kernel == MPCB_KERNEL_ONCHIP && D.nt > 64) { delete h; return fail(MPCB_ERR_INVALID, "on-chip kernel needs nz + mg <= 64"); }
   if (D.nball > 0 && kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_ONCHIP_SMEM) { delete h; return fail(MPCB_ERR_INVALID, "the contractive terminal set is implemented in the on-chip kernels only: needs nz + mg <= 120"); }
-  if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs 64 < nz + mg <= 120 and an operator that fits 227 KB"); }
+  if (kernel == MPCB_KERNEL_ONCHIP_SMEM && !smem_ok) { delete h; return fail(MPCB_ERR_INVALID, "shared-memory kernel needs 64 < nz <= 120 (box-only) or 32 <= nz + mg <= 120 (general rows) and an operator that fits 227 KB"); }
   if (kernel != MPCB_KERNEL_ONCHIP && kernel != MPCB_KERNEL_STREAMED && kernel != MPCB_KERNEL_ONCHIP_SMEM && kernel != MPCB_KERNEL_RICCATI) { delete h; return fail(MPCB_ERR_INVALID, "unknown kernel id"); }
   h->info.kernel = kernel;
   // rho ladder: only where it applies -- inequality general rows (state box; the ball rows are not boxes) on the on-chip kernel

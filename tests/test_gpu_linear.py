@@ -315,7 +315,7 @@ def test_pipelined_host_entry_equals_plain(mpc, qt):
 @pytest.mark.parametrize("H", [10, 20])
 def test_state_constraint_rows(mpc, qt, H):
     """kw `mpc_state_constraint` (linear.jl:62-70): state-box rows on x[:,2..H+1] become general inequality rows
-    (H = 10: nt = 60, on-chip kernel with general rows; H = 20: nt = 120, shared-memory resident general-row kernel).  The box is tightened to
+    (H = 10: nt = 60 and H = 20: nt = 120, both on the shared-memory resident general-row kernel).  The box is tightened to
     [0.55, 0.75] and the references sit partly beyond it, so the optimal trajectories press against the state bounds.
     CUDA vs the condensed twin, and vs the OSQP port run on the reference's own sparse formulation (independent encoding
     and solver) at tight tolerance."""
@@ -326,7 +326,7 @@ def test_state_constraint_rows(mpc, qt, H):
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_state_constraint=True,
                                mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
     m = C.tuning.modeler
-    assert m.info.mg == 4 * H and m.info.kernel == (1 if H == 10 else 3)      # nt = 60: register-resident; nt = 120: shared-memory resident general-row kernel
+    assert m.info.mg == 4 * H and m.info.kernel == 3      # nt = 60 and nt = 120: shared-memory resident general-row kernel (round 2; before: register-resident / streamed)
     rng = np.random.default_rng(5)
     xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
     mpc.update_initialization(C, x0, references=(xref, qt["u_ref"]))
@@ -520,17 +520,21 @@ def test_c_abi_error_behaviour(mpc, qt):
     assert (r["status"] == -2).all() and (r["iters"] == 10).all()
 
 
-def test_rho_ladder_bounds_the_state_box_tail(mpc, qt):
-    """settings.ladder_iter / ladder_kappa: with active state-box rows a batch-wide fixed rho leaves a few problems per 10^4 with
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_rho_ladder_bounds_the_state_box_tail(mpc, qt, kernel):
+    """(kernel 1: the register-resident general-row kernel, forced; 0: the automatic choice, the shared-memory resident general-row kernel at nt = 60.)
+    settings.ladder_iter / ladder_kappa: with active state-box rows a batch-wide fixed rho leaves a few problems per 10^4 with
     thousands of iterations (OSQP adapts rho per problem there).  The ladder re-solves what the first pass leaves unsolved with a
     second cached operator (state-box step sizes x kappa).  CUDA vs the twin of the same two-pass scheme: same problems on the
     second rung, same iteration counts, same solutions; and against the single-pass solve: same optima, a bounded tail."""
     H, n, eps = 10, 20000, 1e-7
     xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
-    kw = dict(mpc_solver="b200", mpc_state_constraint=True, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000)
+    kw = dict(mpc_solver="b200", mpc_state_constraint=True, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000,
+              mpc_b200_kernel=kernel)
     C1 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), **kw)
     C2 = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_b200_ladder_iter=300, mpc_b200_ladder_kappa=10, **kw)
+    assert C1.tuning.modeler.info.kernel == (1 if kernel == 1 else 3)
     rng = np.random.default_rng(7)
     xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
     out = []

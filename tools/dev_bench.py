@@ -6,7 +6,7 @@ import almpc_b200 as mpc
 from almpc_b200 import _lib
 import bench
 
-def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0, kernel=0, cold_init=1):
+def run(H, n, eps, check, sigma, terminal="none", reps=5, full=False, rho=0.0, near=0.0, state_box=False, Qw=None, Rw=None, max_iter=20000, ladder=0, kernel=0, cold_init=0):
     """near > 0: x0 = x_ref + near * N(0, I) with the design reference (feasible terminal constraints); state_box: tight box + references beyond it"""
     A, B, xmin, xmax, umin, umax, x_ref, u_ref, _ = bench.qt_model()
     if state_box: xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
@@ -174,6 +174,24 @@ if __name__ == "__main__":
                     run(20, n, 1e-7, 5, 0.0, state_box=True, kernel=kern, ladder=lad, reps=2)
         run(40, 16384, 1e-7, 10, 0.0, terminal="equality", near=0.02, kernel=0, reps=3)
         run(40, 16384, 1e-7, 10, 0.0, terminal="equality", near=0.02, kernel=2, reps=3)
+    elif a.set == "sbox10":      # state box at H = 10 (nt = 60): register-resident general-row kernel vs the shared-memory resident one (forced)
+        for kern in (1, 3):
+            for lad in (0, 300):
+                run(10, 65536, 1e-7, 5, 0.0, state_box=True, kernel=kern, ladder=lad, reps=2)
+        for kern in (1, 3):
+            run(26, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.02, kernel=kern, reps=3)      # nt = 56
+            run(30, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.02, kernel=kern, reps=3)      # nt = 64
+    elif a.set == "eqab":        # terminal equality, nt = 32 .. 64: register-resident general-row kernel vs the shared-memory resident one (forced)
+        for H in (14, 18, 20, 22):
+            for kern in (1, 3):
+                run(H, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.02, kernel=kern, reps=3)
+        for kern in (1, 3): run(5, 65536, 1e-7, 5, 0.0, state_box=True, kernel=kern, reps=3)      # state box H = 5: nt = 30
+    elif a.set == "eqab2":       # the same A/B on FEASIBLE batches (x0 within 0.004 of the reference): throughput, not the iteration-cap tail
+        for H in (16, 20, 22, 26, 30):
+            for kern in (1, 3):
+                run(H, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.0015, kernel=kern, reps=3)
+    elif a.set == "eq40one":     # one throughput-bound launch of the shared-memory resident general-row kernel (ncu target)
+        run(40, 65536, 1e-7, 10, 0.0, terminal="equality", near=0.0015, kernel=0, reps=2)
     elif a.set == "steady1":
         run(20, 14208 * 8, 1e-300, 5, 0.0, max_iter=50, reps=3)
     elif a.set == "one":
