@@ -564,6 +564,36 @@ def other_configs(mpc, dev, cpu=True):
                              "(other_family): the curves cross between H = 50 and H = 75",
                 "sweep": sweep})
 
+    # ---- not a BASELINE config: the general-row workloads the shared-memory resident general-row kernel (admm_smemg.cuh) took over from the streamed path
+    try:
+        gen = []
+        n = 16384
+        rng7 = np.random.default_rng(7)
+        for label, Hh, extra, x0g, xrg in (
+                ("state box [0.55, 0.75] on x_1..x_H, H=20 (nt=120), rho ladder 300/x10", 20, dict(mpc_state_constraint=True, mpc_b200_ladder_iter=300, mpc_b200_max_iter=20000),
+                 rng7.uniform(0.62, 0.72, (n, 4)), rng7.uniform(0.70, 0.82, (n, 4))),
+                ("terminal equality, H=40 (nt=84), x0 within 0.0015 of the reference (all feasible)", 40, dict(mpc_terminal_ingredient="equality"),
+                 np.tile(x_ref, (n, 1)) + 0.0015 * rng7.standard_normal((n, 4)), np.tile(x_ref, (n, 1)))):
+            sb = "mpc_state_constraint" in extra
+            sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(np.full(4, 0.55) if sb else xmin, np.full(4, 0.75) if sb else xmax), mpc.Hyperrectangle(umin, umax))
+            Cg = mpc.proceed_controller(sys_, "model_predictive_control", Hh, 5, list(x_ref), list(u_ref), mpc_solver="b200", mpc_b200_eps_abs=EPS, mpc_b200_eps_rel=EPS,
+                                        mpc_b200_check_every=CHECK, mpc_b200_sigma=SIGMA, **extra)
+            mg_ = Cg.tuning.modeler
+            io, t = _device_io(_lib, dev, n, 4, 2, Hh, x0g, xrg, np.asarray(u_ref))
+            ms = _time_device(lambda: mg_.solve_batch_device(io, stream()), 3, flush)
+            it = t["iters"].cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
+            fl = executed_flops(mg_.info, it, CHECK)
+            gen.append({"workload": label, "batch": n, "nt": mg_.info.nt, "kernel_id": mg_.info.kernel, "kernel": kernel_name(mg_.info, SIGMA), "ms": ms, "solves_per_s": n / ms * 1e3,
+                        "mean_iters": float(it.mean()), "max_iters": int(it.max()), "solved_frac": float((st == 1).mean()),
+                        "frac_fp64": fl / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS})
+            mg_.close()
+        out.append({"config": "general rows (not a BASELINE config): quadruple tank with state-box / terminal-equality rows at 64 < nt <= 120 -- on the streamed path until round 2 "
+                              "(252 ms and 3.6 ms, profiles/r02/smemg_sbox20_v1.jsonl), now on the shared-memory resident general-row kernel; the state-box time is the iteration "
+                              "tail of a few problems (one warp's latency), not throughput",
+                    "eps_abs": EPS, "eps_rel": EPS, "check_every": CHECK, "sigma": SIGMA, "workloads": gen})
+    except Exception as e:      # an extra record must never take the bench line down
+        out.append({"config": "general rows", "error": repr(e)})
+
     # ---- configs[2]: random stable LTI nx = 64, nu = 16, H = 50, terminal LQR cost + terminal equality, batch 8 192
     rng = np.random.default_rng(1); nx, nu, Hh, n = 64, 16, 50, 8192
     G = rng.standard_normal((nx, nx)); A3 = 0.95 * G / np.abs(np.linalg.eigvals(G)).max(); B3 = rng.standard_normal((nx, nu)) / 8

@@ -54,7 +54,9 @@ extern "C" {
 #define MPCB_KERNEL_AUTO 0
 #define MPCB_KERNEL_ONCHIP 1   /* register/shared-memory resident DMMA ADMM (nz + m_g <= 64) */
 #define MPCB_KERNEL_STREAMED 2 /* per-iteration FP64 tensor GEMM over HBM/L2-resident state */
-#define MPCB_KERNEL_ONCHIP_SMEM 3 /* shared-memory resident DMMA ADMM: box-only problems, 64 < nz <= ~120 */
+#define MPCB_KERNEL_ONCHIP_SMEM 3 /* shared-memory resident DMMA ADMM: box-only problems with 64 < nz <= 120, and (round 2) problems WITH general
+                                     rows -- terminal equality, contractive ball, state box -- with 48 <= nz + m_g <= 120 by default (from 32 when
+                                     asked for): the operator stays in shared memory, the state in per-warp slices, no host synchronisation */
 #define MPCB_KERNEL_RICCATI 4     /* stage-wise ("sparse") ADMM: the x-update by a cached Riccati sweep over the horizon, O(H) per iteration;
                                      box-only problems without the S term, small (nx, nu); the long-horizon kernel (linear.jl:48-60 is the
                                      reference's own stage-wise formulation) */
@@ -76,7 +78,7 @@ typedef struct {
   int32_t check_every;  /* 25 */
   int32_t device;       /* CUDA device ordinal this handle lives on */
   int32_t kernel;       /* MPCB_KERNEL_* */
-  int32_t ladder_iter;  /* 0 (off).  > 0: rho ladder for controllers with state-box rows (on-chip and streamed kernels) -- problems still unsolved
+  int32_t ladder_iter;  /* 0 (off).  > 0: rho ladder for controllers with state-box rows (register- and shared-memory resident kernels, streamed kernel) -- problems still unsolved
                            after ladder_iter iterations continue from their iterate with the step size of the state-box rows
                            multiplied by ladder_kappa (a second cached operator), for the remaining max_iter - ladder_iter iterations.
                            A batch-wide fixed rho leaves a few problems per 10^4 with thousands of iterations when many state
