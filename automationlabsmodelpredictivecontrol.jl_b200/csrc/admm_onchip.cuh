@@ -62,6 +62,10 @@ struct OnchipParams {
   const int32_t* remap;                  // null: ticket = problem index
   const unsigned long long* batch_dev;   // null: `batch` tickets
   int iters_add;
+  // division of a second pass between the slot kernels and the CTA-cooperative kernel (admm_coop.cuh): with a device-side ticket count, a slot
+  // kernel exits at once when the count is <= tickets_skip_le (the cooperative kernel took them), the cooperative kernel when it is > tickets_max
+  long long tickets_skip_le;             // 0 (zero-initialised): never skips real work
+  long long tickets_max;                 // cooperative kernel only; < 0: no limit
   unsigned long long* counter;  // [0] work queue head, [1] CTAs that have drained it; both zero at launch, the last CTA to
                                 // finish re-zeroes them so that back-to-back launches need no memset in between
 };
@@ -208,7 +212,8 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
   double rad = 0.0;    // contractive terminal set: radius sqrt(0.9) |x0 - xref|_2 of this slot's ball
   bool exhausted = false;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
-  const long long batch_eff = P.batch_dev ? (long long)*P.batch_dev : P.batch;
+  long long batch_eff = P.batch_dev ? (long long)*P.batch_dev : P.batch;
+  if (P.batch_dev && batch_eff <= P.tickets_skip_le) batch_eff = 0;
 
   // one product  out = M in  with M in fragment order
   auto mma_pass = [&](const double* __restrict__ sM, const double (&in)[EPL], double (&out)[EPL]) {

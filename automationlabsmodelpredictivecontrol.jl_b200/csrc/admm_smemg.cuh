@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(W * 32, 1) admm_smemg_kernel(const OnchipParam
   double qn = 0.0, rad = 0.0;
   bool exhausted = false;
   const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
-  const long long batch_eff = P.batch_dev ? (long long)*P.batch_dev : P.batch;
+  long long batch_eff = P.batch_dev ? (long long)*P.batch_dev : P.batch;
+  if (P.batch_dev && batch_eff <= P.tickets_skip_le) batch_eff = 0;
 
   // per-thread operands of the check passes, indexed by the k-step of a rolled loop: local memory
   double in_l[EPL], dys_l[EPL];

@@ -26,6 +26,8 @@ namespace mpcb {
 size_t smemk_bytes_host(int NT, int np, bool sig);
 cudaError_t launch_smemk(int NT, const OnchipParams& P, int sm_count, int* attr_set, cudaStream_t st);
 size_t smemg_bytes_host(int NT, int np, bool sig);
+size_t coop_bytes_host(int NT, int np, bool sig);
+cudaError_t launch_coop(int NT, const OnchipParams& P, int sm_count, cudaStream_t st);       // CTA-cooperative straggler kernel (admm_coop.cuh), NT = 24 .. 120
 cudaError_t launch_smemg(int NT, const OnchipParams& P, int sm_count, cudaStream_t st);      // general rows, 64 < nt <= 120 (admm_smemg.cuh)
 }  // namespace mpcb
 
@@ -294,6 +296,17 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
       P2.max_iter = h->st.max_iter - h->st.ladder_iter; P2.iters_add = P.max_iter;
       P2.warm_v = P.v_out; P2.warm_y = P.y_out;
       P2.remap = h->remap.p; P2.batch_dev = h->counter.p + 2;
+      // A SMALL second rung (the usual case: a few problems per 10^3) is latency, not throughput: the CTA-cooperative kernel gives every group of
+      // eight stragglers a whole CTA.  The count lives on the device, so both kernels are enqueued and each looks at it: up to four groups per SM
+      // go to the cooperative kernel, anything larger to the slot kernel.
+      if (D.nball == 0 && h->NT >= 24 && h->NT <= 120 && mpcb::coop_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin) {
+        OnchipParams Pc = P2;
+        Pc.tickets_max = 32LL * h->info.sm_count;
+        e = mpcb::launch_coop(h->NT, Pc, h->info.sm_count, st);
+        if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_coop (second rung) launch: ") + cudaGetErrorString(e));
+        P2.tickets_skip_le = Pc.tickets_max;
+        launches += 1;
+      }
       e = launch_slots(P2);
       if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip (second rung) launch: ") + cudaGetErrorString(e));
       launches += 2;
