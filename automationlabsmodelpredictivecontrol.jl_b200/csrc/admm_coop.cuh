@@ -3,11 +3,11 @@
 // The slot kernels (admm_onchip.cuh, admm_smemg.cuh) give one warp eight problems and the whole operator product: right for throughput,
 // wrong for the stragglers of a state-box batch -- a few dozen problems that need 1 000 .. 2 000 more iterations each, on a device that is
 // otherwise idle.  Their time is one warp's iteration latency (nt = 120: 450 dependent-issue DMMAs + 30 rows of elementwise work ~ 8.8 us).
-// Here ONE CTA of four warps works on ONE group of eight problems: every warp owns a quarter of the n-tiles (output rows) of the product and
+// Here ONE CTA of eight warps works on ONE group of eight problems: every warp owns an eighth of the n-tiles (output rows) of the product and
 // of the per-row state, the operand vector r of the next iteration is exchanged through a double-buffered shared-memory slice, one CTA
 // barrier per iteration.  Same arithmetic per row in the same order as the slot kernels (the k-step order of every accumulator is
 // unchanged), so results are bit-identical to theirs; only the reductions of a check cross warps (maxima: order-free; the support sum of
-// the infeasibility certificate is summed per warp, then over the four warps).
+// the infeasibility certificate is summed per warp, then over the warps).
 // No ball rows (the ladder applies to state-box rows only); launched behind the first rung with the ticket count read from device memory,
 // and it leaves the work to the slot kernel when that count is large (P.tickets_max).
 #pragma once
@@ -18,10 +18,10 @@
 
 namespace mpcb {
 
-constexpr int COOP_WARPS = 4;
+constexpr int COOP_WARPS = 8;
 
 // shared memory: T fragments NT*NT, lo / hi / rho / 1/rho NT each, parameter staging [8][npad], CTA-wide row slices (z, y/rho, q|b, [x], operand x2, check operand)
-// of KS*32 doubles each, reduction scratch [4 warps][8 slots][8 values], one control word
+// of KS*32 doubles each, reduction scratch [warps][8 slots][8 values], one control word
 __host__ __device__ inline size_t coop_bytes(int NT, int np, bool sig) {
   const int npad = (np + 1) & ~1;
   return sizeof(double) * ((size_t)NT * NT + 4 * NT + (size_t)8 * npad + (size_t)(sig ? 7 : 6) * (NT / 4) * 32 + COOP_WARPS * 8 * 8 + 2);
@@ -67,12 +67,22 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coop_kernel(const Onc
 #pragma unroll
     for (int i = 0; i < RPW; i++) out[i] = 0.0;
     const double* fp = frag + lane;
-#pragma unroll 2
-    for (int s = 0; s < KS; s++) {
-      const double a = op[s * 32];
+    if (from_global) {        // the check operator streams from L2: six k-steps of loads in flight per round trip
+#pragma unroll 6
+      for (int s = 0; s < KS; s++) {
+        const double a = op[s * 32];
 #pragma unroll
-      for (int j = 0; j < TPW; j++)
-        if (tn0 + j < NTL) dmma884(out[2 * j], out[2 * j + 1], a, from_global ? __ldg(fp + (s * NTL + tn0 + j) * 32) : fp[(s * NTL + tn0 + j) * 32]);
+        for (int j = 0; j < TPW; j++)
+          if (tn0 + j < NTL) dmma884(out[2 * j], out[2 * j + 1], a, __ldg(fp + (s * NTL + tn0 + j) * 32));
+      }
+    } else {
+#pragma unroll 2
+      for (int s = 0; s < KS; s++) {
+        const double a = op[s * 32];
+#pragma unroll
+        for (int j = 0; j < TPW; j++)
+          if (tn0 + j < NTL) dmma884(out[2 * j], out[2 * j + 1], a, fp[(s * NTL + tn0 + j) * 32]);
+      }
     }
   };
   // per-slot combination of per-warp partials: every thread ends with the same value for its slot
@@ -226,8 +236,15 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coop_kernel(const Onc
       it_s += P.check_every;
 
       // ---------------------------------------------------------------- termination (OSQP criteria at x~, z+, y+)
+      // The dual residual needs a pass with C; a slot can only terminate on it when its primal residual has converged (or at the cap, or with an
+      // infeasibility candidate, whose reported residuals must be complete): while no slot of the group is there, the pass is skipped.
       double rd = 0.0, nD = 0.0;
-      {
+      put(0, quad_max(rp)); put(2, quad_max(nA)); put(4, quad_max(ndy)); put(5, quad_sum(supp));
+      __syncthreads();
+      rp = get_max(0); nA = get_max(2); ndy = get_max(4); supp = get_sum(5);
+      const bool cand0 = (pi >= 0) && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);
+      const bool want_rd = (pi >= 0) && ((rp <= P.eps_abs + P.eps_rel * nA) || cand0 || it_s >= max_iter);
+      if (__syncthreads_or(want_rd ? 1 : 0)) {
         double cc[RPW];
         product(P.Cfrag, sIn, true, cc);                           // [Pc x~ + G' y_g ; G x~], this warp's rows
 #pragma unroll
@@ -241,12 +258,12 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coop_kernel(const Onc
               nD = dmaxf(nD, dmaxf(fabs(cc[2 * j + jj]), fabs(yb)));
             }
           }
+        put(1, quad_max(rd)); put(3, quad_max(nD));
+        __syncthreads();
+        rd = get_max(1); nD = get_max(3);
       }
-      put(0, quad_max(rp)); put(1, quad_max(rd)); put(2, quad_max(nA)); put(3, quad_max(nD)); put(4, quad_max(ndy)); put(5, quad_sum(supp));
-      __syncthreads();
-      rp = get_max(0); rd = get_max(1); nA = get_max(2); nD = get_max(3); ndy = get_max(4); supp = get_sum(5);
-      const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
-      const bool cand = (pi >= 0) && !conv && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);
+      const bool conv = want_rd && (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
+      const bool cand = cand0 && !conv;
       bool pinf = false;
       if (__syncthreads_or(cand ? 1 : 0)) {        // (also the barrier between reading and rewriting the reduction scratch and sIn)
 #pragma unroll

@@ -82,7 +82,9 @@ typedef struct {
                            after ladder_iter iterations continue from their iterate with the step size of the state-box rows
                            multiplied by ladder_kappa (a second cached operator), for the remaining max_iter - ladder_iter iterations.
                            A batch-wide fixed rho leaves a few problems per 10^4 with thousands of iterations when many state
-                           bounds are active (OSQP would adapt rho per problem); the second rung bounds that tail. */
+                           bounds are active (OSQP would adapt rho per problem); the second rung bounds that tail.  On the register- and shared-memory
+                           resident kernels a small second rung (the usual case) runs on a CTA-cooperative kernel -- one CTA per eight stragglers --
+                           without a host round trip: it is latency, not throughput. */
   int32_t ladder_kappa; /* 10 when ladder_iter > 0 and this is <= 0 */
   int32_t n_devices;    /* <= 1: the handle lives on `device`.  2..8: ONE handle drives device_ids[0..n_devices-1] from one process:
                            the per-system constants are replicated on every device at create; a batch is cut into n_devices contiguous shards
