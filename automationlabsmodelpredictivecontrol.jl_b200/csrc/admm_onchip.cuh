@@ -520,8 +520,27 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
     it_s += P.check_every;
 
     // ------------------------------------------------------------------ termination (OSQP criteria at x~, z+, y+)
+    // With general rows the dual residual needs a pass with C; a slot can only terminate on it when its primal residual has converged (or at
+    // the cap, or with an infeasibility candidate, whose reported residuals must be complete): while no slot of the warp is there, it is skipped.
     bool pinf = false;
+    bool prim_ok = true, cand0 = false, want_rd = true;
+    double ndy = 0.0, supp = 0.0;
     if (HAS_G) {
+      rp = quad_max(rp); nA = quad_max(nA);
+#pragma unroll
+      for (int le = 0; le < EPL; le++) {
+        const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
+        const double dy = dys[le];
+        const double off = ((boxbits >> le) & 1u) ? 0.0 : q[le];
+        ndy = dmaxf(ndy, fabs(dy));
+        supp += (sHi[e] + off) * dmaxf(dy, 0.0) + (sLo[e] + off) * (dy < 0.0 ? dy : 0.0);
+      }
+      ndy = quad_max(ndy); supp = quad_sum(supp);
+      prim_ok = rp <= P.eps_abs + P.eps_rel * nA;
+      cand0 = (pi >= 0) && (P.nball == 0) && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);   // no certificate is evaluated for ball rows
+      want_rd = (pi >= 0) && (prim_ok || cand0 || it_s >= max_iter);
+    }
+    if (HAS_G && __any_sync(0xffffffffu, want_rd)) {
       double in[EPL], cc[EPL];
 #pragma unroll
       for (int le = 0; le < EPL; le++) in[le] = ((boxbits >> le) & 1u) ? xt[le] : yo[le];   // [x~; y_g]
@@ -534,20 +553,11 @@ __global__ void __launch_bounds__(ONCHIP_THREADS, MINB) admm_onchip_kernel(const
         }
     }
     if (!HAS_G) { rp = __longlong_as_double((long long)urp); rd = __longlong_as_double((long long)urd); nA = __longlong_as_double((long long)unA); nD = __longlong_as_double((long long)unD); }
-    rp = quad_max(rp); rd = quad_max(rd); nA = quad_max(nA); nD = quad_max(nD);
-    const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
+    if (!HAS_G) { rp = quad_max(rp); nA = quad_max(nA); }
+    rd = quad_max(rd); nD = quad_max(nD);
+    const bool conv = want_rd && (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
     if (HAS_G) {  // OSQP primal infeasibility certificate on delta_y of the last iteration
-      double ndy = 0.0, supp = 0.0;
-#pragma unroll
-      for (int le = 0; le < EPL; le++) {
-        const int e = 8 * (le >> 1) + 2 * l4 + (le & 1);
-        const double dy = dys[le];
-        const double off = ((boxbits >> le) & 1u) ? 0.0 : q[le];
-        ndy = dmaxf(ndy, fabs(dy));
-        supp += (sHi[e] + off) * dmaxf(dy, 0.0) + (sLo[e] + off) * (dy < 0.0 ? dy : 0.0);
-      }
-      ndy = quad_max(ndy); supp = quad_sum(supp);
-      const bool cand = (pi >= 0) && !conv && (P.nball == 0) && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);   // no certificate is evaluated for ball rows
+      const bool cand = cand0 && !conv;
       if (__any_sync(0xffffffffu, cand)) {
         double in[EPL], cc[EPL];
 #pragma unroll

@@ -230,8 +230,14 @@ __global__ void __launch_bounds__(W * 32, 1) admm_smemg_kernel(const OnchipParam
     it_s += P.check_every;
 
     // ------------------------------------------------------------------ termination (OSQP criteria at x~, z+, y+)
+    // The dual residual needs a pass with C; a slot can only terminate on it when its primal residual has converged (or at the cap, or with an
+    // infeasibility candidate, whose reported residuals must be complete): while no slot of the warp is there, the pass is skipped.
     bool pinf = false;
-    {
+    rp = quad_max(rp); nA = quad_max(nA); ndy = quad_max(ndy); supp = quad_sum(supp);
+    const bool prim_ok = rp <= P.eps_abs + P.eps_rel * nA;
+    const bool cand0 = (pi >= 0) && (P.nball == 0) && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);   // no certificate is evaluated for ball rows
+    const bool want_rd = (pi >= 0) && (prim_ok || cand0 || it_s >= max_iter);
+    if (__any_sync(0xffffffffu, want_rd)) {
       double cc[EPL];
       c_pass(cc);                                                 // [Pc x~ + G' y_g ; G x~]
 #pragma unroll
@@ -247,11 +253,10 @@ __global__ void __launch_bounds__(W * 32, 1) admm_smemg_kernel(const OnchipParam
         }
       }
     }
-    rp = quad_max(rp); rd = quad_max(rd); nA = quad_max(nA); nD = quad_max(nD);
-    const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
+    rd = quad_max(rd); nD = quad_max(nD);
+    const bool conv = want_rd && prim_ok && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
     {  // OSQP primal infeasibility certificate on delta_y of the last iteration
-      ndy = quad_max(ndy); supp = quad_sum(supp);
-      const bool cand = (pi >= 0) && !conv && (P.nball == 0) && (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy);   // no certificate is evaluated for ball rows
+      const bool cand = cand0 && !conv;
       if (__any_sync(0xffffffffu, cand)) {
         double cc[EPL];
 #pragma unroll 1

@@ -541,12 +541,12 @@ int mpcb_create_linear(const mpcb_linear_desc* desc, const mpcb_settings* settin
   h->info.device = st.device; h->info.sm_count = prop.multiProcessorCount;
   int kernel = st.kernel;
   const int nt8 = ((D.nt + 7) / 8) * 8;
-  // The general-row variant of the shared-memory kernel also takes nt8 = 48 .. 64 by default: the register-resident general-row kernels run at 255
-  // registers with spills there.  Measured (profiles/r02/smemg_ab_*.jsonl, 65 536 problems, terminal equality): nt8 = 40 0.752 vs 0.749 ms (a tie, and
-  // the register kernel has the shorter single-problem latency: it keeps nt8 <= 40), 48: 1.25 -> 1.06, 56: 2.18 -> 1.54, 64: 3.31 -> 2.07 ms; state box
-  // H = 10 (nt = 60) with the ladder 14.4 -> 11.8 ms.  kernel = 3 reaches it from nt8 = 32.
+  // The general-row variant of the shared-memory kernel also takes nt8 = 56 .. 64 by default.  Measured (profiles/r02/smemg_ab_v2_*.jsonl, 65 536
+  // problems, terminal equality, register-resident vs shared-memory resident): nt8 = 40 0.650 vs 0.737 ms, 48: 0.897 vs 0.951 (nt = 44) and 1.288 vs
+  // 1.210 (nt = 48) -- a toss-up, and the register kernel has the shorter single-problem latency --, 56: 1.93 vs 1.58, 64: 2.08 vs 1.83 ms; state
+  // box H = 10 (nt = 60): 36.1 vs 27.6 ms, with the ladder 7.8 vs 6.0 ms.  kernel = 3 reaches it from nt8 = 32.
   const bool gen_rows = D.mg > 0;
-  const int smem_lo = gen_rows ? (st.kernel == MPCB_KERNEL_ONCHIP_SMEM ? 32 : 48) : 72;
+  const int smem_lo = gen_rows ? (st.kernel == MPCB_KERNEL_ONCHIP_SMEM ? 32 : 56) : 72;
   const bool smem_ok = nt8 >= smem_lo && nt8 <= 120 &&
                        (D.mg == 0 ? mpcb::smemk_bytes_host(nt8, D.np, st.sigma != 0.0) : mpcb::smemg_bytes_host(nt8, D.np, st.sigma != 0.0)) <= (size_t)prop.sharedMemPerBlockOptin;
   h->smem_optin = (size_t)prop.sharedMemPerBlockOptin;

@@ -55,7 +55,7 @@ extern "C" {
 #define MPCB_KERNEL_ONCHIP 1   /* register/shared-memory resident DMMA ADMM (nz + m_g <= 64) */
 #define MPCB_KERNEL_STREAMED 2 /* per-iteration FP64 tensor GEMM over HBM/L2-resident state */
 #define MPCB_KERNEL_ONCHIP_SMEM 3 /* shared-memory resident DMMA ADMM: box-only problems with 64 < nz <= 120, and (round 2) problems WITH general
-                                     rows -- terminal equality, contractive ball, state box -- with 48 <= nz + m_g <= 120 by default (from 32 when
+                                     rows -- terminal equality, contractive ball, state box -- with 48 < nz + m_g <= 120 by default (from 32 when
                                      asked for): the operator stays in shared memory, the state in per-warp slices, no host synchronisation */
 #define MPCB_KERNEL_RICCATI 4     /* stage-wise ("sparse") ADMM: the x-update by a cached Riccati sweep over the horizon, O(H) per iteration;
                                      box-only problems without the S term, small (nx, nu); the long-horizon kernel (linear.jl:48-60 is the
