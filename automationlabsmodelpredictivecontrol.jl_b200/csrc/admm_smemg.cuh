@@ -20,7 +20,7 @@
 namespace mpcb {
 
 // shared memory: T fragments NT*NT, lo / hi / rho / 1/rho NT each, per-warp parameter staging [8][npad], per-warp state (3 or 4) x KS x 32
-__host__ __device__ inline size_t smemg_bytes(int NT, int np, bool sig, int W) {
+__host__ __device__ constexpr size_t smemg_bytes(int NT, int np, bool sig, int W) {
   const int npad = (np + 1) & ~1;
   return sizeof(double) * ((size_t)NT * NT + 4 * NT + (size_t)W * 8 * npad + (size_t)W * (sig ? 4 : 3) * (NT / 4) * 32);
 }

@@ -9,7 +9,7 @@ OBJ=$(mktemp -d)
 trap 'rm -rf "$OBJ"' EXIT
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3,-Wall ${MPCB_NVCC_EXTRA:-}"
 pids=()
-for src in mpcb_api.cu admm_smem.cu admm_smemg.cu admm_coop.cu nmpc_api.cu nmpc_variant_00.cu nmpc_variant_01.cu nmpc_variant_10.cu nmpc_variant_11.cu nmpc_variant_lin_00.cu nmpc_variant_lin_01.cu nmpc_variant_lin_10.cu nmpc_variant_lin_11.cu admm_stream.cu admm_riccati.cu host_design.cpp; do
+for src in mpcb_api.cu admm_smem.cu admm_smemg.cu admm_smemg_sig.cu admm_coop.cu nmpc_api.cu nmpc_variant_00.cu nmpc_variant_01.cu nmpc_variant_10.cu nmpc_variant_11.cu nmpc_variant_lin_00.cu nmpc_variant_lin_01.cu nmpc_variant_lin_10.cu nmpc_variant_lin_11.cu admm_stream.cu admm_riccati.cu host_design.cpp; do
   $NVCC $FLAGS -c "$src" -o "$OBJ/${src%.*}.o" > "$OBJ/${src%.*}.log" 2>&1 &
   pids+=($!)
 done
