@@ -192,6 +192,8 @@ if __name__ == "__main__":
                 run(H, 65536, 1e-7, 5, 0.0, terminal="equality", near=0.0015, kernel=kern, reps=3)
     elif a.set == "eq40one":     # one throughput-bound launch of the shared-memory resident general-row kernel (ncu target)
         run(40, 65536, 1e-7, 10, 0.0, terminal="equality", near=0.0015, kernel=0, reps=2)
+    elif a.set == "coopone":     # one state-box solve with the ladder: first rung on the shared-memory general-row kernel, second on the cooperative kernel (ncu target)
+        run(20, 16384, 1e-7, 5, 0.0, state_box=True, kernel=0, ladder=300, reps=1)
     elif a.set == "steady1":
         run(20, 14208 * 8, 1e-300, 5, 0.0, max_iter=50, reps=3)
     elif a.set == "one":
