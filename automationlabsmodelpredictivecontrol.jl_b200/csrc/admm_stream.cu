@@ -254,10 +254,32 @@ struct CheckParams {
   double* Out;        // optional: raw product (used for A' dy of the certificate), may be null
   int rows, NTp, nz, mode;   // mode 0: dual residual reductions ; 1: store product only
   int kt0;                   // first k-tile (mode 1: the operand is zero on the box columns)
+  // Skipping: a row can only terminate on the dual residual when its primal residual has converged (or at the cap, or as an infeasibility
+  // candidate, whose reported residuals must be complete); the certificate product is needed for candidates only.  A CTA whose BM rows hold no
+  // such row returns before its GEMM tile (same decisions and reported residuals: stream_decide_kernel tests the primal residual first).
+  const int* done; const double* cert;     // cert: [rows][3] ndy, supp, atdy (stream_cert_kernel) or null
+  double eps_abs, eps_rel, eps_pinf;
+  int want_all;                            // the iteration cap is reached: every active row reports its residuals
 };
 __global__ void __launch_bounds__(THREADS, 2) stream_check_kernel(const CheckParams P) {
   extern __shared__ __align__(16) double smem[];
   const int bn0 = blockIdx.x * BN, bm0 = blockIdx.y * BM;
+  if (!P.want_all) {
+    int want = 0;
+    for (int r = threadIdx.x; r < BM; r += THREADS) {
+      const int b = bm0 + r;
+      if (b < P.rows && !P.done[b]) {
+        bool cand = false;
+        if (P.cert != nullptr) { const double ndy = P.cert[(size_t)b * 3], supp = P.cert[(size_t)b * 3 + 1]; cand = (ndy > P.eps_pinf) && (supp < -P.eps_pinf * ndy); }
+        if (P.mode == 1) want |= cand ? 1 : 0;
+        else {
+          const double rp = __longlong_as_double((long long)P.red[(size_t)b * 4]), nA = __longlong_as_double((long long)P.red[(size_t)b * 4 + 2]);
+          want |= (cand || rp <= P.eps_abs + P.eps_rel * nA) ? 1 : 0;
+        }
+      }
+    }
+    if (!__syncthreads_or(want)) return;
+  }
   double acc[4][4][2];
   gemm_tile(P.In, P.C, P.rows, P.NTp, bm0, bn0, acc, smem, P.kt0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
@@ -598,6 +620,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
       if (st.check_every >= 2) {   // G' dy_g into Rout (scratch: it is fully rewritten by the next iteration)
         CheckParams c2; c2.In = sw.DY; c2.C = sc.C; c2.QB = QB; c2.YO = sw.YO; c2.red = red; c2.Out = Rout; c2.rows = rows; c2.NTp = NTp; c2.nz = nz; c2.mode = 1;
         c2.kt0 = nz / BK;
+        c2.done = done; c2.cert = sw.cert; c2.eps_abs = st.eps_abs; c2.eps_rel = st.eps_rel; c2.eps_pinf = st.eps_prim_inf; c2.want_all = 0;
         stream_check_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(c2); nl++;
         stream_cert2_kernel<<<rows, 128, 0, stream>>>(Rout, sw.YO, sw.YP, sw.cert, NTp, nz); nl++;
       }
@@ -608,6 +631,7 @@ cudaError_t stream_solve(const Design& D, const mpcb_settings& st, const StreamC
       e = cudaMemcpy2DAsync(sw.DY + nz, NTp * sizeof(double), sw.YO + nz, NTp * sizeof(double), (NTp - nz) * sizeof(double), rows, cudaMemcpyDeviceToDevice, stream);
       if (e != cudaSuccess) { err = "memcpy2d"; return e; }
       CheckParams c1; c1.In = sw.DY; c1.C = sc.C; c1.QB = QB; c1.YO = sw.YO; c1.red = red; c1.Out = nullptr; c1.rows = rows; c1.NTp = NTp; c1.nz = nz; c1.mode = 0; c1.kt0 = 0;
+      c1.done = done; c1.cert = (st.check_every >= 2) ? sw.cert : nullptr; c1.eps_abs = st.eps_abs; c1.eps_rel = st.eps_rel; c1.eps_pinf = st.eps_prim_inf; c1.want_all = it >= max_iter ? 1 : 0;
       stream_check_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(c1); nl++;
     }
     e = cudaMemsetAsync(sw.count, 0, 2 * sizeof(int), stream);

@@ -99,10 +99,11 @@ def algorithmic_flops(info, iters, check_every):
 
 def executed_flops(info, iters, check_every):
     """What the condensed kernels actually execute: box-only problems get the dual residual in closed form (no termination pass);
-    problems with general rows run one pass with C = [[Pc, G'], [G, 0]] per check."""
+    problems with general rows run a pass with C = [[Pc, G'], [G, 0]] only at the checks where some problem of the warp / row block can
+    terminate (primal residual converged) -- counted here as ONE pass per problem, its last check: a lower bound of what ran."""
     nt, npar = info.nt, 2 * info.nx + info.nu
     it = iters.astype(np.float64)
-    chk = (it / check_every) * 2 * nt * nt if info.mg > 0 else 0.0
+    chk = 2.0 * nt * nt if info.mg > 0 else 0.0
     return float((it * 2 * nt * nt + chk + 2 * nt * npar).sum())
 
 
@@ -625,7 +626,7 @@ def other_configs(mpc, dev, cpu=True):
                          "automatic_rho": rho_auto, "ms_with_automatic_rho": ms_auto, "mean_iters_with_automatic_rho": it_auto}, "mean_iters": float(it.mean()), "max_iters": int(it.max()),
            "solved_frac": float((st == 1).mean()), "infeasible": int((st == -3).sum()), "iteration_cap": int((st == -2).sum()),
            "roofline": {"bound": "tensor", "achieved": fl / (ms * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": fl / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS,
-                        "note": "whole solve (all launches incl. checks, compaction, recovery); flops = iterations x 2 nt^2 + one pass per check with [[Pc,G'],[G,0]], nt = 864 (unpadded), "
+                        "note": "whole solve (all launches incl. checks, compaction, recovery); flops = iterations x 2 nt^2 + ONE pass with [[Pc,G'],[G,0]] per problem (check passes are skipped while no row of a block can terminate), nt = 864 (unpadded), "
                                 "counted per problem up to ITS termination"}}
     if cpu:
         rec["cpu_baseline"] = _cpu_lti(A3, B3, nx, nu, Hh, Cn.tuning.terminal_ingredient.P, x0_h)
