@@ -672,3 +672,29 @@ def test_cold_init_parity_on_every_kernel(mpc, qt, H, kernel, terminal, state_bo
     assert both.mean() > 0.99
     assert r1["iters"][both].mean() < r0["iters"][both].mean()
     assert (np.abs(r1["objective"][both] - r0["objective"][both]) <= 1e-6 * np.maximum(1e-3, np.abs(r0["objective"][both]))).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_rho_ladder_large_second_rung_stays_on_the_slot_kernel(mpc, qt, kernel):
+    """A second rung of more than 32 problems per SM is throughput, not latency: the cooperative kernel leaves it to the slot kernel (both are
+    enqueued and look at the device-side count).  A first rung capped at 25 iterations sends almost the whole batch there; per-problem results
+    equal the twin of the two-pass scheme (a problem's rung does not depend on the others, so the twin runs on a subset)."""
+    H, n, eps = 10, 8000, 1e-7
+    xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_state_constraint=True,
+                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000, mpc_b200_kernel=kernel,
+                               mpc_b200_ladder_iter=25, mpc_b200_ladder_kappa=10)
+    m = C.tuning.modeler
+    assert m.info.kernel == (1 if kernel == 1 else 3)
+    rng = np.random.default_rng(17)
+    xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    res = m.solve_batch(x0, xref, qt["u_ref"], want=("u", "objective"))
+    assert (res["status"] == 1).all() and (res["iters"] > 25).sum() > 32 * 148          # the second rung was far too large for the cooperative kernel
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], C.tuning.terminal_ingredient.P, H, qt["umin"], qt["umax"], xmin, xmax, state_constraint=True)
+    sel = np.sort(rng.choice(n, 500, replace=False))
+    tw = mo.admm_condensed_ladder(c, mo.pack_params(x0[sel], xref[sel], qt["u_ref"]),
+                                  mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000), 25, 10.0)
+    assert (tw["status"] == 1).all() and (res["iters"][sel] == tw["iters"]).mean() > 0.95
+    assert np.abs(res["u"][sel].reshape(len(sel), -1) - tw["v"]).max() < 2e-5

@@ -257,6 +257,9 @@ if __name__ == "__main__":
         run_nmpc("qt_fnn_tanh_model.json", reps=1)
     elif a.set == "lti_tuned":   # config 3 as bench.py runs it: eps 1e-7, the tuned step size, full outputs
         run_lti(scale=1.0, eps=1e-7, rho=296.0242231923552, reps=2, full=True)
+    elif a.set == "lti_check":   # config 3 at the tuned step size: check period 10 (the parity setting) vs 5 now that check GEMMs skip blocks that cannot terminate
+        for chk in (10, 5):
+            run_lti(scale=1.0, eps=1e-7, rho=296.0242231923552, reps=3, full=True, check=chk)
     elif a.set == "lti1":
         run_lti(scale=1.0, reps=1)
     elif a.set == "h50":
