@@ -280,7 +280,14 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
       if (D.mg > 0) return mpcb::launch_smemg(h->NT, Q, h->info.sm_count, st);
       return mpcb::launch_smemk(h->NT, Q, h->info.sm_count, &h->onchip_blocks_per_sm, st);
     };
-    cudaError_t e = launch_slots(P);
+    // A SMALL batch on a controller with general rows (the closed-loop, few-plants-at-a-time use of update_initialization! / calculate!) is one
+    // warp's latency on the slot kernels; the CTA-cooperative kernel gives every group of eight problems a whole CTA (bit-identical results).
+    const bool coop_ok = D.mg > 0 && D.nball == 0 && h->NT >= 24 && h->NT <= 120 && mpcb::coop_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin;
+    static const bool no_small_coop = std::getenv("MPCB_NO_SMALL_COOP") != nullptr;      // A/B switch for measurements
+    const bool small_batch = coop_ok && !no_small_coop && Bn <= 8LL * h->info.sm_count;
+    cudaError_t e;
+    if (small_batch) { OnchipParams Pc = P; Pc.tickets_max = -1; e = mpcb::launch_coop(h->NT, Pc, h->info.sm_count, st); }
+    else e = launch_slots(P);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
     launches += 1;
     if (h->ladder) {
@@ -299,7 +306,7 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
       // A SMALL second rung (the usual case: a few problems per 10^3) is latency, not throughput: the CTA-cooperative kernel gives every group of
       // eight stragglers a whole CTA.  The count lives on the device, so both kernels are enqueued and each looks at it: up to four groups per SM
       // go to the cooperative kernel, anything larger to the slot kernel.
-      if (D.nball == 0 && h->NT >= 24 && h->NT <= 120 && mpcb::coop_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin) {
+      if (coop_ok) {
         OnchipParams Pc = P2;
         Pc.tickets_max = 32LL * h->info.sm_count;
         e = mpcb::launch_coop(h->NT, Pc, h->info.sm_count, st);
