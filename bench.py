@@ -584,7 +584,12 @@ def other_configs(mpc, dev, cpu=True):
             ms = _time_device(lambda: mg_.solve_batch_device(io, stream()), 3, flush)
             it = t["iters"].cpu().numpy().astype(np.float64); st = t["status"].cpu().numpy()
             fl = executed_flops(mg_.info, it, CHECK)
+            # one problem through the host entry (the closed-loop use with a terminal / state constraint): the CTA-cooperative kernel takes small batches
+            ts1 = []
+            for _ in range(33):
+                t0 = time.perf_counter(); mg_.solve_batch(x0g[:1], xrg[:1], np.asarray(u_ref), want=("u0",)); ts1.append((time.perf_counter() - t0) * 1e6)
             gen.append({"workload": label, "batch": n, "nt": mg_.info.nt, "kernel_id": mg_.info.kernel, "kernel": kernel_name(mg_.info, SIGMA), "ms": ms, "solves_per_s": n / ms * 1e3,
+                        "one_problem_cold_start_p50_us": float(np.median(ts1[3:])), "one_problem_kernel": "admm_coop_kernel",
                         "mean_iters": float(it.mean()), "max_iters": int(it.max()), "solved_frac": float((st == 1).mean()),
                         "frac_fp64": fl / (ms * 1e-3) / 1e12 / FP64_PEAK_TFLOPS})
             mg_.close()
