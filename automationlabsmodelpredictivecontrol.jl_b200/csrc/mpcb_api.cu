@@ -85,7 +85,8 @@ struct mpcb_handle {
   // pinned staging for pageable user memory
   PinBuf<double> stage_in, stage_out;
   PinBuf<int32_t> stage_int;
-  PinBuf<double> small_io;     // small batches: inputs and outputs live in one page-locked block the kernels access directly
+  PinBuf<double> small_io;     // small batches: inputs and outputs live in one page-locked block ...
+  DevBuf<double> small_dev;    // ... mirrored in device memory (one copy in, one copy out) unless MPCB_SMALL_ZERO_COPY is set
   int onchip_blocks_per_sm = 0;
   size_t recover_smem_set = 0, recover_wide_smem_set = 0;
 };
@@ -696,7 +697,7 @@ void mpcb_destroy(mpcb_handle* h) {
   mpcb::stream_release(h->sc, h->sw);
   { mpcb::StreamWork none; mpcb::stream_release(h->sc2, none); }
   h->ladder_count.release();
-  h->stage_in.release(); h->stage_out.release(); h->stage_int.release(); h->small_io.release();
+  h->stage_in.release(); h->stage_out.release(); h->stage_int.release(); h->small_io.release(); h->small_dev.release();
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
   if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
@@ -806,13 +807,27 @@ int solve_linear_host(mpcb_handle* h, const mpcb_batch_io* hio) {
       double* out_p[9];
       for (int i = 0; i < 9; i++) out_p[i] = n_out[i] ? take(n_out[i]) : nullptr;
       int32_t* ints = reinterpret_cast<int32_t*>(take((size_t)Bn));
+      // Two modes for the block.  Zero-copy (round 1): the kernels read and write the page-locked block over PCIe -- no DMA operation, but every
+      // dependent access of a kernel is a PCIe round trip (ncu, one problem: solve kernel 35 us, recover kernel 21 us).  Mirrored (round 2, default):
+      // the block has a twin in device memory; ONE copy in (the inputs lead the block), the kernels run on device memory, ONE copy out.
+      static const bool zero_copy = std::getenv("MPCB_SMALL_ZERO_COPY") != nullptr;
+      size_t n_in_total = 0;
+      for (size_t n : n_in) n_in_total += (n + 1) & ~(size_t)1;
+      double* kbase = base;                  // what the kernels see
+      if (!zero_copy) {
+        CUDA_TRY(h->small_dev.ensure(total));
+        kbase = h->small_dev.p;
+        CUDA_TRY(cudaMemcpyAsync(kbase, base, n_in_total * sizeof(double), cudaMemcpyHostToDevice, st));
+      }
+      auto kp = [&](const void* q) { return q ? kbase + (reinterpret_cast<const double*>(q) - base) : nullptr; };
       mpcb_batch_io dio = *hio;
-      dio.x0 = in_p[0]; dio.xref = in_p[1]; dio.uref = in_p[2]; dio.warm_u = in_p[3]; dio.warm_y = in_p[4];
-      dio.u = out_p[0]; dio.e_u = out_p[1]; dio.x = out_p[2]; dio.e_x = out_p[3]; dio.u0 = out_p[4];
-      dio.prim_res = out_p[5]; dio.dual_res = out_p[6]; dio.objective = out_p[7]; dio.y = out_p[8];
-      dio.status = ints; dio.iters = ints + Bn;
+      dio.x0 = kp(in_p[0]); dio.xref = kp(in_p[1]); dio.uref = kp(in_p[2]); dio.warm_u = kp(in_p[3]); dio.warm_y = kp(in_p[4]);
+      dio.u = kp(out_p[0]); dio.e_u = kp(out_p[1]); dio.x = kp(out_p[2]); dio.e_x = kp(out_p[3]); dio.u0 = kp(out_p[4]);
+      dio.prim_res = kp(out_p[5]); dio.dual_res = kp(out_p[6]); dio.objective = kp(out_p[7]); dio.y = kp(out_p[8]);
+      dio.status = reinterpret_cast<int32_t*>(kp(ints)); dio.iters = dio.status + Bn;
       int rc = enqueue_device(h, dio, st, nullptr);
       if (rc != MPCB_OK) return rc;
+      if (!zero_copy) CUDA_TRY(cudaMemcpyAsync(base + n_in_total, kbase + n_in_total, (total - n_in_total) * sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));
       double* dsts[9] = {hio->u, hio->e_u, hio->x, hio->e_x, hio->u0, hio->prim_res, hio->dual_res, hio->objective, hio->y};
       for (int i = 0; i < 9; i++)
