@@ -322,4 +322,201 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coop_kernel(const Onc
   }
 }
 
+// ---- box-only counterpart: small batches on controllers WITHOUT general rows (the reference's own closed-loop use: one plant, one problem per call).
+// Per-row arithmetic of the box-only slot kernels (admm_onchip.cuh / admm_smem.cuh: c = (1 - alpha) z + y / rho and the next operand r per row,
+// closed-form dual residual Pc x~ = r - (sigma + rho) x~, no pass with C), same k-step order per accumulator: results are bit-identical to theirs.
+// shared memory: T fragments, lo / hi NT each, parameter staging [8][npad], CTA-wide slices c, q, [x], operand x2, reduction scratch, control word
+__host__ __device__ inline size_t coopb_bytes(int NT, int np, bool sig) {
+  const int npad = (np + 1) & ~1;
+  return sizeof(double) * ((size_t)NT * NT + 2 * NT + (size_t)8 * npad + (size_t)(sig ? 5 : 4) * (NT / 4) * 32 + COOP_WARPS * 8 * 8 + 2);
+}
+
+template <int NT, bool SIG>
+__global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coopb_kernel(const OnchipParams P) {
+  constexpr int W = COOP_WARPS, THREADS = W * 32;
+  constexpr int KS = NT / 4, NTL = NT / 8, TPW = (NTL + W - 1) / W, RPW = 2 * TPW;
+  extern __shared__ __align__(16) double smem[];
+  double* sT = smem;
+  double* sLo = sT + NT * NT;
+  double* sHi = sLo + NT;
+  const int npad = (P.np + 1) & ~1;
+  double* sPar = sHi + NT;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, l4 = lane & 3;
+  double* sl = sPar + 8 * npad + lane;
+  double* sC = sl;                              // c = (1 - alpha) z + y / rho
+  double* sQ = sl + KS * 32;
+  double* sA0 = sl + 2 * KS * 32;               // operand r of the current / next iteration
+  double* sA1 = sl + 3 * KS * 32;
+  double* sX = sl + 4 * KS * 32;                // only when SIG
+  double* sRed = sPar + 8 * npad + (size_t)(SIG ? 5 : 4) * KS * 32;
+  unsigned long long* sCtl = reinterpret_cast<unsigned long long*>(sRed + W * 8 * 8);
+
+  for (int i = threadIdx.x; i < NT * NT; i += THREADS) sT[i] = P.Tfrag[i];
+  for (int i = threadIdx.x; i < NT; i += THREADS) { sLo[i] = P.lo[i]; sHi[i] = P.hi[i]; }
+  __syncthreads();
+
+  const double sigma = P.sigma, alpha = P.alpha, oma = 1.0 - P.alpha;
+  const double rho_s = P.rho_box, rinv_s = 1.0 / P.rho_box, sig_rho = P.sigma + P.rho_box;
+  const int nz = P.nz;
+  const int max_iter = ((P.max_iter + P.check_every - 1) / P.check_every) * P.check_every;
+  const long long batch_eff = P.batch;
+  const int tn0 = warp * TPW;
+  auto put = [&](int k, double v) { if (l4 == 0) sRed[(warp * 8 + g) * 8 + k] = v; };
+  auto get_max = [&](int k) { double m = sRed[g * 8 + k]; for (int w = 1; w < W; w++) m = dmaxf(m, sRed[(w * 8 + g) * 8 + k]); return m; };
+
+  for (;;) {
+    if (threadIdx.x == 0) sCtl[0] = atomicAdd(P.counter, 1ULL);
+    __syncthreads();
+    const long long base = (long long)sCtl[0] * 8;
+    if (base >= batch_eff) break;
+    long long pi = (base + g < batch_eff) ? base + g : -1;
+    if (warp == 0 && pi >= 0) {
+      for (int j = l4; j < P.np; j += 4) {
+        double v;
+        if (j < P.nx) v = P.x0[pi * P.nx + j];
+        else if (j < 2 * P.nx) v = P.xref[(P.xref_bc ? 0 : pi) * P.nx + (j - P.nx)];
+        else v = P.uref[(P.uref_bc ? 0 : pi) * P.nu + (j - 2 * P.nx)];
+        sPar[g * npad + j] = v;
+      }
+    }
+    __syncthreads();
+    const bool cold_pt = P.Lv != nullptr && P.warm_v == nullptr;
+    double m = 0.0;
+#pragma unroll 1
+    for (int j = 0; j < TPW; j++) {
+      const int t = tn0 + j;
+      if (t >= NTL) break;
+      double a0 = 0.0, a1 = 0.0, u0 = 0.0, u1 = 0.0;
+      if (pi >= 0) {
+        for (int k = 0; k < P.np; k++) {
+          const double pk = sPar[g * npad + k];
+          const double2 l2 = *reinterpret_cast<const double2*>(&P.Lt[k * NT + 8 * t + 2 * l4]);
+          a0 = fma(l2.x, pk, a0); a1 = fma(l2.y, pk, a1);
+        }
+        if (cold_pt)
+          for (int k = 0; k < P.np; k++) {
+            const double pk = sPar[g * npad + k];
+            const double2 l2 = __ldg(reinterpret_cast<const double2*>(&P.Lv[k * NT + 8 * t + 2 * l4]));
+            u0 = fma(l2.x, pk, u0); u1 = fma(l2.y, pk, u1);
+          }
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        const int le = 2 * t + jj, e = 8 * t + 2 * l4 + jj;
+        const double qv = jj ? a1 : a0;
+        m = dmaxf(m, fabs(qv));
+        double v0 = 0.0, ys0 = 0.0;
+        if (pi >= 0) {
+          if (P.warm_v != nullptr) {
+            if (e < nz) v0 = P.warm_v[pi * nz + e];
+            if (e < P.nt) ys0 = P.warm_y[pi * P.nt + e] * rinv_s;
+          } else if (cold_pt && e < nz) {
+            const double vu = jj ? u1 : u0;
+            v0 = dclamp(vu, sLo[e], sHi[e]);
+            ys0 = -MPCB_INIT_KAPPA * (v0 - vu);
+          }
+        }
+        sQ[le * 32] = qv;
+        sC[le * 32] = fma(oma, v0, ys0);
+        sA0[le * 32] = fma(rho_s, v0 - ys0, fma(sigma, v0, -qv));
+        if (SIG) sX[le * 32] = v0;
+      }
+    }
+    put(0, quad_max(m));
+    __syncthreads();
+    const double qn = get_max(0);
+
+    int it_s = 0, cur = 0;
+    for (;;) {
+      double rp = 0.0, rd = 0.0, nA = 0.0, nD = 0.0;
+      double t[RPW], yb[RPW];
+      for (int ii = 0; ii < P.check_every; ii++) {
+        const bool chk = (ii == P.check_every - 1);
+        const double* Ac = cur ? sA1 : sA0;
+        double* An = cur ? sA0 : sA1;
+#pragma unroll
+        for (int i = 0; i < RPW; i++) t[i] = 0.0;
+        {
+          const double* fp = sT + lane;
+#pragma unroll 2
+          for (int s = 0; s < KS; s++) {
+            const double a = Ac[s * 32];
+#pragma unroll
+            for (int j = 0; j < TPW; j++)
+              if (tn0 + j < NTL) dmma884(t[2 * j], t[2 * j + 1], a, fp[(s * NTL + tn0 + j) * 32]);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < TPW; j++) {
+          const int tn = tn0 + j;
+          if (tn < NTL) {
+            const double2 lo2 = *reinterpret_cast<const double2*>(&sLo[8 * tn + 2 * l4]);
+            const double2 hi2 = *reinterpret_cast<const double2*>(&sHi[8 * tn + 2 * l4]);
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++) {
+              const int le = 2 * tn + jj, li = 2 * j + jj;
+              const double qv = sQ[le * 32];
+              const double w = fma(alpha, t[li], sC[le * 32]);
+              const double zn = dclamp(w, jj ? lo2.y : lo2.x, jj ? hi2.y : hi2.x);
+              if (chk) {   // residuals of (x~, z+, y+): Pc x~ = r - (sigma + rho) x~
+                const double pc = fma(-sig_rho, t[li], Ac[le * 32]);
+                const double y1 = rho_s * (w - zn);
+                yb[li] = y1;
+                rp = dmaxf(rp, fabs(t[li] - zn));
+                rd = dmaxf(rd, fabs(pc + qv + y1));
+                nA = dmaxf(nA, dmaxf(fabs(t[li]), fabs(zn)));
+                nD = dmaxf(nD, dmaxf(fabs(pc), fabs(y1)));
+              }
+              sC[le * 32] = fma(-alpha, zn, w);
+              const double d = fma(2.0, zn, -w);
+              if (SIG) {
+                const double xn = fma(alpha, t[li], oma * sX[le * 32]);
+                sX[le * 32] = xn;
+                An[le * 32] = fma(rho_s, d, fma(sigma, xn, -qv));
+              } else {
+                An[le * 32] = fma(rho_s, d, -qv);
+              }
+            }
+          }
+        }
+        __syncthreads();
+        cur ^= 1;
+      }
+      it_s += P.check_every;
+      put(0, quad_max(rp)); put(1, quad_max(rd)); put(2, quad_max(nA)); put(3, quad_max(nD));
+      __syncthreads();
+      rp = get_max(0); rd = get_max(1); nA = get_max(2); nD = get_max(3);
+      const bool conv = (rp <= P.eps_abs + P.eps_rel * nA) && (rd <= P.eps_abs + P.eps_rel * dmaxf(nD, qn));
+      const bool fin = (pi >= 0) && (conv || it_s >= max_iter);
+      if (fin) {
+#pragma unroll
+        for (int j = 0; j < TPW; j++) {
+          const int tn = tn0 + j, e = 8 * tn + 2 * l4;
+          if (tn < NTL) {
+            if (e < nz) P.v_out[pi * nz + e] = t[2 * j];
+            if (e + 1 < nz) P.v_out[pi * nz + e + 1] = t[2 * j + 1];
+            if (P.y_out != nullptr) {
+              if (e < P.nt) P.y_out[pi * P.nt + e] = yb[2 * j];
+              if (e + 1 < P.nt) P.y_out[pi * P.nt + e + 1] = yb[2 * j + 1];
+            }
+          }
+        }
+        if (warp == 0 && l4 == 0) {
+          P.status[pi] = conv ? 1 : -2;
+          P.iters[pi] = it_s + P.iters_add;
+          P.pres[pi] = rp;
+          P.dres[pi] = rd;
+        }
+        pi = -1;
+      }
+      if (__syncthreads_and(pi < 0 ? 1 : 0)) break;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long prev = atomicAdd(P.counter + 1, 1ULL);
+    if (prev == (unsigned long long)gridDim.x - 1ULL) { P.counter[0] = 0ULL; P.counter[1] = 0ULL; }
+  }
+}
+
 }  // namespace mpcb

@@ -13,7 +13,7 @@ cudaError_t launch_smemk_w(const OnchipParams& P, int sm_count, int* attr_set, c
   auto kern = mpcb::admm_smem_kernel<NT, SIG, W>;
   const size_t smem = mpcb::smemk_bytes(NT, P.np, SIG, W);
   if (*attr_set == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);      // the device maximum: another handle with a longer parameter vector must not find the cap lowered
     if (e != cudaSuccess) return e;
     *attr_set = 1;
   }

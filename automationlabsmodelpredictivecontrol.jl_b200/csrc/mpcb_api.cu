@@ -28,6 +28,8 @@ cudaError_t launch_smemk(int NT, const OnchipParams& P, int sm_count, int* attr_
 size_t smemg_bytes_host(int NT, int np, bool sig);
 size_t coop_bytes_host(int NT, int np, bool sig);
 cudaError_t launch_coop(int NT, const OnchipParams& P, int sm_count, cudaStream_t st);       // CTA-cooperative straggler kernel (admm_coop.cuh), NT = 24 .. 120
+size_t coopb_bytes_host(int NT, int np, bool sig);
+cudaError_t launch_coopb(int NT, const OnchipParams& P, int sm_count, cudaStream_t st);      // its box-only counterpart for small batches, NT = 8 .. 120
 cudaError_t launch_smemg(int NT, const OnchipParams& P, int sm_count, cudaStream_t st);      // general rows, 64 < nt <= 120 (admm_smemg.cuh)
 }  // namespace mpcb
 
@@ -86,7 +88,7 @@ struct mpcb_handle {
   PinBuf<double> stage_in, stage_out;
   PinBuf<int32_t> stage_int;
   PinBuf<double> small_io;     // small batches: inputs and outputs live in one page-locked block ...
-  DevBuf<double> small_dev;    // ... mirrored in device memory (one copy in, one copy out) unless MPCB_SMALL_ZERO_COPY is set
+  DevBuf<double> small_dev;    // ... optionally mirrored in device memory (MPCB_SMALL_MIRROR: one copy in, one copy out)
   int onchip_blocks_per_sm = 0;
   size_t recover_smem_set = 0, recover_wide_smem_set = 0;
 };
@@ -106,7 +108,7 @@ cudaError_t launch_onchip_t(const OnchipParams& P, int sm_count, int* blocks_per
   auto kern = mpcb::admm_onchip_kernel<NT, HAS_G, SIG, MINB>;
   const size_t smem = mpcb::onchip_smem_bytes(NT, P.np, HAS_G);
   if (*blocks_per_sm_cache == 0) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);      // the device maximum (see admm_smem.cu)
     if (e != cudaSuccess) return e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, mpcb::ONCHIP_THREADS, smem);
@@ -285,9 +287,11 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     // warp's latency on the slot kernels; the CTA-cooperative kernel gives every group of eight problems a whole CTA (bit-identical results).
     const bool coop_ok = D.mg > 0 && D.nball == 0 && h->NT >= 24 && h->NT <= 120 && mpcb::coop_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin;
     static const bool no_small_coop = std::getenv("MPCB_NO_SMALL_COOP") != nullptr;      // A/B switch for measurements
-    const bool small_batch = coop_ok && !no_small_coop && Bn <= 8LL * h->info.sm_count;
+    const bool coopb_ok = D.mg == 0 && h->NT <= 120 && mpcb::coopb_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin;      // box-only counterpart
+    const bool small_batch = (coop_ok || coopb_ok) && !no_small_coop && Bn <= 8LL * h->info.sm_count;
     cudaError_t e;
-    if (small_batch) { OnchipParams Pc = P; Pc.tickets_max = -1; e = mpcb::launch_coop(h->NT, Pc, h->info.sm_count, st); }
+    if (small_batch && D.mg > 0) { OnchipParams Pc = P; Pc.tickets_max = -1; e = mpcb::launch_coop(h->NT, Pc, h->info.sm_count, st); }
+    else if (small_batch) e = mpcb::launch_coopb(h->NT, P, h->info.sm_count, st);
     else e = launch_slots(P);
     if (e != cudaSuccess) return fail(MPCB_ERR_CUDA, std::string("admm_onchip launch: ") + cudaGetErrorString(e));
     launches += 1;
@@ -807,10 +811,11 @@ int solve_linear_host(mpcb_handle* h, const mpcb_batch_io* hio) {
       double* out_p[9];
       for (int i = 0; i < 9; i++) out_p[i] = n_out[i] ? take(n_out[i]) : nullptr;
       int32_t* ints = reinterpret_cast<int32_t*>(take((size_t)Bn));
-      // Two modes for the block.  Zero-copy (round 1): the kernels read and write the page-locked block over PCIe -- no DMA operation, but every
-      // dependent access of a kernel is a PCIe round trip (ncu, one problem: solve kernel 35 us, recover kernel 21 us).  Mirrored (round 2, default):
-      // the block has a twin in device memory; ONE copy in (the inputs lead the block), the kernels run on device memory, ONE copy out.
-      static const bool zero_copy = std::getenv("MPCB_SMALL_ZERO_COPY") != nullptr;
+      // Two modes for the block.  Zero-copy (default): the kernels read and write the page-locked block over PCIe -- no DMA operation.  Mirrored
+      // (MPCB_SMALL_MIRROR, an A/B knob): the block has a twin in device memory; one copy in (the inputs lead the block), the kernels run on device
+      // memory, one copy out.  Measured, one problem, C ABI p50: with the slot kernels 58.8 (zero-copy) vs 56.1 us (mirrored); with the small-batch
+      // kernels of round 2 (cooperative solve + direct recover, few dependent accesses) 39.1 vs 42.8 us.
+      static const bool zero_copy = std::getenv("MPCB_SMALL_MIRROR") == nullptr;
       size_t n_in_total = 0;
       for (size_t n : n_in) n_in_total += (n + 1) & ~(size_t)1;
       double* kbase = base;                  // what the kernels see

@@ -7,6 +7,7 @@
 // (src/sub/design_mpc.jl:449-456) with all constants.  One thread per problem; the running deviation lives in
 // shared memory as [nx][blockDim] columns (bank-conflict free), every store is a full 8*nx / 8*nu byte run.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -401,6 +402,96 @@ __global__ void __launch_bounds__(RECOVER_THREADS) recover_small_kernel(const Re
   if (P.objective && active) P.objective[p] = J;
 }
 
+// Small batches (the closed-loop, few-plants-at-a-time use): the same per-problem arithmetic as recover_small_kernel -- expression by expression, so the
+// results are bit-identical -- without the shared-memory tiles, chunking and warp-wide copies that make the tiled kernel coalesce for 10^4+ problems and cost
+// it 21 us for ONE problem (ncu): one thread per problem, matrices through the read-only cache, results stored directly.
+template <int NX, int NU>
+__global__ void __launch_bounds__(64) recover_direct_kernel(const RecoverParams P) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.batch) return;
+  const int H = P.H;
+  double sA[NX * NX], sB[NX * NU], sQ[NX * NX], sPt[NX * NX], sR[NU * NU], sS[NU * NU];
+#pragma unroll
+  for (int i = 0; i < NX * NX; i++) { sA[i] = __ldg(P.A + i); sQ[i] = __ldg(P.Q + i); sPt[i] = __ldg(P.Pt + i); }
+#pragma unroll
+  for (int i = 0; i < NX * NU; i++) sB[i] = __ldg(P.B + i);
+#pragma unroll
+  for (int i = 0; i < NU * NU; i++) { sR[i] = __ldg(P.R + i); sS[i] = P.S ? __ldg(P.S + i) : 0.0; }
+  double e[NX], xr[NX], ur[NU], up[NU];
+#pragma unroll
+  for (int i = 0; i < NX; i++) { xr[i] = P.xref[(P.xref_bc ? 0 : p) * NX + i]; e[i] = P.x0[p * NX + i] - xr[i]; }
+#pragma unroll
+  for (int i = 0; i < NU; i++) { ur[i] = P.uref[(P.uref_bc ? 0 : p) * NU + i]; up[i] = 0.0; }
+  double J = 0.0;
+  for (int k = 0; k <= H; k++) {
+    {
+      double quad = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        if (P.e_x) P.e_x[(p * (H + 1) + k) * NX + i] = e[i];
+        if (P.x) P.x[(p * (H + 1) + k) * NX + i] = e[i] + xr[i];
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; j++) s = fma((k == H) ? sPt[j * NX + i] : sQ[j * NX + i], e[j], s);
+        quad = fma(e[i], s, quad);
+      }
+      J += quad;
+    }
+    if (k < H) {
+      double uk[NU], eu[NU];
+#pragma unroll
+      for (int i = 0; i < NU; i++) {
+        uk[i] = P.v[(p * H + k) * NU + i]; eu[i] = uk[i] - ur[i];
+        if (P.u) P.u[(p * H + k) * NU + i] = uk[i];
+        if (P.e_u) P.e_u[(p * H + k) * NU + i] = eu[i];
+        if (k == 0 && P.u0) P.u0[p * NU + i] = uk[i];
+      }
+      if (P.use_R) {
+        double quadr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NU; i++) {
+          double s = 0.0;
+#pragma unroll
+          for (int j = 0; j < NU; j++) s = fma(sR[j * NU + i], eu[j], s);
+          quadr = fma(eu[i], s, quadr);
+        }
+        J += quadr;
+        if (P.use_S) {
+          if (k > 0) {        // delta_u_{k-1} = u_{k-1} - u_k  (design_mpc.jl:429-432)
+            double quads = 0.0;
+#pragma unroll
+            for (int i = 0; i < NU; i++) {
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j < NU; j++) s = fma(sS[j * NU + i], up[j] - uk[j], s);
+              quads = fma(up[i] - uk[i], s, quads);
+            }
+            J += quads;
+          }
+#pragma unroll
+          for (int i = 0; i < NU; i++) up[i] = uk[i];
+        }
+      }
+      double en[NX];
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NX; j++) s = fma(sA[j * NX + i], e[j], s);
+#pragma unroll
+        for (int j = 0; j < NU; j++) s = fma(sB[j * NX + i], eu[j], s);
+        en[i] = s;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; i++) e[i] = en[i];
+    }
+  }
+  if (P.objective) P.objective[p] = J;
+}
+
+inline bool recover_no_direct() { static const bool v = std::getenv("MPCB_NO_SMALL_COOP") != nullptr; return v; }      // A/B switch shared with the small-batch solve
+constexpr long long RECOVER_DIRECT_MAX = 1184;      // batches up to here take the direct kernel (8 problems per SM: the small-batch regime of the solve)
+
 // returns false when no specialisation exists (caller falls back to recover_kernel)
 inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
   const unsigned grid = (unsigned)((R.batch + RECOVER_THREADS - 1) / RECOVER_THREADS);
@@ -420,6 +511,10 @@ inline bool launch_recover_small(const RecoverParams& R, cudaStream_t st) {
   }
 #define MPCB_RS(NX_, NU_)                                                    \
   if (R.nx == NX_ && R.nu == NU_) {                                          \
+    if (R.batch <= RECOVER_DIRECT_MAX && !recover_no_direct()) {             \
+      recover_direct_kernel<NX_, NU_><<<(unsigned)((R.batch + 63) / 64), 64, 0, st>>>(R); \
+      return true;                                                           \
+    }                                                                        \
     if (grid > 444) MPCB_RS1(NX_, NU_, RECOVER_RCH_BATCH)                    \
     MPCB_RS1(NX_, NU_, RECOVER_RCH_FEW)                                      \
   }

@@ -158,13 +158,16 @@ def test_empty_and_ragged_batches(mpc, qt):
     with pytest.raises(mpc.MpcbError):
         m.solve_batch(np.zeros((0, 4)), qt["x_ref"], qt["u_ref"])
     ref = None
-    X0, XREF, uref = qt_batch(qt, 1000, seed=11)
-    for n in (1, 7, 8, 9, 33, 1000):      # not multiples of the 8 problem slots a warp holds
+    X0, XREF, uref = qt_batch(qt, 3000, seed=11)
+    for n in (1, 7, 8, 9, 33, 1000, 1184, 1185, 3000):      # not multiples of the 8 problem slots a warp holds; up to 1 184 (8 per SM) on the cooperative kernel, beyond on the slot kernel
         x0, xref = X0[:n], XREF[:n]
         r = m.solve_batch(x0, xref, uref)
         assert (r["status"] == 1).all() and r["u"].shape == (n, 20, 2)
         if ref is None: ref = r["u"][0].copy()
-        assert np.abs(r["u"][0] - ref).max() < 1e-12       # a problem's answer does not depend on its batch
+        assert np.array_equal(r["u"][0], ref)              # a problem's answer does not depend on its batch -- nor on the kernel that batch size selects
+        if n == 1184: small = {k: r[k][:1000].copy() for k in ("u", "x", "e_x", "e_u", "objective", "iters")}
+        if n == 3000:
+            for k, v in small.items(): assert np.array_equal(r[k][:1000], v), k      # cooperative + direct-recover path == slot + tiled-recover path, bit for bit
 
 
 # ------------------------------------------------------------------------------------------------------------------
