@@ -701,3 +701,24 @@ def test_rho_ladder_large_second_rung_stays_on_the_slot_kernel(mpc, qt, kernel):
                                   mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000), 25, 10.0)
     assert (tw["status"] == 1).all() and (res["iters"][sel] == tw["iters"]).mean() > 0.95
     assert np.abs(res["u"][sel].reshape(len(sel), -1) - tw["v"]).max() < 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H", [10, 20])
+def test_rho_ladder_on_a_small_batch(mpc, qt, H):
+    """Both rungs of the ladder on the cooperative kernel (a batch of at most eight problems per SM): same second-rung set, iteration counts and
+    solutions as the twin of the two-pass scheme."""
+    n, eps = 600, 1e-7
+    xmin, xmax = np.full(4, 0.55), np.full(4, 0.75)
+    sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
+    C = mpc.proceed_controller(sys_, "model_predictive_control", H, 5, list(qt["x_ref"]), list(qt["u_ref"]), mpc_solver="b200", mpc_state_constraint=True,
+                               mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_max_iter=20000, mpc_b200_ladder_iter=100, mpc_b200_ladder_kappa=10)
+    m = C.tuning.modeler
+    rng = np.random.default_rng(41)
+    xref = rng.uniform(0.70, 0.82, (n, 4)); x0 = rng.uniform(0.62, 0.72, (n, 4))
+    res = m.solve_batch(x0, xref, qt["u_ref"], want=("u", "objective"))
+    c = mo.condense(qt["A"], qt["B"], qt["Q"], qt["R"], qt["S"], C.tuning.terminal_ingredient.P, H, qt["umin"], qt["umax"], xmin, xmax, state_constraint=True)
+    tw = mo.admm_condensed_ladder(c, mo.pack_params(x0, xref, qt["u_ref"]), mo.AdmmSettings(rho=m.info.rho, eps_abs=eps, eps_rel=eps, check_every=5, max_iter=20000), 100, 10.0)
+    assert (res["status"] == 1).all() and (tw["status"] == 1).all()
+    assert 5 <= len(tw["second_rung"]) and set(np.flatnonzero(res["iters"] > 100)) == set(tw["second_rung"])
+    assert (res["iters"] == tw["iters"]).mean() > 0.97 and np.abs(res["u"].reshape(n, -1) - tw["v"]).max() < 2e-5
