@@ -650,7 +650,7 @@ def test_cold_init_parity_on_every_kernel(mpc, qt, H, kernel, terminal, state_bo
     """settings.cold_init = 1 (kw `mpc_b200_cold_init`): the cold-start point x = clip(Lv p), y_box = -kappa rho (x - Lv p), z_g = G x of every ADMM
     kernel (register-resident with and without general rows, shared-memory, streamed, stage-wise) against the twin's `cold_start_point`: same
     statuses and iteration counts, solutions to round-off; fewer iterations on average than OSQP's zeros, same optima."""
-    n, eps = 700, 1e-7
+    n, eps = 1300, 1e-7      # more than eight problems per SM: the slot kernels (smaller batches run on the cooperative kernels, which share this code path's arithmetic)
     xmin, xmax = (np.full(4, 0.55), np.full(4, 0.75)) if state_box else (qt["xmin"], qt["xmax"])
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(qt["A"], qt["B"], mpc.Hyperrectangle(xmin, xmax), mpc.Hyperrectangle(qt["umin"], qt["umax"]))
     kw = dict(mpc_solver="b200", mpc_terminal_ingredient=terminal, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_sigma=sigma,
