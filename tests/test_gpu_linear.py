@@ -383,6 +383,7 @@ def test_closed_loop_on_gpu_equals_host_loop(mpc, qt):
     assert np.abs(dev["x_traj"][:, -1] - xref).max() < np.abs(x0 - xref).max()
 
 
+@pytest.mark.parametrize("n", [333, 1333])      # below / above the small-batch threshold (8 problems per SM): cooperative kernels / slot kernels
 @pytest.mark.parametrize("nx,nu,H,terminal,sigma,S_w", [
     (2, 1, 7, "none", 0.0, 0.0),        # nz = 7: odd, scalar stores, recover_small<2,1>
     (3, 1, 30, "none", 1e-6, 0.0),      # odd nx: 8-byte cooperative stores in recover
@@ -396,14 +397,14 @@ def test_closed_loop_on_gpu_equals_host_loop(mpc, qt):
     (20, 3, 8, "none", 0.0, 1.5),       # nx >= 16: the cooperative wide recover kernel (one thread group per problem), with the S term
     (33, 2, 10, "none", 1e-6, 0.0),     # nx = 33: thread groups of 64 with 31 idle lanes
 ])
-def test_random_systems_sweep(mpc, nx, nu, H, terminal, sigma, S_w):
+def test_random_systems_sweep(mpc, nx, nu, H, terminal, sigma, S_w, n):
     """Odd sizes, every kernel path, every recover path: random stable systems, CUDA vs the condensed twin (iteration counts,
     solutions) and vs the result reconstruction of the oracle."""
     rng = np.random.default_rng(100 * nx + 10 * nu + H)
     G = rng.standard_normal((nx, nx)); A = 0.9 * G / np.abs(np.linalg.eigvals(G)).max(); B = rng.standard_normal((nx, nu)) / 2
     umin, umax = -np.ones(nu), np.ones(nu)
     sys_ = mpc.ConstrainedLinearControlDiscreteSystem(A, B, mpc.Hyperrectangle(-50 * np.ones(nx), 50 * np.ones(nx)), mpc.Hyperrectangle(umin, umax))
-    n, eps = 333, 1e-7
+    eps = 1e-7
     C = mpc.proceed_controller(sys_, "model_predictive_control", H, 1, [0.0] * nx, [0.0] * nu, mpc_solver="b200", mpc_Q=10.0, mpc_R=1.0, mpc_S=S_w,
                                mpc_terminal_ingredient=terminal, mpc_b200_eps_abs=eps, mpc_b200_eps_rel=eps, mpc_b200_check_every=5, mpc_b200_sigma=sigma,
                                mpc_b200_max_iter=20000)
