@@ -370,6 +370,19 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coopb_kernel(const On
     const long long base = (long long)sCtl[0] * 8;
     if (base >= batch_eff) break;
     long long pi = (base + g < batch_eff) ? base + g : -1;
+    // the warm start sits next to the parameters in (possibly page-locked host) memory: both round trips are started together
+    double wv[RPW], wy[RPW];
+#pragma unroll
+    for (int j = 0; j < TPW; j++)
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        const int e = 8 * (tn0 + j) + 2 * l4 + jj;
+        wv[2 * j + jj] = 0.0; wy[2 * j + jj] = 0.0;
+        if (P.warm_v != nullptr && pi >= 0 && tn0 + j < NTL) {
+          if (e < nz) wv[2 * j + jj] = P.warm_v[pi * nz + e];
+          if (e < P.nt) wy[2 * j + jj] = P.warm_y[pi * P.nt + e];
+        }
+      }
     if (warp == 0 && pi >= 0) {
       for (int j = l4; j < P.np; j += 4) {
         double v;
@@ -382,10 +395,10 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coopb_kernel(const On
     __syncthreads();
     const bool cold_pt = P.Lv != nullptr && P.warm_v == nullptr;
     double m = 0.0;
-#pragma unroll 1
+#pragma unroll
     for (int j = 0; j < TPW; j++) {
       const int t = tn0 + j;
-      if (t >= NTL) break;
+      if (t >= NTL) continue;
       double a0 = 0.0, a1 = 0.0, u0 = 0.0, u1 = 0.0;
       if (pi >= 0) {
         for (int k = 0; k < P.np; k++) {
@@ -408,8 +421,8 @@ __global__ void __launch_bounds__(COOP_WARPS * 32, 1) admm_coopb_kernel(const On
         double v0 = 0.0, ys0 = 0.0;
         if (pi >= 0) {
           if (P.warm_v != nullptr) {
-            if (e < nz) v0 = P.warm_v[pi * nz + e];
-            if (e < P.nt) ys0 = P.warm_y[pi * P.nt + e] * rinv_s;
+            v0 = wv[2 * j + jj];
+            ys0 = wy[2 * j + jj] * rinv_s;
           } else if (cold_pt && e < nz) {
             const double vu = jj ? u1 : u0;
             v0 = dclamp(vu, sLo[e], sHi[e]);
