@@ -228,7 +228,10 @@ int mpcb_get_timing(const mpcb_handle* h, mpcb_timing* t);
  *   Pc nz x nz, Lq nz x (2nx+nu), G mg x nz, Lb mg x (2nx+nu), T nt x nt  (all column-major) */
 int mpcb_get_design(const mpcb_handle* h, double* Pc, double* Lq, double* G, double* Lb, double* T);
 
-/* The hot path: replaces update_initialization! + calculate! (computation_mpc.jl:17-55) for `batch` problems. */
+/* The hot path: replaces update_initialization! + calculate! (computation_mpc.jl:17-55) for `batch` problems.
+ * A problem's results do not depend on the batch it is solved in: batches of up to eight problems per SM (the reference's own closed-loop use is one
+ * problem per call) run on CTA-cooperative kernels and a direct recover kernel that are bit-identical to the throughput kernels of larger batches; with
+ * up to 96 KB of inputs + outputs the kernels work directly on one page-locked block (no DMA operation): two launches and one synchronisation. */
 int mpcb_solve_linear_batch(mpcb_handle* h, const mpcb_batch_io* host_io);
 /* Same with device-resident buffers on the handle's device (device_ids[0] of a multi-device handle); `cuda_stream` is a cudaStream_t
  * (NULL = default stream).  Asynchronous: returns after enqueueing -- EXCEPT for controllers on MPCB_KERNEL_STREAMED, whose check
