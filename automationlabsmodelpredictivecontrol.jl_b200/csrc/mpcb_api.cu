@@ -288,7 +288,13 @@ int enqueue_device(mpcb_handle* h, const mpcb_batch_io& io, cudaStream_t st, cud
     const bool coop_ok = D.mg > 0 && D.nball == 0 && h->NT >= 24 && h->NT <= 120 && mpcb::coop_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin;
     static const bool no_small_coop = std::getenv("MPCB_NO_SMALL_COOP") != nullptr;      // A/B switch for measurements
     const bool coopb_ok = D.mg == 0 && h->NT <= 120 && mpcb::coopb_bytes_host(h->NT, D.np, h->st.sigma != 0.0) <= h->smem_optin;      // box-only counterpart
-    const bool small_batch = (coop_ok || coopb_ok) && !no_small_coop && Bn <= 8LL * h->info.sm_count;
+    // How small is small (profiles/r02/small_threshold_probe.jsonl, box-only QT, device-resident, solve + recover): against the register-resident slot kernel
+    // (NT <= 64) the cooperative kernel wins up to 8 problems per SM (H = 20: 74 vs 93 us at 1 184 problems, 128 vs 105 us at 2 368); against the
+    // shared-memory resident ones (NT >= 72: one CTA of 4 .. 8 warps per SM, each warp alone on its scheduler) up to 32 per SM (H = 50: 183 vs 638 us at
+    // 1 184 problems, 333 vs 669 at 2 368, 585 vs 668 at 4 736, 1 081 vs 844 at 9 472).
+    static const long long small_env = [] { const char* e = std::getenv("MPCB_SMALL_PER_SM"); return e ? std::atoll(e) : 0LL; }();      // A/B knob
+    const long long small_per_sm = small_env > 0 ? small_env : (h->NT >= 72 ? 32LL : 8LL);
+    const bool small_batch = (coop_ok || coopb_ok) && !no_small_coop && Bn <= small_per_sm * h->info.sm_count;
     cudaError_t e;
     if (small_batch && D.mg > 0) { OnchipParams Pc = P; Pc.tickets_max = -1; e = mpcb::launch_coop(h->NT, Pc, h->info.sm_count, st); }
     else if (small_batch) e = mpcb::launch_coopb(h->NT, P, h->info.sm_count, st);

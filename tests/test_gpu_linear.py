@@ -202,7 +202,7 @@ def test_streamed_matches_twin_and_exact(mpc, qt, H, force, sigma, expect):
 
 def test_streamed_equals_onchip(mpc, qt):
     """Two independent kernels, one algorithm: identical iteration counts and (to rounding) identical solutions."""
-    n = 1500
+    n = 5000          # above the small-batch thresholds (8 problems per SM, 32 for the shared-memory resident kernels): the slot kernels
     x0, xref, uref = qt_batch(qt, n, seed=22)
     out = []
     for kern in (1, 2):
@@ -383,7 +383,7 @@ def test_closed_loop_on_gpu_equals_host_loop(mpc, qt):
     assert np.abs(dev["x_traj"][:, -1] - xref).max() < np.abs(x0 - xref).max()
 
 
-@pytest.mark.parametrize("n", [333, 1333])      # below / above the small-batch threshold (8 problems per SM): cooperative kernels / slot kernels
+@pytest.mark.parametrize("n", [333, 5000])      # below / above the small-batch thresholds (8 problems per SM, 32 for the shared-memory resident kernels): cooperative / slot kernels
 @pytest.mark.parametrize("nx,nu,H,terminal,sigma,S_w", [
     (2, 1, 7, "none", 0.0, 0.0),        # nz = 7: odd, scalar stores, recover_small<2,1>
     (3, 1, 30, "none", 1e-6, 0.0),      # odd nx: 8-byte cooperative stores in recover
