@@ -1,4 +1,5 @@
-// CTA-cooperative ADMM for the LAST FEW problems of a batch with general rows (second rung of the rho ladder; sm_100a, round 2).
+// CTA-cooperative ADMM for FEW problems (sm_100a, round 2): the second rung of the rho ladder, and every small batch (mpcb_api.cu: up to 8 problems per SM,
+// 32 where it replaces a shared-memory resident kernel).  First the general-row kernel, then its box-only counterpart.
 //
 // The slot kernels (admm_onchip.cuh, admm_smemg.cuh) give one warp eight problems and the whole operator product: right for throughput,
 // wrong for the stragglers of a state-box batch -- a few dozen problems that need 1 000 .. 2 000 more iterations each, on a device that is

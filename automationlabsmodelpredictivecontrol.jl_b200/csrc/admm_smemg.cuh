@@ -1,5 +1,5 @@
-// Shared-memory resident batched ADMM WITH general rows (terminal equality / contractive ball / state box) for 64 < nt <= 120
-// (sm_100a, round 2): the general-row counterpart of admm_smem.cuh.  Before it, every controller with general rows and nt > 64 went
+// Shared-memory resident batched ADMM WITH general rows (terminal equality / contractive ball / state box) for 48 < nt <= 120 (compiled from
+// nt8 = 32; the automatic choice from nt8 = 56, mpcb_api.cu) (sm_100a, round 2): the general-row counterpart of admm_smem.cuh.  Before it, every controller with general rows and nt > 64 went
 // to the streamed GEMM path, whose check period costs ~0.2-0.5 ms of launches plus a host synchronisation however few rows are left --
 // exactly wrong for the long iteration tails of active state-box rows (H = 20 with the state box: nt = 120, a few problems of 10^4 need
 // thousands of iterations).  Here a problem never leaves the SM and the call never synchronises with the host.
