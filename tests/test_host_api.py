@@ -96,3 +96,23 @@ def test_controller_type_fields(mpc):
 def test_dare_rejects_bad_input(mpc):
     with pytest.raises(mpc.MpcbError):
         mpc.dare(np.eye(2) * 2.0, np.zeros((2, 1)), np.eye(2), np.eye(1))     # unstable and uncontrollable: no stabilising solution
+
+
+def test_settings_fields_agree_between_header_python_and_julia(mpc):
+    """mpcb_settings is passed by pointer across three languages: the field order of include/mpcb200.h, of the ctypes mirror and of the Julia
+    shim must be the same list (a size check alone would not notice two int32 fields swapped)."""
+    import pathlib, re
+    from almpc_b200 import _lib as L
+    root = pathlib.Path(__file__).resolve().parents[1]
+    hdr = (root / "include" / "mpcb200.h").read_text()
+    body = hdr[hdr.index("typedef struct {", hdr.index("Solver settings.")):hdr.index("} mpcb_settings;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    c_fields = re.findall(r"(?:double|int32_t)\s+(\w+)(?:\[\d+\])?\s*;", body)
+    py_fields = [n for n, _ in L.Settings._fields_]
+    assert c_fields == py_fields, (c_fields, py_fields)
+    jl = (root / "automationlabsmodelpredictivecontrol.jl_b200" / "julia" / "B200ModelPredictiveControl.jl").read_text()
+    jbody = jl[jl.index("struct MpcbSettings"):jl.index("end", jl.index("struct MpcbSettings"))]
+    jl_fields = re.findall(r"(\w+)::(?:Cdouble|Int32|NTuple)", jbody)
+    assert jl_fields == c_fields, (jl_fields, c_fields)
+    s = L.default_settings()
+    assert s.cold_init == 0 and s.ladder_iter == 0 and s.n_devices == 0      # opt-in features are off in the defaults
